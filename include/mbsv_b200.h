@@ -1,0 +1,196 @@
+/*
+ * mbsv_b200.h — C ABI of libmbsv_b200.so, the B200-native (CUDA sm_100a) drop-in for the MCMC sampler of
+ * raphael-group/multibreak-sv.
+ *
+ * The reference has no plugin/FFI interface; the seam this library replaces is
+ *     MultiBreakSV.runMCMC(String)                          src/MultiBreakSV.java:773-877
+ * (initializeMatrix :990-1099, iterate :1101-1182, naiveMove :1184-1289, svMove :1291-1353,
+ *  incrementAllCounters :879-988, MultiBreakSVAssignmentMatrix.computeLogProb/setBreakpoints), called once from
+ * main (:137-141) after fillNonSingletonArray (:128) and before writeFinalFiles (:144).
+ * A Java host binds these entry points with Panama FFM (java.lang.foreign) — see INTEGRATION.md; in this
+ * repository they are driven by the C++ host mirror (mbsv_host_*) and by Python ctypes.
+ *
+ * Conventions
+ *   - primitives and pointers only; no callbacks; no structs by value; every entry point returns int
+ *     (0 = OK, negative = mbsv_status) except where noted.
+ *   - the caller owns every buffer it passes (inputs and outputs); mbsv_problem_create copies its inputs,
+ *     so they may be released as soon as it returns.  The library owns the device memory behind the
+ *     opaque handle.  mbsv_last_error() is library-owned, thread-local, valid until the next call.
+ *   - no C++ exception or abort() crosses the boundary; nothing is printed.
+ *   - one caller thread per handle (the reference is single-threaded with static state,
+ *     MultiBreakSV.java:50-63,78); distinct handles are independent.  mbsv_run is synchronous.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with MBSV_ERR_CUDA.
+ */
+#ifndef MBSV_B200_H
+#define MBSV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBSV_ABI_VERSION 1
+
+typedef enum mbsv_status {
+    MBSV_OK = 0,
+    MBSV_ERR_ARG = -1,         /* bad argument / malformed descriptor */
+    MBSV_ERR_CUDA = -2,        /* CUDA runtime error or no device */
+    MBSV_ERR_NCCL = -3,        /* reserved for the multi-GPU reduce */
+    MBSV_ERR_OOM = -4,         /* host or device allocation failed */
+    MBSV_ERR_INVARIANT = -5,   /* the reference would have thrown Error (MultiBreakSV.java:1122-1130,1142-1144;
+                                  MultiBreakSVAssignmentMatrix.java:375-376) */
+    MBSV_ERR_UNSUPPORTED = -6, /* input the reference itself mishandles (see DESIGN.md "rejected inputs") */
+    MBSV_ERR_IO = -7           /* host mirror: file could not be read / parsed */
+} mbsv_status;
+
+typedef enum mbsv_mode {
+    MBSV_MODE_REPLAY_EXACT = 0, /* the reference MH chain with its quirks; every proposal re-sums the whole
+                                   log-posterior in the reference's order (supports.keySet(), experiments.keySet()) */
+    MBSV_MODE_FAST = 1          /* same RNG stream and proposals; Delta-log-posterior; difference tallies */
+} mbsv_mode;
+
+/*
+ * One batch of S >= 1 independent problems ("subproblems": what one JVM run of the reference sees, e.g. one
+ * subset-N.clusters file of generateIndependentSubproblems.pl).  Fragments, alignments, alignment-ESP
+ * entries, clusters and AlterSV entries of a subproblem are contiguous; all indices below are global.
+ *
+ * What each array is in the reference (all file:line relative to src/):
+ *   sub_frag_ptr      fragments of subproblem s = [sub_frag_ptr[s], sub_frag_ptr[s+1]), listed in
+ *                     fragments.keySet() iteration order (MultiBreakSV.java:62,999,1401)
+ *   sub_cluster_ptr   clusters of subproblem s, in breakpoints.keySet() order (MultiBreakSV.java:61,750,892)
+ *   sub_sv_ptr        entries of bpsWithNonSingletonSupport (MultiBreakSV.java:65,748-771), construction order
+ *   frag_aln_ptr      Fragment.fragmentalignments after intersectClustersAndFragments (:484-505); the index
+ *                     inside a fragment is the AssignmentIndex of the output file
+ *   aln_numerrors/len FragmentAlignment.numerrors / .len (FragmentAlignment.java:33-34)
+ *   aln_exp           index of FragmentAlignment.exp in experiments.keySet() order
+ *   aln_esp_ptr       FragmentAlignment.alignments (the ESPs of the alignment)
+ *   aln_esp_cluster   cluster of esp2cid.get(esp) (MultiBreakSV.java:56,1620) when selecting the alignment
+ *                     makes that ESP count towards the cluster's support (the ESP is a leaf of the cluster's
+ *                     diagram and esp2fragmentID.get(esp) is this fragment, AM.java:291-315); otherwise -1
+ *   aln_esp_leaf      leaf slot of that ESP inside its cluster (used for connected components only)
+ *   cluster_kind      0 = cluster (GASV localization != -1), 1 = connected component (MultiBreakSV.java:452-455)
+ *   supports_order    clusters of each subproblem in A.supports.keySet() order (AM.java:53-66,137): the
+ *                     summation order of computeLogProb
+ *   cluster_hist_ptr  where cluster c's support histogram lives in results.cluster_hist; must provide at
+ *                     least (number of leaves + 1) bins (MultiBreakSVBreakpoint.supportslong)
+ *   cluster_leaf_ptr, leaf_owner          diagram.leaves and esp2fragmentID of each leaf (-1: no such fragment)
+ *   cluster_root_ptr, root_leaf_ptr/_leaf diagram.roots and their ESPs as leaf slots (MultiBreakSVDiagram.java:56-139)
+ *   sv_cluster, sv_frag_ptr, sv_frag      AlterSV: the distinct single-alignment fragments toggled for each
+ *                     eligible cluster (MultiBreakSV.java:1303-1330); sv_numchanged = numchanged (:1311)
+ *   exp_pseq, exp_lambda, logprobcov      Experiment.pseq / .lambdaD / .logprobcov[0..max_support]
+ *                     (Experiment.java:32-35, MultiBreakSV.java:612-614), experiments.keySet() order
+ */
+typedef struct mbsv_problem_desc {
+    int32_t abi_version;     /* MBSV_ABI_VERSION */
+    int32_t n_sub;
+    int32_t n_frag;
+    int32_t n_aln;
+    int32_t n_aln_esp;
+    int32_t n_cluster;
+    int32_t n_exp;
+    int32_t max_support;     /* logprobcov row length - 1 (MultiBreakSV.java:87,426-427) */
+    int32_t n_sv;
+    int32_t n_sv_frag;
+    int32_t n_leaf;
+    int32_t n_root;
+    int32_t n_root_leaf;
+    int32_t n_hist;          /* length of results.cluster_hist */
+    const int32_t* sub_frag_ptr;     /* [n_sub+1] */
+    const int32_t* sub_cluster_ptr;  /* [n_sub+1] */
+    const int32_t* sub_sv_ptr;       /* [n_sub+1], may be NULL when n_sv == 0 */
+    const int32_t* frag_aln_ptr;     /* [n_frag+1] */
+    const int32_t* aln_numerrors;    /* [n_aln] */
+    const int32_t* aln_len;          /* [n_aln] */
+    const int32_t* aln_exp;          /* [n_aln] */
+    const int32_t* aln_esp_ptr;      /* [n_aln+1] */
+    const int32_t* aln_esp_cluster;  /* [n_aln_esp] */
+    const int32_t* aln_esp_leaf;     /* [n_aln_esp], may be NULL when no connected components */
+    const uint8_t* cluster_kind;     /* [n_cluster] */
+    const int32_t* supports_order;   /* [n_cluster] */
+    const int32_t* cluster_hist_ptr; /* [n_cluster+1] */
+    const int32_t* cluster_leaf_ptr; /* [n_cluster+1] */
+    const int32_t* leaf_owner;       /* [n_leaf] */
+    const int32_t* cluster_root_ptr; /* [n_cluster+1] */
+    const int32_t* root_leaf_ptr;    /* [n_root+1] */
+    const int32_t* root_leaf;        /* [n_root_leaf] */
+    const int32_t* sv_cluster;       /* [n_sv] */
+    const int32_t* sv_frag_ptr;      /* [n_sv+1] */
+    const int32_t* sv_frag;          /* [n_sv_frag] */
+    const int32_t* sv_numchanged;    /* [n_sv] */
+    const double* exp_pseq;          /* [n_exp] */
+    const double* exp_lambda;        /* [n_exp] */
+    const double* logprobcov;        /* [n_exp][max_support+1] */
+} mbsv_problem_desc;
+
+typedef struct mbsv_run_params {
+    int32_t mode;            /* mbsv_mode */
+    int32_t n_chains;        /* chains per subproblem; chain c is seeded seed + c */
+    int32_t num_iters;       /* --numiterations (MultiBreakSV.java:83,228) */
+    int32_t burnin;          /* numiters/10, 0 -> 10 (MultiBreakSV.java:186-193); the long-burn-in window is
+                                iter > num_iters - burnin (:903,926,962) */
+    double perr;             /* --perr (MultiBreakSV.java:50,229) */
+    int64_t seed;            /* 123456 in the reference (MultiBreakSV.java:78) */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t java_int_wrap;   /* 1: per-experiment error/length totals wrap like Java int (AM.java:38-39,218-219) */
+    const int32_t* init_assign; /* [n_frag] initial assignment for every chain (the --matchfile path,
+                                   MultiBreakSV.java:1030-1085; no RNG draws are consumed), or NULL for the
+                                   random initialisation of :999-1015 */
+    int32_t trace;           /* 1: fill the trace_* arrays (mcmc.txt columns + accepted-move log) */
+    int32_t reserved;
+} mbsv_run_params;
+
+/* Output buffers (caller-allocated host memory; NULL pointers are skipped). */
+typedef struct mbsv_results {
+    uint32_t* aln_count;       /* [n_aln]  long-window count per alignment, pooled over chains:
+                                  Fragment.avgAssignmentslong[j] * burnin (MultiBreakSV.java:962-969,856-860) */
+    uint32_t* frag_err_count;  /* [n_frag] Fragment.avgNoassignmentlong * burnin */
+    uint32_t* cluster_hist;    /* [n_hist] MultiBreakSVBreakpoint.supportslong[1..]; bin 0 is left 0, the host
+                                  derives it as the reference does (MultiBreakSV.java:1764-1771) */
+    int32_t* final_assign;     /* [n_chains][n_frag] the returned assignment matrix */
+    double* final_logprob;     /* [n_sub][n_chains] A.logprob after the last iteration (:839) */
+    int64_t* counters;         /* [n_sub][n_chains][5] proposalCounts[0], moveCounts[0], proposalCounts[1],
+                                  moveCounts[1] (:842-843), fragment-reassignments */
+    uint64_t* rng_state;       /* [n_sub][n_chains] java.util.Random seed field after the run */
+    int32_t* error;            /* [n_sub][n_chains] 0 or mbsv_status of that chain */
+    double* trace_logprob;     /* [n_sub][n_chains][num_iters]   (trace only) */
+    int32_t* trace_move_frag;  /* -1 no move; >= 0 fragment of an accepted Naive move; -(2+k) accepted AlterSV
+                                  move of the subproblem's k-th eligible cluster */
+    int32_t* trace_move_assign;/* new assignment of that fragment */
+    int32_t* initial_assign;   /* [n_chains][n_frag] state after initializeMatrix */
+    double* initial_logprob;   /* [n_sub][n_chains]  "Initialized Log Probability" (:789) */
+    double kernel_ms;          /* out: device time of the sampler kernels (CUDA events) */
+} mbsv_results;
+
+typedef struct mbsv_problem mbsv_problem;
+
+int mbsv_abi_version(void);
+int mbsv_device_count(void);                      /* >= 0, or MBSV_ERR_CUDA */
+const char* mbsv_last_error(void);
+const char* mbsv_status_string(int status);
+
+/* Validates and copies the descriptor, uploads the packed CSR to `device`. */
+int mbsv_problem_create(const mbsv_problem_desc* desc, int32_t device, mbsv_problem** out);
+int mbsv_problem_destroy(mbsv_problem* p);
+
+/* Runs n_chains chains of num_iters iterations on every subproblem (blocking). */
+int mbsv_run(mbsv_problem* p, const mbsv_run_params* params, mbsv_results* results);
+
+/* Same, but every non-NULL pointer in `results` is DEVICE memory on params->device (e.g. a torch tensor);
+   used by the multi-GPU path so that tallies can be reduced with NCCL without a host round trip. */
+int mbsv_run_device(mbsv_problem* p, const mbsv_run_params* params, mbsv_results* results);
+
+/* Introspection for benchmarks / tests. */
+int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n);   /* see DESIGN.md */
+int64_t mbsv_last_launch_count(void);             /* kernels launched by the last mbsv_run on this thread */
+
+/* Host-side math the Java host would otherwise do itself (fdlibm-equivalent, no FMA contraction). */
+double mbsv_log(double x);
+double mbsv_exp(double x);
+/* logprobcov[k] = logPoisson(k; lambda) for k = 1..max_support, [0] = 0 (MultiBreakSV.java:612-614,1644-1649) */
+int mbsv_fill_logprobcov(double lambda, int32_t max_support, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBSV_B200_H */

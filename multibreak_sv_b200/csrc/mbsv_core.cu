@@ -1,0 +1,549 @@
+// libmbsv_b200.so — core C ABI (include/mbsv_b200.h): descriptor validation, device packing, launch
+// planning and the sampler launches.  There is no CPU fallback in this file or anywhere in the product.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/mbsv_b200.h"
+#include "jmath.cuh"
+#include "sampler_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(_e == cudaErrorMemoryAllocation ? MBSV_ERR_OOM : MBSV_ERR_CUDA,              \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                         \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& v) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+constexpr int MAX_EXP = 4;
+constexpr int WARPS_PER_CTA = 4;
+
+}  // namespace
+
+struct mbsv_problem {
+    int device = 0;
+    mbsv::DevProblem dp{};
+    // host-side planning data
+    int n_sub = 0, n_frag = 0, n_aln = 0, n_cluster = 0, n_exp = 0, n_hist = 0;
+    std::vector<int> sub_W;       // state rows of a chain of subproblem s (F_s + C_s*E)
+    std::vector<int> sub_order;   // subproblems by ascending sub_W (stable)
+    int64_t csr_bytes = 0;
+    // device CSR
+    DevBuf<int> d_sub_frag_ptr, d_sub_cluster_ptr, d_sub_sv_ptr, d_frag_aln_ptr, d_aln_esp_slot, d_supports_local,
+        d_cluster_hist_ptr, d_sv_frag_ptr, d_sv_frag, d_sv_numchanged, d_sub_order, d_sub_W;
+    DevBuf<int4> d_aln_rec;
+    DevBuf<double> d_sub_logF, d_T, d_logint, d_pseq, d_logp, d_log1mp;
+    cudaStream_t streams[8] = {};
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done[8] = {};
+    bool streams_ok = false;
+};
+
+extern "C" {
+
+int mbsv_abi_version(void) { return MBSV_ABI_VERSION; }
+
+const char* mbsv_last_error(void) { return g_err.c_str(); }
+
+const char* mbsv_status_string(int s) {
+    switch (s) {
+        case MBSV_OK: return "ok";
+        case MBSV_ERR_ARG: return "bad argument";
+        case MBSV_ERR_CUDA: return "CUDA error";
+        case MBSV_ERR_NCCL: return "NCCL error";
+        case MBSV_ERR_OOM: return "out of memory";
+        case MBSV_ERR_INVARIANT: return "reference invariant violated";
+        case MBSV_ERR_UNSUPPORTED: return "unsupported input";
+        case MBSV_ERR_IO: return "I/O error";
+        default: return "unknown";
+    }
+}
+
+int mbsv_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(MBSV_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return n;
+}
+
+double mbsv_log(double x) { return mbsv::jm_log(x); }
+double mbsv_exp(double x) { return mbsv::jm_exp(x); }
+
+int mbsv_fill_logprobcov(double lambda, int32_t max_support, double* out) {
+    if (!out || max_support < 0) return fail(MBSV_ERR_ARG, "mbsv_fill_logprobcov: bad argument");
+    out[0] = 0.0;
+    const double ll = mbsv::jm_log(lambda);
+    for (int k = 1; k <= max_support; ++k) {
+        double val = -lambda + k * ll;                       // MultiBreakSV.java:1645
+        for (int i = 1; i <= k; ++i) val -= mbsv::jm_log((double)i);
+        out[k] = val;
+    }
+    return MBSV_OK;
+}
+
+int64_t mbsv_last_launch_count(void) { return g_launches; }
+
+static int validate(const mbsv_problem_desc* d) {
+    if (!d) return fail(MBSV_ERR_ARG, "descriptor is NULL");
+    if (d->abi_version != MBSV_ABI_VERSION) return fail(MBSV_ERR_ARG, "abi_version mismatch");
+    if (d->n_sub < 1 || d->n_frag < 1 || d->n_aln < 1 || d->n_cluster < 0 || d->n_exp < 1 || d->max_support < 0)
+        return fail(MBSV_ERR_ARG, "descriptor sizes out of range");
+    if (d->n_exp > MAX_EXP) return fail(MBSV_ERR_UNSUPPORTED, "more than 4 experiments");
+    if (!d->sub_frag_ptr || !d->sub_cluster_ptr || !d->frag_aln_ptr || !d->aln_numerrors || !d->aln_len || !d->aln_exp ||
+        !d->aln_esp_ptr || (d->n_aln_esp > 0 && !d->aln_esp_cluster) || (d->n_cluster > 0 && (!d->cluster_kind ||
+        !d->supports_order || !d->cluster_hist_ptr)) || !d->exp_pseq || !d->logprobcov)
+        return fail(MBSV_ERR_ARG, "descriptor has a NULL required array");
+    if (d->n_sv > 0 && (!d->sub_sv_ptr || !d->sv_frag_ptr || !d->sv_frag || !d->sv_numchanged))
+        return fail(MBSV_ERR_ARG, "descriptor has n_sv > 0 but NULL AlterSV arrays");
+    auto mono = [&](const int32_t* p, int n, int last, const char* name) -> int {
+        if (p[0] != 0 || p[n] != last) return fail(MBSV_ERR_ARG, std::string(name) + ": bad first/last offset");
+        for (int i = 0; i < n; ++i) if (p[i + 1] < p[i]) return fail(MBSV_ERR_ARG, std::string(name) + ": not monotone");
+        return 0;
+    };
+    int rc;
+    if ((rc = mono(d->sub_frag_ptr, d->n_sub, d->n_frag, "sub_frag_ptr"))) return rc;
+    if ((rc = mono(d->sub_cluster_ptr, d->n_sub, d->n_cluster, "sub_cluster_ptr"))) return rc;
+    if ((rc = mono(d->frag_aln_ptr, d->n_frag, d->n_aln, "frag_aln_ptr"))) return rc;
+    if ((rc = mono(d->aln_esp_ptr, d->n_aln, d->n_aln_esp, "aln_esp_ptr"))) return rc;
+    if (d->n_cluster > 0 && (rc = mono(d->cluster_hist_ptr, d->n_cluster, d->n_hist, "cluster_hist_ptr"))) return rc;
+    if (d->n_sv > 0) {
+        if ((rc = mono(d->sub_sv_ptr, d->n_sub, d->n_sv, "sub_sv_ptr"))) return rc;
+        if ((rc = mono(d->sv_frag_ptr, d->n_sv, d->n_sv_frag, "sv_frag_ptr"))) return rc;
+    }
+    for (int s = 0; s < d->n_sub; ++s)
+        if (d->sub_frag_ptr[s + 1] == d->sub_frag_ptr[s])
+            return fail(MBSV_ERR_ARG, "a subproblem has no fragments (the reference would index an empty keySet, "
+                                      "MultiBreakSV.java:1401)");
+    for (int f = 0; f < d->n_frag; ++f)
+        if (d->frag_aln_ptr[f + 1] == d->frag_aln_ptr[f]) return fail(MBSV_ERR_ARG, "a fragment has no alignment");
+    for (int c = 0; c < d->n_cluster; ++c)
+        if (d->cluster_kind[c] != 0)
+            return fail(MBSV_ERR_UNSUPPORTED, "connected-component clusters (GASV localization -1) are not yet handled "
+                                              "on the device");
+    for (int a = 0; a < d->n_aln; ++a) {
+        if (d->aln_exp[a] < 0 || d->aln_exp[a] >= d->n_exp) return fail(MBSV_ERR_ARG, "aln_exp out of range");
+        if (d->aln_esp_ptr[a + 1] - d->aln_esp_ptr[a] >= (1 << 23)) return fail(MBSV_ERR_ARG, "alignment with too many ESPs");
+    }
+    return 0;
+}
+
+int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem** out) {
+    if (!out) return fail(MBSV_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = validate(d);
+    if (rc) return rc;
+    const int S = d->n_sub, F = d->n_frag, A = d->n_aln, K = d->n_aln_esp, C = d->n_cluster, E = d->n_exp;
+    // which subproblem a cluster / fragment belongs to
+    std::vector<int> cl_sub(C), fr_sub(F);
+    for (int s = 0; s < S; ++s) {
+        for (int c = d->sub_cluster_ptr[s]; c < d->sub_cluster_ptr[s + 1]; ++c) cl_sub[c] = s;
+        for (int f = d->sub_frag_ptr[s]; f < d->sub_frag_ptr[s + 1]; ++f) fr_sub[f] = s;
+    }
+    std::vector<int4> rec(A);
+    std::vector<int> slot(K, -1);
+    std::vector<int> cluster_cap(C, 0);   // how many alignment-ESP entries can count towards a cluster at once
+    int maxn = 1;
+    for (int f = 0; f < F; ++f) {
+        const int s = fr_sub[f];
+        maxn = std::max(maxn, d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]);
+        std::vector<int> best(0);
+        for (int a = d->frag_aln_ptr[f]; a < d->frag_aln_ptr[f + 1]; ++a) {
+            const int x = d->aln_exp[a];
+            const int j0 = d->aln_esp_ptr[a], j1 = d->aln_esp_ptr[a + 1];
+            rec[a] = make_int4(d->aln_numerrors[a], d->aln_len[a], j0, x | ((j1 - j0) << 8));
+            for (int j = j0; j < j1; ++j) {
+                const int c = d->aln_esp_cluster[j];
+                if (c == -1) continue;
+                if (c < d->sub_cluster_ptr[s] || c >= d->sub_cluster_ptr[s + 1])
+                    return fail(MBSV_ERR_ARG, "aln_esp_cluster points outside the fragment's subproblem");
+                slot[j] = (c - d->sub_cluster_ptr[s]) * E + x;
+            }
+        }
+    }
+    // A cluster's support can never exceed its histogram length - 1 nor max_support (logprobcov index).
+    {
+        // upper bound: per fragment the max over its alignments of entries into cluster c, summed over fragments
+        std::vector<int> per_frag(C, 0), stamp(C, -1), total(C, 0);
+        for (int f = 0; f < F; ++f) {
+            std::vector<int> touched;
+            for (int a = d->frag_aln_ptr[f]; a < d->frag_aln_ptr[f + 1]; ++a) {
+                std::vector<std::pair<int, int>> cnt;
+                for (int j = d->aln_esp_ptr[a]; j < d->aln_esp_ptr[a + 1]; ++j) {
+                    const int c = d->aln_esp_cluster[j];
+                    if (c < 0) continue;
+                    bool found = false;
+                    for (auto& pr : cnt) if (pr.first == c) { ++pr.second; found = true; }
+                    if (!found) cnt.push_back({c, 1});
+                }
+                for (auto& pr : cnt) {
+                    if (stamp[pr.first] != f) { stamp[pr.first] = f; per_frag[pr.first] = 0; touched.push_back(pr.first); }
+                    per_frag[pr.first] = std::max(per_frag[pr.first], pr.second);
+                }
+            }
+            for (int c : touched) total[c] += per_frag[c];
+        }
+        for (int c = 0; c < C; ++c) {
+            if (total[c] > d->max_support)
+                return fail(MBSV_ERR_UNSUPPORTED, "a cluster can collect more selected ESPs than max_support "
+                                                  "(the reference would index logprobcov out of bounds)");
+            if (total[c] + 1 > d->cluster_hist_ptr[c + 1] - d->cluster_hist_ptr[c])
+                return fail(MBSV_ERR_ARG, "cluster_hist_ptr leaves too few bins for a cluster");
+        }
+    }
+    std::vector<int> sup_local(C);
+    for (int s = 0; s < S; ++s) {
+        const int c0 = d->sub_cluster_ptr[s], c1 = d->sub_cluster_ptr[s + 1];
+        std::vector<char> seen(c1 - c0, 0);
+        for (int i = c0; i < c1; ++i) {
+            const int c = d->supports_order[i];
+            if (c < c0 || c >= c1 || seen[c - c0]) return fail(MBSV_ERR_ARG, "supports_order is not a permutation of the subproblem's clusters");
+            seen[c - c0] = 1;
+            sup_local[i] = c - c0;
+        }
+    }
+    std::vector<int> sub_sv_ptr(S + 1, 0), sv_frag_ptr(1, 0), sv_frag, sv_numchanged;
+    if (d->n_sv > 0) {
+        sub_sv_ptr.assign(d->sub_sv_ptr, d->sub_sv_ptr + S + 1);
+        sv_frag_ptr.assign(d->sv_frag_ptr, d->sv_frag_ptr + d->n_sv + 1);
+        sv_frag.assign(d->sv_frag, d->sv_frag + d->n_sv_frag);
+        sv_numchanged.assign(d->sv_numchanged, d->sv_numchanged + d->n_sv);
+        for (int s = 0; s < S; ++s)
+            for (int k = sub_sv_ptr[s]; k < sub_sv_ptr[s + 1]; ++k)
+                for (int q = sv_frag_ptr[k]; q < sv_frag_ptr[k + 1]; ++q) {
+                    const int f = sv_frag[q];
+                    if (f < d->sub_frag_ptr[s] || f >= d->sub_frag_ptr[s + 1] ||
+                        d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f] != 1)
+                        return fail(MBSV_ERR_ARG, "sv_frag must list single-alignment fragments of the same subproblem");
+                }
+    }
+    std::vector<double> logF(S), logint(maxn + 1, 0.0), logp(E), log1mp(E);
+    for (int s = 0; s < S; ++s) logF[s] = mbsv::jm_log((double)(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]));
+    for (int n = 1; n <= maxn; ++n) logint[n] = mbsv::jm_log((double)n);
+    for (int x = 0; x < E; ++x) { logp[x] = mbsv::jm_log(d->exp_pseq[x]); log1mp[x] = mbsv::jm_log(1 - d->exp_pseq[x]); }
+
+    // every host-side check is done; from here on a CUDA device is required (no CPU fallback)
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(MBSV_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+
+    mbsv_problem* p = new (std::nothrow) mbsv_problem();
+    if (!p) return fail(MBSV_ERR_OOM, "host allocation failed");
+    p->device = device;
+    p->n_sub = S; p->n_frag = F; p->n_aln = A; p->n_cluster = C; p->n_exp = E; p->n_hist = d->n_hist;
+    p->sub_W.resize(S);
+    for (int s = 0; s < S; ++s)
+        p->sub_W[s] = (d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]) + (d->sub_cluster_ptr[s + 1] - d->sub_cluster_ptr[s]) * E;
+    p->sub_order.resize(S);
+    std::iota(p->sub_order.begin(), p->sub_order.end(), 0);
+    std::stable_sort(p->sub_order.begin(), p->sub_order.end(), [&](int a, int b) { return p->sub_W[a] < p->sub_W[b]; });
+
+    auto up = [&](auto& buf, const auto& vec) -> cudaError_t { return buf.upload(vec); };
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    chk(up(p->d_sub_frag_ptr, std::vector<int>(d->sub_frag_ptr, d->sub_frag_ptr + S + 1)));
+    chk(up(p->d_sub_cluster_ptr, std::vector<int>(d->sub_cluster_ptr, d->sub_cluster_ptr + S + 1)));
+    chk(up(p->d_sub_sv_ptr, sub_sv_ptr));
+    chk(up(p->d_frag_aln_ptr, std::vector<int>(d->frag_aln_ptr, d->frag_aln_ptr + F + 1)));
+    chk(up(p->d_aln_rec, rec));
+    chk(up(p->d_aln_esp_slot, slot));
+    chk(up(p->d_supports_local, sup_local));
+    chk(up(p->d_cluster_hist_ptr, C > 0 ? std::vector<int>(d->cluster_hist_ptr, d->cluster_hist_ptr + C + 1) : std::vector<int>(1, 0)));
+    chk(up(p->d_sv_frag_ptr, sv_frag_ptr));
+    chk(up(p->d_sv_frag, sv_frag));
+    chk(up(p->d_sv_numchanged, sv_numchanged));
+    chk(up(p->d_sub_logF, logF));
+    chk(up(p->d_T, std::vector<double>(d->logprobcov, d->logprobcov + (size_t)E * (d->max_support + 1))));
+    chk(up(p->d_logint, logint));
+    chk(up(p->d_pseq, std::vector<double>(d->exp_pseq, d->exp_pseq + E)));
+    chk(up(p->d_logp, logp));
+    chk(up(p->d_log1mp, log1mp));
+    chk(up(p->d_sub_order, p->sub_order));
+    chk(up(p->d_sub_W, p->sub_W));
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(e == cudaErrorMemoryAllocation ? MBSV_ERR_OOM : MBSV_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e));
+    }
+    p->csr_bytes = (int64_t)(S + 1) * 12 + (int64_t)(F + 1) * 4 + (int64_t)A * 16 + (int64_t)K * 4 + (int64_t)C * 8;
+    mbsv::DevProblem& dp = p->dp;
+    dp.n_sub = S; dp.n_frag = F; dp.n_aln = A; dp.n_cluster = C; dp.n_exp = E; dp.max_support = d->max_support; dp.maxn = maxn;
+    dp.sub_frag_ptr = p->d_sub_frag_ptr.p; dp.sub_cluster_ptr = p->d_sub_cluster_ptr.p; dp.sub_sv_ptr = p->d_sub_sv_ptr.p;
+    dp.sub_logF = p->d_sub_logF.p; dp.frag_aln_ptr = p->d_frag_aln_ptr.p; dp.aln_rec = p->d_aln_rec.p;
+    dp.aln_esp_slot = p->d_aln_esp_slot.p; dp.supports_order_local = p->d_supports_local.p;
+    dp.cluster_hist_ptr = p->d_cluster_hist_ptr.p; dp.sv_frag_ptr = p->d_sv_frag_ptr.p; dp.sv_frag = p->d_sv_frag.p;
+    dp.sv_numchanged = p->d_sv_numchanged.p; dp.T = p->d_T.p; dp.logint = p->d_logint.p; dp.exp_pseq = p->d_pseq.p;
+    dp.exp_logp = p->d_logp.p; dp.exp_log1mp = p->d_log1mp.p;
+    dp.log2pi = mbsv::jm_log(2.0) + mbsv::jm_log(3.141592653589793);
+    for (int i = 0; i < 8; ++i) {
+        chk(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+        chk(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+    }
+    chk(cudaEventCreate(&p->ev_start));
+    chk(cudaEventCreate(&p->ev_stop));
+    if (e != cudaSuccess) { delete p; return fail(MBSV_ERR_CUDA, std::string("stream setup: ") + cudaGetErrorString(e)); }
+    p->streams_ok = true;
+    *out = p;
+    return MBSV_OK;
+}
+
+int mbsv_problem_destroy(mbsv_problem* p) {
+    if (!p) return MBSV_OK;
+    cudaSetDevice(p->device);
+    if (p->streams_ok) {
+        for (int i = 0; i < 8; ++i) { cudaStreamDestroy(p->streams[i]); cudaEventDestroy(p->ev_done[i]); }
+        cudaEventDestroy(p->ev_start);
+        cudaEventDestroy(p->ev_stop);
+    }
+    delete p;
+    return MBSV_OK;
+}
+
+int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n) {
+    if (!p || !out) return fail(MBSV_ERR_ARG, "mbsv_problem_stats: NULL");
+    int64_t v[6] = {p->n_sub, p->n_frag, p->n_aln, p->n_cluster, p->csr_bytes,
+                    p->sub_W.empty() ? 0 : *std::max_element(p->sub_W.begin(), p->sub_W.end())};
+    for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+    return MBSV_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+using KernelFn = void (*)(const mbsv::DevProblem, const mbsv::DevRun);
+
+template <int MODE, bool TRACE, bool SMEM>
+KernelFn pick_e(int E) {
+    switch (E) {
+        case 1: return mbsv::mbsv_chain_kernel<MODE, TRACE, SMEM, 1>;
+        case 2: return mbsv::mbsv_chain_kernel<MODE, TRACE, SMEM, 2>;
+        default: return mbsv::mbsv_chain_kernel<MODE, TRACE, SMEM, 4>;
+    }
+}
+KernelFn pick(int mode, bool trace, bool smem, int E) {
+    if (mode == 0) {
+        if (trace) return smem ? pick_e<0, true, true>(E) : pick_e<0, true, false>(E);
+        return smem ? pick_e<0, false, true>(E) : pick_e<0, false, false>(E);
+    }
+    if (trace) return smem ? pick_e<1, true, true>(E) : pick_e<1, true, false>(E);
+    return smem ? pick_e<1, false, true>(E) : pick_e<1, false, false>(E);
+}
+
+struct OutBufs {
+    DevBuf<unsigned int> aln_count, frag_err, hist;
+    DevBuf<int> final_assign, error, tr_frag, tr_assign, init_assign_out, init_assign_in;
+    DevBuf<double> final_logprob, tr_logprob, init_logprob;
+    DevBuf<long long> counters, row_off;
+    DevBuf<unsigned long long> rng_state;
+    DevBuf<int> workspace;
+};
+
+int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool results_on_device) {
+    g_launches = 0;
+    if (!p || !rp || !res) return fail(MBSV_ERR_ARG, "mbsv_run: NULL argument");
+    if (rp->mode != MBSV_MODE_REPLAY_EXACT && rp->mode != MBSV_MODE_FAST) return fail(MBSV_ERR_ARG, "unknown mode");
+    if (rp->n_chains < 1 || rp->num_iters < 0 || rp->burnin < 0) return fail(MBSV_ERR_ARG, "bad run parameters");
+    if (!(rp->perr >= 0 && rp->perr <= 1)) return fail(MBSV_ERR_ARG, "--perr must be a value between 0 and 1.");
+    if (rp->device != p->device) return fail(MBSV_ERR_ARG, "run device differs from the problem's device");
+    const int64_t win_base = std::max<int64_t>((int64_t)rp->num_iters - rp->burnin + 1, 0);
+    const int64_t nwin = std::max<int64_t>((int64_t)rp->num_iters - win_base, 0);
+    if (nwin * rp->n_chains >= (1LL << 32)) return fail(MBSV_ERR_ARG, "window length x chains overflows the 32-bit tallies");
+    if (rp->trace && (!res->trace_logprob || !res->trace_move_frag || !res->trace_move_assign))
+        return fail(MBSV_ERR_ARG, "trace requested without trace buffers");
+    CUDA_TRY(cudaSetDevice(p->device));
+
+    const int S = p->n_sub, X = rp->n_chains;
+    const int64_t n_items = (int64_t)S * X;
+    const int64_t n_warps64 = (n_items + 31) / 32;
+    if (n_warps64 > 0x7fffffff / 32) return fail(MBSV_ERR_ARG, "too many chains for one launch");
+    const int n_warps = (int)n_warps64;
+    const int64_t sc_total = n_items;
+
+    OutBufs ob;
+    mbsv::DevRun dr{};
+    dr.n_chains = X; dr.num_iters = rp->num_iters; dr.burnin = rp->burnin; dr.win_base = (int)win_base;
+    dr.java_int_wrap = rp->java_int_wrap; dr.perr = rp->perr; dr.logperr = mbsv::jm_log(rp->perr);
+    dr.log1mperr = mbsv::jm_log(1 - rp->perr); dr.seed = rp->seed;
+    dr.sub_order = p->d_sub_order.p; dr.sub_W = p->d_sub_W.p; dr.n_items = n_items;
+
+    if (rp->init_assign) {
+        if (results_on_device) dr.init_assign = rp->init_assign;
+        else {
+            CUDA_TRY(ob.init_assign_in.alloc(p->n_frag));
+            CUDA_TRY(cudaMemcpy(ob.init_assign_in.p, rp->init_assign, sizeof(int) * p->n_frag, cudaMemcpyHostToDevice));
+            dr.init_assign = ob.init_assign_in.p;
+        }
+    }
+    // outputs
+    const size_t trN = rp->trace ? (size_t)sc_total * rp->num_iters : 0;
+    if (results_on_device) {
+        dr.aln_count = res->aln_count; dr.frag_err_count = res->frag_err_count; dr.cluster_hist = res->cluster_hist;
+        dr.final_assign = res->final_assign; dr.final_logprob = res->final_logprob; dr.counters = (long long*)res->counters;
+        dr.rng_state = (unsigned long long*)res->rng_state; dr.error = res->error;
+        dr.trace_logprob = res->trace_logprob; dr.trace_move_frag = res->trace_move_frag; dr.trace_move_assign = res->trace_move_assign;
+        dr.initial_assign = res->initial_assign; dr.initial_logprob = res->initial_logprob;
+        if (!dr.aln_count || !dr.frag_err_count || !dr.cluster_hist) return fail(MBSV_ERR_ARG, "tally buffers are required");
+    } else {
+        CUDA_TRY(ob.aln_count.alloc(p->n_aln)); CUDA_TRY(ob.frag_err.alloc(p->n_frag)); CUDA_TRY(ob.hist.alloc(std::max(1, p->n_hist)));
+        dr.aln_count = ob.aln_count.p; dr.frag_err_count = ob.frag_err.p; dr.cluster_hist = ob.hist.p;
+        if (res->final_assign) { CUDA_TRY(ob.final_assign.alloc((size_t)X * p->n_frag)); dr.final_assign = ob.final_assign.p; }
+        if (res->final_logprob) { CUDA_TRY(ob.final_logprob.alloc(sc_total)); dr.final_logprob = ob.final_logprob.p; }
+        if (res->counters) { CUDA_TRY(ob.counters.alloc(sc_total * 5)); dr.counters = ob.counters.p; }
+        if (res->rng_state) { CUDA_TRY(ob.rng_state.alloc(sc_total)); dr.rng_state = ob.rng_state.p; }
+        CUDA_TRY(ob.error.alloc(sc_total)); dr.error = ob.error.p;
+        if (rp->trace) {
+            CUDA_TRY(ob.tr_logprob.alloc(trN)); CUDA_TRY(ob.tr_frag.alloc(trN)); CUDA_TRY(ob.tr_assign.alloc(trN));
+            dr.trace_logprob = ob.tr_logprob.p; dr.trace_move_frag = ob.tr_frag.p; dr.trace_move_assign = ob.tr_assign.p;
+        }
+        if (res->initial_assign) { CUDA_TRY(ob.init_assign_out.alloc((size_t)X * p->n_frag)); dr.initial_assign = ob.init_assign_out.p; }
+        if (res->initial_logprob) { CUDA_TRY(ob.init_logprob.alloc(sc_total)); dr.initial_logprob = ob.init_logprob.p; }
+    }
+    cudaStream_t s0 = p->streams[0];
+    CUDA_TRY(cudaMemsetAsync(dr.aln_count, 0, sizeof(unsigned) * p->n_aln, s0));
+    CUDA_TRY(cudaMemsetAsync(dr.frag_err_count, 0, sizeof(unsigned) * p->n_frag, s0));
+    if (p->n_hist > 0) CUDA_TRY(cudaMemsetAsync(dr.cluster_hist, 0, sizeof(unsigned) * p->n_hist, s0));
+    if (dr.error) CUDA_TRY(cudaMemsetAsync(dr.error, 0, sizeof(int) * sc_total, s0));
+
+    // ---- plan: warps of 32 consecutive (sorted subproblem, chain) items; size classes by state rows ----
+    std::vector<int> cls = {16, 32, 64, 128};
+    if (const char* env = std::getenv("MBSV_SMEM_CLASSES")) {
+        cls.clear();
+        for (const char* q = env; *q;) { cls.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+    }
+    auto warp_rows = [&](int w) -> int {
+        const int64_t last = std::min<int64_t>((int64_t)w * 32 + 31, n_items - 1);
+        return std::max(1, p->sub_W[p->sub_order[last / X]]);
+    };
+    // warps are sorted by rows: find class boundaries by binary search
+    std::vector<int> bounds;   // first warp of each class; last entry = first warp of the global class
+    {
+        int lo = 0;
+        for (size_t k = 0; k < cls.size(); ++k) {
+            bounds.push_back(lo);
+            int a = lo, b = n_warps;
+            while (a < b) { int m = a + (b - a) / 2; if (warp_rows(m) <= cls[k]) a = m + 1; else b = m; }
+            lo = a;
+        }
+        bounds.push_back(lo);
+    }
+    const int g0 = bounds.back();
+    if (g0 < n_warps) {
+        std::vector<long long> off(n_warps - g0);
+        long long acc = 0;
+        for (int w = g0; w < n_warps; ++w) { off[w - g0] = acc; acc += warp_rows(w); }
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        if ((size_t)acc * 128 > free_b) return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory");
+        CUDA_TRY(ob.workspace.alloc((size_t)acc * 32));
+        CUDA_TRY(ob.row_off.upload(off));
+    }
+
+    CUDA_TRY(cudaEventRecord(p->ev_start, s0));
+    int nstream = 0;
+    for (size_t k = 0; k <= cls.size(); ++k) {
+        const bool smem = k < cls.size();
+        const int wb = bounds[k], we = smem ? bounds[k + 1] : n_warps;
+        if (we <= wb) continue;
+        mbsv::DevRun r = dr;
+        r.warp_begin = wb; r.warp_end = we;
+        r.rows_per_warp = smem ? cls[k] : 0;
+        r.warp_row_off = smem ? nullptr : ob.row_off.p;
+        r.workspace = smem ? nullptr : ob.workspace.p;
+        r.global_warp0 = g0;
+        KernelFn fn = pick(rp->mode, rp->trace != 0, smem, p->n_exp);
+        const size_t shm = smem ? (size_t)WARPS_PER_CTA * cls[k] * 128 : 0;
+        if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        cudaStream_t st = p->streams[1 + (nstream % 7)];
+        CUDA_TRY(cudaStreamWaitEvent(st, p->ev_start, 0));
+        const int grid = (we - wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        fn<<<grid, WARPS_PER_CTA * 32, shm, st>>>(p->dp, r);
+        CUDA_TRY(cudaGetLastError());
+        ++g_launches;
+        CUDA_TRY(cudaEventRecord(p->ev_done[1 + (nstream % 7)], st));
+        CUDA_TRY(cudaStreamWaitEvent(s0, p->ev_done[1 + (nstream % 7)], 0));
+        ++nstream;
+    }
+    CUDA_TRY(cudaEventRecord(p->ev_stop, s0));
+    CUDA_TRY(cudaStreamSynchronize(s0));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop));
+    res->kernel_ms = ms;
+
+    // chain errors
+    std::vector<int> herr;
+    int worst = 0;
+    if (dr.error) {
+        herr.resize(sc_total);
+        CUDA_TRY(cudaMemcpy(herr.data(), dr.error, sizeof(int) * sc_total, cudaMemcpyDeviceToHost));
+        for (int v : herr) if (v) { worst = v; break; }
+    }
+    if (!results_on_device) {
+        auto down = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+            if (!dst || !src || !bytes) return cudaSuccess;
+            return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+        };
+        CUDA_TRY(down(res->aln_count, dr.aln_count, sizeof(unsigned) * p->n_aln));
+        CUDA_TRY(down(res->frag_err_count, dr.frag_err_count, sizeof(unsigned) * p->n_frag));
+        CUDA_TRY(down(res->cluster_hist, dr.cluster_hist, sizeof(unsigned) * p->n_hist));
+        CUDA_TRY(down(res->final_assign, dr.final_assign, sizeof(int) * (size_t)X * p->n_frag));
+        CUDA_TRY(down(res->final_logprob, dr.final_logprob, sizeof(double) * sc_total));
+        CUDA_TRY(down(res->counters, dr.counters, sizeof(long long) * sc_total * 5));
+        CUDA_TRY(down(res->rng_state, dr.rng_state, sizeof(unsigned long long) * sc_total));
+        if (res->error) std::memcpy(res->error, herr.data(), sizeof(int) * sc_total);
+        CUDA_TRY(down(res->trace_logprob, dr.trace_logprob, sizeof(double) * trN));
+        CUDA_TRY(down(res->trace_move_frag, dr.trace_move_frag, sizeof(int) * trN));
+        CUDA_TRY(down(res->trace_move_assign, dr.trace_move_assign, sizeof(int) * trN));
+        CUDA_TRY(down(res->initial_assign, dr.initial_assign, sizeof(int) * (size_t)X * p->n_frag));
+        CUDA_TRY(down(res->initial_logprob, dr.initial_logprob, sizeof(double) * sc_total));
+    }
+    if (worst) return fail(worst, "a chain hit an invariant the reference turns into an Error (see results.error)");
+    return MBSV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+int mbsv_run(mbsv_problem* p, const mbsv_run_params* params, mbsv_results* results) {
+    return run_impl(p, params, results, false);
+}
+int mbsv_run_device(mbsv_problem* p, const mbsv_run_params* params, mbsv_results* results) {
+    return run_impl(p, params, results, true);
+}
+}

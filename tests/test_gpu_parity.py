@@ -1,0 +1,120 @@
+"""Parity of the CUDA sampler (through the C ABI) against the CPU oracle.  Integer outputs — trajectory,
+tallies, counters, RNG state, final state — must be bit-exact; log-probabilities must be bit-exact too because
+both sides run the same individually-rounded fdlibm arithmetic."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import to_packed
+
+pytestmark = pytest.mark.gpu
+
+KAT6_SHA = "27aa9c30b1a4ac191a2942d3a8930d0fc723a978ee800960c2a7ed375e6bfcc6"
+
+
+def assert_same(o, g, trace=False, logprob_exact=True):
+    assert np.array_equal(o.error, g.error)
+    assert np.array_equal(o.counters, g.counters)
+    assert np.array_equal(o.rng_state, g.rng_state)
+    assert np.array_equal(o.initial_assign, g.initial_assign)
+    assert np.array_equal(o.final_assign, g.final_assign)
+    assert np.array_equal(o.aln_count, g.aln_count)
+    assert np.array_equal(o.frag_err_count, g.frag_err_count)
+    assert np.array_equal(o.cluster_hist, g.cluster_hist)
+    if logprob_exact:
+        assert np.array_equal(o.initial_logprob, g.initial_logprob)
+        assert np.array_equal(o.final_logprob, g.final_logprob)
+    if trace:
+        assert np.array_equal(o.trace_move_frag, g.trace_move_frag)
+        assert np.array_equal(o.trace_move_assign, g.trace_move_assign)
+        if logprob_exact:
+            assert np.array_equal(o.trace_logprob, g.trace_logprob)
+
+
+def test_example_replay_exact(oracle, mbsv, example_problem):
+    """BASELINE config 1: the shipped example, seed 123456, 10,000 iterations, REPLAY_EXACT."""
+    dp = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
+    g = dp.run(mbsv.MODE_REPLAY_EXACT, 10000, trace=True)
+    o = oracle.run(example_problem, "faithful", 10000, trace=True)
+    assert_same(o, g, trace=True)
+    assert g.counters[0, 0].tolist() == [5006, 1174, 0, 0, 5006]
+    assert int(g.rng_state[0, 0]) == 0x226A00D3B97D
+    st = oracle.replay_states(example_problem, g.initial_assign[0], g.trace_move_frag[0, 0], g.trace_move_assign[0, 0])
+    order = example_problem.names["sorted_frag"]
+    h = hashlib.sha256()
+    for row in st:
+        h.update((",".join(str(row[i]) for i in order) + "\n").encode())
+    assert h.hexdigest() == KAT6_SHA
+
+
+def test_example_fast_matches_incremental_and_replay(oracle, mbsv, example_problem):
+    dp = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
+    g = dp.run(mbsv.MODE_FAST, 10000, trace=True, java_int_wrap=True)
+    o = oracle.run(example_problem, "incremental", 10000, trace=True)
+    assert_same(o, g, trace=True)
+    r = dp.run(mbsv.MODE_REPLAY_EXACT, 10000, trace=True)
+    assert np.array_equal(r.trace_move_frag, g.trace_move_frag)
+    assert np.array_equal(r.aln_count, g.aln_count) and np.array_equal(r.cluster_hist, g.cluster_hist)
+
+
+@pytest.mark.parametrize("iters", [1, 9, 10, 24, 25, 99, 1000])
+def test_example_window_edges(oracle, mbsv, example_problem, iters):
+    """burnin = N/10 (0 -> 10): windows longer than the run, empty windows, N < 25 (quirk Q10 does not apply)."""
+    dp = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
+    for mode, om in ((mbsv.MODE_REPLAY_EXACT, "faithful"), (mbsv.MODE_FAST, "incremental")):
+        g = dp.run(mode, iters, trace=True, java_int_wrap=True)
+        o = oracle.run(example_problem, om, iters, trace=True)
+        assert_same(o, g, trace=True)
+
+
+def test_example_multichain_and_init(oracle, mbsv, example_problem):
+    dp = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
+    g = dp.run(mbsv.MODE_FAST, 5000, n_chains=40, java_int_wrap=True)
+    o = oracle.run(example_problem, "incremental", 5000, n_chains=40)
+    assert_same(o, g)
+    init = np.array([3, -1, 0, 2], np.int32)          # the --matchfile path: host-supplied initial state
+    g = dp.run(mbsv.MODE_REPLAY_EXACT, 3000, init_assign=init, trace=True)
+    o = oracle.run(example_problem, "faithful", 3000, init_assign=init, trace=True)
+    assert_same(o, g, trace=True)
+    assert np.array_equal(g.initial_assign[0], init)
+
+
+@pytest.mark.parametrize("cfg,nfrag,chains,iters", [("cfg2", 3000, 1, 3000), ("cfg3", 1500, 4, 2000),
+                                                    ("cfg4", 6000, 3, 2000), ("cfg4", 2500, 33, 1500)])
+def test_synthetic_both_modes(oracle, mbsv, cfg, nfrag, chains, iters):
+    """Synthetic batches of independent subproblems (all size classes incl. the global-workspace path)."""
+    from multibreak_sv_b200 import synth
+    p = synth.generate(cfg, n_frag=nfrag, shuffle_orders=True)
+    op = oracle.Problem(p.scalars, p.arrays)
+    dp = mbsv.DeviceProblem(p)
+    o = oracle.run(op, "incremental", iters, n_chains=chains, nthreads=8, java_int_wrap=False)
+    g = dp.run(mbsv.MODE_FAST, iters, n_chains=chains)
+    assert_same(o, g)
+    o = oracle.run(op, "faithful", iters, n_chains=chains, nthreads=8, trace=True)
+    g = dp.run(mbsv.MODE_REPLAY_EXACT, iters, n_chains=chains, trace=True)
+    assert_same(o, g, trace=True)
+    assert g.launches >= 1
+
+
+def test_fast_trace_equals_replay_trace_synthetic(mbsv):
+    """FAST and REPLAY_EXACT consume the same RNG stream and take the same decisions."""
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg4", n_frag=4000, shuffle_orders=True, seed=99)
+    dp = mbsv.DeviceProblem(p)
+    a = dp.run(mbsv.MODE_FAST, 2000, n_chains=2, trace=True)
+    b = dp.run(mbsv.MODE_REPLAY_EXACT, 2000, n_chains=2, trace=True, java_int_wrap=False)
+    assert np.array_equal(a.trace_move_frag, b.trace_move_frag)
+    assert np.array_equal(a.aln_count, b.aln_count)
+    assert np.array_equal(a.rng_state, b.rng_state)
+
+
+def test_device_math_matches_host(mbsv, oracle):
+    """jm_log/jm_exp host build == oracle's restatement (bitwise) on a grid; the device build is exercised by the
+    trajectory tests above (any ulp difference changes trace_logprob)."""
+    L = mbsv.load_library()
+    xs = np.concatenate([np.linspace(1e-6, 50, 4001), np.arange(1, 3000, dtype=float)])
+    for x in xs:
+        assert L.mbsv_log(float(x)) == oracle.jlog(float(x))
+    for x in np.linspace(-60, 10, 5001):
+        assert L.mbsv_exp(float(x)) == oracle.jexp(float(x))
