@@ -159,6 +159,8 @@ typedef struct mbsv_results {
     int32_t* trace_move_assign;/* new assignment of that fragment */
     int32_t* initial_assign;   /* [n_chains][n_frag] state after initializeMatrix */
     double* initial_logprob;   /* [n_sub][n_chains]  "Initialized Log Probability" (:789) */
+    int64_t* totals;           /* [6] sums over all chains of the five counters above, then the first non-zero
+                                  chain status; lets large batches skip the per-chain arrays */
     double kernel_ms;          /* out: device time of the sampler kernels (CUDA events) */
 } mbsv_results;
 
@@ -183,6 +185,15 @@ int mbsv_run_device(mbsv_problem* p, const mbsv_run_params* params, mbsv_results
 /* Introspection for benchmarks / tests. */
 int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n);   /* see DESIGN.md */
 int64_t mbsv_last_launch_count(void);             /* kernels launched by the last mbsv_run on this thread */
+/* out[i*5..] = {state rows per warp of the size class (0 = global-workspace class), warps, grid, dynamic shared
+   memory bytes, device milliseconds} for each of those launches; returns their number. */
+int mbsv_last_launch_info(double* out, int32_t max_launches);
+
+/* Multi-GPU sharding of independent subproblems (the reference's only scale-out is one JVM
+   per subset-N.clusters file, doc/MultiBreakSV-Manual.txt:411-473): longest-processing-time-first greedy —
+   subproblems by descending weight (ties: lower index first), each to the currently least loaded of n_parts
+   (ties: lowest part).  out_part[i] in [0, n_parts). */
+int mbsv_lpt_shard(const int64_t* weights, int64_t n, int32_t n_parts, int32_t* out_part);
 
 /* Host-side math the Java host would otherwise do itself (fdlibm-equivalent, no FMA contraction). */
 double mbsv_log(double x);

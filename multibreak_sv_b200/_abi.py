@@ -59,12 +59,12 @@ class Results(C.Structure):
     _fields_ = [("aln_count", U32P), ("frag_err_count", U32P), ("cluster_hist", U32P), ("final_assign", I32P),
                 ("final_logprob", F64P), ("counters", I64P), ("rng_state", U64P), ("error", I32P),
                 ("trace_logprob", F64P), ("trace_move_frag", I32P), ("trace_move_assign", I32P),
-                ("initial_assign", I32P), ("initial_logprob", F64P), ("kernel_ms", C.c_double)]
+                ("initial_assign", I32P), ("initial_logprob", F64P), ("totals", I64P), ("kernel_ms", C.c_double)]
 
 
 EXPORTS = ["mbsv_abi_version", "mbsv_device_count", "mbsv_last_error", "mbsv_status_string", "mbsv_problem_create",
            "mbsv_problem_destroy", "mbsv_run", "mbsv_run_device", "mbsv_problem_stats", "mbsv_last_launch_count",
-           "mbsv_log", "mbsv_exp", "mbsv_fill_logprobcov"]
+           "mbsv_log", "mbsv_exp", "mbsv_fill_logprobcov", "mbsv_lpt_shard", "mbsv_last_launch_info"]
 
 _lib = None
 
@@ -99,6 +99,8 @@ def load_library():
     L.mbsv_log.argtypes = [C.c_double]; L.mbsv_log.restype = C.c_double
     L.mbsv_exp.argtypes = [C.c_double]; L.mbsv_exp.restype = C.c_double
     L.mbsv_fill_logprobcov.argtypes = [C.c_double, C.c_int32, F64P]; L.mbsv_fill_logprobcov.restype = C.c_int
+    L.mbsv_last_launch_info.argtypes = [F64P, C.c_int32]; L.mbsv_last_launch_info.restype = C.c_int
+    L.mbsv_lpt_shard.argtypes = [I64P, C.c_int64, C.c_int32, I32P]; L.mbsv_lpt_shard.restype = C.c_int
     if L.mbsv_abi_version() != MBSV_ABI_VERSION:
         raise ImportError("libmbsv_b200.so ABI version mismatch")
     _lib = L
@@ -150,11 +152,13 @@ class RunOutput:
     trace_move_assign: np.ndarray | None
     kernel_ms: float
     launches: int
+    totals: np.ndarray | None = None     # [6] proposals/moves/reassignments summed over chains, first chain status
 
     @property
     def result_bytes(self) -> int:
         return int(sum(a.nbytes for a in (self.aln_count, self.frag_err_count, self.cluster_hist, self.final_assign,
-                                          self.final_logprob, self.counters, self.rng_state, self.error)))
+                                          self.final_logprob, self.counters, self.rng_state, self.error, self.totals)
+                       if a is not None))
 
 
 def reference_burnin(num_iters: int) -> int:
@@ -187,7 +191,7 @@ class DeviceProblem:
 
     def run(self, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 1, perr: float = 0.001,
             seed: int = 123456, burnin: int | None = None, java_int_wrap: bool | None = None, init_assign=None,
-            trace: bool = False, want_state: bool = True) -> RunOutput:
+            trace: bool = False, want_state: bool = True, per_chain: bool = True) -> RunOutput:
         """MultiBreakSV.runMCMC (MultiBreakSV.java:773-877) for every (subproblem, chain), on the GPU."""
         s = self.packed.scalars
         S, F = s["n_sub"], s["n_frag"]
@@ -209,10 +213,13 @@ class DeviceProblem:
             aln_count=np.zeros(s["n_aln"], np.uint32), frag_err_count=np.zeros(F, np.uint32),
             cluster_hist=np.zeros(s["n_hist"], np.uint32),
             final_assign=np.zeros((n_chains, F) if want_state else (0, 0), np.int32),
-            final_logprob=np.zeros((S, n_chains), np.float64), counters=np.zeros((S, n_chains, 5), np.int64),
-            rng_state=np.zeros((S, n_chains), np.uint64), error=np.zeros((S, n_chains), np.int32),
+            final_logprob=np.zeros((S, n_chains) if per_chain else (0, 0), np.float64),
+            counters=np.zeros((S, n_chains, 5) if per_chain else (0, 0, 0), np.int64),
+            rng_state=np.zeros((S, n_chains) if per_chain else (0, 0), np.uint64),
+            error=np.zeros((S, n_chains) if per_chain else (0, 0), np.int32),
             initial_assign=np.zeros((n_chains, F) if want_state else (0, 0), np.int32),
-            initial_logprob=np.zeros((S, n_chains), np.float64),
+            initial_logprob=np.zeros((S, n_chains) if per_chain else (0, 0), np.float64),
+            totals=np.zeros(6, np.int64),
             trace_logprob=np.zeros((S, n_chains, num_iters), np.float64) if trace else None,
             trace_move_frag=np.zeros((S, n_chains, num_iters), np.int32) if trace else None,
             trace_move_assign=np.zeros((S, n_chains, num_iters), np.int32) if trace else None,
@@ -221,7 +228,7 @@ class DeviceProblem:
         ft = dict(Results._fields_)
         for k in ["aln_count", "frag_err_count", "cluster_hist", "final_assign", "final_logprob", "counters",
                   "rng_state", "error", "trace_logprob", "trace_move_frag", "trace_move_assign", "initial_assign",
-                  "initial_logprob"]:
+                  "initial_logprob", "totals"]:
             a = getattr(out, k)
             setattr(r, k, a.ctypes.data_as(ft[k]) if a is not None and a.size else ft[k]())
         st = self.lib.mbsv_run(self.handle, C.byref(rp), C.byref(r))
@@ -231,3 +238,32 @@ class DeviceProblem:
         if st != 0 and st != -5:
             check(st)
         return out
+
+    def launch_info(self) -> list[dict]:
+        buf = np.zeros(8 * 5, np.float64)
+        n = self.lib.mbsv_last_launch_info(buf.ctypes.data_as(F64P), 8)
+        return [dict(rows=int(buf[i * 5]), warps=int(buf[i * 5 + 1]), grid=int(buf[i * 5 + 2]),
+                     smem_bytes=int(buf[i * 5 + 3]), ms=float(buf[i * 5 + 4])) for i in range(n)]
+
+    def run_device(self, tensors: dict, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 1,
+                   perr: float = 0.001, seed: int = 123456, burnin: int | None = None, java_int_wrap: bool = False):
+        """mbsv_run_device: `tensors` maps result-field names to DEVICE pointers (e.g. torch tensor.data_ptr()) on
+        this problem's GPU; aln_count, frag_err_count, cluster_hist and totals are required.  Returns
+        (status, kernel_ms)."""
+        rp = RunParams()
+        rp.mode = mode
+        rp.n_chains = n_chains
+        rp.num_iters = num_iters
+        rp.burnin = reference_burnin(num_iters) if burnin is None else burnin
+        rp.perr = perr
+        rp.seed = seed
+        rp.device = self.device
+        rp.java_int_wrap = int(java_int_wrap)
+        r = Results()
+        ft = dict(Results._fields_)
+        for k, ptr in tensors.items():
+            setattr(r, k, C.cast(C.c_void_p(int(ptr)), ft[k]))
+        st = self.lib.mbsv_run_device(self.handle, C.byref(rp), C.byref(r))
+        if st != 0 and st != -5:
+            check(st)
+        return st, r.kernel_ms

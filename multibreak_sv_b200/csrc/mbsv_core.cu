@@ -12,12 +12,14 @@
 
 #include "../../include/mbsv_b200.h"
 #include "jmath.cuh"
-#include "sampler_kernel.cuh"
+#include "sampler_types.cuh"
 
 namespace {
 
 thread_local std::string g_err;
 thread_local int64_t g_launches = 0;
+struct LaunchInfo { int rows; int warps; int grid; int smem_bytes; float ms; };
+thread_local std::vector<LaunchInfo> g_launch_info;
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -67,9 +69,9 @@ struct mbsv_problem {
     DevBuf<int> d_sub_frag_ptr, d_sub_cluster_ptr, d_sub_sv_ptr, d_frag_aln_ptr, d_aln_esp_slot, d_supports_local,
         d_cluster_hist_ptr, d_sv_frag_ptr, d_sv_frag, d_sv_numchanged, d_sub_order, d_sub_W;
     DevBuf<int4> d_aln_rec;
-    DevBuf<double> d_sub_logF, d_T, d_logint, d_pseq, d_logp, d_log1mp;
+    DevBuf<double> d_sub_logF, d_sub_neglogNsv, d_T, d_logint, d_pseq, d_logp, d_log1mp;
     cudaStream_t streams[8] = {};
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done[8] = {};
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done[8] = {}, ev_cls0[8] = {}, ev_cls1[8] = {};
     bool streams_ok = false;
 };
 
@@ -116,6 +118,38 @@ int mbsv_fill_logprobcov(double lambda, int32_t max_support, double* out) {
 }
 
 int64_t mbsv_last_launch_count(void) { return g_launches; }
+
+// Per-launch details of the last mbsv_run on this thread: out[i*5..] = {state rows per warp (0 = global
+// workspace class), warps, grid, dynamic smem bytes, milliseconds}.  Returns the number of launches.
+int mbsv_last_launch_info(double* out, int32_t max_launches) {
+    int n = 0;
+    for (const auto& li : g_launch_info) {
+        if (n >= max_launches) break;
+        if (out) { out[n * 5] = li.rows; out[n * 5 + 1] = li.warps; out[n * 5 + 2] = li.grid; out[n * 5 + 3] = li.smem_bytes; out[n * 5 + 4] = li.ms; }
+        ++n;
+    }
+    return n;
+}
+
+int mbsv_lpt_shard(const int64_t* weights, int64_t n, int32_t n_parts, int32_t* out_part) {
+    if (!weights || !out_part || n < 0 || n_parts < 1) return fail(MBSV_ERR_ARG, "mbsv_lpt_shard: bad argument");
+    std::vector<int64_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return weights[a] > weights[b]; });
+    // min-heap on (load, part)
+    std::vector<std::pair<int64_t, int32_t>> heap;
+    for (int32_t p = 0; p < n_parts; ++p) heap.push_back({0, p});
+    auto cmp = [](const std::pair<int64_t, int32_t>& a, const std::pair<int64_t, int32_t>& b) { return a > b; };
+    std::make_heap(heap.begin(), heap.end(), cmp);
+    for (int64_t i : idx) {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        auto& top = heap.back();
+        out_part[i] = top.second;
+        top.first += weights[i];
+        std::push_heap(heap.begin(), heap.end(), cmp);
+    }
+    return MBSV_OK;
+}
 
 static int validate(const mbsv_problem_desc* d) {
     if (!d) return fail(MBSV_ERR_ARG, "descriptor is NULL");
@@ -250,8 +284,17 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                         return fail(MBSV_ERR_ARG, "sv_frag must list single-alignment fragments of the same subproblem");
                 }
     }
-    std::vector<double> logF(S), logint(maxn + 1, 0.0), logp(E), log1mp(E);
-    for (int s = 0; s < S; ++s) logF[s] = mbsv::jm_log((double)(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]));
+    // the exact-binomial branch (n*p <= 5 or n*(1-p) <= 5, MultiBreakSV.java:1664) only sees n <= 5/min(p, 1-p)
+    for (int x = 0; x < E; ++x) {
+        const double pmin = std::min(d->exp_pseq[x], 1 - d->exp_pseq[x]);
+        if (pmin > 0) maxn = std::max(maxn, (int)std::min(65536.0, 5.0 / pmin + 2));
+    }
+    std::vector<double> logF(S), neglogNsv(S, 0.0), logint(maxn + 1, 0.0), logp(E), log1mp(E);
+    for (int s = 0; s < S; ++s) {
+        logF[s] = mbsv::jm_log((double)(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]));
+        const int nsv = sub_sv_ptr[s + 1] - sub_sv_ptr[s];
+        if (nsv > 0) neglogNsv[s] = -mbsv::jm_log((double)nsv);
+    }
     for (int n = 1; n <= maxn; ++n) logint[n] = mbsv::jm_log((double)n);
     for (int x = 0; x < E; ++x) { logp[x] = mbsv::jm_log(d->exp_pseq[x]); log1mp[x] = mbsv::jm_log(1 - d->exp_pseq[x]); }
 
@@ -287,6 +330,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     chk(up(p->d_sv_frag, sv_frag));
     chk(up(p->d_sv_numchanged, sv_numchanged));
     chk(up(p->d_sub_logF, logF));
+    chk(up(p->d_sub_neglogNsv, neglogNsv));
     chk(up(p->d_T, std::vector<double>(d->logprobcov, d->logprobcov + (size_t)E * (d->max_support + 1))));
     chk(up(p->d_logint, logint));
     chk(up(p->d_pseq, std::vector<double>(d->exp_pseq, d->exp_pseq + E)));
@@ -302,15 +346,20 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     mbsv::DevProblem& dp = p->dp;
     dp.n_sub = S; dp.n_frag = F; dp.n_aln = A; dp.n_cluster = C; dp.n_exp = E; dp.max_support = d->max_support; dp.maxn = maxn;
     dp.sub_frag_ptr = p->d_sub_frag_ptr.p; dp.sub_cluster_ptr = p->d_sub_cluster_ptr.p; dp.sub_sv_ptr = p->d_sub_sv_ptr.p;
-    dp.sub_logF = p->d_sub_logF.p; dp.frag_aln_ptr = p->d_frag_aln_ptr.p; dp.aln_rec = p->d_aln_rec.p;
+    dp.sub_logF = p->d_sub_logF.p; dp.sub_neglogNsv = p->d_sub_neglogNsv.p; dp.frag_aln_ptr = p->d_frag_aln_ptr.p; dp.aln_rec = p->d_aln_rec.p;
     dp.aln_esp_slot = p->d_aln_esp_slot.p; dp.supports_order_local = p->d_supports_local.p;
     dp.cluster_hist_ptr = p->d_cluster_hist_ptr.p; dp.sv_frag_ptr = p->d_sv_frag_ptr.p; dp.sv_frag = p->d_sv_frag.p;
     dp.sv_numchanged = p->d_sv_numchanged.p; dp.T = p->d_T.p; dp.logint = p->d_logint.p; dp.exp_pseq = p->d_pseq.p;
     dp.exp_logp = p->d_logp.p; dp.exp_log1mp = p->d_log1mp.p;
     dp.log2pi = mbsv::jm_log(2.0) + mbsv::jm_log(3.141592653589793);
+    int prio_lo = 0, prio_hi = 0;
+    chk(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int i = 0; i < 8; ++i) {
-        chk(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+        // streams[1] runs the longest-running class (large subproblems) and gets the highest priority
+        chk(cudaStreamCreateWithPriority(&p->streams[i], cudaStreamNonBlocking, i == 1 ? prio_hi : prio_lo));
         chk(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+        chk(cudaEventCreate(&p->ev_cls0[i]));
+        chk(cudaEventCreate(&p->ev_cls1[i]));
     }
     chk(cudaEventCreate(&p->ev_start));
     chk(cudaEventCreate(&p->ev_stop));
@@ -324,7 +373,10 @@ int mbsv_problem_destroy(mbsv_problem* p) {
     if (!p) return MBSV_OK;
     cudaSetDevice(p->device);
     if (p->streams_ok) {
-        for (int i = 0; i < 8; ++i) { cudaStreamDestroy(p->streams[i]); cudaEventDestroy(p->ev_done[i]); }
+        for (int i = 0; i < 8; ++i) {
+            cudaStreamDestroy(p->streams[i]); cudaEventDestroy(p->ev_done[i]);
+            cudaEventDestroy(p->ev_cls0[i]); cudaEventDestroy(p->ev_cls1[i]);
+        }
         cudaEventDestroy(p->ev_start);
         cudaEventDestroy(p->ev_stop);
     }
@@ -347,23 +399,10 @@ int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-using KernelFn = void (*)(const mbsv::DevProblem, const mbsv::DevRun);
-
-template <int MODE, bool TRACE, bool SMEM>
-KernelFn pick_e(int E) {
-    switch (E) {
-        case 1: return mbsv::mbsv_chain_kernel<MODE, TRACE, SMEM, 1>;
-        case 2: return mbsv::mbsv_chain_kernel<MODE, TRACE, SMEM, 2>;
-        default: return mbsv::mbsv_chain_kernel<MODE, TRACE, SMEM, 4>;
-    }
-}
+using mbsv::KernelFn;
 KernelFn pick(int mode, bool trace, bool smem, int E) {
-    if (mode == 0) {
-        if (trace) return smem ? pick_e<0, true, true>(E) : pick_e<0, true, false>(E);
-        return smem ? pick_e<0, false, true>(E) : pick_e<0, false, false>(E);
-    }
-    if (trace) return smem ? pick_e<1, true, true>(E) : pick_e<1, true, false>(E);
-    return smem ? pick_e<1, false, true>(E) : pick_e<1, false, false>(E);
+    if (trace) return mbsv::get_kernel_trace(mode, smem, E);
+    return mode == 0 ? mbsv::get_kernel_replay(smem, E) : mbsv::get_kernel_fast(smem, E);
 }
 
 struct OutBufs {
@@ -371,12 +410,13 @@ struct OutBufs {
     DevBuf<int> final_assign, error, tr_frag, tr_assign, init_assign_out, init_assign_in;
     DevBuf<double> final_logprob, tr_logprob, init_logprob;
     DevBuf<long long> counters, row_off;
-    DevBuf<unsigned long long> rng_state;
+    DevBuf<unsigned long long> rng_state, totals;
     DevBuf<int> workspace;
 };
 
 int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool results_on_device) {
     g_launches = 0;
+    g_launch_info.clear();
     if (!p || !rp || !res) return fail(MBSV_ERR_ARG, "mbsv_run: NULL argument");
     if (rp->mode != MBSV_MODE_REPLAY_EXACT && rp->mode != MBSV_MODE_FAST) return fail(MBSV_ERR_ARG, "unknown mode");
     if (rp->n_chains < 1 || rp->num_iters < 0 || rp->burnin < 0) return fail(MBSV_ERR_ARG, "bad run parameters");
@@ -419,6 +459,8 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         dr.rng_state = (unsigned long long*)res->rng_state; dr.error = res->error;
         dr.trace_logprob = res->trace_logprob; dr.trace_move_frag = res->trace_move_frag; dr.trace_move_assign = res->trace_move_assign;
         dr.initial_assign = res->initial_assign; dr.initial_logprob = res->initial_logprob;
+        dr.totals = (unsigned long long*)res->totals;
+        if (!dr.totals) return fail(MBSV_ERR_ARG, "mbsv_run_device needs results.totals (the chain status is read from it)");
         if (!dr.aln_count || !dr.frag_err_count || !dr.cluster_hist) return fail(MBSV_ERR_ARG, "tally buffers are required");
     } else {
         CUDA_TRY(ob.aln_count.alloc(p->n_aln)); CUDA_TRY(ob.frag_err.alloc(p->n_frag)); CUDA_TRY(ob.hist.alloc(std::max(1, p->n_hist)));
@@ -427,7 +469,8 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         if (res->final_logprob) { CUDA_TRY(ob.final_logprob.alloc(sc_total)); dr.final_logprob = ob.final_logprob.p; }
         if (res->counters) { CUDA_TRY(ob.counters.alloc(sc_total * 5)); dr.counters = ob.counters.p; }
         if (res->rng_state) { CUDA_TRY(ob.rng_state.alloc(sc_total)); dr.rng_state = ob.rng_state.p; }
-        CUDA_TRY(ob.error.alloc(sc_total)); dr.error = ob.error.p;
+        if (res->error) { CUDA_TRY(ob.error.alloc(sc_total)); dr.error = ob.error.p; }
+        CUDA_TRY(ob.totals.alloc(6)); dr.totals = ob.totals.p;
         if (rp->trace) {
             CUDA_TRY(ob.tr_logprob.alloc(trN)); CUDA_TRY(ob.tr_frag.alloc(trN)); CUDA_TRY(ob.tr_assign.alloc(trN));
             dr.trace_logprob = ob.tr_logprob.p; dr.trace_move_frag = ob.tr_frag.p; dr.trace_move_assign = ob.tr_assign.p;
@@ -440,6 +483,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     CUDA_TRY(cudaMemsetAsync(dr.frag_err_count, 0, sizeof(unsigned) * p->n_frag, s0));
     if (p->n_hist > 0) CUDA_TRY(cudaMemsetAsync(dr.cluster_hist, 0, sizeof(unsigned) * p->n_hist, s0));
     if (dr.error) CUDA_TRY(cudaMemsetAsync(dr.error, 0, sizeof(int) * sc_total, s0));
+    CUDA_TRY(cudaMemsetAsync(dr.totals, 0, sizeof(unsigned long long) * 6, s0));
 
     // ---- plan: warps of 32 consecutive (sorted subproblem, chain) items; size classes by state rows ----
     std::vector<int> cls = {16, 32, 64, 128};
@@ -477,7 +521,9 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
 
     CUDA_TRY(cudaEventRecord(p->ev_start, s0));
     int nstream = 0;
-    for (size_t k = 0; k <= cls.size(); ++k) {
+    // largest state first: the global-workspace class (few, slow chains) starts before the bulk of small chains
+    for (size_t kk = 0; kk <= cls.size(); ++kk) {
+        const size_t k = cls.size() - kk;
         const bool smem = k < cls.size();
         const int wb = bounds[k], we = smem ? bounds[k + 1] : n_warps;
         if (we <= wb) continue;
@@ -493,8 +539,12 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         cudaStream_t st = p->streams[1 + (nstream % 7)];
         CUDA_TRY(cudaStreamWaitEvent(st, p->ev_start, 0));
         const int grid = (we - wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        if (nstream >= 7) return fail(MBSV_ERR_ARG, "too many size classes");
+        CUDA_TRY(cudaEventRecord(p->ev_cls0[1 + nstream], st));
         fn<<<grid, WARPS_PER_CTA * 32, shm, st>>>(p->dp, r);
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(p->ev_cls1[1 + nstream], st));
+        g_launch_info.push_back({smem ? cls[k] : 0, we - wb, grid, (int)shm, 0.f});
         ++g_launches;
         CUDA_TRY(cudaEventRecord(p->ev_done[1 + (nstream % 7)], st));
         CUDA_TRY(cudaStreamWaitEvent(s0, p->ev_done[1 + (nstream % 7)], 0));
@@ -505,15 +555,13 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop));
     res->kernel_ms = ms;
+    for (size_t i = 0; i < g_launch_info.size(); ++i)
+        cudaEventElapsedTime(&g_launch_info[i].ms, p->ev_cls0[1 + i], p->ev_cls1[1 + i]);
 
-    // chain errors
-    std::vector<int> herr;
-    int worst = 0;
-    if (dr.error) {
-        herr.resize(sc_total);
-        CUDA_TRY(cudaMemcpy(herr.data(), dr.error, sizeof(int) * sc_total, cudaMemcpyDeviceToHost));
-        for (int v : herr) if (v) { worst = v; break; }
-    }
+    // chain status
+    long long htot[6] = {0, 0, 0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpy(htot, dr.totals, sizeof(htot), cudaMemcpyDeviceToHost));
+    const int worst = (int)htot[5];
     if (!results_on_device) {
         auto down = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
             if (!dst || !src || !bytes) return cudaSuccess;
@@ -526,7 +574,8 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         CUDA_TRY(down(res->final_logprob, dr.final_logprob, sizeof(double) * sc_total));
         CUDA_TRY(down(res->counters, dr.counters, sizeof(long long) * sc_total * 5));
         CUDA_TRY(down(res->rng_state, dr.rng_state, sizeof(unsigned long long) * sc_total));
-        if (res->error) std::memcpy(res->error, herr.data(), sizeof(int) * sc_total);
+        CUDA_TRY(down(res->error, dr.error, sizeof(int) * sc_total));
+        if (res->totals) std::memcpy(res->totals, htot, sizeof(htot));
         CUDA_TRY(down(res->trace_logprob, dr.trace_logprob, sizeof(double) * trN));
         CUDA_TRY(down(res->trace_move_frag, dr.trace_move_frag, sizeof(int) * trN));
         CUDA_TRY(down(res->trace_move_assign, dr.trace_move_assign, sizeof(int) * trN));

@@ -18,68 +18,23 @@
 #include <cstdint>
 
 #include "jmath.cuh"
+#include "sampler_types.cuh"
 
 namespace mbsv {
 
-struct DevProblem {
-    int n_sub, n_frag, n_aln, n_cluster, n_exp, max_support, maxn;
-    const int* sub_frag_ptr;
-    const int* sub_cluster_ptr;
-    const int* sub_sv_ptr;
-    const double* sub_logF;          // log(F_s)  (Math.log(fragments.size()), MultiBreakSV.java:1219-1271)
-    const int* frag_aln_ptr;
-    const int4* aln_rec;             // {numerrors, len, first ESP entry, exp | nesp << 8}
-    const int* aln_esp_slot;         // per alignment-ESP entry: local count slot cluster*E + exp, or -1
-    const int* supports_order_local; // per subproblem: local cluster indices in A.supports.keySet() order
-    const int* cluster_hist_ptr;
-    const int* sv_frag_ptr;
-    const int* sv_frag;
-    const int* sv_numchanged;
-    const double* T;                 // logprobcov [E][max_support+1]
-    const double* logint;            // log(n), n = 0..maxn
-    const double* exp_pseq;
-    const double* exp_logp;
-    const double* exp_log1mp;
-    double log2pi;                   // Math.log(2)+Math.log(Math.PI)
-};
-
-struct DevRun {
-    int n_chains, num_iters, burnin, win_base, java_int_wrap;
-    double perr, logperr, log1mperr;
-    long long seed;
-    const int* init_assign;
-    // plan: item g = warp*32 + lane is chain (g % n_chains) of subproblem sub_order[g / n_chains]
-    const int* sub_order;            // subproblems by ascending state size
-    const int* sub_W;                // state rows per chain of each subproblem
-    long long n_items;               // n_sub * n_chains
-    const long long* warp_row_off;   // [warp - global_warp0] row offset into workspace (global class)
-    int* workspace;
-    int warp_begin, warp_end, rows_per_warp, global_warp0;
-    // outputs (device)
-    unsigned int* aln_count;
-    unsigned int* frag_err_count;
-    unsigned int* cluster_hist;
-    int* final_assign;
-    double* final_logprob;
-    long long* counters;
-    unsigned long long* rng_state;
-    int* error;
-    double* trace_logprob;
-    int* trace_move_frag;
-    int* trace_move_assign;
-    int* initial_assign;
-    double* initial_logprob;
-};
-
-// MultiBreakSV.java:1661-1695 (logBinomial, logbinomialcoefficient, logNormal)
-__device__ __noinline__ double log_binomial_dev(long long k, long long n, double p, double logp, double log1mp,
-                                                double log2pi) {
+// logtab[i] = jm_log(i) for 0 < i <= ntab: the exact branch walks Math.log(i) - Math.log(j) over small integers.
+static __device__ __noinline__ double log_binomial_dev(long long k, long long n, double p, double logp, double log1mp,
+                                                double log2pi, const double* __restrict__ logtab, int ntab) {
     double dn = (double)n;
     if (dn * p <= 5 || dn * (1 - p) <= 5) {
         double t = 0;
         long long r = k, m = n - k;
         if (r < m) r = m;
-        for (long long i = n, j = 1; i > r; --i, ++j) t = t + jm_log((double)i) - jm_log((double)j);
+        if (n <= ntab && n >= 1) {
+            for (long long i = n, j = 1; i > r; --i, ++j) t = t + logtab[i] - logtab[j];
+        } else {
+            for (long long i = n, j = 1; i > r; --i, ++j) t = t + jm_log((double)i) - jm_log((double)j);
+        }
         return t + (double)k * logp + (double)(n - k) * log1mp;
     }
     double mu = dn * p;
@@ -88,31 +43,38 @@ __device__ __noinline__ double log_binomial_dev(long long k, long long n, double
     return -(d * d) / (2 * sig) - (log2pi + jm_log(sig)) / 2;
 }
 
-__device__ __noinline__ double exp_dev(double x) { return jm_exp(x); }
+static __device__ __noinline__ double exp_dev(double x) { return jm_exp(x); }
 
 #define MBSV_ST(i) st[(size_t)(i) << 5]
 
+#ifndef MBSV_MIN_BLOCKS
+#define MBSV_MIN_BLOCKS 5
+#endif
+
 template <int MODE, bool TRACE, bool SMEM, int MAXE>
-__global__ void __launch_bounds__(128) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
+__global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
                                                          const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const int warp = R.warp_begin + blockIdx.x * 4 + wic;
     if (warp >= R.warp_end) return;
-    const long long item = (long long)warp * 32 + lane;
-    if (item >= R.n_items) return;
+    // Lanes beyond the last item stay in the warp as idle passengers (zero-sized problem, no iterations, no
+    // writes): the main loop below synchronises the full warp.
+    const long long item_raw = (long long)warp * 32 + lane;
+    const bool alive = item_raw < R.n_items;
+    const long long item = alive ? item_raw : R.n_items - 1;
     const int sub = R.sub_order[item / R.n_chains];
     const int chain = (int)(item % R.n_chains);
     int* st = SMEM ? (smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane)
                    : (R.workspace + (size_t)R.warp_row_off[warp - R.global_warp0] * 32 + lane);
 
-    const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
-    const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
+    const int f0 = P.sub_frag_ptr[sub], F = alive ? P.sub_frag_ptr[sub + 1] - f0 : 0;
+    const int c0 = P.sub_cluster_ptr[sub], C = alive ? P.sub_cluster_ptr[sub + 1] - c0 : 0;
     const int E = P.n_exp;
     const int sv0 = P.sub_sv_ptr[sub], nsv = P.sub_sv_ptr[sub + 1] - sv0;
     const int Tstride = P.max_support + 1;
     const long long sc = (long long)sub * R.n_chains + chain;
-    const int N = R.num_iters;
+    const int N = alive ? R.num_iters : 0;
     const double logF = P.sub_logF[sub];
     const double neglogF = -logF;
     const double perr = R.perr, logperr = R.logperr;
@@ -127,11 +89,13 @@ __global__ void __launch_bounds__(128) mbsv_chain_kernel(const __grid_constant__
     for (int x = 0; x < MAXE; ++x) { Etot[x] = 0; Ltot[x] = 0; LB[x] = 0.0; }
     int nerr = 0;
     int err = 0;
-    long long n_naive_prop = 0, n_naive_acc = 0, n_sv_prop = 0, n_sv_acc = 0, n_reassign = 0;
+    int n_naive_prop = 0, n_naive_acc = 0, n_sv_prop = 0, n_sv_acc = 0;   // <= num_iters each
+    long long n_reassign = 0;
 
     auto wrapi = [&](long long t) -> long long { return R.java_int_wrap ? (long long)(int)(unsigned int)(unsigned long long)t : t; };
     auto lb_of = [&](int x, long long e, long long l) -> double {
-        return log_binomial_dev(wrapi(e), wrapi(l), P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi);
+        return log_binomial_dev(wrapi(e), wrapi(l), P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi, P.logint,
+                                P.maxn);
     };
     // Apply the count changes of fragment f moving from alignment `from` to `to` (-1 = error); dir=false
     // reverts without touching dcov.  Counts, totals and nerr are updated in place.
@@ -267,31 +231,46 @@ __global__ void __launch_bounds__(128) mbsv_chain_kernel(const __grid_constant__
         for (int x = 0; x < MAXE; ++x) if (x < E) LB[x] = lb_of(x, Etot[x], Ltot[x]);
     }
     double logprob = full_logprob();
-    if (R.initial_logprob) R.initial_logprob[sc] = logprob;
+    if (alive && R.initial_logprob) R.initial_logprob[sc] = logprob;
 
     // ---------------- iterations (MultiBreakSV.java:796-837, 1101-1182) ----------------
+    const int q_base = P.sv_frag_ptr[sv0];   // only dereferenced when nsv > 0
+    const double neglogNsv = P.sub_neglogNsv[sub];
     int iter = 0;
-    while (iter < N && err == 0) {
-        // lazy chain: with probability 1/2 stay (:1106-1113)
-        double r = rng.nextDouble();
-        if (r < 0.5) {
-            if (TRACE) {
-                R.trace_logprob[sc * N + iter] = logprob;
-                R.trace_move_frag[sc * N + iter] = -1;
-                R.trace_move_assign[sc * N + iter] = -1;
+    bool done = false;
+    for (;;) {
+        // Lazy chain: with probability 1/2 stay (:1106-1113).  Lazy iterations only advance the RNG (tallies
+        // are difference tallies), so each lane skips them in a tight loop; the warp-wide vote below is the
+        // convergence point that brings all 32 lanes back together for the proposal code.
+        double r = 0.0;
+        bool live = false;
+        if (!done) {
+            while (iter < N) {
+                r = rng.nextDouble();
+                if (!(r < 0.5)) { live = true; break; }
+                if (TRACE) {
+                    R.trace_logprob[sc * N + iter] = logprob;
+                    R.trace_move_frag[sc * N + iter] = -1;
+                    R.trace_move_assign[sc * N + iter] = -1;
+                }
+                ++iter;
             }
-            ++iter;
-            continue;
+            done = !live;
         }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (!live) continue;
         const int t = iter;
         r = rng.nextDouble();
         const bool naive = (r < 0.9) || (nsv == 0);
-        int f = -1, a0 = 0, prev = -1, now = -1, svk = -1;
+        // A proposal is a list of single-fragment moves: one for Naive, the cluster's single-alignment
+        // fragments for AlterSV.  Both kinds run through the same code below.
+        int f = -1, a0 = 0, prev = -1, now = -1, svk = -1, q0 = 0, nmoves = 1;
         double Alogq, Anewlogq;
+        const double u = rng.nextDouble();
         if (naive) {
             // ---- naiveMove (:1184-1273) ----
             ++n_naive_prop; ++n_reassign;
-            f = (int)(rng.nextDouble() * dF);
+            f = (int)(u * dF);
             a0 = P.frag_aln_ptr[f0 + f];
             const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
             prev = MBSV_ST(f);
@@ -321,30 +300,29 @@ __global__ void __launch_bounds__(128) mbsv_chain_kernel(const __grid_constant__
                 Anewlogq = neglogF + R.log1mperr - P.logint[n - 1];
                 Alogq = Anewlogq;
             }
-            if (now == prev) { err = -5; break; }   // Error at :1122-1123
+            if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
         } else {
             // ---- svMove (:1291-1343) ----
             ++n_sv_prop;
-            svk = (int)(rng.nextDouble() * (double)nsv);
+            svk = (int)(u * (double)nsv);
             n_reassign += P.sv_numchanged[sv0 + svk];
-            const double l = jm_log((double)nsv);
-            Alogq = -l;
-            Anewlogq = -l;
+            q0 = P.sv_frag_ptr[sv0 + svk];
+            nmoves = P.sv_frag_ptr[sv0 + svk + 1] - q0;
+            Alogq = neglogNsv;
+            Anewlogq = neglogNsv;
         }
         // ---- tentative application ----
         double dcov = 0.0, derr = 0.0;
         unsigned touched = 0;
-        long long E0[MAXE], L0[MAXE];
-#pragma unroll
-        for (int x = 0; x < MAXE; ++x) { E0[x] = Etot[x]; L0[x] = Ltot[x]; }
-        const int nerr0 = nerr;
-        if (naive) move_counts(a0, prev, now, dcov, derr, touched);
-        else {
-            for (int q = P.sv_frag_ptr[sv0 + svk]; q < P.sv_frag_ptr[sv0 + svk + 1]; ++q) {
-                const int g = P.sv_frag[q] - f0;
-                const int pv = MBSV_ST(g);
-                move_counts(P.frag_aln_ptr[f0 + g], pv, pv == -1 ? 0 : -1, dcov, derr, touched);
+        for (int q = 0; q < nmoves; ++q) {
+            int ga0 = a0, from = prev, to = now;
+            if (!naive) {
+                const int g = P.sv_frag[q0 + q] - f0;
+                ga0 = P.frag_aln_ptr[f0 + g];
+                from = MBSV_ST(g);
+                to = (from == -1) ? 0 : -1;
             }
+            move_counts(ga0, from, to, dcov, derr, touched);
         }
         // ---- acceptance ratio (:1146) ----
         double newLB[MAXE];
@@ -377,52 +355,53 @@ __global__ void __launch_bounds__(128) mbsv_chain_kernel(const __grid_constant__
             logprob = newlogprob;
 #pragma unroll
             for (int x = 0; x < MAXE; ++x) LB[x] = newLB[x];
-            if (naive) {
-                ++n_naive_acc;
-                MBSV_ST(f) = now;
-                if (t > win_base) {
-                    tally_frag(f, a0, prev, now, t);
-                    retally_fragment(a0, prev, now, t);
-                    reapply_fragment(a0, prev, now);
-                }
-            } else {
-                ++n_sv_acc;
-                const int q0 = P.sv_frag_ptr[sv0 + svk], q1 = P.sv_frag_ptr[sv0 + svk + 1];
-                if (t > win_base) {
-                    for (int q = q1 - 1; q >= q0; --q) {
-                        const int g = P.sv_frag[q] - f0;
-                        const int pv = MBSV_ST(g);
-                        retally_fragment(P.frag_aln_ptr[f0 + g], pv, pv == -1 ? 0 : -1, t);
+            if (naive) ++n_naive_acc; else ++n_sv_acc;
+            if (t > win_base) {
+                // support-histogram difference tallies: walk the move backwards, then re-apply it
+                for (int q = nmoves - 1; q >= 0; --q) {
+                    int ga0 = a0, from = prev, to = now;
+                    if (!naive) {
+                        const int g = P.sv_frag[q0 + q] - f0;
+                        ga0 = P.frag_aln_ptr[f0 + g];
+                        from = MBSV_ST(g);              // the assignment is written last: still the old value
+                        to = (from == -1) ? 0 : -1;
                     }
-                    for (int q = q0; q < q1; ++q) {
-                        const int g = P.sv_frag[q] - f0;
-                        const int pv = MBSV_ST(g);
-                        const int ga0 = P.frag_aln_ptr[f0 + g];
-                        reapply_fragment(ga0, pv, pv == -1 ? 0 : -1);
-                        tally_frag(g, ga0, pv, pv == -1 ? 0 : -1, t);
-                    }
+                    retally_fragment(ga0, from, to, t);
                 }
-                for (int q = q0; q < q1; ++q) {
-                    const int g = P.sv_frag[q] - f0;
+                for (int q = 0; q < nmoves; ++q) {
+                    int g = f, ga0 = a0, from = prev, to = now;
+                    if (!naive) {
+                        g = P.sv_frag[q0 + q] - f0;
+                        ga0 = P.frag_aln_ptr[f0 + g];
+                        from = MBSV_ST(g);
+                        to = (from == -1) ? 0 : -1;
+                    }
+                    reapply_fragment(ga0, from, to);
+                    tally_frag(g, ga0, from, to, t);
+                }
+            }
+            for (int q = 0; q < nmoves; ++q) {
+                if (naive) MBSV_ST(f) = now;
+                else {
+                    const int g = P.sv_frag[q0 + q] - f0;
                     const int pv = MBSV_ST(g);
                     MBSV_ST(g) = (pv == -1) ? 0 : -1;
                 }
             }
         } else {
-            // revert
+            // revert the counts (the assignments were never written)
             double d1 = 0.0, d2 = 0.0;
             unsigned tt = 0;
-            if (naive) move_counts(a0, now, prev, d1, d2, tt);
-            else {
-                for (int q = P.sv_frag_ptr[sv0 + svk + 1] - 1; q >= P.sv_frag_ptr[sv0 + svk]; --q) {
-                    const int g = P.sv_frag[q] - f0;
-                    const int pv = MBSV_ST(g);   // assignment was not written yet: pv is still the old value
-                    move_counts(P.frag_aln_ptr[f0 + g], pv == -1 ? 0 : -1, pv, d1, d2, tt);
+            for (int q = nmoves - 1; q >= 0; --q) {
+                int ga0 = a0, from = prev, to = now;
+                if (!naive) {
+                    const int g = P.sv_frag[q0 + q] - f0;
+                    ga0 = P.frag_aln_ptr[f0 + g];
+                    from = MBSV_ST(g);
+                    to = (from == -1) ? 0 : -1;
                 }
+                move_counts(ga0, to, from, d1, d2, tt);
             }
-#pragma unroll
-            for (int x = 0; x < MAXE; ++x) { Etot[x] = E0[x]; Ltot[x] = L0[x]; }
-            nerr = nerr0;
         }
         if (TRACE) {
             R.trace_logprob[sc * N + iter] = logprob;
@@ -431,8 +410,10 @@ __global__ void __launch_bounds__(128) mbsv_chain_kernel(const __grid_constant__
         }
         ++iter;
     }
+    (void)q_base;
 
     // ---------------- epilogue: final tallies, state, counters ----------------
+    if (!alive) return;
     if (err == 0) {
         const long long nwin = (long long)N - win_base;
         if (nwin > 0) {
@@ -460,6 +441,22 @@ __global__ void __launch_bounds__(128) mbsv_chain_kernel(const __grid_constant__
     }
     if (R.rng_state) R.rng_state[sc] = rng.state();
     if (R.error) R.error[sc] = err;
+    if (R.totals) {
+        // one atomic per counter per warp (lanes that exited early simply do not take part)
+        const unsigned m = __activemask();
+        long long v[5] = {n_naive_prop, n_naive_acc, n_sv_prop, n_sv_acc, n_reassign};
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            long long x = v[i];
+            for (int o = 16; o > 0; o >>= 1) {
+                const long long y = __shfl_xor_sync(m, x, o);
+                const int src = lane ^ o;
+                if ((m >> src) & 1u) x += y;
+            }
+            if (lane == (__ffs(m) - 1)) atomicAdd(&R.totals[i], (unsigned long long)x);
+        }
+        if (err) atomicCAS(&R.totals[5], 0ULL, (unsigned long long)(long long)err);
+    }
 }
 
 }  // namespace mbsv

@@ -1,0 +1,69 @@
+// Plain-data launch arguments of the sampler kernels (shared by the host API and the kernel translation units).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mbsv {
+
+struct DevProblem {
+    int n_sub, n_frag, n_aln, n_cluster, n_exp, max_support, maxn;
+    const int* sub_frag_ptr;
+    const int* sub_cluster_ptr;
+    const int* sub_sv_ptr;
+    const double* sub_logF;          // log(F_s)  (Math.log(fragments.size()), MultiBreakSV.java:1219-1271)
+    const double* sub_neglogNsv;     // -log(bpsWithNonSingletonSupport.size())  (MultiBreakSV.java:1342-1343)
+    const int* frag_aln_ptr;
+    const int4* aln_rec;             // {numerrors, len, first ESP entry, exp | nesp << 8}
+    const int* aln_esp_slot;         // per alignment-ESP entry: local count slot cluster*E + exp, or -1
+    const int* supports_order_local; // per subproblem: local cluster indices in A.supports.keySet() order
+    const int* cluster_hist_ptr;
+    const int* sv_frag_ptr;
+    const int* sv_frag;
+    const int* sv_numchanged;
+    const double* T;                 // logprobcov [E][max_support+1]
+    const double* logint;            // log(n), n = 1..maxn (maxn >= max alignments per fragment and the
+                                     // largest n the exact-binomial branch can see, capped at 65536)
+    const double* exp_pseq;
+    const double* exp_logp;
+    const double* exp_log1mp;
+    double log2pi;                   // Math.log(2)+Math.log(Math.PI)
+};
+
+struct DevRun {
+    int n_chains, num_iters, burnin, win_base, java_int_wrap;
+    double perr, logperr, log1mperr;
+    long long seed;
+    const int* init_assign;
+    // plan: item g = warp*32 + lane is chain (g % n_chains) of subproblem sub_order[g / n_chains]
+    const int* sub_order;            // subproblems by ascending state size
+    const int* sub_W;                // state rows per chain of each subproblem
+    long long n_items;               // n_sub * n_chains
+    const long long* warp_row_off;   // [warp - global_warp0] row offset into workspace (global class)
+    int* workspace;
+    int warp_begin, warp_end, rows_per_warp, global_warp0;
+    // outputs (device)
+    unsigned int* aln_count;
+    unsigned int* frag_err_count;
+    unsigned int* cluster_hist;
+    int* final_assign;
+    double* final_logprob;
+    long long* counters;
+    unsigned long long* rng_state;
+    int* error;
+    double* trace_logprob;
+    int* trace_move_frag;
+    int* trace_move_assign;
+    int* initial_assign;
+    double* initial_logprob;
+    unsigned long long* totals;      // [6]
+};
+
+// MultiBreakSV.java:1661-1695 (logBinomial, logbinomialcoefficient, logNormal)
+
+using KernelFn = void (*)(const DevProblem, const DevRun);
+// kernel selectors, one per translation unit (kern_fast.cu / kern_replay.cu / kern_trace.cu)
+KernelFn get_kernel_fast(bool smem, int n_exp);                 // MODE_FAST, no trace: the throughput path
+KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_EXACT, no trace
+KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
+
+}  // namespace mbsv

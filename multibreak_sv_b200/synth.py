@@ -72,18 +72,56 @@ def _ragged_arange(counts: np.ndarray) -> np.ndarray:
     return np.arange(ptr[-1]) - np.repeat(ptr[:-1], counts)
 
 
-def generate(cfg: SynthConfig | str, n_frag: int | None = None, seed: int | None = None,
-             shuffle_orders: bool = False) -> PackedProblem:
-    """Build the CSR of a synthetic batch of independent subproblems.
+@dataclass
+class Skeleton:
+    """The part of a synthetic batch that fixes the work per subproblem: subproblem sizes, and for every
+    fragment its platform and number of candidate alignments.  Cheap to draw for N x 5M fragments, so every
+    rank can draw the same global skeleton, shard it (sharding.lpt_shard) and build only its own share."""
+    sizes: np.ndarray       # [S] fragments per subproblem
+    frag_is_pe: np.ndarray  # [F]
+    nal: np.ndarray         # [F] alignments per fragment
 
-    shuffle_orders: permute supports_order inside each subproblem (exercises the summation-order dependence
-    of REPLAY_EXACT); the benchmark keeps the identity.
-    """
+    @property
+    def weights(self) -> np.ndarray:
+        """fragment x alignment count of each subproblem (SURVEY §8e LPT weight, per chain)."""
+        ptr = np.concatenate([[0], np.cumsum(self.sizes)])
+        csum = np.concatenate([[0], np.cumsum(self.nal)])
+        return (csum[ptr[1:]] - csum[ptr[:-1]]).astype(np.int64)
+
+    def select(self, subs: np.ndarray) -> "Skeleton":
+        ptr = np.concatenate([[0], np.cumsum(self.sizes)])
+        sz = self.sizes[subs]
+        idx = np.repeat(ptr[subs], sz) + _ragged_arange(sz)
+        return Skeleton(sz, self.frag_is_pe[idx], self.nal[idx])
+
+
+def draw_skeleton(cfg: SynthConfig | str, n_frag: int | None = None, seed: int | None = None) -> Skeleton:
     if isinstance(cfg, str):
         cfg = CONFIGS[cfg]
     F = int(cfg.n_frag if n_frag is None else n_frag)
     rng = np.random.default_rng(cfg.seed if seed is None else seed)
     sizes = _sub_sizes(rng, cfg, F)
+    frag_is_pe = rng.random(F) < cfg.pe_frac
+    # alignments per fragment: PE 1+Poisson(1); long reads 1+min(15, Geom(0.25)) (<= 16)
+    nal = np.where(frag_is_pe, 1 + rng.poisson(1.0, F), 1 + np.minimum(15, rng.geometric(0.25, F))).astype(np.int64)
+    return Skeleton(sizes, frag_is_pe, nal)
+
+
+def generate(cfg: SynthConfig | str, n_frag: int | None = None, seed: int | None = None,
+             shuffle_orders: bool = False, skeleton: Skeleton | None = None) -> PackedProblem:
+    """Build the CSR of a synthetic batch of independent subproblems.
+
+    shuffle_orders: permute supports_order inside each subproblem (exercises the summation-order dependence
+    of REPLAY_EXACT); the benchmark keeps the identity.
+    skeleton: build exactly these subproblems (a shard of a larger skeleton) instead of drawing new ones.
+    """
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    if skeleton is None:
+        skeleton = draw_skeleton(cfg, n_frag, seed)
+    rng = np.random.default_rng((cfg.seed if seed is None else seed) + 7919)
+    sizes, frag_is_pe, nal = skeleton.sizes, skeleton.frag_is_pe, skeleton.nal
+    F = int(sizes.sum())
     S = len(sizes)
     sub_frag_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     frag_sub = np.repeat(np.arange(S), sizes)
@@ -98,13 +136,8 @@ def generate(cfg: SynthConfig | str, n_frag: int | None = None, seed: int | None
     pseq = np.array([EXPERIMENTS[l][0] for l in labels])
     lam = np.array([EXPERIMENTS[l][1] for l in labels])
     E = len(labels)
-    frag_is_pe = rng.random(F) < cfg.pe_frac
     frag_exp = np.where(frag_is_pe, labels.index("illumina") if "illumina" in labels else 0,
                         labels.index("pacbio") if "pacbio" in labels else 0).astype(np.int32)
-
-    # alignments per fragment: PE 1+Poisson(1); long reads 1+min(15, Geom(0.25)-1 ... ) (<= 16)
-    nal = np.where(frag_is_pe, 1 + rng.poisson(1.0, F), 1 + np.minimum(15, rng.geometric(0.25, F)))
-    nal = nal.astype(np.int64)
     A = int(nal.sum())
     frag_aln_ptr = np.concatenate([[0], np.cumsum(nal)])
     aln_frag = np.repeat(np.arange(F), nal)

@@ -83,6 +83,7 @@ struct orc_results {
     int32_t* trace_move_assign;
     int32_t* initial_assign;   // [n_chains][n_frag] state after initializeMatrix, or NULL
     double* initial_logprob;   // [n_sub][n_chains] or NULL
+    int64_t* totals;           // [6] or NULL
     double kernel_ms;
 };
 
@@ -115,6 +116,8 @@ int orc_run(const orc_desc* d, const orc_params* p, orc_results* r, int nthreads
     std::memset(r->cluster_hist, 0, sizeof(uint32_t) * (size_t)d->n_hist);
     std::atomic<int> next{0};
     std::atomic<int> worst{0};
+    std::atomic<long long> tot[5];
+    for (auto& t : tot) t.store(0);
     auto worker = [&]() {
         for (;;) {
             int s = next.fetch_add(1);
@@ -144,6 +147,8 @@ int orc_run(const orc_desc* d, const orc_params* p, orc_results* r, int nthreads
                     k[0] = cr.naive_proposed; k[1] = cr.naive_accepted; k[2] = cr.sv_proposed; k[3] = cr.sv_accepted;
                     k[4] = cr.reassignments;
                 }
+                tot[0] += cr.naive_proposed; tot[1] += cr.naive_accepted; tot[2] += cr.sv_proposed; tot[3] += cr.sv_accepted;
+                tot[4] += cr.reassignments;
                 if (r->rng_state) r->rng_state[sc] = cr.rng_state;
                 if (r->error) r->error[sc] = cr.error;
                 if (cr.error) worst.store(cr.error);
@@ -156,6 +161,7 @@ int orc_run(const orc_desc* d, const orc_params* p, orc_results* r, int nthreads
         for (int i = 0; i < nthreads; ++i) th.emplace_back(worker);
         for (auto& t : th) t.join();
     }
+    if (r->totals) { for (int i = 0; i < 5; ++i) r->totals[i] = tot[i].load(); r->totals[5] = worst.load(); }
     return worst.load();
 }
 

@@ -54,7 +54,7 @@ class OrcResults(C.Structure):
     _fields_ = [("aln_count", U32P), ("frag_err_count", U32P), ("cluster_hist", U32P), ("final_assign", I32P),
                 ("final_logprob", F64P), ("counters", I64P), ("rng_state", U64P), ("error", I32P),
                 ("trace_logprob", F64P), ("trace_move_frag", I32P), ("trace_move_assign", I32P),
-                ("initial_assign", I32P), ("initial_logprob", F64P), ("kernel_ms", C.c_double)]
+                ("initial_assign", I32P), ("initial_logprob", F64P), ("totals", I64P), ("kernel_ms", C.c_double)]
 
 
 def build(force: bool = False) -> str:
@@ -269,6 +269,7 @@ class RunResult:
     trace_move_assign: np.ndarray | None = None
     initial_assign: np.ndarray | None = None    # [n_chains, n_frag]
     initial_logprob: np.ndarray | None = None   # [n_sub, n_chains]
+    totals: np.ndarray | None = None            # [6]
     kernel_ms: float = 0.0
     rc: int = 0
 
@@ -287,7 +288,8 @@ def alloc_results(prob: Problem, n_chains: int, num_iters: int, trace: bool, res
         cluster_hist=np.zeros(s["n_hist"], np.uint32), final_assign=np.zeros((n_chains, s["n_frag"]), np.int32),
         final_logprob=np.zeros((S, n_chains), np.float64), counters=np.zeros((S, n_chains, 5), np.int64),
         rng_state=np.zeros((S, n_chains), np.uint64), error=np.zeros((S, n_chains), np.int32),
-        initial_assign=np.zeros((n_chains, s["n_frag"]), np.int32), initial_logprob=np.zeros((S, n_chains), np.float64))
+        initial_assign=np.zeros((n_chains, s["n_frag"]), np.int32), initial_logprob=np.zeros((S, n_chains), np.float64),
+        totals=np.zeros(6, np.int64))
     if trace:
         r.trace_logprob = np.zeros((S, n_chains, num_iters), np.float64)
         r.trace_move_frag = np.zeros((S, n_chains, num_iters), np.int32)
@@ -295,7 +297,7 @@ def alloc_results(prob: Problem, n_chains: int, num_iters: int, trace: bool, res
     cr = results_type()
     ft = dict(results_type._fields_)
     for k in ["aln_count", "frag_err_count", "cluster_hist", "final_assign", "final_logprob", "counters", "rng_state",
-              "error", "trace_logprob", "trace_move_frag", "trace_move_assign", "initial_assign", "initial_logprob"]:
+              "error", "trace_logprob", "trace_move_frag", "trace_move_assign", "initial_assign", "initial_logprob", "totals"]:
         a = getattr(r, k)
         setattr(cr, k, a.ctypes.data_as(ft[k]) if a is not None else ft[k]())
     return r, cr

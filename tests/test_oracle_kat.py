@@ -30,21 +30,43 @@ def test_kat1_java_random(oracle):
     assert oracle.random_bounded(0, 100, 8).tolist() == [60, 48, 29, 47, 15, 53, 91, 61]
 
 
+def _jhash(s):
+    h = 0
+    for c in s:
+        h = (31 * h + ord(c)) & 0xFFFFFFFF
+    return h
+
+
+def _closed_form_order(keys, cap):
+    """Without removals/tree bins, HashMap iteration order == sort by (bucket at the final capacity, insertion)."""
+    return [k for _, _, k in sorted(((_jhash(k) ^ (_jhash(k) >> 16)) & (cap - 1), i, k) for i, k in enumerate(keys))]
+
+
 def test_string_hash_and_hashmap_order(oracle):
     assert oracle.string_hash("") == 0
     assert oracle.string_hash("a") == 97
     assert oracle.string_hash("hello") == 99162322           # public constant
-    assert oracle.string_hash("longread_118671") == int(np.int32(sum(ord(c) * 31 ** (14 - i) for i, c in
-                                                                     enumerate("longread_118671")) & 0xFFFFFFFF))
+    h = sum(ord(c) * 31 ** (14 - i) for i, c in enumerate("longread_118671")) & 0xFFFFFFFF
+    assert oracle.string_hash("longread_118671") == (h - (1 << 32) if h >= (1 << 31) else h)
     order, cap, tree = oracle.hashmap_order(["longread_118669", "longread_118671", "longread_118673", "longread_118674"])
     assert order == KAT2_FRAGS and cap == 16 and not tree
     # Integer-like keys "0".."12": hash = char code(s); order by bucket
     keys = [str(i) for i in range(13)]
     order, cap, _ = oracle.hashmap_order(keys)
-    assert cap == 32 and order == ["0", "1", "2", "3", "4", "5", "6", "7", "8", "9", "10", "11", "12"]
+    assert cap == 32 and order == ["11", "12", "0", "1", "2", "3", "4", "5", "6", "7", "8", "9", "10"]
+    assert order == _closed_form_order(keys, 32)
+    rng = np.random.default_rng(11)
+    for n in (5, 12, 13, 24, 25, 100, 1000, 5000):
+        ks = [f"longread_{v}" for v in rng.choice(10 ** 6, n, replace=False)]
+        order, cap, tree = oracle.hashmap_order(ks)
+        want_cap = 16
+        while n > 0.75 * want_cap:
+            want_cap *= 2
+        assert not tree and cap == want_cap and order == _closed_form_order(ks, cap)
     # removal does not shrink the table and keeps the relative order of the others
+    order1, _, _ = oracle.hashmap_order(keys)
     order2, cap2, _ = oracle.hashmap_order(keys, removed=["3", "11"])
-    assert cap2 == 32 and order2 == [k for k in order if k not in ("3", "11")]
+    assert cap2 == 32 and order2 == [k for k in order1 if k not in ("3", "11")]
 
 
 def test_kat2_kat3_kat4_example_structure(oracle, example_problem):
