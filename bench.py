@@ -322,18 +322,34 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg = algorithmic_bytes(p, proposals, accepted)                      # this rank, per step
     achieved = alg / (kernel_ms / 1e3 / args.steps) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    # DRAM traffic comes from an `ncu --set full` capture (profiles/traffic.json); it only fills `traffic` when the
+    # capture was taken on this same workload, otherwise it is reported beside it with its own configuration.
+    traffic, traffic_other = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            if tj.get("n_frag") == sc["n_frag"] and tj.get("iters") == args.iters and tj.get("chains") == args.chains:
+                traffic = tj.get("dram_bytes_per_launch")
+            else:
+                traffic_other = tj
         except Exception:
-            traffic = None
+            pass
+    issue = None
+    ipath = os.path.join(ROOT, "profiles", "issue.json")
+    if os.path.exists(ipath):
+        try:
+            issue = json.load(open(ipath))
+        except Exception:
+            issue = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "mbsv_chain_kernel<FAST> (all size classes)",
-                "kernel_ms_per_step": kernel_ms / args.steps,
-                "note": "algorithmic bytes are served from shared memory / L1 / L2 (state is SM-resident); the "
-                        "binding limit is SM issue rate, see profiles/ and DESIGN.md"}
+                "traffic": traffic, "traffic_reduced_config": traffic_other, "peak_source": peak_src,
+                "kernel": "mbsv_chain_kernel<FAST> (all size classes, one launch per state-size class)",
+                "kernel_ms_per_step": kernel_ms / args.steps, "algorithmic_bytes_per_step": alg,
+                "binding": issue,
+                "note": "algorithmic bytes are served from shared memory / L1 / L2 (chain state is SM-resident), so "
+                        "HBM is not the binding roofline; `binding` holds the ncu issue-slot figures of the dominant "
+                        "launch (profiles/), see DESIGN.md section 4"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

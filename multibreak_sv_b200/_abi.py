@@ -12,7 +12,9 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmbsv_b200.so")
+# MBSV_B200_LIB selects an alternative build of the same library (kernel-tuning experiments); it is still a
+# CUDA build of this repository's sources, never a fallback.
+LIB_PATH = os.environ.get("MBSV_B200_LIB") or os.path.join(_HERE, "libmbsv_b200.so")
 
 I32P = C.POINTER(C.c_int32)
 U8P = C.POINTER(C.c_uint8)

@@ -14,8 +14,10 @@
 
 #if defined(__CUDACC__)
 #define JM_HD __host__ __device__ __forceinline__
+#define JM_CX __host__ __device__ constexpr
 #else
 #define JM_HD inline
+#define JM_CX constexpr
 #endif
 
 namespace mbsv {
@@ -43,7 +45,11 @@ JM_HD double jm_make(int32_t hi, uint32_t lo) {
 }
 JM_HD double jm_bits(uint64_t u) { return jm_make((int32_t)(u >> 32), (uint32_t)u); }
 
-// fdlibm e_log.c
+// fdlibm e_log.c.  The two polynomial-correction forms (selected by `i > 0`) and the k == 0 special cases are
+// evaluated through one straight-line path and a select; both rewrites are bit-identical to fdlibm's
+// branches (negation commutes with IEEE subtraction/division, and adding dk*ln2 terms with dk == +0.0 is
+// exact), they only remove warp divergence.  The rare paths (zero, negative, subnormal, inf/NaN,
+// |x-1| < 2^-20) keep their branches.
 JM_HD double jm_log(double x) {
     const double ln2_hi = jm_bits(0x3fe62e42fee00000ULL), ln2_lo = jm_bits(0x3dea39ef35793c76ULL);
     const double two54 = jm_bits(0x4350000000000000ULL);
@@ -65,37 +71,37 @@ JM_HD double jm_log(double x) {
     int32_t i = (hx + 0x95f64) & 0x100000;
     x = jm_make(hx | (i ^ 0x3ff00000), lx);
     k += (i >> 20);
-    double f = x - 1.0;
-    double dk, R;
+    const double f = x - 1.0;
+    const double dk = (double)k;
     if ((0x000fffff & (2 + hx)) < 3) {
         if (f == 0.0) {
             if (k == 0) return 0.0;
-            dk = (double)k; return dk * ln2_hi + dk * ln2_lo;
+            return dk * ln2_hi + dk * ln2_lo;
         }
-        R = f * f * (0.5 - 0.33333333333333333 * f);
+        const double R = f * f * (0.5 - 0.33333333333333333 * f);
         if (k == 0) return f - R;
-        dk = (double)k; return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+        return dk * ln2_hi - ((R - dk * ln2_lo) - f);
     }
-    double s = f / (2.0 + f);
-    dk = (double)k;
-    double z = s * s;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
     i = hx - 0x6147a;
-    double w = z * z;
-    int32_t j = 0x6b851 - hx;
-    double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
-    double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    const double w = z * z;
+    const int32_t j = 0x6b851 - hx;
+    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
     i |= j;
-    R = t2 + t1;
-    if (i > 0) {
-        double hfsq = 0.5 * f * f;
-        if (k == 0) return f - (hfsq - s * (hfsq + R));
-        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
-    }
-    if (k == 0) return f - s * (f - R);
-    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dkhi = dk * ln2_hi, dklo = dk * ln2_lo;
+    const double A = dkhi - ((hfsq - (s * (hfsq + R) + dklo)) - f);   // i > 0
+    const double B = dkhi - ((s * (f - R) - dklo) - f);               // i <= 0
+    return i > 0 ? A : B;
 }
 
-// fdlibm e_exp.c
+// fdlibm e_exp.c.  The three argument-reduction cases (|x| <= 0.5 ln2, < 1.5 ln2, general) run through the
+// general formula with k = 0, +-1, k: bit-identical (k*ln2HI is exact for those k, 0 - q == -q, and
+// (x*c)/(c-2) == -((x*c)/(2-c))), and free of divergence.  Overflow/underflow/NaN and |x| < 2^-28 keep
+// their (rare) branches.
 JM_HD double jm_exp(double x) {
     const double huge = 1.0e+300;
     const double twom1000 = jm_bits(0x0170000000000000ULL);
@@ -106,10 +112,8 @@ JM_HD double jm_exp(double x) {
     const double P1 = jm_bits(0x3FC555555555553EULL), P2 = jm_bits(0xBF66C16C16BEBD93ULL),
                  P3 = jm_bits(0x3F11566AAF25DE2CULL), P4 = jm_bits(0xBEBBBD41C5D26BF1ULL),
                  P5 = jm_bits(0x3E66376972BEA4D0ULL);
-    double hi = 0.0, lo = 0.0;
-    int32_t k = 0;
     uint32_t hx = (uint32_t)jm_hi(x);
-    int32_t xsb = (int32_t)((hx >> 31) & 1);
+    const int32_t xsb = (int32_t)((hx >> 31) & 1);
     hx &= 0x7fffffff;
     if (hx >= 0x40862E42) {
         if (hx >= 0x7ff00000) {
@@ -119,24 +123,17 @@ JM_HD double jm_exp(double x) {
         if (x > o_threshold) return huge * huge;
         if (x < u_threshold) return twom1000 * twom1000;
     }
-    if (hx > 0x3fd62e42) {
-        if (hx < 0x3FF0A2B2) {
-            hi = xsb ? x + ln2HI : x - ln2HI;          // x - ln2HI[xsb], ln2HI[1] = -ln2HI[0]
-            lo = xsb ? -ln2LO : ln2LO;
-            k = 1 - xsb - xsb;
-        } else {
-            k = (int32_t)(invln2 * x + (xsb ? -0.5 : 0.5));
-            double t = (double)k;
-            hi = x - t * ln2HI;
-            lo = t * ln2LO;
-        }
-        x = hi - lo;
-    } else if (hx < 0x3e300000) {
+    if (hx < 0x3e300000) {
         if (huge + x > 1.0) return 1.0 + x;
-    } else k = 0;
-    double t = x * x;
-    double c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
-    if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
+    }
+    int32_t k = 0;
+    if (hx > 0x3fd62e42) k = (int32_t)(invln2 * x + (xsb ? -0.5 : 0.5));
+    const double tk = (double)k;
+    const double hi = x - tk * ln2HI;
+    const double lo = tk * ln2LO;
+    x = hi - lo;
+    const double t = x * x;
+    const double c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
     double y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
     if (k >= -1021) return jm_make(jm_hi(y) + (k << 20), jm_lo(y));
     y = jm_make(jm_hi(y) + ((k + 1000) << 20), jm_lo(y));
@@ -150,6 +147,9 @@ struct JavaRandom {
     static constexpr uint64_t MULT = 0x5DEECE66DULL, ADD = 0xBULL, MASK = (1ULL << 48) - 1;
     // two steps at once: s2 = MULT^2 * s + (MULT*ADD + ADD)
     static constexpr uint64_t MULT2 = (MULT * MULT) & MASK, ADD2 = (MULT * ADD + ADD) & MASK;
+    // jump-ahead: the state m steps after s is jump_mul(m) * s + jump_add(m)  (mod 2^48)
+    static JM_CX uint64_t jump_mul(int m) { uint64_t a = 1; for (int i = 0; i < m; ++i) a = (a * MULT) & MASK; return a; }
+    static JM_CX uint64_t jump_add(int m) { uint64_t c = 0; for (int i = 0; i < m; ++i) c = (c * MULT + ADD) & MASK; return c; }
     JM_HD void seed(int64_t sd) { s = ((uint64_t)sd ^ MULT) & MASK; }
     JM_HD uint32_t next(int bits) {
         s = s * MULT + ADD;
@@ -161,7 +161,15 @@ struct JavaRandom {
         s = s2;
         uint64_t a = (s1 & MASK) >> 22;    // next(26)
         uint64_t b = (s2 & MASK) >> 21;    // next(27)
+#if defined(__CUDA_ARCH__)
+        // ((a << 27) + b) * 2^-53 without the 64-bit int->double conversion: 2^52 + v is built from bits,
+        // every step below is exact, so the value equals the host expression.
+        const double da = __hiloint2double(0x43300000, (int)a) - 4503599627370496.0;
+        const double db = __hiloint2double(0x43300000, (int)b) - 4503599627370496.0;
+        return da * 0x1.0p-26 + db * 0x1.0p-53;
+#else
         return (double)(int64_t)((a << 27) + b) * 0x1.0p-53;
+#endif
     }
     JM_HD int32_t nextInt(int32_t bound) {
         int32_t r = (int32_t)next(31);

@@ -31,7 +31,8 @@ static __device__ __noinline__ double log_binomial_dev(long long k, long long n,
         long long r = k, m = n - k;
         if (r < m) r = m;
         if (n <= ntab && n >= 1) {
-            for (long long i = n, j = 1; i > r; --i, ++j) t = t + logtab[i] - logtab[j];
+            const int ri = (int)(r < 0 ? 0 : r);
+            for (int i = (int)n, j = 1; i > ri; --i, ++j) t = t + logtab[i] - logtab[j];
         } else {
             for (long long i = n, j = 1; i > r; --i, ++j) t = t + jm_log((double)i) - jm_log((double)j);
         }
@@ -244,18 +245,50 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
         // convergence point that brings all 32 lanes back together for the proposal code.
         double r = 0.0;
         bool live = false;
-        if (!done) {
-            while (iter < N) {
-                r = rng.nextDouble();
-                if (!(r < 0.5)) { live = true; break; }
-                if (TRACE) {
+        if (TRACE) {
+            if (!done) {
+                while (iter < N) {
+                    r = rng.nextDouble();
+                    if (!(r < 0.5)) { live = true; break; }
                     R.trace_logprob[sc * N + iter] = logprob;
                     R.trace_move_frag[sc * N + iter] = -1;
                     R.trace_move_assign[sc * N + iter] = -1;
+                    ++iter;
                 }
-                ++iter;
+                done = !live;
             }
-            done = !live;
+        } else if (!done) {
+            // Branch-free look-ahead over the next LAZY_J iterations: iteration j is lazy iff its first LCG
+            // step (2j+1 steps from here) has bit 47 clear (nextDouble() < 0.5 <=> next(26) < 2^25).  All
+            // candidates are independent multiply-adds of the current state by jump-ahead constants.
+            constexpr int LAZY_J = 8;
+            const uint64_t s0 = rng.s;
+            uint64_t cand[LAZY_J];
+            unsigned bits = 0;
+#pragma unroll
+            for (int j = 0; j < LAZY_J; ++j) {
+                cand[j] = s0 * JavaRandom::jump_mul(2 * j + 1) + JavaRandom::jump_add(2 * j + 1);
+                bits |= ((unsigned)(cand[j] >> 47) & 1u) << j;
+            }
+            const int jstar = bits ? (__ffs(bits) - 1) : LAZY_J;
+            const int remaining = N - iter;
+            const int lim = remaining < LAZY_J ? remaining : LAZY_J;
+            if (jstar < lim) {
+                uint64_t sel = cand[0];
+#pragma unroll
+                for (int j = 1; j < LAZY_J; ++j) if (jstar == j) sel = cand[j];
+                rng.s = sel * JavaRandom::MULT + JavaRandom::ADD;   // second LCG step of that nextDouble()
+                iter += jstar;
+                live = true;
+            } else if (lim == LAZY_J) {
+                rng.s = s0 * JavaRandom::jump_mul(2 * LAZY_J) + JavaRandom::jump_add(2 * LAZY_J);
+                iter += LAZY_J;
+                done = iter >= N;
+            } else {
+                for (int j = 0; j < lim; ++j) rng.s = rng.s * JavaRandom::MULT2 + JavaRandom::ADD2;
+                iter += lim;
+                done = true;
+            }
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (!live) continue;

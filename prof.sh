@@ -1,9 +1,6 @@
 set -x
 mkdir -p gpurun_out
 SMALL="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --n-frag 200000 --iters 500"
-python bench.py > gpurun_out/bench_default.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01.csv python bench.py > gpurun_out/ncu_launches.log 2>&1
 $SMALL > gpurun_out/plain_small.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:mbsv_chain -s 5 -c 5 -o gpurun_out/prof_r01 $SMALL > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/bench_default.log
-tail -3 gpurun_out/ncu_full.log
+ncu --set full --clock-control none --import-source on -k regex:mbsv_chain -s 5 -c 5 -o gpurun_out/prof_r01b $SMALL > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log | cut -c1-300

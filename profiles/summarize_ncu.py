@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Turn an .ncu-rep (ncu --set full) into the small text summaries kept under profiles/.
+
+    python profiles/summarize_ncu.py gpurun_out/prof_r01b.ncu-rep profiles/r01_ncu_full
+
+writes <out>_metrics.csv (one row per captured launch), <out>_lines.txt (CUDA source lines ranked by executed
+warp-instructions with their average active lanes) and prints the dominant kernel's DRAM traffic per launch.
+"""
+import collections
+import csv
+import json
+import subprocess
+import sys
+
+METRICS = [
+    "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "gpu__time_duration.sum",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_issued.avg.pct_of_peak_sustained_active",
+    "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__sass_average_branch_targets_threads_uniform.pct", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__average_warp_latency_per_inst_issued.ratio",
+]
+STALLS = ["wait", "no_instruction", "branch_resolving", "long_scoreboard", "short_scoreboard", "not_selected",
+          "math_pipe_throttle", "dispatch_stall", "lg_throttle", "mio_throttle", "barrier", "selected"]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    cols = ["Kernel Name"] + [m for m in METRICS if m in idx] + \
+           [f"smsp__average_warps_issue_stalled_{s}_per_issue_active.ratio" for s in STALLS
+            if f"smsp__average_warps_issue_stalled_{s}_per_issue_active.ratio" in idx]
+    with open(out + "_metrics.csv", "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(cols)
+        w.writerow([units[idx[c]] for c in cols])
+        for r in data:
+            w.writerow([r[idx[c]] for c in cols])
+    # dominant launch = longest duration
+    dur = [float(r[idx["gpu__time_duration.sum"]]) for r in data]
+    k = max(range(len(data)), key=lambda i: dur[i])
+
+    def to_bytes(v, u):
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    traffic = sum(to_bytes(data[k][idx[m]], units[idx[m]]) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    print(json.dumps({"dominant_launch": k, "kernel": data[k][idx["Kernel Name"]], "grid": data[k][idx["launch__grid_size"]],
+                      "duration": data[k][idx["gpu__time_duration.sum"]] + " " + units[idx["gpu__time_duration.sum"]],
+                      "dram_bytes_per_launch": traffic}))
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--launch-skip", str(k),
+                          "--launch-count", "1"], capture_output=True, text=True).stdout
+    agg = collections.OrderedDict()
+    cur_file = cur_line = cur_src = None
+    h = None
+    for r in csv.reader(src.splitlines()):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur_file = r[1].split("/")[-1]
+            continue
+        if r[0] == "Function Name":
+            continue
+        if r[0] == "Line No":
+            h = r
+            iE, iT, iS = h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("# Samples")
+            continue
+        if h is None:
+            continue
+        if r[0] != "":
+            cur_line, cur_src = r[0], r[1]
+        try:
+            e, t, s = int(r[iE] or 0), int(r[iT] or 0), int(r[iS] or 0)
+        except (ValueError, IndexError):
+            continue
+        a = agg.setdefault((cur_file, cur_line), [0, 0, 0, cur_src])
+        a[0] += e; a[1] += t; a[2] += s
+    tot = sum(a[0] for a in agg.values()) or 1
+    tott = sum(a[1] for a in agg.values())
+    tots = sum(a[2] for a in agg.values()) or 1
+    with open(out + "_lines.txt", "w") as fh:
+        fh.write(f"dominant launch #{k}: {data[k][idx['Kernel Name']]} grid {data[k][idx['launch__grid_size']]}\n")
+        fh.write(f"warp-instructions {tot}  thread-instructions {tott}  avg active lanes {tott / tot:.2f}\n")
+        fh.write("share-of-warp-inst  share-of-stall-samples  avg-active-lanes  file:line  source\n")
+        for (f, l), (e, t, s, sline) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:60]:
+            fh.write(f"{100 * e / tot:5.1f}%  {100 * s / tots:5.1f}%  {t / max(e, 1):5.1f}  {f}:{l}  {sline.strip()[:110]}\n")
+
+
+if __name__ == "__main__":
+    main()
