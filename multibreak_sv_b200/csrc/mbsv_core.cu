@@ -73,6 +73,9 @@ struct mbsv_problem {
     cudaStream_t streams[8] = {};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done[8] = {}, ev_cls0[8] = {}, ev_cls1[8] = {};
     bool streams_ok = false;
+    bool has_cc = false;
+    DevBuf<int> d_cluster_cc_off, d_sub_cc_scratch, d_sub_cc_maxleaf, d_cluster_leaf_ptr, d_leaf_owner, d_aln_esp_leaf,
+        d_cluster_root_ptr, d_root_leaf_ptr, d_root_leaf;
 };
 
 extern "C" {
@@ -184,10 +187,29 @@ static int validate(const mbsv_problem_desc* d) {
                                       "MultiBreakSV.java:1401)");
     for (int f = 0; f < d->n_frag; ++f)
         if (d->frag_aln_ptr[f + 1] == d->frag_aln_ptr[f]) return fail(MBSV_ERR_ARG, "a fragment has no alignment");
-    for (int c = 0; c < d->n_cluster; ++c)
-        if (d->cluster_kind[c] != 0)
-            return fail(MBSV_ERR_UNSUPPORTED, "connected-component clusters (GASV localization -1) are not yet handled "
-                                              "on the device");
+    bool any_cc = false;
+    for (int c = 0; c < d->n_cluster; ++c) {
+        if (d->cluster_kind[c] > 1) return fail(MBSV_ERR_ARG, "cluster_kind must be 0 (cluster) or 1 (connected component)");
+        any_cc = any_cc || d->cluster_kind[c] == 1;
+    }
+    if (any_cc) {
+        if (!d->cluster_leaf_ptr || !d->leaf_owner || !d->aln_esp_leaf || !d->cluster_root_ptr || !d->root_leaf_ptr || !d->root_leaf)
+            return fail(MBSV_ERR_ARG, "connected components need the leaf/root arrays and aln_esp_leaf");
+        if ((rc = mono(d->cluster_leaf_ptr, d->n_cluster, d->n_leaf, "cluster_leaf_ptr"))) return rc;
+        if ((rc = mono(d->cluster_root_ptr, d->n_cluster, d->n_root, "cluster_root_ptr"))) return rc;
+        if ((rc = mono(d->root_leaf_ptr, d->n_root, d->n_root_leaf, "root_leaf_ptr"))) return rc;
+        for (int c = 0; c < d->n_cluster; ++c) {
+            if (d->cluster_kind[c] != 1) continue;
+            const int nl = d->cluster_leaf_ptr[c + 1] - d->cluster_leaf_ptr[c];
+            if (nl > d->max_support)
+                return fail(MBSV_ERR_UNSUPPORTED, "a connected component has more leaves than max_support");
+            if (nl + 1 > d->cluster_hist_ptr[c + 1] - d->cluster_hist_ptr[c])
+                return fail(MBSV_ERR_ARG, "cluster_hist_ptr leaves too few bins for a connected component");
+            for (int r = d->cluster_root_ptr[c]; r < d->cluster_root_ptr[c + 1]; ++r)
+                for (int j = d->root_leaf_ptr[r]; j < d->root_leaf_ptr[r + 1]; ++j)
+                    if (d->root_leaf[j] < 0 || d->root_leaf[j] >= nl) return fail(MBSV_ERR_ARG, "root_leaf out of range");
+        }
+    }
     for (int a = 0; a < d->n_aln; ++a) {
         if (d->aln_exp[a] < 0 || d->aln_exp[a] >= d->n_exp) return fail(MBSV_ERR_ARG, "aln_exp out of range");
         if (d->aln_esp_ptr[a + 1] - d->aln_esp_ptr[a] >= (1 << 23)) return fail(MBSV_ERR_ARG, "alignment with too many ESPs");
@@ -224,7 +246,13 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                 if (c == -1) continue;
                 if (c < d->sub_cluster_ptr[s] || c >= d->sub_cluster_ptr[s + 1])
                     return fail(MBSV_ERR_ARG, "aln_esp_cluster points outside the fragment's subproblem");
-                slot[j] = (c - d->sub_cluster_ptr[s]) * E + x;
+                if (d->cluster_kind[c] == 1) {
+                    const int nl = d->cluster_leaf_ptr[c + 1] - d->cluster_leaf_ptr[c];
+                    if (d->aln_esp_leaf[j] < 0 || d->aln_esp_leaf[j] >= nl) return fail(MBSV_ERR_ARG, "aln_esp_leaf out of range");
+                    slot[j] = -(2 + (c - d->sub_cluster_ptr[s]));      // connected component: recomputed, not counted
+                } else {
+                    slot[j] = (c - d->sub_cluster_ptr[s]) * E + x;
+                }
             }
         }
     }
@@ -238,7 +266,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                 std::vector<std::pair<int, int>> cnt;
                 for (int j = d->aln_esp_ptr[a]; j < d->aln_esp_ptr[a + 1]; ++j) {
                     const int c = d->aln_esp_cluster[j];
-                    if (c < 0) continue;
+                    if (c < 0 || d->cluster_kind[c] == 1) continue;
                     bool found = false;
                     for (auto& pr : cnt) if (pr.first == c) { ++pr.second; found = true; }
                     if (!found) cnt.push_back({c, 1});
@@ -309,8 +337,22 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     p->device = device;
     p->n_sub = S; p->n_frag = F; p->n_aln = A; p->n_cluster = C; p->n_exp = E; p->n_hist = d->n_hist;
     p->sub_W.resize(S);
-    for (int s = 0; s < S; ++s)
-        p->sub_W[s] = (d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]) + (d->sub_cluster_ptr[s + 1] - d->sub_cluster_ptr[s]) * E;
+    // chain state rows: assignments + counts (+ per conn-comp {stamp, current and saved multisets} + set-cover scratch)
+    std::vector<int> cluster_cc_off(C, -1), sub_cc_scratch(S, -1), sub_cc_maxleaf(S, 0);
+    for (int s = 0; s < S; ++s) {
+        int W = (d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]) + (d->sub_cluster_ptr[s + 1] - d->sub_cluster_ptr[s]) * E;
+        int off = 0, maxleaf = 0, maxroot = 0;
+        for (int c = d->sub_cluster_ptr[s]; c < d->sub_cluster_ptr[s + 1]; ++c) {
+            if (d->cluster_kind[c] != 1) continue;
+            const int nr = d->cluster_root_ptr[c + 1] - d->cluster_root_ptr[c];
+            cluster_cc_off[c] = off;
+            off += 1 + 2 * E * (1 + nr);
+            maxleaf = std::max(maxleaf, d->cluster_leaf_ptr[c + 1] - d->cluster_leaf_ptr[c]);
+            maxroot = std::max(maxroot, nr);
+        }
+        if (off > 0) { sub_cc_scratch[s] = off; sub_cc_maxleaf[s] = maxleaf; W += off + maxleaf + maxroot; p->has_cc = true; }
+        p->sub_W[s] = W;
+    }
     p->sub_order.resize(S);
     std::iota(p->sub_order.begin(), p->sub_order.end(), 0);
     std::stable_sort(p->sub_order.begin(), p->sub_order.end(), [&](int a, int b) { return p->sub_W[a] < p->sub_W[b]; });
@@ -336,6 +378,17 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     chk(up(p->d_pseq, std::vector<double>(d->exp_pseq, d->exp_pseq + E)));
     chk(up(p->d_logp, logp));
     chk(up(p->d_log1mp, log1mp));
+    if (p->has_cc) {
+        chk(up(p->d_cluster_cc_off, cluster_cc_off));
+        chk(up(p->d_sub_cc_scratch, sub_cc_scratch));
+        chk(up(p->d_sub_cc_maxleaf, sub_cc_maxleaf));
+        chk(up(p->d_cluster_leaf_ptr, std::vector<int>(d->cluster_leaf_ptr, d->cluster_leaf_ptr + C + 1)));
+        chk(up(p->d_leaf_owner, std::vector<int>(d->leaf_owner, d->leaf_owner + d->n_leaf)));
+        chk(up(p->d_aln_esp_leaf, std::vector<int>(d->aln_esp_leaf, d->aln_esp_leaf + K)));
+        chk(up(p->d_cluster_root_ptr, std::vector<int>(d->cluster_root_ptr, d->cluster_root_ptr + C + 1)));
+        chk(up(p->d_root_leaf_ptr, std::vector<int>(d->root_leaf_ptr, d->root_leaf_ptr + d->n_root + 1)));
+        chk(up(p->d_root_leaf, std::vector<int>(d->root_leaf, d->root_leaf + d->n_root_leaf)));
+    }
     chk(up(p->d_sub_order, p->sub_order));
     chk(up(p->d_sub_W, p->sub_W));
     if (e != cudaSuccess) {
@@ -348,6 +401,9 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     dp.sub_frag_ptr = p->d_sub_frag_ptr.p; dp.sub_cluster_ptr = p->d_sub_cluster_ptr.p; dp.sub_sv_ptr = p->d_sub_sv_ptr.p;
     dp.sub_logF = p->d_sub_logF.p; dp.sub_neglogNsv = p->d_sub_neglogNsv.p; dp.frag_aln_ptr = p->d_frag_aln_ptr.p; dp.aln_rec = p->d_aln_rec.p;
     dp.aln_esp_slot = p->d_aln_esp_slot.p; dp.supports_order_local = p->d_supports_local.p;
+    dp.cluster_cc_off = p->d_cluster_cc_off.p; dp.sub_cc_scratch = p->d_sub_cc_scratch.p; dp.sub_cc_maxleaf = p->d_sub_cc_maxleaf.p;
+    dp.cluster_leaf_ptr = p->d_cluster_leaf_ptr.p; dp.leaf_owner = p->d_leaf_owner.p; dp.aln_esp_leaf = p->d_aln_esp_leaf.p;
+    dp.cluster_root_ptr = p->d_cluster_root_ptr.p; dp.root_leaf_ptr = p->d_root_leaf_ptr.p; dp.root_leaf = p->d_root_leaf.p;
     dp.cluster_hist_ptr = p->d_cluster_hist_ptr.p; dp.sv_frag_ptr = p->d_sv_frag_ptr.p; dp.sv_frag = p->d_sv_frag.p;
     dp.sv_numchanged = p->d_sv_numchanged.p; dp.T = p->d_T.p; dp.logint = p->d_logint.p; dp.exp_pseq = p->d_pseq.p;
     dp.exp_logp = p->d_logp.p; dp.exp_log1mp = p->d_log1mp.p;
@@ -533,7 +589,8 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.warp_row_off = smem ? nullptr : ob.row_off.p;
         r.workspace = smem ? nullptr : ob.workspace.p;
         r.global_warp0 = g0;
-        KernelFn fn = pick(rp->mode, rp->trace != 0, smem, p->n_exp);
+        KernelFn fn = p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, smem)
+                                : pick(rp->mode, rp->trace != 0, smem, p->n_exp);
         const size_t shm = smem ? (size_t)WARPS_PER_CTA * cls[k] * 128 : 0;
         if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         cudaStream_t st = p->streams[1 + (nstream % 7)];

@@ -52,7 +52,9 @@ static __device__ __noinline__ double exp_dev(double x) { return jm_exp(x); }
 #define MBSV_MIN_BLOCKS 5
 #endif
 
-template <int MODE, bool TRACE, bool SMEM, int MAXE>
+// CC = the batch contains connected-component clusters (GASV localization -1): their support is the sorted
+// multiset of a greedy set cover (MultiBreakSVAssignmentMatrix.java:337-409) kept per chain next to the counts.
+template <int MODE, bool TRACE, bool SMEM, int MAXE, bool CC = false>
 __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
                                                          const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
@@ -138,15 +140,114 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
             ++nerr;
         }
     };
+    // ---- connected components (CC only) ----------------------------------------------------------------
+    // State after the counts: per conn-comp cluster {stamp, current multisets E x (len, values[nroots]),
+    // saved multisets (same shape)}, then per-subproblem scratch {leaf flags, root flags}.
+    const int cc_base = F + C * E;
+    const bool has_cc = CC && alive && P.sub_cc_scratch[sub] >= 0;
+    auto cc_nroots = [&](int cl) -> int { return P.cluster_root_ptr[c0 + cl + 1] - P.cluster_root_ptr[c0 + cl]; };
+    auto cc_lpc = [&](int cl) -> double {
+        const int nr = cc_nroots(cl);
+        const int b0 = cc_base + P.cluster_cc_off[c0 + cl] + 1;
+        double lpc = 0.0;
+        for (int x = 0; x < E; ++x) {
+            const int b = b0 + x * (1 + nr);
+            const int len = MBSV_ST(b);
+            for (int i = 0; i < len; ++i) lpc = lpc + P.T[(size_t)x * Tstride + MBSV_ST(b + 1 + i)];
+        }
+        return lpc;
+    };
+    // setBreakpoints for one connected component from the current assignments (AM.java:264-414)
+    auto cc_recompute = [&](int cl) {
+        const int cg = c0 + cl;
+        const int l0 = P.cluster_leaf_ptr[cg], nl = P.cluster_leaf_ptr[cg + 1] - l0;
+        const int r0 = P.cluster_root_ptr[cg], nr = P.cluster_root_ptr[cg + 1] - r0;
+        const int b0 = cc_base + P.cluster_cc_off[cg] + 1;
+        const int sl = cc_base + P.sub_cc_scratch[sub];       // leaf flags: exp + 1 (0 = not selected), bit 8 = found
+        const int sr = sl + P.sub_cc_maxleaf[sub];            // root flags: 1 = already taken
+        int numselected = 0;
+        for (int l = 0; l < nl; ++l) {
+            int flag = 0;
+            const int fg = P.leaf_owner[l0 + l];
+            if (fg >= 0) {
+                const int a = MBSV_ST(fg - f0);
+                if (a != -1) {
+                    const int4 rec = P.aln_rec[P.frag_aln_ptr[fg] + a];
+                    const int ne = rec.w >> 8;
+                    for (int j = 0; j < ne; ++j)
+                        if (P.aln_esp_slot[rec.z + j] == -(2 + cl) && P.aln_esp_leaf[rec.z + j] == l) { flag = (rec.w & 0xff) + 1; ++numselected; }
+                }
+            }
+            MBSV_ST(sl + l) = flag;
+        }
+        for (int x = 0; x < E; ++x) MBSV_ST(b0 + x * (1 + nr)) = 0;
+        if (numselected == 0) return;
+        for (int x = 0; x < E; ++x) {
+            const int b = b0 + x * (1 + nr);
+            for (int l = 0; l < nl; ++l) MBSV_ST(sl + l) &= 0xff;
+            for (int r = 0; r < nr; ++r) MBSV_ST(sr + r) = 0;
+            int len = 0;
+            for (;;) {
+                int maxcount = 0, maxind = -1;
+                for (int r = 0; r < nr; ++r) {
+                    if (MBSV_ST(sr + r)) continue;
+                    int cur = 0;
+                    for (int j = P.root_leaf_ptr[r0 + r]; j < P.root_leaf_ptr[r0 + r + 1]; ++j)
+                        if (MBSV_ST(sl + P.root_leaf[j]) == x + 1) ++cur;
+                    if (cur > maxcount) { maxcount = cur; maxind = r; }
+                }
+                if (maxind == -1) {
+                    for (int l = 0; l < nl; ++l) if (MBSV_ST(sl + l) == x + 1) err = -5;   // Error at AM.java:375-376
+                    break;
+                }
+                for (int j = P.root_leaf_ptr[r0 + maxind]; j < P.root_leaf_ptr[r0 + maxind + 1]; ++j)
+                    if ((MBSV_ST(sl + P.root_leaf[j]) & 0xff) == x + 1) MBSV_ST(sl + P.root_leaf[j]) = (x + 1) | 0x100;
+                // sorted insert (Collections.sort at AM.java:403)
+                int pos = len;
+                while (pos > 0 && MBSV_ST(b + pos) > maxcount) { MBSV_ST(b + 1 + pos) = MBSV_ST(b + pos); --pos; }
+                MBSV_ST(b + 1 + pos) = maxcount;
+                ++len;
+                MBSV_ST(sr + maxind) = 1;
+                bool all = true;
+                for (int l = 0; l < nl; ++l) if (MBSV_ST(sl + l) == x + 1) all = false;
+                if (all) break;
+            }
+            MBSV_ST(b) = len;
+        }
+    };
+    // visit the connected components touched by fragment-alignment `al` (entries coded -(2+cluster))
+    auto cc_visit = [&](int al, auto&& fn) {
+        const int4 rec = P.aln_rec[al];
+        const int ne = rec.w >> 8;
+        for (int j = 0; j < ne; ++j) {
+            const int code = P.aln_esp_slot[rec.z + j];
+            if (code < -1) fn(-code - 2);
+        }
+    };
+    auto cc_hist = [&](int cl, int which, unsigned d) {   // which: 0 current multisets, 1 saved multisets
+        const int nr = cc_nroots(cl);
+        const int b0 = cc_base + P.cluster_cc_off[c0 + cl] + 1 + which * E * (1 + nr);
+        unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + cl];
+        for (int x = 0; x < E; ++x) {
+            const int b = b0 + x * (1 + nr);
+            const int len = MBSV_ST(b);
+            for (int i = 0; i < len; ++i) atomicAdd(&h[MBSV_ST(b + 1 + i)], d);
+        }
+    };
+
     // MultiBreakSVAssignmentMatrix.java:130-246 in the reference's summation order.
     auto full_logprob = [&]() -> double {
         double lp = 0;
         for (int i = 0; i < C; ++i) {
             const int cl = P.supports_order_local[c0 + i];
             double lpc = 0.0;
-            for (int x = 0; x < E; ++x) {
-                const int n = MBSV_ST(F + cl * E + x);
-                if (n > 0) lpc = lpc + P.T[(size_t)x * Tstride + n];
+            if (CC && P.cluster_cc_off[c0 + cl] >= 0) {
+                lpc = cc_lpc(cl);
+            } else {
+                for (int x = 0; x < E; ++x) {
+                    const int n = MBSV_ST(F + cl * E + x);
+                    if (n > 0) lpc = lpc + P.T[(size_t)x * Tstride + n];
+                }
             }
             lp += lpc;
         }
@@ -210,7 +311,7 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
 
     // ---------------- initializeMatrix (MultiBreakSV.java:990-1099) ----------------
     {
-        const int W = F + C * E;
+        const int W = alive ? R.sub_W[sub] : 0;
         for (int i = 0; i < W; ++i) MBSV_ST(i) = 0;
         double dc = 0.0, de = 0.0;
         unsigned tch = 0;
@@ -230,6 +331,8 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
         }
 #pragma unroll
         for (int x = 0; x < MAXE; ++x) if (x < E) LB[x] = lb_of(x, Etot[x], Ltot[x]);
+        if (has_cc)
+            for (int cl = 0; cl < C; ++cl) if (P.cluster_cc_off[c0 + cl] >= 0) cc_recompute(cl);
     }
     double logprob = full_logprob();
     if (alive && R.initial_logprob) R.initial_logprob[sc] = logprob;
@@ -357,6 +460,38 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
             }
             move_counts(ga0, from, to, dcov, derr, touched);
         }
+        bool written = false;
+        if (has_cc) {
+            // conn-comps derive their selected ESPs from the assignments: write them tentatively, then
+            // recompute every touched component once (stamp = t + 1), saving the old multisets
+            written = true;
+            for (int q = 0; q < nmoves; ++q) {
+                if (naive) MBSV_ST(f) = now;
+                else { const int g = P.sv_frag[q0 + q] - f0; const int pv = MBSV_ST(g); MBSV_ST(g) = (pv == -1) ? 0 : -1; }
+            }
+            auto touch = [&](int cl) {
+                const int o = cc_base + P.cluster_cc_off[c0 + cl];
+                if (MBSV_ST(o) == t + 1) return;
+                MBSV_ST(o) = t + 1;
+                const int sz = E * (1 + cc_nroots(cl));
+                const double before = cc_lpc(cl);
+                for (int i = 0; i < sz; ++i) MBSV_ST(o + 1 + sz + i) = MBSV_ST(o + 1 + i);
+                cc_recompute(cl);
+                dcov = dcov + (cc_lpc(cl) - before);
+            };
+            for (int q = 0; q < nmoves; ++q) {
+                int ga0 = a0, from = prev, to = now;
+                if (!naive) {
+                    const int g = P.sv_frag[q0 + q] - f0;
+                    ga0 = P.frag_aln_ptr[f0 + g];
+                    to = MBSV_ST(g);
+                    from = (to == -1) ? 0 : -1;
+                }
+                if (from != -1) cc_visit(ga0 + from, touch);
+                if (to != -1) cc_visit(ga0 + to, touch);
+            }
+            if (err) { done = true; continue; }   // set cover failed to cover: the reference throws Error
+        }
         // ---- acceptance ratio (:1146) ----
         double newLB[MAXE];
         double newlogprob, arg;
@@ -396,7 +531,8 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
                     if (!naive) {
                         const int g = P.sv_frag[q0 + q] - f0;
                         ga0 = P.frag_aln_ptr[f0 + g];
-                        from = MBSV_ST(g);              // the assignment is written last: still the old value
+                        const int cur = MBSV_ST(g);     // old value unless the CC path already wrote the new one
+                        from = written ? ((cur == -1) ? 0 : -1) : cur;
                         to = (from == -1) ? 0 : -1;
                     }
                     retally_fragment(ga0, from, to, t);
@@ -406,34 +542,80 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
                     if (!naive) {
                         g = P.sv_frag[q0 + q] - f0;
                         ga0 = P.frag_aln_ptr[f0 + g];
-                        from = MBSV_ST(g);
+                        const int cur = MBSV_ST(g);
+                        from = written ? ((cur == -1) ? 0 : -1) : cur;
                         to = (from == -1) ? 0 : -1;
                     }
                     reapply_fragment(ga0, from, to);
                     tally_frag(g, ga0, from, to, t);
                 }
             }
-            for (int q = 0; q < nmoves; ++q) {
-                if (naive) MBSV_ST(f) = now;
-                else {
-                    const int g = P.sv_frag[q0 + q] - f0;
-                    const int pv = MBSV_ST(g);
-                    MBSV_ST(g) = (pv == -1) ? 0 : -1;
+            if (has_cc) {
+                // conn-comp multisets that changed: old elements leave, new ones enter; clear the stamps
+                const unsigned d = t > win_base ? (unsigned)(t - win_base) : 0u;
+                auto settle = [&](int cl) {
+                    const int o = cc_base + P.cluster_cc_off[c0 + cl];
+                    if (MBSV_ST(o) != t + 1) return;
+                    MBSV_ST(o) = 0;
+                    if (d) { cc_hist(cl, 1, d); cc_hist(cl, 0, 0u - d); }
+                };
+                for (int q = 0; q < nmoves; ++q) {
+                    int ga0 = a0, from = prev, to = now;
+                    if (!naive) {
+                        const int g = P.sv_frag[q0 + q] - f0;
+                        ga0 = P.frag_aln_ptr[f0 + g];
+                        to = MBSV_ST(g);
+                        from = (to == -1) ? 0 : -1;
+                    }
+                    if (from != -1) cc_visit(ga0 + from, settle);
+                    if (to != -1) cc_visit(ga0 + to, settle);
+                }
+            }
+            if (!written) {
+                for (int q = 0; q < nmoves; ++q) {
+                    if (naive) MBSV_ST(f) = now;
+                    else {
+                        const int g = P.sv_frag[q0 + q] - f0;
+                        const int pv = MBSV_ST(g);
+                        MBSV_ST(g) = (pv == -1) ? 0 : -1;
+                    }
                 }
             }
         } else {
-            // revert the counts (the assignments were never written)
+            // revert the counts (and, on the CC path, the tentative assignments and the saved multisets)
             double d1 = 0.0, d2 = 0.0;
             unsigned tt = 0;
+            if (has_cc) {
+                auto restore = [&](int cl) {
+                    const int o = cc_base + P.cluster_cc_off[c0 + cl];
+                    if (MBSV_ST(o) != t + 1) return;
+                    MBSV_ST(o) = 0;
+                    const int sz = E * (1 + cc_nroots(cl));
+                    for (int i = 0; i < sz; ++i) MBSV_ST(o + 1 + i) = MBSV_ST(o + 1 + sz + i);
+                };
+                for (int q = 0; q < nmoves; ++q) {
+                    int ga0 = a0, from = prev, to = now;
+                    if (!naive) {
+                        const int g = P.sv_frag[q0 + q] - f0;
+                        ga0 = P.frag_aln_ptr[f0 + g];
+                        to = MBSV_ST(g);
+                        from = (to == -1) ? 0 : -1;
+                    }
+                    if (from != -1) cc_visit(ga0 + from, restore);
+                    if (to != -1) cc_visit(ga0 + to, restore);
+                }
+            }
             for (int q = nmoves - 1; q >= 0; --q) {
-                int ga0 = a0, from = prev, to = now;
+                int g = f, ga0 = a0, from = prev, to = now;
                 if (!naive) {
-                    const int g = P.sv_frag[q0 + q] - f0;
+                    g = P.sv_frag[q0 + q] - f0;
                     ga0 = P.frag_aln_ptr[f0 + g];
-                    from = MBSV_ST(g);
+                    const int cur = MBSV_ST(g);
+                    from = written ? ((cur == -1) ? 0 : -1) : cur;
                     to = (from == -1) ? 0 : -1;
                 }
                 move_counts(ga0, to, from, d1, d2, tt);
+                if (written) MBSV_ST(g) = from;
             }
         }
         if (TRACE) {
@@ -457,6 +639,7 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
                 else atomicAdd(&R.aln_count[P.frag_aln_ptr[f0 + f] + a], d);
             }
             for (int cl = 0; cl < C; ++cl) {
+                if (CC && P.cluster_cc_off[c0 + cl] >= 0) { cc_hist(cl, 0, d); continue; }
                 unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + cl];
                 for (int x = 0; x < E; ++x) {
                     const int n = MBSV_ST(F + cl * E + x);

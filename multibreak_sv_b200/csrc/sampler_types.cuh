@@ -16,6 +16,16 @@ struct DevProblem {
     const int4* aln_rec;             // {numerrors, len, first ESP entry, exp | nesp << 8}
     const int* aln_esp_slot;         // per alignment-ESP entry: local count slot cluster*E + exp, or -1
     const int* supports_order_local; // per subproblem: local cluster indices in A.supports.keySet() order
+    // connected components (all NULL-safe: only dereferenced by the CC kernels)
+    const int* cluster_cc_off;       // per cluster: offset of its multiset block in the chain's cc region, -1 = simple
+    const int* sub_cc_scratch;       // per subproblem: offset of the set-cover scratch in the cc region, -1 = no conn-comp
+    const int* sub_cc_maxleaf;       // per subproblem: max leaves of a conn-comp (size of the leaf-flag scratch)
+    const int* cluster_leaf_ptr;
+    const int* leaf_owner;
+    const int* aln_esp_leaf;
+    const int* cluster_root_ptr;
+    const int* root_leaf_ptr;
+    const int* root_leaf;
     const int* cluster_hist_ptr;
     const int* sv_frag_ptr;
     const int* sv_frag;
@@ -65,5 +75,6 @@ using KernelFn = void (*)(const DevProblem, const DevRun);
 KernelFn get_kernel_fast(bool smem, int n_exp);                 // MODE_FAST, no trace: the throughput path
 KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_EXACT, no trace
 KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
+KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with connected-component clusters
 
 }  // namespace mbsv

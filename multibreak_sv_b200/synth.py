@@ -108,12 +108,14 @@ def draw_skeleton(cfg: SynthConfig | str, n_frag: int | None = None, seed: int |
 
 
 def generate(cfg: SynthConfig | str, n_frag: int | None = None, seed: int | None = None,
-             shuffle_orders: bool = False, skeleton: Skeleton | None = None) -> PackedProblem:
+             shuffle_orders: bool = False, skeleton: Skeleton | None = None, conncomp_frac: float = 0.0) -> PackedProblem:
     """Build the CSR of a synthetic batch of independent subproblems.
 
     shuffle_orders: permute supports_order inside each subproblem (exercises the summation-order dependence
     of REPLAY_EXACT); the benchmark keeps the identity.
     skeleton: build exactly these subproblems (a shard of a larger skeleton) instead of drawing new ones.
+    conncomp_frac: fraction of the clusters with >= 3 ESPs that become GASV connected components (localization -1)
+    with 2-4 overlapping maximal sub-clusters (tests only: built with a Python loop).
     """
     if isinstance(cfg, str):
         cfg = CONFIGS[cfg]
@@ -205,6 +207,33 @@ def generate(cfg: SynthConfig | str, n_frag: int | None = None, seed: int | None
         key = rng.random(C) + cl_sub          # permute inside each subproblem
         supports_order = np.argsort(key, kind="stable").astype(np.int32)
 
+    cluster_kind = np.zeros(C, np.uint8)
+    cluster_root_ptr = np.arange(C + 1, dtype=np.int32)
+    root_leaf_ptr = cluster_leaf_ptr.astype(np.int32)
+    root_leaf = leaf_slot_sorted.astype(np.int32)
+    if conncomp_frac > 0:
+        cand = np.nonzero((nleaf >= 3) & (rng.random(C) < conncomp_frac))[0]
+        cluster_kind[cand] = 1
+        is_cc = cluster_kind == 1
+        crp, rlp, rl = [0], [0], []
+        for c in range(C):
+            nl = int(nleaf[c])
+            if not is_cc[c]:
+                rl.extend(range(nl)); rlp.append(len(rl)); crp.append(len(rlp) - 1)
+                continue
+            nroot = int(rng.integers(2, 5))
+            member = rng.random((nroot, nl)) < 0.55
+            member[rng.integers(0, nroot, nl), np.arange(nl)] = True       # every leaf is in some sub-cluster
+            for r in range(nroot):
+                idx = np.nonzero(member[r])[0]
+                if len(idx) == 0:
+                    idx = np.array([int(rng.integers(0, nl))])
+                rl.extend(idx.tolist()); rlp.append(len(rl))
+            crp.append(len(rlp) - 1)
+        cluster_root_ptr = np.array(crp, np.int32)
+        root_leaf_ptr = np.array(rlp, np.int32)
+        root_leaf = np.array(rl, np.int32)
+
     L = load_library()
     T = np.zeros((E, max_support + 1), np.float64)
     import ctypes as C_
@@ -215,15 +244,15 @@ def generate(cfg: SynthConfig | str, n_frag: int | None = None, seed: int | None
         sub_frag_ptr=sub_frag_ptr.astype(np.int32), sub_cluster_ptr=sub_cluster_ptr.astype(np.int32),
         sub_sv_ptr=sub_sv_ptr, frag_aln_ptr=frag_aln_ptr.astype(np.int32), aln_numerrors=aln_numerrors,
         aln_len=aln_len, aln_exp=aln_exp.astype(np.int32), aln_esp_ptr=aln_esp_ptr.astype(np.int32),
-        aln_esp_cluster=esp_cluster, aln_esp_leaf=aln_esp_leaf, cluster_kind=np.zeros(C, np.uint8),
+        aln_esp_cluster=esp_cluster, aln_esp_leaf=aln_esp_leaf, cluster_kind=cluster_kind,
         supports_order=supports_order, cluster_hist_ptr=cluster_hist_ptr.astype(np.int32),
         cluster_leaf_ptr=cluster_leaf_ptr.astype(np.int32), leaf_owner=leaf_owner,
-        cluster_root_ptr=np.arange(C + 1, dtype=np.int32), root_leaf_ptr=cluster_leaf_ptr.astype(np.int32),
-        root_leaf=leaf_slot_sorted.astype(np.int32), sv_cluster=sv_cluster, sv_frag_ptr=sv_frag_ptr, sv_frag=sv_frag,
+        cluster_root_ptr=cluster_root_ptr, root_leaf_ptr=root_leaf_ptr,
+        root_leaf=root_leaf, sv_cluster=sv_cluster, sv_frag_ptr=sv_frag_ptr, sv_frag=sv_frag,
         sv_numchanged=sv_numchanged, exp_pseq=pseq, exp_lambda=lam, logprobcov=T.reshape(-1))
     scalars = dict(abi_version=1, n_sub=S, n_frag=F, n_aln=A, n_aln_esp=K, n_cluster=C, n_exp=E,
-                   max_support=max_support, n_sv=len(sv_cluster), n_sv_frag=len(sv_frag), n_leaf=K, n_root=C,
-                   n_root_leaf=K, n_hist=int(cluster_hist_ptr[-1]))
+                   max_support=max_support, n_sv=len(sv_cluster), n_sv_frag=len(sv_frag), n_leaf=K,
+                   n_root=len(root_leaf_ptr) - 1, n_root_leaf=len(root_leaf), n_hist=int(cluster_hist_ptr[-1]))
     p = PackedProblem(scalars, arrays)
     p.exp_labels = labels
     p.config = cfg
@@ -263,11 +292,20 @@ def write_reference_files(p: PackedProblem, outdir: str, frag_numbers: np.ndarra
     with open(paths["experiments"], "w") as fh:
         fh.write("ExperimentLabel\tPseq\tLambdaD\n")
         for x, l in enumerate(labels):
-            fh.write(f"{l}\t{a['exp_pseq'][x]!r}\t{a['exp_lambda'][x]!r}\n")
+            fh.write(f"{l}\t{float(a['exp_pseq'][x])!r}\t{float(a['exp_lambda'][x])!r}\n")
     members = [[] for _ in range(C)]
     for j, c in enumerate(a["aln_esp_cluster"]):
         members[c].append(esp_name[j])
+    # leaf slot -> ESP name (leaves are the entries sorted by cluster, in entry order)
+    order = np.argsort(a["aln_esp_cluster"], kind="stable")
     with open(paths["clusters"], "w") as fh:
         for c in range(C):
-            fh.write(f"c{c + 1}\t{len(members[c])}\t100.0\tD\t{', '.join(members[c])}\t1\t1\t1, 2, 3, 4\n")
+            names = [esp_name[int(j)] for j in order[a["cluster_leaf_ptr"][c]:a["cluster_leaf_ptr"][c + 1]]]
+            if a["cluster_kind"][c] == 0:
+                fh.write(f"c{c + 1}\t{len(names)}\t100.0\tD\t{', '.join(names)}\t1\t1\t1, 2, 3, 4\n")
+            else:
+                fh.write(f"c{c + 1}\t{len(names)}\t-1\tD\t{', '.join(names)}\t1\t1\t\n")
+                for k, r in enumerate(range(a["cluster_root_ptr"][c], a["cluster_root_ptr"][c + 1])):
+                    sub = [names[int(l)] for l in a["root_leaf"][a["root_leaf_ptr"][r]:a["root_leaf_ptr"][r + 1]]]
+                    fh.write(f"c{c + 1}.{k + 1}\t{len(sub)}\t90.0\tD\t{', '.join(sub)}\t1\t1\t1, 2, 3, 4\n")
     return paths

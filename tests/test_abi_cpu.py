@@ -75,8 +75,12 @@ def test_descriptor_validation(mbsv, example_problem):
     bad.arrays["frag_aln_ptr"] = p.arrays["frag_aln_ptr"][::-1].copy()
     assert create(bad) == -1
     bad = to_packed(mbsv, example_problem)
+    bad.arrays["cluster_kind"] = np.full_like(p.arrays["cluster_kind"], 2)
+    assert create(bad) == -1
+    bad = to_packed(mbsv, example_problem)                 # connected components need their leaf/root arrays
     bad.arrays["cluster_kind"] = np.ones_like(p.arrays["cluster_kind"])
-    assert create(bad) == -6
+    bad.arrays["root_leaf"] = p.arrays["root_leaf"] + 100
+    assert create(bad) == -1 and b"root_leaf" in L.mbsv_last_error()
     bad = to_packed(mbsv, example_problem)
     so = p.arrays["supports_order"].copy()
     so[0] = so[1]

@@ -97,6 +97,24 @@ def test_synthetic_both_modes(oracle, mbsv, cfg, nfrag, chains, iters):
     assert g.launches >= 1
 
 
+@pytest.mark.parametrize("cfg,nfrag,chains,iters", [("cfg4", 3000, 2, 2000), ("cfg3", 800, 33, 1200)])
+def test_connected_components(oracle, mbsv, cfg, nfrag, chains, iters):
+    """GASV connected components (localization -1): greedy set cover multisets on the device."""
+    from multibreak_sv_b200 import synth
+    p = synth.generate(cfg, n_frag=nfrag, shuffle_orders=True, conncomp_frac=0.5)
+    assert int(p.arrays["cluster_kind"].sum()) > 10
+    op = oracle.Problem(p.scalars, p.arrays)
+    dp = mbsv.DeviceProblem(p)
+    o = oracle.run(op, "incremental", iters, n_chains=chains, nthreads=8, java_int_wrap=False, trace=True)
+    g = dp.run(mbsv.MODE_FAST, iters, n_chains=chains, trace=True)
+    assert_same(o, g, trace=True)
+    o = oracle.run(op, "faithful", iters, n_chains=chains, nthreads=8, trace=True)
+    g = dp.run(mbsv.MODE_REPLAY_EXACT, iters, n_chains=chains, trace=True)
+    assert_same(o, g, trace=True)
+    g2 = dp.run(mbsv.MODE_FAST, iters, n_chains=chains)          # non-trace kernels (look-ahead lazy skip)
+    assert np.array_equal(g2.cluster_hist, g.cluster_hist) and np.array_equal(g2.rng_state, g.rng_state)
+
+
 def test_fast_trace_equals_replay_trace_synthetic(mbsv):
     """FAST and REPLAY_EXACT consume the same RNG stream and take the same decisions."""
     from multibreak_sv_b200 import synth
