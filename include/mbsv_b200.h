@@ -137,7 +137,11 @@ typedef struct mbsv_run_params {
                                    MultiBreakSV.java:1030-1085; no RNG draws are consumed), or NULL for the
                                    random initialisation of :999-1015 */
     int32_t trace;           /* 1: fill the trace_* arrays (mcmc.txt columns + accepted-move log) */
-    int32_t reserved;
+    int32_t memo_states;     /* MBSV_MODE_FAST: subproblems without connected components whose joint state space
+                                prod(n_f + 1) is at most memo_states evaluate a proposal with the full log-posterior
+                                of the proposed state, i.e. REPLAY arithmetic — the reference's own memo of state
+                                log-probabilities (MultiBreakSV.java:58,1133-1137); the device keeps one table per
+                                subproblem in shared memory.  0 disables; 256 is the tuned default. */
 } mbsv_run_params;
 
 /* Output buffers (caller-allocated host memory; NULL pointers are skipped). */
@@ -185,7 +189,7 @@ int mbsv_run_device(mbsv_problem* p, const mbsv_run_params* params, mbsv_results
 /* Introspection for benchmarks / tests. */
 int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n);   /* see DESIGN.md */
 int64_t mbsv_last_launch_count(void);             /* kernels launched by the last mbsv_run on this thread */
-/* out[i*5..] = {state rows per warp of the size class (0 = global-workspace class), warps, grid, dynamic shared
+/* out[i*5..] = {tile rows per warp of the size class (0 = global-workspace class, negative = memoised kernel), warps, grid, dynamic shared
    memory bytes, device milliseconds} for each of those launches; returns their number. */
 int mbsv_last_launch_info(double* out, int32_t max_launches);
 

@@ -53,7 +53,7 @@ class RunParams(C.Structure):
     """mbsv_run_params"""
     _fields_ = [("mode", C.c_int32), ("n_chains", C.c_int32), ("num_iters", C.c_int32), ("burnin", C.c_int32),
                 ("perr", C.c_double), ("seed", C.c_int64), ("device", C.c_int32), ("java_int_wrap", C.c_int32),
-                ("init_assign", I32P), ("trace", C.c_int32), ("reserved", C.c_int32)]
+                ("init_assign", I32P), ("trace", C.c_int32), ("memo_states", C.c_int32)]
 
 
 class Results(C.Structure):
@@ -193,7 +193,7 @@ class DeviceProblem:
 
     def run(self, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 1, perr: float = 0.001,
             seed: int = 123456, burnin: int | None = None, java_int_wrap: bool | None = None, init_assign=None,
-            trace: bool = False, want_state: bool = True, per_chain: bool = True) -> RunOutput:
+            trace: bool = False, want_state: bool = True, per_chain: bool = True, memo_states: int = 256) -> RunOutput:
         """MultiBreakSV.runMCMC (MultiBreakSV.java:773-877) for every (subproblem, chain), on the GPU."""
         s = self.packed.scalars
         S, F = s["n_sub"], s["n_frag"]
@@ -211,6 +211,7 @@ class DeviceProblem:
             ia = np.ascontiguousarray(init_assign, np.int32)
             rp.init_assign = ia.ctypes.data_as(I32P)
         rp.trace = int(trace)
+        rp.memo_states = memo_states
         out = RunOutput(
             aln_count=np.zeros(s["n_aln"], np.uint32), frag_err_count=np.zeros(F, np.uint32),
             cluster_hist=np.zeros(s["n_hist"], np.uint32),
@@ -242,13 +243,14 @@ class DeviceProblem:
         return out
 
     def launch_info(self) -> list[dict]:
-        buf = np.zeros(8 * 5, np.float64)
-        n = self.lib.mbsv_last_launch_info(buf.ctypes.data_as(F64P), 8)
+        buf = np.zeros(20 * 5, np.float64)
+        n = self.lib.mbsv_last_launch_info(buf.ctypes.data_as(F64P), 20)
         return [dict(rows=int(buf[i * 5]), warps=int(buf[i * 5 + 1]), grid=int(buf[i * 5 + 2]),
                      smem_bytes=int(buf[i * 5 + 3]), ms=float(buf[i * 5 + 4])) for i in range(n)]
 
     def run_device(self, tensors: dict, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 1,
-                   perr: float = 0.001, seed: int = 123456, burnin: int | None = None, java_int_wrap: bool = False):
+                   perr: float = 0.001, seed: int = 123456, burnin: int | None = None, java_int_wrap: bool = False,
+                   memo_states: int = 256):
         """mbsv_run_device: `tensors` maps result-field names to DEVICE pointers (e.g. torch tensor.data_ptr()) on
         this problem's GPU; aln_count, frag_err_count, cluster_hist and totals are required.  Returns
         (status, kernel_ms)."""
@@ -261,6 +263,7 @@ class DeviceProblem:
         rp.seed = seed
         rp.device = self.device
         rp.java_int_wrap = int(java_int_wrap)
+        rp.memo_states = memo_states
         r = Results()
         ft = dict(Results._fields_)
         for k, ptr in tensors.items():

@@ -18,7 +18,7 @@ namespace {
 
 thread_local std::string g_err;
 thread_local int64_t g_launches = 0;
-struct LaunchInfo { int rows; int warps; int grid; int smem_bytes; float ms; };
+struct LaunchInfo { int rows; int warps; int grid; int smem_bytes; float ms; int memo; };
 thread_local std::vector<LaunchInfo> g_launch_info;
 
 int fail(int code, const std::string& msg) {
@@ -54,6 +54,7 @@ struct DevBuf {
 
 constexpr int MAX_EXP = 4;
 constexpr int WARPS_PER_CTA = 4;
+constexpr int NSTREAM = 20;
 
 }  // namespace
 
@@ -62,16 +63,24 @@ struct mbsv_problem {
     mbsv::DevProblem dp{};
     // host-side planning data
     int n_sub = 0, n_frag = 0, n_aln = 0, n_cluster = 0, n_exp = 0, n_hist = 0;
-    std::vector<int> sub_W;       // state rows of a chain of subproblem s (F_s + C_s*E)
-    std::vector<int> sub_order;   // subproblems by ascending sub_W (stable)
+    std::vector<int> sub_W;       // state rows of a chain of subproblem s (F_s + C_s*E + conn-comp blocks)
+    std::vector<int> sub_F;       // fragments of subproblem s
+    std::vector<int> sub_nstates; // joint state space prod(n_f + 1), saturated at 2^30; 0 when it has a conn-comp
+    // launch plan, depends on mbsv_run_params.memo_states (cached for the last value used)
+    int plan_memo = -1, plan_tab = -1;
+    std::vector<int> sub_rows;    // tile rows of a warp of subproblem s (state + memo table)
+    std::vector<int> sub_memo;    // joint states when the subproblem uses the memoised arithmetic, else 0
+    std::vector<char> sub_tab;    // 1: runs in the memoised kernel (table in shared memory)
+    std::vector<int> sub_order;   // memoised-kernel subproblems first, each group by ascending sub_rows (stable)
+    int n_tab_subs = 0;
     int64_t csr_bytes = 0;
     // device CSR
     DevBuf<int> d_sub_frag_ptr, d_sub_cluster_ptr, d_sub_sv_ptr, d_frag_aln_ptr, d_aln_esp_slot, d_supports_local,
-        d_cluster_hist_ptr, d_sv_frag_ptr, d_sv_frag, d_sv_numchanged, d_sub_order, d_sub_W;
+        d_cluster_hist_ptr, d_sv_frag_ptr, d_sv_frag, d_sv_numchanged, d_sub_order, d_sub_W, d_sub_memo;
     DevBuf<int4> d_aln_rec;
     DevBuf<double> d_sub_logF, d_sub_neglogNsv, d_T, d_logint, d_pseq, d_logp, d_log1mp;
-    cudaStream_t streams[8] = {};
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done[8] = {}, ev_cls0[8] = {}, ev_cls1[8] = {};
+    cudaStream_t streams[NSTREAM] = {};
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done[NSTREAM] = {}, ev_cls0[NSTREAM] = {}, ev_cls1[NSTREAM] = {};
     bool streams_ok = false;
     bool has_cc = false;
     DevBuf<int> d_cluster_cc_off, d_sub_cc_scratch, d_sub_cc_maxleaf, d_cluster_leaf_ptr, d_leaf_owner, d_aln_esp_leaf,
@@ -123,12 +132,12 @@ int mbsv_fill_logprobcov(double lambda, int32_t max_support, double* out) {
 int64_t mbsv_last_launch_count(void) { return g_launches; }
 
 // Per-launch details of the last mbsv_run on this thread: out[i*5..] = {state rows per warp (0 = global
-// workspace class), warps, grid, dynamic smem bytes, milliseconds}.  Returns the number of launches.
+// workspace class; negative = memoised kernel), warps, grid, dynamic smem bytes, milliseconds}.  Returns the count.
 int mbsv_last_launch_info(double* out, int32_t max_launches) {
     int n = 0;
     for (const auto& li : g_launch_info) {
         if (n >= max_launches) break;
-        if (out) { out[n * 5] = li.rows; out[n * 5 + 1] = li.warps; out[n * 5 + 2] = li.grid; out[n * 5 + 3] = li.smem_bytes; out[n * 5 + 4] = li.ms; }
+        if (out) { out[n * 5] = li.memo ? -li.rows : li.rows; out[n * 5 + 1] = li.warps; out[n * 5 + 2] = li.grid; out[n * 5 + 3] = li.smem_bytes; out[n * 5 + 4] = li.ms; }
         ++n;
     }
     return n;
@@ -352,10 +361,12 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         }
         if (off > 0) { sub_cc_scratch[s] = off; sub_cc_maxleaf[s] = maxleaf; W += off + maxleaf + maxroot; p->has_cc = true; }
         p->sub_W[s] = W;
+        long long nst = off > 0 ? 0 : 1;
+        for (int f = d->sub_frag_ptr[s]; f < d->sub_frag_ptr[s + 1] && nst > 0 && nst < (1LL << 30); ++f)
+            nst *= (long long)(d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]) + 1;
+        p->sub_nstates.push_back((int)std::min<long long>(nst, 1LL << 30));
+        p->sub_F.push_back(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]);
     }
-    p->sub_order.resize(S);
-    std::iota(p->sub_order.begin(), p->sub_order.end(), 0);
-    std::stable_sort(p->sub_order.begin(), p->sub_order.end(), [&](int a, int b) { return p->sub_W[a] < p->sub_W[b]; });
 
     auto up = [&](auto& buf, const auto& vec) -> cudaError_t { return buf.upload(vec); };
     cudaError_t e = cudaSuccess;
@@ -389,7 +400,6 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         chk(up(p->d_root_leaf_ptr, std::vector<int>(d->root_leaf_ptr, d->root_leaf_ptr + d->n_root + 1)));
         chk(up(p->d_root_leaf, std::vector<int>(d->root_leaf, d->root_leaf + d->n_root_leaf)));
     }
-    chk(up(p->d_sub_order, p->sub_order));
     chk(up(p->d_sub_W, p->sub_W));
     if (e != cudaSuccess) {
         delete p;
@@ -410,7 +420,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     dp.log2pi = mbsv::jm_log(2.0) + mbsv::jm_log(3.141592653589793);
     int prio_lo = 0, prio_hi = 0;
     chk(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NSTREAM; ++i) {
         // streams[1] runs the longest-running class (large subproblems) and gets the highest priority
         chk(cudaStreamCreateWithPriority(&p->streams[i], cudaStreamNonBlocking, i == 1 ? prio_hi : prio_lo));
         chk(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
@@ -429,7 +439,7 @@ int mbsv_problem_destroy(mbsv_problem* p) {
     if (!p) return MBSV_OK;
     cudaSetDevice(p->device);
     if (p->streams_ok) {
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NSTREAM; ++i) {
             cudaStreamDestroy(p->streams[i]); cudaEventDestroy(p->ev_done[i]);
             cudaEventDestroy(p->ev_cls0[i]); cudaEventDestroy(p->ev_cls1[i]);
         }
@@ -442,9 +452,11 @@ int mbsv_problem_destroy(mbsv_problem* p) {
 
 int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n) {
     if (!p || !out) return fail(MBSV_ERR_ARG, "mbsv_problem_stats: NULL");
-    int64_t v[6] = {p->n_sub, p->n_frag, p->n_aln, p->n_cluster, p->csr_bytes,
-                    p->sub_W.empty() ? 0 : *std::max_element(p->sub_W.begin(), p->sub_W.end())};
-    for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+    int64_t memo = 0;
+    for (int v2 : p->sub_memo) memo += v2 > 0;
+    int64_t v[7] = {p->n_sub, p->n_frag, p->n_aln, p->n_cluster, p->csr_bytes,
+                    p->sub_W.empty() ? 0 : *std::max_element(p->sub_W.begin(), p->sub_W.end()), memo};
+    for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
     return MBSV_OK;
 }
 
@@ -459,6 +471,37 @@ using mbsv::KernelFn;
 KernelFn pick(int mode, bool trace, bool smem, int E) {
     if (trace) return mbsv::get_kernel_trace(mode, smem, E);
     return mode == 0 ? mbsv::get_kernel_replay(smem, E) : mbsv::get_kernel_fast(smem, E);
+}
+
+// (Re)build the launch plan: which subproblems use the memoised arithmetic (memo_states), which of those run in the
+// memoised kernel (only when every warp holds chains of one subproblem, i.e. n_chains % 32 == 0, and the table fits
+// the largest shared-memory class), tile rows per warp, launch order.
+constexpr int MAX_SMEM_ROWS = 128;
+int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
+    if (p->plan_memo == memo_states && p->plan_tab == (int)tab_ok) return 0;
+    const int S = p->n_sub;
+    p->sub_rows.resize(S); p->sub_memo.assign(S, 0); p->sub_tab.assign(S, 0); p->sub_order.resize(S);
+    p->n_tab_subs = 0;
+    for (int s = 0; s < S; ++s) {
+        int rows = p->sub_W[s];
+        const int nst = p->sub_nstates[s];
+        if (memo_states > 0 && nst > 0 && nst <= memo_states) {
+            p->sub_memo[s] = nst;
+            const int with_table = rows + (2 * nst + p->sub_F[s] + 31) / 32;   // log-posterior table + fragment strides
+            if (tab_ok && with_table <= MAX_SMEM_ROWS) { p->sub_tab[s] = 1; rows = with_table; ++p->n_tab_subs; }
+        }
+        p->sub_rows[s] = rows;
+    }
+    std::iota(p->sub_order.begin(), p->sub_order.end(), 0);
+    std::stable_sort(p->sub_order.begin(), p->sub_order.end(), [&](int a, int b) {
+        if (p->sub_tab[a] != p->sub_tab[b]) return p->sub_tab[a] > p->sub_tab[b];
+        return p->sub_rows[a] < p->sub_rows[b];
+    });
+    CUDA_TRY(p->d_sub_order.upload(p->sub_order));
+    CUDA_TRY(p->d_sub_memo.upload(p->sub_memo));
+    p->plan_memo = memo_states;
+    p->plan_tab = (int)tab_ok;
+    return 0;
 }
 
 struct OutBufs {
@@ -483,7 +526,9 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     if (nwin * rp->n_chains >= (1LL << 32)) return fail(MBSV_ERR_ARG, "window length x chains overflows the 32-bit tallies");
     if (rp->trace && (!res->trace_logprob || !res->trace_move_frag || !res->trace_move_assign))
         return fail(MBSV_ERR_ARG, "trace requested without trace buffers");
+    if (rp->memo_states < 0) return fail(MBSV_ERR_ARG, "memo_states must be >= 0");
     CUDA_TRY(cudaSetDevice(p->device));
+    if (int prc = ensure_plan(p, rp->memo_states, rp->n_chains % 32 == 0)) return prc;
 
     const int S = p->n_sub, X = rp->n_chains;
     const int64_t n_items = (int64_t)S * X;
@@ -497,7 +542,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     dr.n_chains = X; dr.num_iters = rp->num_iters; dr.burnin = rp->burnin; dr.win_base = (int)win_base;
     dr.java_int_wrap = rp->java_int_wrap; dr.perr = rp->perr; dr.logperr = mbsv::jm_log(rp->perr);
     dr.log1mperr = mbsv::jm_log(1 - rp->perr); dr.seed = rp->seed;
-    dr.sub_order = p->d_sub_order.p; dr.sub_W = p->d_sub_W.p; dr.n_items = n_items;
+    dr.sub_order = p->d_sub_order.p; dr.sub_W = p->d_sub_W.p; dr.sub_memo = p->d_sub_memo.p; dr.n_items = n_items;
 
     if (rp->init_assign) {
         if (results_on_device) dr.init_assign = rp->init_assign;
@@ -542,28 +587,38 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     CUDA_TRY(cudaMemsetAsync(dr.totals, 0, sizeof(unsigned long long) * 6, s0));
 
     // ---- plan: warps of 32 consecutive (sorted subproblem, chain) items; size classes by state rows ----
-    std::vector<int> cls = {16, 32, 64, 128};
+    std::vector<int> cls = {16, 24, 32, 48, 64, 96, 128};
     if (const char* env = std::getenv("MBSV_SMEM_CLASSES")) {
         cls.clear();
         for (const char* q = env; *q;) { cls.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
     }
     auto warp_rows = [&](int w) -> int {
         const int64_t last = std::min<int64_t>((int64_t)w * 32 + 31, n_items - 1);
-        return std::max(1, p->sub_W[p->sub_order[last / X]]);
+        return std::max(1, p->sub_rows[p->sub_order[last / X]]);
     };
-    // warps are sorted by rows: find class boundaries by binary search
-    std::vector<int> bounds;   // first warp of each class; last entry = first warp of the global class
-    {
-        int lo = 0;
-        for (size_t k = 0; k < cls.size(); ++k) {
-            bounds.push_back(lo);
-            int a = lo, b = n_warps;
+    // Two groups of warps, each sorted by rows: [0, wsplit) memoised-kernel subproblems, [wsplit, n_warps) the rest.
+    // (n_chains % 32 == 0 whenever the first group is non-empty, so the split falls on a warp boundary.)
+    const int wsplit = (int)(((int64_t)p->n_tab_subs * X) / 32);
+    struct Launch { int wb, we, rows; bool smem, memo; };
+    std::vector<Launch> launches;
+    auto add_group = [&](int g0, int g1, bool memo) {
+        int lo = g0;
+        for (size_t k = 0; k < cls.size() && lo < g1; ++k) {
+            int a = lo, b = g1;
             while (a < b) { int m = a + (b - a) / 2; if (warp_rows(m) <= cls[k]) a = m + 1; else b = m; }
+            if (a > lo) launches.push_back({lo, a, cls[k], true, memo});
             lo = a;
         }
-        bounds.push_back(lo);
+        if (lo < g1) launches.push_back({lo, g1, 0, false, memo});
+    };
+    add_group(0, wsplit, true);
+    add_group(wsplit, n_warps, false);
+    int g0 = n_warps;
+    for (const Launch& l : launches) {
+        if (l.smem) continue;
+        if (l.memo) return fail(MBSV_ERR_ARG, "internal: memoised subproblem does not fit the shared-memory classes");
+        g0 = l.wb;
     }
-    const int g0 = bounds.back();
     if (g0 < n_warps) {
         std::vector<long long> off(n_warps - g0);
         long long acc = 0;
@@ -574,37 +629,40 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         CUDA_TRY(ob.workspace.alloc((size_t)acc * 32));
         CUDA_TRY(ob.row_off.upload(off));
     }
+    // largest state first: the global-workspace class (few, slow chains) starts before the bulk of small chains
+    std::stable_sort(launches.begin(), launches.end(), [](const Launch& a, const Launch& b) {
+        const int ra = a.smem ? a.rows : 1 << 30, rb = b.smem ? b.rows : 1 << 30;
+        return ra > rb;
+    });
+    if ((int)launches.size() > NSTREAM - 1) return fail(MBSV_ERR_ARG, "too many size classes");
 
     CUDA_TRY(cudaEventRecord(p->ev_start, s0));
     int nstream = 0;
-    // largest state first: the global-workspace class (few, slow chains) starts before the bulk of small chains
-    for (size_t kk = 0; kk <= cls.size(); ++kk) {
-        const size_t k = cls.size() - kk;
-        const bool smem = k < cls.size();
-        const int wb = bounds[k], we = smem ? bounds[k + 1] : n_warps;
-        if (we <= wb) continue;
+    for (const Launch& l : launches) {
         mbsv::DevRun r = dr;
-        r.warp_begin = wb; r.warp_end = we;
-        r.rows_per_warp = smem ? cls[k] : 0;
-        r.warp_row_off = smem ? nullptr : ob.row_off.p;
-        r.workspace = smem ? nullptr : ob.workspace.p;
+        r.warp_begin = l.wb; r.warp_end = l.we;
+        r.rows_per_warp = l.smem ? l.rows : 0;
+        r.warp_row_off = l.smem ? nullptr : ob.row_off.p;
+        r.workspace = l.smem ? nullptr : ob.workspace.p;
         r.global_warp0 = g0;
-        KernelFn fn = p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, smem)
-                                : pick(rp->mode, rp->trace != 0, smem, p->n_exp);
-        const size_t shm = smem ? (size_t)WARPS_PER_CTA * cls[k] * 128 : 0;
+        KernelFn fn = l.memo ? mbsv::get_kernel_memo(rp->trace != 0)
+                     : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
+                                 : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);
+        const size_t shm = l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
         if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        cudaStream_t st = p->streams[1 + (nstream % 7)];
+        // MBSV_SERIAL_LAUNCHES=1 (tuning aid): run the size classes back to back on one stream
+        static const bool serial = std::getenv("MBSV_SERIAL_LAUNCHES") != nullptr;
+        cudaStream_t st = serial ? p->streams[1] : p->streams[1 + nstream];
         CUDA_TRY(cudaStreamWaitEvent(st, p->ev_start, 0));
-        const int grid = (we - wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        if (nstream >= 7) return fail(MBSV_ERR_ARG, "too many size classes");
+        const int grid = (l.we - l.wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         CUDA_TRY(cudaEventRecord(p->ev_cls0[1 + nstream], st));
         fn<<<grid, WARPS_PER_CTA * 32, shm, st>>>(p->dp, r);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(p->ev_cls1[1 + nstream], st));
-        g_launch_info.push_back({smem ? cls[k] : 0, we - wb, grid, (int)shm, 0.f});
+        g_launch_info.push_back({l.smem ? l.rows : 0, l.we - l.wb, grid, (int)shm, 0.f, l.memo ? 1 : 0});
         ++g_launches;
-        CUDA_TRY(cudaEventRecord(p->ev_done[1 + (nstream % 7)], st));
-        CUDA_TRY(cudaStreamWaitEvent(s0, p->ev_done[1 + (nstream % 7)], 0));
+        CUDA_TRY(cudaEventRecord(p->ev_done[1 + nstream], st));
+        CUDA_TRY(cudaStreamWaitEvent(s0, p->ev_done[1 + nstream], 0));
         ++nstream;
     }
     CUDA_TRY(cudaEventRecord(p->ev_stop, s0));

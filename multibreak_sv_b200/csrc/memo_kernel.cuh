@@ -1,0 +1,292 @@
+// Memoised sampler kernel: subproblems whose joint state space prod(n_f + 1) is small (mbsv_run_params.
+// memo_states) and that contain no connected component.
+//
+// The reference itself memoises the log-posterior of every state it has visited, keyed by the state string
+// (MultiBreakSV.java:58,1133-1137; the value is the same as a recomputation).  Here every warp holds
+// 32 chains of ONE subproblem (the planner only routes chain counts that are multiples of 32 here), builds the table
+// log-posterior[state] once in shared memory — computeLogProb in the reference's summation order
+// (MultiBreakSVAssignmentMatrix.java:130-246), the entries spread over the lanes — and then a proposal costs the RNG draws,
+// two table reads, one exp and the acceptance test.  Counts are only maintained for the support tallies and follow
+// accepted moves; nothing is applied tentatively, so there is nothing to revert.
+//
+// Arithmetic: (LP[new] + Alogq) - (LP[old] + Anewlogq), i.e. exactly MultiBreakSV.java:1146 — both modes
+// (REPLAY_EXACT and FAST) are served by this kernel with identical bits.
+#pragma once
+#include "sampler_common.cuh"
+
+namespace mbsv {
+
+#ifndef MBSV_MEMO_MIN_BLOCKS
+#define MBSV_MEMO_MIN_BLOCKS 8
+#endif
+
+template <bool TRACE>
+__global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(const __grid_constant__ DevProblem P,
+                                                                              const __grid_constant__ DevRun R) {
+    extern __shared__ int smem_tile[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int warp = R.warp_begin + blockIdx.x * 4 + wic;
+    if (warp >= R.warp_end) return;
+    const long long item_raw = (long long)warp * 32 + lane;
+    const bool alive = item_raw < R.n_items;
+    const long long item = alive ? item_raw : R.n_items - 1;
+    const int sub = R.sub_order[item / R.n_chains];          // warp-uniform (n_chains % 32 == 0)
+    const int chain = (int)(item % R.n_chains);
+    int* st = smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane;
+
+    const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
+    const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
+    const int E = P.n_exp;
+    const int sv0 = P.sub_sv_ptr[sub], nsv = P.sub_sv_ptr[sub + 1] - sv0;
+    const int Tstride = P.max_support + 1;
+    const long long sc = (long long)sub * R.n_chains + chain;
+    const int N = alive ? R.num_iters : 0;
+    const int W = R.sub_W[sub];
+    const int nst = R.sub_memo[sub];
+    double* tab = reinterpret_cast<double*>(smem_tile + ((size_t)wic * R.rows_per_warp + W) * 32);
+    int* strides = reinterpret_cast<int*>(tab + nst);
+    const double logperr = R.logperr;
+    const int win_base = R.win_base;
+
+    // ---------------- table: log-posterior of every joint state (fragment 0 = least significant digit) ----------------
+    {
+        const int nalive = __popc(__ballot_sync(0xffffffffu, alive));
+        if (alive) {
+            for (int idx = lane; idx < nst; idx += nalive) {
+                for (int i = F; i < F + C * E; ++i) MBSV_ST(i) = 0;
+                long long Et[MBSV_MAX_EXP], Lt[MBSV_MAX_EXP];
+                for (int x = 0; x < MBSV_MAX_EXP; ++x) { Et[x] = 0; Lt[x] = 0; }
+                int nerr = 0, rem = idx;
+                for (int f = 0; f < F; ++f) {
+                    const int a0 = P.frag_aln_ptr[f0 + f];
+                    const int n1 = P.frag_aln_ptr[f0 + f + 1] - a0 + 1;
+                    const int a = rem % n1 - 1;
+                    rem /= n1;
+                    if (a == -1) { ++nerr; continue; }
+                    const int4 rec = P.aln_rec[a0 + a];
+                    const int x = rec.w & 0xff, ne = rec.w >> 8;
+                    for (int j = 0; j < ne; ++j) {
+                        const int slot = P.aln_esp_slot[rec.z + j];
+                        if (slot >= 0) MBSV_ST(F + slot) += 1;
+                    }
+                    Et[x] += rec.x; Lt[x] += rec.y;
+                }
+                double lp = 0;
+                for (int i = 0; i < C; ++i) {
+                    const int cl = P.supports_order_local[c0 + i];
+                    double lpc = 0.0;
+                    for (int x = 0; x < E; ++x) {
+                        const int n = MBSV_ST(F + cl * E + x);
+                        if (n > 0) lpc = lpc + P.T[(size_t)x * Tstride + n];
+                    }
+                    lp += lpc;
+                }
+                lp += 0.0;
+                lp += (double)nerr * logperr;
+                for (int x = 0; x < E; ++x) {
+                    long long e = Et[x], l = Lt[x];
+                    if (R.java_int_wrap) { e = (long long)(int)(unsigned)(unsigned long long)e; l = (long long)(int)(unsigned)(unsigned long long)l; }
+                    lp += log_binomial_dev(e, l, P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi, P.logint, P.maxn);
+                }
+                tab[idx] = lp;
+            }
+            if (lane == 0) {
+                int sprod = 1;
+                for (int f = 0; f < F; ++f) { strides[f] = sprod; sprod *= P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f] + 1; }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---------------- initializeMatrix (MultiBreakSV.java:990-1099) ----------------
+    JavaRandom rng;
+    rng.seed(R.seed + chain);
+    int sidx = 0;
+    if (alive) {
+        for (int i = 0; i < W; ++i) MBSV_ST(i) = 0;
+        for (int f = 0; f < F; ++f) {
+            const int a0 = P.frag_aln_ptr[f0 + f];
+            const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
+            int a;
+            if (R.init_assign) a = R.init_assign[f0 + f];
+            else {
+                if (rng.nextDouble() < R.perr) a = -1;
+                else a = rng.nextInt(n);
+            }
+            MBSV_ST(f) = a;
+            sidx += (a + 1) * strides[f];
+            if (a != -1) {
+                const int4 rec = P.aln_rec[a0 + a];
+                const int ne = rec.w >> 8;
+                for (int j = 0; j < ne; ++j) {
+                    const int slot = P.aln_esp_slot[rec.z + j];
+                    if (slot >= 0) MBSV_ST(F + slot) += 1;
+                }
+            }
+            if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
+        }
+    }
+    double logprob = alive ? tab[sidx] : 0.0;
+    if (alive && R.initial_logprob) R.initial_logprob[sc] = logprob;
+
+    // Counts follow an accepted single-fragment move; inside the long-burn-in window every unit step also emits
+    // the support-histogram difference tallies (value n leaves: +d, value n' enters: -d).
+    auto apply_move = [&](int g, int a0, int from, int to, unsigned d) {
+        if (from != -1) {
+            const int4 rec = P.aln_rec[a0 + from];
+            const int ne = rec.w >> 8;
+            for (int j = 0; j < ne; ++j) {
+                const int slot = P.aln_esp_slot[rec.z + j];
+                if (slot < 0) continue;
+                const int n = MBSV_ST(F + slot);
+                if (d) {
+                    unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                    if (n > 0) atomicAdd(&h[n], d);
+                    if (n - 1 > 0) atomicAdd(&h[n - 1], 0u - d);
+                }
+                MBSV_ST(F + slot) = n - 1;
+            }
+        }
+        if (to != -1) {
+            const int4 rec = P.aln_rec[a0 + to];
+            const int ne = rec.w >> 8;
+            for (int j = 0; j < ne; ++j) {
+                const int slot = P.aln_esp_slot[rec.z + j];
+                if (slot < 0) continue;
+                const int n = MBSV_ST(F + slot);
+                if (d) {
+                    unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                    if (n > 0) atomicAdd(&h[n], d);
+                    atomicAdd(&h[n + 1], 0u - d);
+                }
+                MBSV_ST(F + slot) = n + 1;
+            }
+        }
+        if (d) {
+            if (from == -1) atomicAdd(&R.frag_err_count[f0 + g], d); else atomicAdd(&R.aln_count[a0 + from], d);
+            if (to == -1) atomicAdd(&R.frag_err_count[f0 + g], 0u - d); else atomicAdd(&R.aln_count[a0 + to], 0u - d);
+        }
+        MBSV_ST(g) = to;
+    };
+
+    // ---------------- iterations (MultiBreakSV.java:796-837, 1101-1182) ----------------
+    const double neglogF = -P.sub_logF[sub];
+    const double neglogNsv = P.sub_neglogNsv[sub];
+    int n_naive_prop = 0, n_naive_acc = 0, n_sv_prop = 0, n_sv_acc = 0;
+    long long n_sv_reassign = 0;
+    int err = 0;
+    int iter = 0;
+    bool done = false;
+    for (;;) {
+        bool live = false;
+        if (TRACE) {
+            if (!done) {
+                while (iter < N) {
+                    const double r0 = rng.nextDouble();
+                    if (!(r0 < 0.5)) { live = true; break; }
+                    R.trace_logprob[sc * N + iter] = logprob;
+                    R.trace_move_frag[sc * N + iter] = -1;
+                    R.trace_move_assign[sc * N + iter] = -1;
+                    ++iter;
+                }
+                done = !live;
+            }
+        } else if (!done) {
+            lazy_skip(rng, iter, N, live, done);
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (!live) continue;
+        const int t = iter;
+        double r = rng.nextDouble();
+        const bool naive = (r < 0.9) || (nsv == 0);
+        const double u = rng.nextDouble();
+        int f = -1, a0 = 0, prev = -1, now = -1, svk = -1, q0 = 0, nmoves = 1;
+        double Alogq, Anewlogq;
+        int newidx = sidx;
+        if (naive) {
+            ++n_naive_prop;
+            f = (int)(u * (double)F);
+            a0 = P.frag_aln_ptr[f0 + f];
+            const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
+            prev = MBSV_ST(f);
+            naive_pick(rng, n, prev, neglogF, R.perr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
+            if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
+            newidx += (now - prev) * strides[f];
+        } else {
+            ++n_sv_prop;
+            svk = (int)(u * (double)nsv);
+            n_sv_reassign += P.sv_numchanged[sv0 + svk];
+            q0 = P.sv_frag_ptr[sv0 + svk];
+            nmoves = P.sv_frag_ptr[sv0 + svk + 1] - q0;
+            Alogq = neglogNsv;
+            Anewlogq = neglogNsv;
+            for (int q = 0; q < nmoves; ++q) {
+                const int g = P.sv_frag[q0 + q] - f0;
+                const int from = MBSV_ST(g);
+                newidx += ((from == -1) ? 1 : -1) * strides[g];
+            }
+        }
+        const double newlogprob = tab[newidx];
+        const double arg = (newlogprob + Alogq) - (logprob + Anewlogq);      // :1146
+        const double e = exp_dev(arg);
+        const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);             // Math.min(1, e)
+        r = rng.nextDouble();
+        const bool accept = ratio > r;
+        if (accept) {
+            logprob = newlogprob;
+            sidx = newidx;
+            const unsigned d = t > win_base ? (unsigned)(t - win_base) : 0u;
+            if (naive) {
+                ++n_naive_acc;
+                apply_move(f, a0, prev, now, d);
+            } else {
+                ++n_sv_acc;
+                for (int q = 0; q < nmoves; ++q) {
+                    const int g = P.sv_frag[q0 + q] - f0;
+                    const int from = MBSV_ST(g);
+                    apply_move(g, P.frag_aln_ptr[f0 + g], from, (from == -1) ? 0 : -1, d);
+                }
+            }
+        }
+        if (TRACE) {
+            R.trace_logprob[sc * N + iter] = logprob;
+            R.trace_move_frag[sc * N + iter] = accept ? (naive ? f0 + f : -(2 + svk)) : -1;
+            R.trace_move_assign[sc * N + iter] = (accept && naive) ? now : -1;
+        }
+        ++iter;
+    }
+
+    // ---------------- epilogue ----------------
+    if (!alive) return;
+    if (err == 0) {
+        const long long nwin = (long long)N - win_base;
+        if (nwin > 0) {
+            const unsigned d = (unsigned)nwin;
+            for (int f = 0; f < F; ++f) {
+                const int a = MBSV_ST(f);
+                if (a == -1) atomicAdd(&R.frag_err_count[f0 + f], d);
+                else atomicAdd(&R.aln_count[P.frag_aln_ptr[f0 + f] + a], d);
+            }
+            for (int cl = 0; cl < C; ++cl) {
+                unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + cl];
+                for (int x = 0; x < E; ++x) {
+                    const int n = MBSV_ST(F + cl * E + x);
+                    if (n > 0) atomicAdd(&h[n], d);
+                }
+            }
+        }
+    }
+    if (R.final_assign)
+        for (int f = 0; f < F; ++f) R.final_assign[(size_t)chain * P.n_frag + f0 + f] = MBSV_ST(f);
+    if (R.final_logprob) R.final_logprob[sc] = logprob;
+    const long long n_reassign = (long long)n_naive_prop + n_sv_reassign;
+    if (R.counters) {
+        long long* k = R.counters + sc * 5;
+        k[0] = n_naive_prop; k[1] = n_naive_acc; k[2] = n_sv_prop; k[3] = n_sv_acc; k[4] = n_reassign;
+    }
+    if (R.rng_state) R.rng_state[sc] = rng.state();
+    if (R.error) R.error[sc] = err;
+    if (R.totals) warp_add_totals(R.totals, lane, n_naive_prop, n_naive_acc, n_sv_prop, n_sv_acc, n_reassign, err);
+}
+
+}  // namespace mbsv

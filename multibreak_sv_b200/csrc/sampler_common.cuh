@@ -1,0 +1,135 @@
+// Device helpers shared by the sampler kernels (sampler_kernel.cuh: generic MH kernel; memo_kernel.cuh: memoised
+// kernel): Java-compatible math wrappers, the lazy-iteration look-ahead, the Naive proposal draw, counter reduction.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "jmath.cuh"
+#include "sampler_types.cuh"
+
+namespace mbsv {
+
+#define MBSV_MAX_EXP 4
+
+// logtab[i] = jm_log(i) for 0 < i <= ntab: the exact branch walks Math.log(i) - Math.log(j) over small integers.
+#ifdef MBSV_INLINE_MATH
+#define MBSV_MATH_INLINE __forceinline__
+#else
+#define MBSV_MATH_INLINE __noinline__
+#endif
+static __device__ MBSV_MATH_INLINE double log_binomial_dev(long long k, long long n, double p, double logp, double log1mp,
+                                                double log2pi, const double* __restrict__ logtab, int ntab) {
+    double dn = (double)n;
+    if (dn * p <= 5 || dn * (1 - p) <= 5) {
+        double t = 0;
+        long long r = k, m = n - k;
+        if (r < m) r = m;
+        if (n <= ntab && n >= 1) {
+            const int ri = (int)(r < 0 ? 0 : r);
+            for (int i = (int)n, j = 1; i > ri; --i, ++j) t = t + logtab[i] - logtab[j];
+        } else {
+            for (long long i = n, j = 1; i > r; --i, ++j) t = t + jm_log((double)i) - jm_log((double)j);
+        }
+        return t + (double)k * logp + (double)(n - k) * log1mp;
+    }
+    double mu = dn * p;
+    double sig = dn * p * (1 - p);
+    double d = (double)k - mu;
+    return -(d * d) / (2 * sig) - (log2pi + jm_log(sig)) / 2;
+}
+
+static __device__ MBSV_MATH_INLINE double exp_dev(double x) { return jm_exp(x); }
+
+#define MBSV_ST(i) st[(size_t)(i) << 5]
+
+
+// Lazy chain (MultiBreakSV.java:1106-1113): with probability 1/2 an iteration only consumes one nextDouble().
+// Branch-free look-ahead over the next LAZY_J iterations: iteration j is lazy iff its first LCG step (2j+1 steps
+// from the current state) has bit 47 clear (nextDouble() < 0.5 <=> next(26) < 2^25).  All candidates are
+// independent multiply-adds of the current state by jump-ahead constants.  On return either `live` (the chain
+// sits on a non-lazy iteration `iter`, its lazy-coin draw consumed) or the look-ahead window was all lazy
+// (`iter` advanced, call again) or the chain is `done`.
+__device__ __forceinline__ void lazy_skip(JavaRandom& rng, int& iter, const int N, bool& live, bool& done) {
+    constexpr int LAZY_J = 8;
+    const uint64_t s0 = rng.s;
+    uint64_t cand[LAZY_J];
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < LAZY_J; ++j) {
+        cand[j] = s0 * JavaRandom::jump_mul(2 * j + 1) + JavaRandom::jump_add(2 * j + 1);
+        bits |= ((unsigned)(cand[j] >> 47) & 1u) << j;
+    }
+    const int jstar = bits ? (__ffs(bits) - 1) : LAZY_J;
+    const int remaining = N - iter;
+    const int lim = remaining < LAZY_J ? remaining : LAZY_J;
+    if (jstar < lim) {
+        uint64_t sel = cand[0];
+#pragma unroll
+        for (int j = 1; j < LAZY_J; ++j) if (jstar == j) sel = cand[j];
+        rng.s = sel * JavaRandom::MULT + JavaRandom::ADD;   // second LCG step of that nextDouble()
+        iter += jstar;
+        live = true;
+    } else if (lim == LAZY_J) {
+        rng.s = s0 * JavaRandom::jump_mul(2 * LAZY_J) + JavaRandom::jump_add(2 * LAZY_J);
+        iter += LAZY_J;
+        done = iter >= N;
+    } else {
+        for (int j = 0; j < lim; ++j) rng.s = rng.s * JavaRandom::MULT2 + JavaRandom::ADD2;
+        iter += lim;
+        done = true;
+    }
+}
+
+// naiveMove (MultiBreakSV.java:1198-1272): new assignment of a fragment with n alignments currently at `prev`, and the
+// proposal log-probabilities of the reverse (Alogq) and forward (Anewlogq) moves.  Includes quirk Q1: the scan over
+// "the other n-1" is biased when prev == 0.  The cumulative sums are accumulated exactly as the reference does.
+__device__ __forceinline__ void naive_pick(JavaRandom& rng, const int n, const int prev, const double neglogF,
+                                           const double perr, const double logperr, const double log1mperr,
+                                           const double* __restrict__ logint, int& now, double& Alogq, double& Anewlogq) {
+    double r = rng.nextDouble();
+    if (prev == -1) {
+        int thisassign = 0;
+        const double inc = (double)1 / n;
+        double sum = inc;
+        while (thisassign < n - 1 && r > sum) { ++thisassign; sum += inc; }
+        now = thisassign;
+        if (n == 1) { Alogq = neglogF + 0.0; Anewlogq = neglogF + 0.0; }
+        else { Alogq = neglogF + logperr; Anewlogq = neglogF - logint[n]; }
+    } else if (r < perr || n == 1) {
+        now = -1;
+        if (n == 1) { Alogq = neglogF + 0.0; Anewlogq = neglogF + 0.0; }
+        else { Alogq = neglogF - logint[n]; Anewlogq = neglogF + logperr; }
+    } else {
+        int thisassign = 0;
+        r = rng.nextDouble();
+        const double inc = (double)1 / (n - 1);
+        double sum = inc;
+        while (thisassign < n - 1 && (thisassign == prev || r > sum)) {
+            ++thisassign;
+            if (thisassign != prev) sum += inc;
+        }
+        now = thisassign;
+        Anewlogq = neglogF + log1mperr - logint[n - 1];
+        Alogq = Anewlogq;
+    }
+}
+
+// One atomic per counter per converged group of lanes.
+__device__ __forceinline__ void warp_add_totals(unsigned long long* totals, int lane, long long v0, long long v1,
+                                                long long v2, long long v3, long long v4, int err) {
+    const unsigned m = __activemask();
+    long long v[5] = {v0, v1, v2, v3, v4};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        long long x = v[i];
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long y = __shfl_xor_sync(m, x, o);
+            const int src = lane ^ o;
+            if ((m >> src) & 1u) x += y;
+        }
+        if (lane == (__ffs(m) - 1)) atomicAdd(&totals[i], (unsigned long long)x);
+    }
+    if (err) atomicCAS(&totals[5], 0ULL, (unsigned long long)(long long)err);
+}
+
+}  // namespace mbsv

@@ -17,36 +17,9 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
-#include "jmath.cuh"
-#include "sampler_types.cuh"
+#include "sampler_common.cuh"
 
 namespace mbsv {
-
-// logtab[i] = jm_log(i) for 0 < i <= ntab: the exact branch walks Math.log(i) - Math.log(j) over small integers.
-static __device__ __noinline__ double log_binomial_dev(long long k, long long n, double p, double logp, double log1mp,
-                                                double log2pi, const double* __restrict__ logtab, int ntab) {
-    double dn = (double)n;
-    if (dn * p <= 5 || dn * (1 - p) <= 5) {
-        double t = 0;
-        long long r = k, m = n - k;
-        if (r < m) r = m;
-        if (n <= ntab && n >= 1) {
-            const int ri = (int)(r < 0 ? 0 : r);
-            for (int i = (int)n, j = 1; i > ri; --i, ++j) t = t + logtab[i] - logtab[j];
-        } else {
-            for (long long i = n, j = 1; i > r; --i, ++j) t = t + jm_log((double)i) - jm_log((double)j);
-        }
-        return t + (double)k * logp + (double)(n - k) * log1mp;
-    }
-    double mu = dn * p;
-    double sig = dn * p * (1 - p);
-    double d = (double)k - mu;
-    return -(d * d) / (2 * sig) - (log2pi + jm_log(sig)) / 2;
-}
-
-static __device__ __noinline__ double exp_dev(double x) { return jm_exp(x); }
-
-#define MBSV_ST(i) st[(size_t)(i) << 5]
 
 #ifndef MBSV_MIN_BLOCKS
 #define MBSV_MIN_BLOCKS 5
@@ -85,6 +58,11 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
 
     JavaRandom rng;
     rng.seed(R.seed + chain);
+
+    // Memo-eligible subproblems (mbsv_run_params.memo_states) use REPLAY arithmetic; the table-driven version lives in
+    // memo_kernel.cuh, a lane that lands here (chain count not a multiple of 32) re-sums the posterior per proposal.
+    const int nst = (alive && R.sub_memo) ? R.sub_memo[sub] : 0;
+    const bool use_full = (MODE == 0) || (nst > 0);
 
     long long Etot[MAXE], Ltot[MAXE];
     double LB[MAXE];
@@ -361,37 +339,7 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
                 done = !live;
             }
         } else if (!done) {
-            // Branch-free look-ahead over the next LAZY_J iterations: iteration j is lazy iff its first LCG
-            // step (2j+1 steps from here) has bit 47 clear (nextDouble() < 0.5 <=> next(26) < 2^25).  All
-            // candidates are independent multiply-adds of the current state by jump-ahead constants.
-            constexpr int LAZY_J = 8;
-            const uint64_t s0 = rng.s;
-            uint64_t cand[LAZY_J];
-            unsigned bits = 0;
-#pragma unroll
-            for (int j = 0; j < LAZY_J; ++j) {
-                cand[j] = s0 * JavaRandom::jump_mul(2 * j + 1) + JavaRandom::jump_add(2 * j + 1);
-                bits |= ((unsigned)(cand[j] >> 47) & 1u) << j;
-            }
-            const int jstar = bits ? (__ffs(bits) - 1) : LAZY_J;
-            const int remaining = N - iter;
-            const int lim = remaining < LAZY_J ? remaining : LAZY_J;
-            if (jstar < lim) {
-                uint64_t sel = cand[0];
-#pragma unroll
-                for (int j = 1; j < LAZY_J; ++j) if (jstar == j) sel = cand[j];
-                rng.s = sel * JavaRandom::MULT + JavaRandom::ADD;   // second LCG step of that nextDouble()
-                iter += jstar;
-                live = true;
-            } else if (lim == LAZY_J) {
-                rng.s = s0 * JavaRandom::jump_mul(2 * LAZY_J) + JavaRandom::jump_add(2 * LAZY_J);
-                iter += LAZY_J;
-                done = iter >= N;
-            } else {
-                for (int j = 0; j < lim; ++j) rng.s = rng.s * JavaRandom::MULT2 + JavaRandom::ADD2;
-                iter += lim;
-                done = true;
-            }
+            lazy_skip(rng, iter, N, live, done);
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (!live) continue;
@@ -410,32 +358,7 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
             a0 = P.frag_aln_ptr[f0 + f];
             const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
             prev = MBSV_ST(f);
-            r = rng.nextDouble();
-            if (prev == -1) {
-                int thisassign = 0;
-                const double inc = (double)1 / n;
-                double sum = inc;
-                while (thisassign < n - 1 && r > sum) { ++thisassign; sum += inc; }
-                now = thisassign;
-                if (n == 1) { Alogq = neglogF + 0.0; Anewlogq = neglogF + 0.0; }
-                else { Alogq = neglogF + logperr; Anewlogq = neglogF - P.logint[n]; }
-            } else if (r < perr || n == 1) {
-                now = -1;
-                if (n == 1) { Alogq = neglogF + 0.0; Anewlogq = neglogF + 0.0; }
-                else { Alogq = neglogF - P.logint[n]; Anewlogq = neglogF + logperr; }
-            } else {
-                int thisassign = 0;
-                r = rng.nextDouble();
-                const double inc = (double)1 / (n - 1);
-                double sum = inc;
-                while (thisassign < n - 1 && (thisassign == prev || r > sum)) {
-                    ++thisassign;
-                    if (thisassign != prev) sum += inc;
-                }
-                now = thisassign;
-                Anewlogq = neglogF + R.log1mperr - P.logint[n - 1];
-                Alogq = Anewlogq;
-            }
+            naive_pick(rng, n, prev, neglogF, perr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
             if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
         } else {
             // ---- svMove (:1291-1343) ----
@@ -447,9 +370,14 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
             Alogq = neglogNsv;
             Anewlogq = neglogNsv;
         }
-        // ---- tentative application ----
+        // ---- evaluate the proposal ----
         double dcov = 0.0, derr = 0.0;
         unsigned touched = 0;
+        bool written = false;
+        double newLB[MAXE];
+        double newlogprob, arg;
+        {
+        // ---- tentative application ----
         for (int q = 0; q < nmoves; ++q) {
             int ga0 = a0, from = prev, to = now;
             if (!naive) {
@@ -460,7 +388,6 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
             }
             move_counts(ga0, from, to, dcov, derr, touched);
         }
-        bool written = false;
         if (has_cc) {
             // conn-comps derive their selected ESPs from the assignments: write them tentatively, then
             // recompute every touched component once (stamp = t + 1), saving the old multisets
@@ -493,9 +420,7 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
             if (err) { done = true; continue; }   // set cover failed to cover: the reference throws Error
         }
         // ---- acceptance ratio (:1146) ----
-        double newLB[MAXE];
-        double newlogprob, arg;
-        if (MODE == 0) {
+        if (use_full) {
             // full re-sum in the reference's order; the assignment change only enters through nerr, counts, totals
 #pragma unroll
             for (int x = 0; x < MAXE; ++x) newLB[x] = LB[x];
@@ -514,6 +439,7 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
             const double delta = (dcov + derr) + dlb;
             newlogprob = logprob + delta;
             arg = (delta + Alogq) - Anewlogq;
+        }
         }
         const double e = exp_dev(arg);
         const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);   // Math.min(1, e)
@@ -657,22 +583,7 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
     }
     if (R.rng_state) R.rng_state[sc] = rng.state();
     if (R.error) R.error[sc] = err;
-    if (R.totals) {
-        // one atomic per counter per warp (lanes that exited early simply do not take part)
-        const unsigned m = __activemask();
-        long long v[5] = {n_naive_prop, n_naive_acc, n_sv_prop, n_sv_acc, n_reassign};
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            long long x = v[i];
-            for (int o = 16; o > 0; o >>= 1) {
-                const long long y = __shfl_xor_sync(m, x, o);
-                const int src = lane ^ o;
-                if ((m >> src) & 1u) x += y;
-            }
-            if (lane == (__ffs(m) - 1)) atomicAdd(&R.totals[i], (unsigned long long)x);
-        }
-        if (err) atomicCAS(&R.totals[5], 0ULL, (unsigned long long)(long long)err);
-    }
+    if (R.totals) warp_add_totals(R.totals, lane, n_naive_prop, n_naive_acc, n_sv_prop, n_sv_acc, n_reassign, err);
 }
 
 }  // namespace mbsv

@@ -47,6 +47,7 @@ struct DevRun {
     // plan: item g = warp*32 + lane is chain (g % n_chains) of subproblem sub_order[g / n_chains]
     const int* sub_order;            // subproblems by ascending state size
     const int* sub_W;                // state rows per chain of each subproblem
+    const int* sub_memo;             // per subproblem: joint states if it takes the memoised path, else 0 (or NULL)
     long long n_items;               // n_sub * n_chains
     const long long* warp_row_off;   // [warp - global_warp0] row offset into workspace (global class)
     int* workspace;
@@ -76,5 +77,6 @@ KernelFn get_kernel_fast(bool smem, int n_exp);                 // MODE_FAST, no
 KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_EXACT, no trace
 KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
 KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with connected-component clusters
+KernelFn get_kernel_memo(bool trace);                           // memoised subproblems (memo_kernel.cuh)
 
 }  // namespace mbsv

@@ -66,7 +66,7 @@ struct orc_params {
     int32_t java_int_wrap;
     const int32_t* init_assign;   // [n_frag] or NULL
     int32_t trace;
-    int32_t reserved;
+    int32_t memo_states;
 };
 
 struct orc_results {
@@ -126,6 +126,7 @@ int orc_run(const orc_desc* d, const orc_params* p, orc_results* r, int nthreads
             RunParams rp;
             rp.mode = p->mode; rp.num_iters = p->num_iters; rp.burnin = p->burnin; rp.perr = p->perr;
             rp.java_int_wrap = p->java_int_wrap;
+            rp.memo_states = p->memo_states;
             rp.init_assign = p->init_assign ? p->init_assign + v.f0 : nullptr;
             for (int c = 0; c < p->n_chains; ++c) {
                 size_t sc = (size_t)s * p->n_chains + c;

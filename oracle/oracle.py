@@ -47,7 +47,7 @@ class OrcDesc(C.Structure):
 class OrcParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("n_chains", C.c_int32), ("num_iters", C.c_int32), ("burnin", C.c_int32),
                 ("perr", C.c_double), ("seed", C.c_int64), ("device", C.c_int32), ("java_int_wrap", C.c_int32),
-                ("init_assign", I32P), ("trace", C.c_int32), ("reserved", C.c_int32)]
+                ("init_assign", I32P), ("trace", C.c_int32), ("memo_states", C.c_int32)]
 
 
 class OrcResults(C.Structure):
@@ -305,7 +305,7 @@ def alloc_results(prob: Problem, n_chains: int, num_iters: int, trace: bool, res
 
 def run(prob: Problem, mode: str = "faithful", num_iters: int = 10000, n_chains: int = 1, perr: float = 0.001,
         seed: int = 123456, burnin: int | None = None, java_int_wrap: bool = True, init_assign=None,
-        trace: bool = False, nthreads: int = 1) -> RunResult:
+        trace: bool = False, nthreads: int = 1, memo_states: int = 256) -> RunResult:
     """MultiBreakSV.runMCMC (MultiBreakSV.java:773-877) on every (subproblem, chain) of `prob`, on the CPU."""
     d = prob.desc(OrcDesc)
     p = OrcParams()
@@ -321,6 +321,7 @@ def run(prob: Problem, mode: str = "faithful", num_iters: int = 10000, n_chains:
         ia = np.ascontiguousarray(init_assign, np.int32)
         p.init_assign = ia.ctypes.data_as(I32P)
     p.trace = int(trace)
+    p.memo_states = memo_states
     r, cr = alloc_results(prob, n_chains, num_iters, trace)
     r.rc = lib().orc_run(C.byref(d), C.byref(p), C.byref(cr), nthreads)
     return r

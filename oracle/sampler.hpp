@@ -66,6 +66,9 @@ struct RunParams {
     int64_t seed = 123456;
     int java_int_wrap = 1;        // totals wrap like Java int (MultiBreakSVAssignmentMatrix.java:38-39,218-219)
     const int32_t* init_assign = nullptr;   // [F] local (matchfile path, :1030-1085) or null
+    int32_t memo_states = 0;      // INCREMENTAL: problems without connected components whose joint state space
+                                  // prod(n_f + 1) is at most this use the full log-posterior of the proposed state
+                                  // (the reference's own memo of state log-probs, MultiBreakSV.java:1133-1137)
 };
 
 // Optional per-iteration trace (mcmc.txt columns + accepted-move log).
@@ -123,6 +126,7 @@ struct Chain {
     uint32_t* cluster_hist;                      // compact, cluster_hist_ptr
     ChainResult res;
     int32_t win_base;                            // first iteration inside the long-burn-in window
+    bool use_full = false;                       // evaluate proposals with full_logprob() (FAITHFUL, or memo-eligible)
     // scratch reused across iterations (no heap traffic in the hot loop)
     std::vector<int> s_dirty, s_dd;
     std::vector<uint8_t> s_touched, s_tt;
@@ -150,6 +154,14 @@ struct Chain {
         // window: iter > numiters - burnin  (MultiBreakSV.java:903,926,962)
         int64_t b = (int64_t)rp.num_iters - rp.burnin + 1;
         win_base = (int32_t)std::max<int64_t>(b, 0);
+        use_full = rp.mode == 0;
+        if (rp.mode == 1 && rp.memo_states > 0) {
+            bool cc = false;
+            for (int cl = 0; cl < v.C; ++cl) cc = cc || !simple(cl);
+            int64_t nst = 1;
+            for (int f = 0; f < v.F && nst <= rp.memo_states; ++f) nst *= (int64_t)nalign(f) + 1;
+            use_full = !cc && nst <= rp.memo_states;
+        }
     }
 
     inline int aln0(int f) const { return v.frag_aln_ptr[v.f0 + f]; }
@@ -448,7 +460,7 @@ struct Chain {
         // ---- acceptance ratio ----
         double newlogprob, arg;
         std::vector<double>& newLB = s_newLB; newLB = LB;
-        if (rp.mode == 0) {
+        if (use_full) {
             newlogprob = full_logprob();
             arg = (newlogprob + p.Alogq) - (logprob + p.Anewlogq);               // :1146
         } else {

@@ -44,9 +44,9 @@ def main():
         w.writerow([units[idx[c]] for c in cols])
         for r in data:
             w.writerow([r[idx[c]] for c in cols])
-    # dominant launch = longest duration
-    dur = [float(r[idx["gpu__time_duration.sum"]]) for r in data]
-    k = max(range(len(data)), key=lambda i: dur[i])
+    # dominant launch = the one that executed the most warp-instructions (the bulk of the chains)
+    inst = [float(r[idx["smsp__inst_executed.sum"]]) for r in data]
+    k = max(range(len(data)), key=lambda i: inst[i])
 
     def to_bytes(v, u):
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
