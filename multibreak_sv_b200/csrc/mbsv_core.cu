@@ -7,7 +7,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mbsv_b200.h"
@@ -44,6 +46,11 @@ struct DevBuf {
         n = count;
         if (count == 0) return cudaSuccess;
         return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload_raw(const T* src, size_t count) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
     }
     cudaError_t upload(const std::vector<T>& v) {
         cudaError_t e = alloc(v.size());
@@ -232,78 +239,85 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     int rc = validate(d);
     if (rc) return rc;
     const int S = d->n_sub, F = d->n_frag, A = d->n_aln, K = d->n_aln_esp, C = d->n_cluster, E = d->n_exp;
-    // which subproblem a cluster / fragment belongs to
-    std::vector<int> cl_sub(C), fr_sub(F);
-    for (int s = 0; s < S; ++s) {
-        for (int c = d->sub_cluster_ptr[s]; c < d->sub_cluster_ptr[s + 1]; ++c) cl_sub[c] = s;
-        for (int f = d->sub_frag_ptr[s]; f < d->sub_frag_ptr[s + 1]; ++f) fr_sub[f] = s;
-    }
+    // Packing + per-subproblem checks, parallel over subproblems (they are independent and contiguous).
     std::vector<int4> rec(A);
     std::vector<int> slot(K, -1);
-    std::vector<int> cluster_cap(C, 0);   // how many alignment-ESP entries can count towards a cluster at once
-    int maxn = 1;
-    for (int f = 0; f < F; ++f) {
-        const int s = fr_sub[f];
-        maxn = std::max(maxn, d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]);
-        std::vector<int> best(0);
-        for (int a = d->frag_aln_ptr[f]; a < d->frag_aln_ptr[f + 1]; ++a) {
-            const int x = d->aln_exp[a];
-            const int j0 = d->aln_esp_ptr[a], j1 = d->aln_esp_ptr[a + 1];
-            rec[a] = make_int4(d->aln_numerrors[a], d->aln_len[a], j0, x | ((j1 - j0) << 8));
-            for (int j = j0; j < j1; ++j) {
-                const int c = d->aln_esp_cluster[j];
-                if (c == -1) continue;
-                if (c < d->sub_cluster_ptr[s] || c >= d->sub_cluster_ptr[s + 1])
-                    return fail(MBSV_ERR_ARG, "aln_esp_cluster points outside the fragment's subproblem");
-                if (d->cluster_kind[c] == 1) {
-                    const int nl = d->cluster_leaf_ptr[c + 1] - d->cluster_leaf_ptr[c];
-                    if (d->aln_esp_leaf[j] < 0 || d->aln_esp_leaf[j] >= nl) return fail(MBSV_ERR_ARG, "aln_esp_leaf out of range");
-                    slot[j] = -(2 + (c - d->sub_cluster_ptr[s]));      // connected component: recomputed, not counted
-                } else {
-                    slot[j] = (c - d->sub_cluster_ptr[s]) * E + x;
-                }
-            }
-        }
-    }
-    // A cluster's support can never exceed its histogram length - 1 nor max_support (logprobcov index).
-    {
-        // upper bound: per fragment the max over its alignments of entries into cluster c, summed over fragments
-        std::vector<int> per_frag(C, 0), stamp(C, -1), total(C, 0);
-        for (int f = 0; f < F; ++f) {
-            std::vector<int> touched;
-            for (int a = d->frag_aln_ptr[f]; a < d->frag_aln_ptr[f + 1]; ++a) {
-                std::vector<std::pair<int, int>> cnt;
-                for (int j = d->aln_esp_ptr[a]; j < d->aln_esp_ptr[a + 1]; ++j) {
-                    const int c = d->aln_esp_cluster[j];
-                    if (c < 0 || d->cluster_kind[c] == 1) continue;
-                    bool found = false;
-                    for (auto& pr : cnt) if (pr.first == c) { ++pr.second; found = true; }
-                    if (!found) cnt.push_back({c, 1});
-                }
-                for (auto& pr : cnt) {
-                    if (stamp[pr.first] != f) { stamp[pr.first] = f; per_frag[pr.first] = 0; touched.push_back(pr.first); }
-                    per_frag[pr.first] = std::max(per_frag[pr.first], pr.second);
-                }
-            }
-            for (int c : touched) total[c] += per_frag[c];
-        }
-        for (int c = 0; c < C; ++c) {
-            if (total[c] > d->max_support)
-                return fail(MBSV_ERR_UNSUPPORTED, "a cluster can collect more selected ESPs than max_support "
-                                                  "(the reference would index logprobcov out of bounds)");
-            if (total[c] + 1 > d->cluster_hist_ptr[c + 1] - d->cluster_hist_ptr[c])
-                return fail(MBSV_ERR_ARG, "cluster_hist_ptr leaves too few bins for a cluster");
-        }
-    }
     std::vector<int> sup_local(C);
-    for (int s = 0; s < S; ++s) {
-        const int c0 = d->sub_cluster_ptr[s], c1 = d->sub_cluster_ptr[s + 1];
-        std::vector<char> seen(c1 - c0, 0);
-        for (int i = c0; i < c1; ++i) {
-            const int c = d->supports_order[i];
-            if (c < c0 || c >= c1 || seen[c - c0]) return fail(MBSV_ERR_ARG, "supports_order is not a permutation of the subproblem's clusters");
-            seen[c - c0] = 1;
-            sup_local[i] = c - c0;
+    int maxn = 1;
+    {
+        const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        std::vector<int> t_maxn(nthreads, 1);
+        std::vector<int> t_err(nthreads, 0);
+        std::vector<std::string> t_msg(nthreads);
+        std::atomic<int> next{0};
+        const int CHUNK = 1024;
+        auto worker = [&](int tid) {
+            std::vector<int> in_aln, stamp_aln, per_frag, stamp_frag, total;   // indexed by local cluster
+            std::vector<char> seen;
+            std::vector<int> touched;
+            auto bad = [&](int code, const char* msg) { if (!t_err[tid]) { t_err[tid] = code; t_msg[tid] = msg; } };
+            for (;;) {
+                const int s_begin = next.fetch_add(CHUNK);
+                if (s_begin >= S) break;
+                const int s_end = std::min(S, s_begin + CHUNK);
+                for (int s = s_begin; s < s_end; ++s) {
+                    const int c0 = d->sub_cluster_ptr[s], c1 = d->sub_cluster_ptr[s + 1], Cs = c1 - c0;
+                    if ((int)in_aln.size() < Cs) {
+                        in_aln.resize(Cs); stamp_aln.resize(Cs); per_frag.resize(Cs); stamp_frag.resize(Cs); total.resize(Cs); seen.resize(Cs);
+                    }
+                    for (int i = 0; i < Cs; ++i) { stamp_aln[i] = -1; stamp_frag[i] = -1; total[i] = 0; seen[i] = 0; }
+                    for (int f = d->sub_frag_ptr[s]; f < d->sub_frag_ptr[s + 1]; ++f) {
+                        t_maxn[tid] = std::max(t_maxn[tid], d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]);
+                        touched.clear();
+                        for (int a = d->frag_aln_ptr[f]; a < d->frag_aln_ptr[f + 1]; ++a) {
+                            const int x = d->aln_exp[a];
+                            const int j0 = d->aln_esp_ptr[a], j1 = d->aln_esp_ptr[a + 1];
+                            rec[a] = make_int4(d->aln_numerrors[a], d->aln_len[a], j0, x | ((j1 - j0) << 8));
+                            for (int j = j0; j < j1; ++j) {
+                                const int c = d->aln_esp_cluster[j];
+                                if (c == -1) continue;
+                                if (c < c0 || c >= c1) { bad(MBSV_ERR_ARG, "aln_esp_cluster points outside the fragment's subproblem"); continue; }
+                                const int cl = c - c0;
+                                if (d->cluster_kind[c] == 1) {
+                                    const int nl = d->cluster_leaf_ptr[c + 1] - d->cluster_leaf_ptr[c];
+                                    if (d->aln_esp_leaf[j] < 0 || d->aln_esp_leaf[j] >= nl) bad(MBSV_ERR_ARG, "aln_esp_leaf out of range");
+                                    slot[j] = -(2 + cl);               // connected component: recomputed, not counted
+                                    continue;
+                                }
+                                slot[j] = cl * E + x;
+                                // upper bound of the cluster's support: per fragment the max over its alignments of the
+                                // entries into the cluster, summed over fragments
+                                if (stamp_aln[cl] != a) { stamp_aln[cl] = a; in_aln[cl] = 0; }
+                                ++in_aln[cl];
+                                if (stamp_frag[cl] != f) { stamp_frag[cl] = f; per_frag[cl] = 0; touched.push_back(cl); }
+                                per_frag[cl] = std::max(per_frag[cl], in_aln[cl]);
+                            }
+                        }
+                        for (int cl : touched) total[cl] += per_frag[cl];
+                    }
+                    for (int cl = 0; cl < Cs; ++cl) {
+                        if (total[cl] > d->max_support)
+                            bad(MBSV_ERR_UNSUPPORTED, "a cluster can collect more selected ESPs than max_support "
+                                                      "(the reference would index logprobcov out of bounds)");
+                        if (total[cl] + 1 > d->cluster_hist_ptr[c0 + cl + 1] - d->cluster_hist_ptr[c0 + cl])
+                            bad(MBSV_ERR_ARG, "cluster_hist_ptr leaves too few bins for a cluster");
+                    }
+                    for (int i = c0; i < c1; ++i) {
+                        const int c = d->supports_order[i];
+                        if (c < c0 || c >= c1 || seen[c - c0]) { bad(MBSV_ERR_ARG, "supports_order is not a permutation of the subproblem's clusters"); continue; }
+                        seen[c - c0] = 1;
+                        sup_local[i] = c - c0;
+                    }
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
+        worker(0);
+        for (auto& t : th) t.join();
+        for (int t = 0; t < nthreads; ++t) {
+            if (t_err[t]) return fail(t_err[t], t_msg[t]);
+            maxn = std::max(maxn, t_maxn[t]);
         }
     }
     std::vector<int> sub_sv_ptr(S + 1, 0), sv_frag_ptr(1, 0), sv_frag, sv_numchanged;
@@ -371,14 +385,14 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     auto up = [&](auto& buf, const auto& vec) -> cudaError_t { return buf.upload(vec); };
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    chk(up(p->d_sub_frag_ptr, std::vector<int>(d->sub_frag_ptr, d->sub_frag_ptr + S + 1)));
-    chk(up(p->d_sub_cluster_ptr, std::vector<int>(d->sub_cluster_ptr, d->sub_cluster_ptr + S + 1)));
+    chk(p->d_sub_frag_ptr.upload_raw(d->sub_frag_ptr, S + 1));
+    chk(p->d_sub_cluster_ptr.upload_raw(d->sub_cluster_ptr, S + 1));
     chk(up(p->d_sub_sv_ptr, sub_sv_ptr));
-    chk(up(p->d_frag_aln_ptr, std::vector<int>(d->frag_aln_ptr, d->frag_aln_ptr + F + 1)));
+    chk(p->d_frag_aln_ptr.upload_raw(d->frag_aln_ptr, F + 1));
     chk(up(p->d_aln_rec, rec));
     chk(up(p->d_aln_esp_slot, slot));
     chk(up(p->d_supports_local, sup_local));
-    chk(up(p->d_cluster_hist_ptr, C > 0 ? std::vector<int>(d->cluster_hist_ptr, d->cluster_hist_ptr + C + 1) : std::vector<int>(1, 0)));
+    if (C > 0) chk(p->d_cluster_hist_ptr.upload_raw(d->cluster_hist_ptr, C + 1)); else chk(up(p->d_cluster_hist_ptr, std::vector<int>(1, 0)));
     chk(up(p->d_sv_frag_ptr, sv_frag_ptr));
     chk(up(p->d_sv_frag, sv_frag));
     chk(up(p->d_sv_numchanged, sv_numchanged));
