@@ -1,0 +1,83 @@
+/*
+ * mbsv_host.h — host-side mirror of the reference driver around the sampler (same library, libmbsv_b200.so).
+ *
+ * The reference's driver is Java (class MultiBreakSV, src/MultiBreakSV.java); where no JVM exists this C++ mirror
+ * plays its part so that the product runs file -> file.  Function names follow the reference's methods:
+ *
+ *   mbsv_host_get_fragment_alignments   getFragmentAlignments  :551-602  (readExperimentFile :319, readAssignmentFile
+ *                                       :333, readClustersFile :402, intersectClustersAndFragments :475)
+ *   mbsv_host_construct_cluster_diagrams constructClusterDiagrams :658-739 (+ MultiBreakSVDiagram.java:56-139)
+ *   mbsv_host_precompute_priors         precomputePriors :604-656   (logprobcov tables)
+ *   mbsv_host_fill_non_singleton_array  fillNonSingletonArray :748-771
+ *   mbsv_host_run_mcmc                  runMCMC :773-877             (-> mbsv_problem_create + mbsv_run)
+ *   mbsv_host_write_final_files         writeFinalFiles :1712-1859   (.finalbreakpoints.longburnin, .finalassignment.longburnin)
+ *   mbsv_host_write_mcmc_file           the per-iteration mcmc.txt of runMCMC :779-828
+ *   mbsv_host_write_state_counts        writeStateCounts :1934-1949  (.samplingprobs)
+ *
+ * Java semantics reproduced: Scanner tokenisation, String.split/trim, Java 8+ HashMap<String,..> iteration order
+ * (fragments, breakpoints, supports, experiments), Double.toString.
+ *
+ * A host object holds ONE problem (what one JVM run of the reference sees).  mbsv_host_batch_* concatenates several
+ * hosts (e.g. one per subset-N.clusters file of generateIndependentSubproblems.pl) into one mbsv_problem_desc.
+ */
+#ifndef MBSV_HOST_H
+#define MBSV_HOST_H
+
+#include <stdint.h>
+
+#include "mbsv_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mbsv_host mbsv_host;
+typedef struct mbsv_host_batch mbsv_host_batch;
+
+int mbsv_host_create(mbsv_host** out);
+int mbsv_host_destroy(mbsv_host* h);
+
+/* --clusterfile --assignmentfile --experimentfile [--readclustersfirst]  (MultiBreakSV.java:211-267) */
+int mbsv_host_set_files(mbsv_host* h, const char* clusterfile, const char* assignmentfile, const char* experimentfile,
+                        int32_t clusters_first);
+int mbsv_host_get_fragment_alignments(mbsv_host* h);
+int mbsv_host_construct_cluster_diagrams(mbsv_host* h);
+int mbsv_host_precompute_priors(mbsv_host* h);
+int mbsv_host_fill_non_singleton_array(mbsv_host* h);
+/* all four steps above, in main()'s order (MultiBreakSV.java:119-128) */
+int mbsv_host_load(mbsv_host* h);
+
+/* The packed problem of this host (pointers stay valid until the host is destroyed or reloaded). */
+int mbsv_host_desc(mbsv_host* h, mbsv_problem_desc* out);
+/* Names: kind 0 fragment id (fragments.keySet() order), 1 cluster id (breakpoints.keySet() order), 2 experiment label,
+   3 ESP of alignment-ESP entry i, 4 warning text (i ignored), 5 reason the input is rejected (empty = accepted). */
+const char* mbsv_host_name(mbsv_host* h, int32_t kind, int32_t i);
+/* fragment indices in the sorted order writeFinalFiles uses (getFragmentIDs :1703-1709) */
+int mbsv_host_sorted_fragments(mbsv_host* h, int32_t* out);
+
+/* runMCMC: one chain, seed 123456, burnin/skip derived from num_iters as the reference does (:186-193) unless
+   params is given.  Results are kept inside the host for the writers; `results` (may be NULL) receives a view. */
+int mbsv_host_run_mcmc(mbsv_host* h, int32_t num_iters, double perr, int32_t mode, int32_t device, int32_t save_space,
+                       const int32_t* init_assign, mbsv_results* results);
+/* Inject results computed elsewhere (tests without a GPU; batched runs): counts are copied. */
+int mbsv_host_set_results(mbsv_host* h, int32_t num_iters, int32_t burnin, const uint32_t* aln_count,
+                          const uint32_t* frag_err_count, const uint32_t* cluster_hist);
+
+int mbsv_host_write_final_files(mbsv_host* h, const char* prefix);
+int mbsv_host_write_mcmc_file(mbsv_host* h, const char* path);
+int mbsv_host_write_state_counts(mbsv_host* h, const char* path);
+
+/* Batch: S hosts -> one descriptor (subproblem s = host s). */
+int mbsv_host_batch_create(mbsv_host* const* hosts, int32_t n, mbsv_host_batch** out);
+int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* out);
+int mbsv_host_batch_destroy(mbsv_host_batch* b);
+
+/* Java's Double.toString (shortest repr, JDK 19+ behaviour) into buf; returns the length. */
+int mbsv_java_double_to_string(double v, char* buf, int32_t buflen);
+/* keySet() order of a java.util.HashMap<String,?> after inserting the n NUL-separated keys (test hook). */
+int mbsv_java_hashmap_order(const char* keys, int32_t n, int32_t* out_order, int32_t* out_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBSV_HOST_H */

@@ -100,6 +100,9 @@ int mbsv_abi_version(void) { return MBSV_ABI_VERSION; }
 
 const char* mbsv_last_error(void) { return g_err.c_str(); }
 
+// used by the host mirror (mbsv_host.cpp) so that both halves of the library report through mbsv_last_error()
+void mbsv_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
+
 const char* mbsv_status_string(int s) {
     switch (s) {
         case MBSV_OK: return "ok";

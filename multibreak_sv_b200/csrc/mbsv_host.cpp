@@ -1,0 +1,861 @@
+// Host-side mirror of the reference driver (include/mbsv_host.h): parses the three input files with the
+// reference's semantics, packs them into mbsv_problem_desc, runs the sampler through the C ABI and writes the
+// reference's output files.  No sampling happens here: mbsv_host_run_mcmc calls mbsv_problem_create / mbsv_run.
+#include "../../include/mbsv_host.h"
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+}  // namespace
+extern "C" void mbsv_internal_set_error(const char* msg);   // mbsv_core.cu
+namespace {
+int hfail(int code, const std::string& msg) { mbsv_internal_set_error(msg.c_str()); return code; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Java semantics
+// ---------------------------------------------------------------------------------------------------------
+uint32_t java_hash(const std::string& s) {            // String.hashCode then HashMap.hash spreading
+    uint32_t h = 0;
+    for (unsigned char c : s) h = 31u * h + c;
+    return h ^ (h >> 16);
+}
+
+// Iteration order of a java.util.HashMap<String,?> (Java 8+) without materialising buckets: within a bucket
+// entries stay in insertion order (tail insertion; resize splits preserve order; removal unlinks), so the
+// keySet() order is "by bucket index at the final capacity, then by insertion".  The capacity is tracked through
+// every put: doubling when size exceeds 0.75 capacity, and treeifyBin()'s extra doubling when a bin receives its
+// 9th entry while the table is smaller than 64.  A bin that would be treeified at capacity >= 64 changes the
+// order in ways we do not model: `tree_bin` is raised and the input is rejected.
+struct JavaMapOrder {
+    std::vector<uint32_t> hash;
+    std::vector<char> alive;
+    std::vector<int> bin;     // live entries per bucket
+    int cap = 0, thr = 0, size = 0;
+    bool tree_bin = false;
+    void resize() {
+        if (cap == 0) { cap = 16; thr = 12; }
+        else { cap *= 2; thr *= 2; }
+        bin.assign(cap, 0);
+        for (size_t i = 0; i < hash.size(); ++i) if (alive[i]) ++bin[hash[i] & (cap - 1)];
+    }
+    int put(const std::string& key) {                 // key must be new
+        if (cap == 0) resize();
+        const uint32_t h = java_hash(key);
+        hash.push_back(h);
+        alive.push_back(1);
+        const int before = bin[h & (cap - 1)]++;
+        if (before >= 8) { if (cap < 64) resize(); else tree_bin = true; }
+        if (++size > thr) resize();
+        return (int)hash.size() - 1;
+    }
+    void remove(int id) {
+        if (!alive[id]) return;
+        alive[id] = 0;
+        --bin[hash[id] & (cap - 1)];
+        --size;
+    }
+    std::vector<int> order() const {
+        std::vector<int> o;
+        for (size_t i = 0; i < hash.size(); ++i) if (alive[i]) o.push_back((int)i);
+        const uint32_t m = cap ? (uint32_t)cap - 1 : 0;
+        std::stable_sort(o.begin(), o.end(), [&](int a, int b) { return (hash[a] & m) < (hash[b] & m); });
+        return o;
+    }
+};
+
+bool java_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31); }
+
+struct Scanner {                                      // java.util.Scanner over an in-memory file
+    std::string buf;
+    size_t pos = 0;
+    bool hasNext() const { size_t p = pos; while (p < buf.size() && java_ws((unsigned char)buf[p])) ++p; return p < buf.size(); }
+    bool hasNextLine() const { return pos < buf.size(); }
+    std::string next() {
+        while (pos < buf.size() && java_ws((unsigned char)buf[pos])) ++pos;
+        const size_t a = pos;
+        while (pos < buf.size() && !java_ws((unsigned char)buf[pos])) ++pos;
+        return buf.substr(a, pos - a);
+    }
+    std::string nextLine() {
+        const size_t a = pos;
+        while (pos < buf.size() && buf[pos] != '\n' && buf[pos] != '\r') ++pos;
+        std::string line = buf.substr(a, pos - a);
+        if (pos < buf.size()) pos += (buf[pos] == '\r' && pos + 1 < buf.size() && buf[pos + 1] == '\n') ? 2 : 1;
+        return line;
+    }
+};
+
+std::vector<std::string> split(const std::string& s, const std::string& sep) {   // String.split(literal)
+    std::vector<std::string> out;
+    size_t p = 0, q;
+    bool any = false;
+    while ((q = s.find(sep, p)) != std::string::npos) { any = true; out.push_back(s.substr(p, q - p)); p = q + sep.size(); }
+    if (!any) return {s};
+    out.push_back(s.substr(p));
+    while (!out.empty() && out.back().empty()) out.pop_back();
+    return out;
+}
+std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && (unsigned char)s[a] <= ' ') ++a;
+    while (b > a && (unsigned char)s[b - 1] <= ' ') --b;
+    return s.substr(a, b - a);
+}
+bool parse_int(const std::string& s, int& out) {
+    if (s.empty()) return false;
+    size_t i = (s[0] == '-' || s[0] == '+') ? 1 : 0;
+    if (i >= s.size()) return false;
+    long long v = 0;
+    for (; i < s.size(); ++i) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        v = v * 10 + (s[i] - '0');
+        if (v > 2147483648LL) return false;
+    }
+    if (s[0] == '-') v = -v;
+    if (v > 2147483647LL || v < -2147483648LL) return false;
+    out = (int)v;
+    return true;
+}
+bool parse_double(const std::string& s, double& out) {
+    char* end = nullptr;
+    out = std::strtod(s.c_str(), &end);
+    return end != s.c_str() && *end == 0;
+}
+bool slurp(const std::string& path, std::string& out) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return false;
+    std::stringstream ss;
+    ss << in.rdbuf();
+    out = ss.str();
+    return true;
+}
+
+// Double.toString: shortest digits that round-trip, decimal for 1e-3 <= |v| < 1e7, else d.dddE[-]n
+std::string java_double(double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "Infinity" : "-Infinity";
+    if (v == 0) return std::signbit(v) ? "-0.0" : "0.0";
+    char tmp[64];
+    auto res = std::to_chars(tmp, tmp + sizeof tmp, std::fabs(v), std::chars_format::scientific);
+    std::string sci(tmp, res.ptr);                     // d[.ddd]e[+-]xx
+    const size_t epos = sci.find('e');
+    std::string digits;
+    for (size_t i = 0; i < epos; ++i) if (sci[i] != '.') digits.push_back(sci[i]);
+    const int exp10 = std::atoi(sci.c_str() + epos + 1);
+    std::string out = std::signbit(v) ? "-" : "";
+    const double a = std::fabs(v);
+    if (a >= 1e-3 && a < 1e7) {
+        if (exp10 >= 0) {
+            std::string ip = digits.substr(0, std::min<size_t>(digits.size(), exp10 + 1));
+            while ((int)ip.size() < exp10 + 1) ip.push_back('0');
+            std::string fp = digits.size() > (size_t)exp10 + 1 ? digits.substr(exp10 + 1) : "0";
+            out += ip + "." + fp;
+        } else {
+            out += "0." + std::string(-exp10 - 1, '0') + digits;
+        }
+    } else {
+        out += digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "E" + std::to_string(exp10);
+    }
+    return out;
+}
+
+struct Alignment { std::vector<int> esps; int numerrors = 0, len = 0, exp = -1; };   // FragmentAlignment
+struct Fragment { std::string id; std::vector<Alignment> alns; };                    // Fragment
+struct Diagram { bool is_cluster = true; std::vector<int> leaves; std::vector<std::vector<int>> roots; bool built = false; };
+
+}  // namespace
+
+struct mbsv_host {
+    std::string clusterfile, assignmentfile, experimentfile;
+    bool clusters_first = false;
+    // ---- parsed state (field names follow the reference) ----
+    std::vector<std::string> exp_label; std::vector<double> exp_pseq, exp_lambda;   // by experiment id
+    std::unordered_map<std::string, int> exp_id; JavaMapOrder experiments;
+    std::vector<std::string> esp_name; std::unordered_map<std::string, int> esp_id_of;
+    std::vector<Fragment> frags; std::unordered_map<std::string, int> frag_id_of; JavaMapOrder fragments;
+    std::vector<int> esp2fragment;            // ESP id -> fragment id (last writer), -1
+    std::vector<char> in_allesps;
+    std::vector<int> esp2cid;                 // ESP id -> cluster id (as in `clust`), -1
+    std::vector<std::string> cl_name; std::unordered_map<std::string, int> cl_id_of; std::vector<char> cl_is_cluster;
+    JavaMapOrder clust, breakpoints;          // cluster id == insertion id in `clust`
+    std::vector<int> bp_of_cl, cl_of_bp;      // cluster id <-> breakpoints entry id (-1: none)
+    int max_support = 0;
+    std::vector<Diagram> diagrams;            // by cluster id
+    std::string warning, unsupported;
+    // ---- packed problem ----
+    std::vector<int> frag_order, cl_order;    // fragment ids / cluster ids in keySet() order
+    std::vector<int32_t> sub_frag_ptr, sub_cluster_ptr, sub_sv_ptr, frag_aln_ptr, aln_numerrors, aln_len, aln_exp, aln_esp_ptr,
+        aln_esp_cluster, aln_esp_leaf, supports_order, cluster_hist_ptr, cluster_leaf_ptr, leaf_owner, cluster_root_ptr,
+        root_leaf_ptr, root_leaf, sv_cluster, sv_frag_ptr, sv_frag, sv_numchanged, sorted_frag;
+    std::vector<int> aln_esp_espid;
+    std::vector<uint8_t> cluster_kind;
+    std::vector<double> pk_pseq, pk_lambda, logprobcov;
+    bool packed = false, priors = false, sv_filled = false;
+    // ---- results ----
+    int num_iters = 0, burnin = 0, skip = 1;
+    std::vector<uint32_t> r_aln, r_frag, r_hist;
+    std::vector<int32_t> r_init, r_trace_frag, r_trace_assign;
+    std::vector<double> r_trace_logprob;
+    bool have_results = false, have_trace = false;
+
+    int esp(const std::string& name) {
+        auto it = esp_id_of.find(name);
+        if (it != esp_id_of.end()) return it->second;
+        const int id = (int)esp_name.size();
+        esp_id_of.emplace(name, id);
+        esp_name.push_back(name);
+        esp2fragment.push_back(-1); in_allesps.push_back(0); esp2cid.push_back(-1);
+        return id;
+    }
+    void clear() { *this = mbsv_host(); }
+};
+
+struct mbsv_host_batch {
+    std::vector<int32_t> sub_frag_ptr, sub_cluster_ptr, sub_sv_ptr, frag_aln_ptr, aln_numerrors, aln_len, aln_exp, aln_esp_ptr,
+        aln_esp_cluster, aln_esp_leaf, supports_order, cluster_hist_ptr, cluster_leaf_ptr, leaf_owner, cluster_root_ptr,
+        root_leaf_ptr, root_leaf, sv_cluster, sv_frag_ptr, sv_frag, sv_numchanged;
+    std::vector<uint8_t> cluster_kind;
+    std::vector<double> pseq, lambda, logprobcov;
+    int max_support = 0, n_exp = 0;
+};
+
+namespace {
+
+// MultiBreakSV.java:319-331
+int read_experiment_file(mbsv_host* h) {
+    Scanner sc;
+    if (!slurp(h->experimentfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->experimentfile);
+    if (!sc.hasNextLine()) return hfail(MBSV_ERR_IO, "empty experiment file");
+    sc.nextLine();
+    while (sc.hasNext()) {
+        const std::string label = sc.next();
+        double p, l;
+        if (!sc.hasNext() || !parse_double(sc.next(), p) || !sc.hasNext() || !parse_double(sc.next(), l))
+            return hfail(MBSV_ERR_IO, "InputMismatchException in experiment file");
+        auto it = h->exp_id.find(label);
+        if (it == h->exp_id.end()) {
+            h->exp_id.emplace(label, (int)h->exp_label.size());
+            h->exp_label.push_back(label); h->exp_pseq.push_back(p); h->exp_lambda.push_back(l);
+            h->experiments.put(label);
+        } else { h->exp_pseq[it->second] = p; h->exp_lambda[it->second] = l; }
+    }
+    return 0;
+}
+
+// MultiBreakSV.java:333-400
+int read_assignment_file(mbsv_host* h) {
+    Scanner sc;
+    if (!slurp(h->assignmentfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->assignmentfile);
+    if (!sc.hasNextLine()) return hfail(MBSV_ERR_IO, "empty assignment file");
+    sc.nextLine();
+    while (sc.hasNext()) {
+        const std::string fragmentID = sc.next();
+        if (!sc.hasNext()) return hfail(MBSV_ERR_IO, "Error parsing line. Check assignmentfile format.");
+        const std::vector<std::string> esps = split(sc.next(), ",");
+        int numerrors, length;
+        if (!sc.hasNext() || !parse_int(sc.next(), numerrors) || !sc.hasNext() || !parse_int(sc.next(), length) || !sc.hasNext())
+            return hfail(MBSV_ERR_IO, "Error parsing line. Check assignmentfile format.");
+        const std::string explabel = sc.next();
+        auto ex = h->exp_id.find(explabel);
+        if (ex == h->exp_id.end()) return hfail(MBSV_ERR_IO, "ERROR: Experiment Label " + explabel + " not in Experiments file.");
+        std::vector<int> ids;
+        for (const auto& e : esps) ids.push_back(h->esp(e));
+        if (h->clusters_first) {
+            bool any = false;
+            for (int id : ids) if (h->in_allesps[id]) { any = true; break; }
+            if (!any) continue;
+        }
+        auto it = h->frag_id_of.find(fragmentID);
+        int fid;
+        if (it == h->frag_id_of.end()) {
+            fid = (int)h->frags.size();
+            h->frag_id_of.emplace(fragmentID, fid);
+            h->frags.push_back(Fragment{fragmentID, {}});
+            h->fragments.put(fragmentID);
+        } else fid = it->second;
+        Alignment al;
+        al.esps = ids; al.numerrors = numerrors; al.len = length; al.exp = ex->second;
+        h->frags[fid].alns.push_back(al);
+        for (int id : ids) { h->in_allesps[id] = 1; h->esp2fragment[id] = fid; }
+    }
+    return 0;
+}
+
+// MultiBreakSV.java:402-473
+int read_clusters_file(mbsv_host* h) {
+    Scanner sc;
+    if (!slurp(h->clusterfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->clusterfile);
+    h->max_support = 0;
+    bool warn = false;
+    while (sc.hasNext()) {
+        const std::vector<std::string> row = split(sc.nextLine(), "\t");
+        if (row[0] == "cID") continue;
+        const std::string& cID = row[0];
+        if (cID.find('.') != std::string::npos) continue;
+        int n;
+        if (row.size() < 2) return hfail(MBSV_ERR_IO, "ArrayIndexOutOfBounds: clusters row has < 2 columns");
+        if (!parse_int(row[1], n)) return hfail(MBSV_ERR_IO, "NumberFormatException: " + row[1]);
+        if (h->max_support < n) h->max_support = n;
+        if (row.size() < 5) return hfail(MBSV_ERR_IO, "ArrayIndexOutOfBounds: clusters row has < 5 columns");
+        auto it = h->cl_id_of.find(cID);
+        int cid = it == h->cl_id_of.end() ? -1 : it->second;
+        auto ensure = [&]() {                       // clust.put(cID, ...) — a repeated cID keeps its slot
+            if (cid >= 0) return;
+            cid = (int)h->cl_name.size();
+            h->cl_id_of.emplace(cID, cid);
+            h->cl_name.push_back(cID); h->cl_is_cluster.push_back(1); h->bp_of_cl.push_back(-1);
+            h->diagrams.emplace_back();
+            h->clust.put(cID);
+        };
+        bool some = false;
+        for (const auto& raw : split(row[4], ",")) {
+            const int id = h->esp(trim(raw));
+            if (!h->clusters_first && !h->in_allesps[id]) { warn = true; continue; }
+            some = true;
+            ensure();
+            h->esp2cid[id] = cid;
+            if (h->clusters_first) h->in_allesps[id] = 1;
+        }
+        if (!h->clusters_first && !some) continue;
+        ensure();
+        h->cl_is_cluster[cid] = row[2] == "-1" ? 0 : 1;
+    }
+    if (warn) h->warning = "WARNING! Some fragments in clusters are NOT in ESP file";
+    // breakpoints are filled by iterating `clust` (:464-470)
+    for (int cid : h->clust.order()) {
+        h->bp_of_cl[cid] = h->breakpoints.put(h->cl_name[cid]);
+        h->cl_of_bp.push_back(cid);
+    }
+    if (h->clust.tree_bin) h->breakpoints.tree_bin = true;
+    return 0;
+}
+
+// MultiBreakSV.java:475-550
+void intersect_clusters_and_fragments(mbsv_host* h) {
+    for (int fe : h->fragments.order()) {
+        Fragment& fr = h->frags[fe];
+        std::vector<Alignment> keep;
+        for (const Alignment& al : fr.alns) {
+            bool all = true;
+            for (int e : al.esps) if (h->esp2cid[e] < 0) { all = false; break; }
+            if (all) keep.push_back(al);
+        }
+        if (keep.empty()) h->fragments.remove(fe); else fr.alns.swap(keep);
+    }
+    std::vector<char> used(h->cl_name.size(), 0);
+    for (int fe : h->fragments.order())
+        for (const Alignment& al : h->frags[fe].alns)
+            for (int e : al.esps) used[h->esp2cid[e]] = 1;
+    for (int be : h->breakpoints.order())
+        if (!used[h->cl_of_bp[be]]) { h->breakpoints.remove(be); h->bp_of_cl[h->cl_of_bp[be]] = -1; }
+}
+
+// MultiBreakSV.java:658-746 + MultiBreakSVDiagram.java:56-139
+int construct_cluster_diagrams(mbsv_host* h) {
+    Scanner sc;
+    if (!slurp(h->clusterfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->clusterfile);
+    std::vector<std::string> row;
+    auto advance = [&]() -> bool { if (!sc.hasNext()) return false; row = split(sc.nextLine(), "\t"); return true; };
+    bool have = advance();
+    while (have) {
+        if (row[0] == "cID") { have = advance(); continue; }
+        if (row.size() < 5) return hfail(MBSV_ERR_IO, "ArrayIndexOutOfBounds: clusters row has < 5 columns");
+        const std::string cID = row[0], local = row[2], names = row[4];
+        auto it = h->cl_id_of.find(cID);
+        if (it == h->cl_id_of.end() || h->bp_of_cl[it->second] < 0) { have = advance(); continue; }
+        const int cid = it->second;
+        Diagram d;
+        d.built = true;
+        std::unordered_set<int> seen;
+        auto add_root = [&](const std::string& list) {
+            std::vector<int> r;
+            for (const auto& e : split(list, ", ")) {
+                const int id = h->esp(e);
+                r.push_back(id);
+                if (seen.insert(id).second) d.leaves.push_back(id);
+            }
+            d.roots.push_back(r);
+        };
+        if (local != "-1") {
+            d.is_cluster = true;
+            add_root(names);
+            have = advance();
+        } else {
+            d.is_cluster = false;
+            have = advance();
+            while (have && row[0].compare(0, cID.size(), cID) == 0) {
+                if (row.size() < 5) return hfail(MBSV_ERR_IO, "ArrayIndexOutOfBounds: sub-cluster row");
+                add_root(row[4]);
+                have = advance();
+            }
+        }
+        for (int e : d.leaves) if (h->esp2cid[e] >= 0) h->esp2cid[e] = cid;
+        h->diagrams[cid] = d;
+    }
+    for (int be : h->breakpoints.order())
+        if (!h->diagrams[h->cl_of_bp[be]].built) return hfail(MBSV_ERR_IO, "NullPointerException: no diagram for " + h->cl_name[h->cl_of_bp[be]]);
+    return 0;
+}
+
+// Flatten into mbsv_problem_desc arrays (same layout as the oracle's packing; compared integer-for-integer in tests).
+int pack(mbsv_host* h) {
+    const std::vector<int> eorder = h->experiments.order();
+    const int E = (int)eorder.size();
+    std::vector<int> exp_idx(h->exp_label.size(), -1);
+    h->pk_pseq.clear(); h->pk_lambda.clear();
+    for (int i = 0; i < E; ++i) { exp_idx[eorder[i]] = i; h->pk_pseq.push_back(h->exp_pseq[eorder[i]]); h->pk_lambda.push_back(h->exp_lambda[eorder[i]]); }
+    // clusters in breakpoints.keySet() order
+    h->cl_order.clear();
+    for (int be : h->breakpoints.order()) h->cl_order.push_back(h->cl_of_bp[be]);
+    const int C = (int)h->cl_order.size();
+    std::vector<int> cl_idx(h->cl_name.size(), -1);
+    for (int i = 0; i < C; ++i) cl_idx[h->cl_order[i]] = i;
+    h->cluster_kind.assign(C, 0);
+    for (int i = 0; i < C; ++i) h->cluster_kind[i] = h->cl_is_cluster[h->cl_order[i]] ? 0 : 1;
+    {   // A.supports is a fresh HashMap filled by iterating breakpoints (MultiBreakSVAssignmentMatrix.java:53-66)
+        JavaMapOrder sup;
+        for (int i = 0; i < C; ++i) sup.put(h->cl_name[h->cl_order[i]]);
+        h->supports_order.clear();
+        for (int id : sup.order()) h->supports_order.push_back(id);
+        if (sup.tree_bin) h->breakpoints.tree_bin = true;
+    }
+    // fragments in fragments.keySet() order
+    h->frag_order = h->fragments.order();
+    const int F = (int)h->frag_order.size();
+    std::vector<int> frag_idx(h->frags.size(), -1);
+    for (int i = 0; i < F; ++i) frag_idx[h->frag_order[i]] = i;
+    // leaves / roots
+    h->cluster_leaf_ptr.assign(1, 0); h->leaf_owner.clear(); h->cluster_root_ptr.assign(1, 0); h->root_leaf_ptr.assign(1, 0);
+    h->root_leaf.clear();
+    std::vector<int> leaf_count(h->esp_name.size(), 0);
+    std::vector<std::unordered_map<int, int>> slot_of(C);
+    for (int i = 0; i < C; ++i) {
+        const Diagram& d = h->diagrams[h->cl_order[i]];
+        if (d.is_cluster != (h->cluster_kind[i] == 0)) h->unsupported = "cluster kind mismatch for " + h->cl_name[h->cl_order[i]];
+        for (int e : d.leaves) {
+            slot_of[i][e] = (int)h->leaf_owner.size() - h->cluster_leaf_ptr[i];
+            ++leaf_count[e];
+            const int fe = h->esp2fragment[e];
+            h->leaf_owner.push_back(fe >= 0 && h->fragments.alive[fe] ? frag_idx[fe] : -1);
+        }
+        h->cluster_leaf_ptr.push_back((int)h->leaf_owner.size());
+        for (const auto& r : d.roots) {
+            std::unordered_set<int> seen;
+            for (int e : r) {
+                if (!seen.insert(e).second) h->unsupported = "ESP " + h->esp_name[e] + " listed twice in one row of cluster " + h->cl_name[h->cl_order[i]];
+                h->root_leaf.push_back(slot_of[i].at(e));
+            }
+            h->root_leaf_ptr.push_back((int)h->root_leaf.size());
+        }
+        h->cluster_root_ptr.push_back((int)h->root_leaf_ptr.size() - 1);
+        if (h->cluster_leaf_ptr[i + 1] - h->cluster_leaf_ptr[i] > h->max_support)
+            h->unsupported = "cluster " + h->cl_name[h->cl_order[i]] + " has more ESPs than its declared count (logprobcov overflow)";
+    }
+    for (size_t e = 0; e < leaf_count.size(); ++e)
+        if (leaf_count[e] > 1) h->unsupported = "ESP " + h->esp_name[e] + " is a leaf of more than one cluster";
+    // alignments
+    h->frag_aln_ptr.assign(1, 0); h->aln_esp_ptr.assign(1, 0);
+    h->aln_numerrors.clear(); h->aln_len.clear(); h->aln_exp.clear(); h->aln_esp_cluster.clear(); h->aln_esp_leaf.clear();
+    h->aln_esp_espid.clear();
+    for (int i = 0; i < F; ++i) {
+        const Fragment& fr = h->frags[h->frag_order[i]];
+        for (const Alignment& al : fr.alns) {
+            h->aln_numerrors.push_back(al.numerrors); h->aln_len.push_back(al.len); h->aln_exp.push_back(exp_idx[al.exp]);
+            std::unordered_set<int> seen;
+            for (int e : al.esps) {
+                if (!seen.insert(e).second) h->unsupported = "ESP " + h->esp_name[e] + " listed twice in one alignment of " + fr.id;
+                const int c = cl_idx[h->esp2cid[e]];
+                auto ls = slot_of[c].find(e);
+                const bool contributes = ls != slot_of[c].end() && h->leaf_owner[h->cluster_leaf_ptr[c] + ls->second] == i;
+                h->aln_esp_cluster.push_back(contributes ? c : -1);
+                h->aln_esp_leaf.push_back(contributes ? ls->second : -1);
+                h->aln_esp_espid.push_back(e);
+            }
+            h->aln_esp_ptr.push_back((int)h->aln_esp_cluster.size());
+        }
+        h->frag_aln_ptr.push_back((int)h->aln_numerrors.size());
+    }
+    h->sorted_frag.resize(F);
+    for (int i = 0; i < F; ++i) h->sorted_frag[i] = i;
+    std::sort(h->sorted_frag.begin(), h->sorted_frag.end(),
+              [&](int a, int b) { return h->frags[h->frag_order[a]].id < h->frags[h->frag_order[b]].id; });
+    const std::vector<int32_t> nleaf_ptr = h->cluster_leaf_ptr;
+    h->cluster_hist_ptr.assign(1, 0);
+    for (int i = 0; i < C; ++i) h->cluster_hist_ptr.push_back(h->cluster_hist_ptr.back() + (nleaf_ptr[i + 1] - nleaf_ptr[i]) + 1);
+    h->sub_frag_ptr = {0, F};
+    h->sub_cluster_ptr = {0, C};
+    h->packed = true;
+    return 0;
+}
+
+// MultiBreakSV.java:604-656: logprobcov[k] = logPoisson(k; lambdaD), k = 1..maxSupport (prior[] == 0)
+int precompute_priors(mbsv_host* h) {
+    const int E = (int)h->pk_pseq.size();
+    h->logprobcov.assign((size_t)E * (h->max_support + 1), 0.0);
+    for (int x = 0; x < E; ++x)
+        if (int rc = mbsv_fill_logprobcov(h->pk_lambda[x], h->max_support, h->logprobcov.data() + (size_t)x * (h->max_support + 1))) return rc;
+    h->priors = true;
+    return 0;
+}
+
+// MultiBreakSV.java:748-771 and the toggle lists of svMove :1303-1330
+void fill_non_singleton_array(mbsv_host* h) {
+    const int C = (int)h->cl_order.size();
+    h->sv_cluster.clear(); h->sv_frag.clear(); h->sv_numchanged.clear(); h->sv_frag_ptr.assign(1, 0);
+    for (int c = 0; c < C; ++c) {
+        int unique = 0;
+        std::vector<int> uniq;
+        for (int l = h->cluster_leaf_ptr[c]; l < h->cluster_leaf_ptr[c + 1]; ++l) {
+            const int f = h->leaf_owner[l];
+            if (f >= 0 && h->frag_aln_ptr[f + 1] - h->frag_aln_ptr[f] == 1) {
+                ++unique;
+                if (std::find(uniq.begin(), uniq.end(), f) == uniq.end()) uniq.push_back(f);
+            }
+        }
+        if (unique > 1) {
+            h->sv_cluster.push_back(c);
+            h->sv_numchanged.push_back(unique);
+            for (int f : uniq) h->sv_frag.push_back(f);
+            h->sv_frag_ptr.push_back((int)h->sv_frag.size());
+        }
+    }
+    h->sub_sv_ptr = {0, (int)h->sv_cluster.size()};
+    h->sv_filled = true;
+}
+
+template <typename T> const T* ptr_or_null(const std::vector<T>& v) { return v.empty() ? nullptr : v.data(); }
+
+}  // namespace
+
+extern "C" {
+
+int mbsv_host_create(mbsv_host** out) {
+    if (!out) return hfail(MBSV_ERR_ARG, "out is NULL");
+    *out = new (std::nothrow) mbsv_host();
+    return *out ? MBSV_OK : hfail(MBSV_ERR_OOM, "allocation failed");
+}
+int mbsv_host_destroy(mbsv_host* h) { delete h; return MBSV_OK; }
+
+int mbsv_host_set_files(mbsv_host* h, const char* clusterfile, const char* assignmentfile, const char* experimentfile,
+                        int32_t clusters_first) {
+    if (!h || !clusterfile || !assignmentfile || !experimentfile) return hfail(MBSV_ERR_ARG, "Cluster, assignment and experiment files are required.");
+    h->clear();
+    h->clusterfile = clusterfile; h->assignmentfile = assignmentfile; h->experimentfile = experimentfile;
+    h->clusters_first = clusters_first != 0;
+    return MBSV_OK;
+}
+
+int mbsv_host_get_fragment_alignments(mbsv_host* h) {
+    if (!h) return hfail(MBSV_ERR_ARG, "host is NULL");
+    int rc;
+    if ((rc = read_experiment_file(h))) return rc;
+    if (h->clusters_first) { if ((rc = read_clusters_file(h)) || (rc = read_assignment_file(h))) return rc; }
+    else { if ((rc = read_assignment_file(h)) || (rc = read_clusters_file(h))) return rc; }
+    intersect_clusters_and_fragments(h);
+    return MBSV_OK;
+}
+int mbsv_host_construct_cluster_diagrams(mbsv_host* h) {
+    if (!h) return hfail(MBSV_ERR_ARG, "host is NULL");
+    if (int rc = construct_cluster_diagrams(h)) return rc;
+    return pack(h);
+}
+int mbsv_host_precompute_priors(mbsv_host* h) {
+    if (!h || !h->packed) return hfail(MBSV_ERR_ARG, "construct the cluster diagrams first");
+    return precompute_priors(h);
+}
+int mbsv_host_fill_non_singleton_array(mbsv_host* h) {
+    if (!h || !h->packed) return hfail(MBSV_ERR_ARG, "construct the cluster diagrams first");
+    fill_non_singleton_array(h);
+    return MBSV_OK;
+}
+int mbsv_host_load(mbsv_host* h) {
+    int rc;
+    if ((rc = mbsv_host_get_fragment_alignments(h)) || (rc = mbsv_host_construct_cluster_diagrams(h)) ||
+        (rc = mbsv_host_precompute_priors(h)) || (rc = mbsv_host_fill_non_singleton_array(h))) return rc;
+    if (h->experiments.tree_bin || h->fragments.tree_bin || h->breakpoints.tree_bin)
+        h->unsupported = "a java.util.HashMap bin would be treeified: iteration order not reproducible";
+    return MBSV_OK;
+}
+
+int mbsv_host_desc(mbsv_host* h, mbsv_problem_desc* d) {
+    if (!h || !d || !h->packed || !h->priors || !h->sv_filled) return hfail(MBSV_ERR_ARG, "mbsv_host_load first");
+    if (!h->unsupported.empty()) return hfail(MBSV_ERR_UNSUPPORTED, h->unsupported);
+    std::memset(d, 0, sizeof *d);
+    d->abi_version = MBSV_ABI_VERSION;
+    d->n_sub = 1;
+    d->n_frag = (int)h->frag_order.size(); d->n_aln = (int)h->aln_numerrors.size(); d->n_aln_esp = (int)h->aln_esp_cluster.size();
+    d->n_cluster = (int)h->cl_order.size(); d->n_exp = (int)h->pk_pseq.size(); d->max_support = h->max_support;
+    d->n_sv = (int)h->sv_cluster.size(); d->n_sv_frag = (int)h->sv_frag.size(); d->n_leaf = (int)h->leaf_owner.size();
+    d->n_root = (int)h->root_leaf_ptr.size() - 1; d->n_root_leaf = (int)h->root_leaf.size(); d->n_hist = h->cluster_hist_ptr.back();
+    d->sub_frag_ptr = h->sub_frag_ptr.data(); d->sub_cluster_ptr = h->sub_cluster_ptr.data(); d->sub_sv_ptr = h->sub_sv_ptr.data();
+    d->frag_aln_ptr = h->frag_aln_ptr.data(); d->aln_numerrors = ptr_or_null(h->aln_numerrors); d->aln_len = ptr_or_null(h->aln_len);
+    d->aln_exp = ptr_or_null(h->aln_exp); d->aln_esp_ptr = h->aln_esp_ptr.data(); d->aln_esp_cluster = ptr_or_null(h->aln_esp_cluster);
+    d->aln_esp_leaf = ptr_or_null(h->aln_esp_leaf); d->cluster_kind = ptr_or_null(h->cluster_kind);
+    d->supports_order = ptr_or_null(h->supports_order); d->cluster_hist_ptr = h->cluster_hist_ptr.data();
+    d->cluster_leaf_ptr = h->cluster_leaf_ptr.data(); d->leaf_owner = ptr_or_null(h->leaf_owner);
+    d->cluster_root_ptr = h->cluster_root_ptr.data(); d->root_leaf_ptr = h->root_leaf_ptr.data(); d->root_leaf = ptr_or_null(h->root_leaf);
+    d->sv_cluster = ptr_or_null(h->sv_cluster); d->sv_frag_ptr = h->sv_frag_ptr.data(); d->sv_frag = ptr_or_null(h->sv_frag);
+    d->sv_numchanged = ptr_or_null(h->sv_numchanged); d->exp_pseq = h->pk_pseq.data(); d->exp_lambda = h->pk_lambda.data();
+    d->logprobcov = h->logprobcov.data();
+    return MBSV_OK;
+}
+
+const char* mbsv_host_name(mbsv_host* h, int32_t kind, int32_t i) {
+    if (!h) return nullptr;
+    switch (kind) {
+        case 0: return (i >= 0 && i < (int)h->frag_order.size()) ? h->frags[h->frag_order[i]].id.c_str() : nullptr;
+        case 1: return (i >= 0 && i < (int)h->cl_order.size()) ? h->cl_name[h->cl_order[i]].c_str() : nullptr;
+        case 2: { const auto o = h->experiments.order(); return (i >= 0 && i < (int)o.size()) ? h->exp_label[o[i]].c_str() : nullptr; }
+        case 3: return (i >= 0 && i < (int)h->aln_esp_espid.size()) ? h->esp_name[h->aln_esp_espid[i]].c_str() : nullptr;
+        case 4: return h->warning.c_str();
+        case 5: return h->unsupported.c_str();
+        default: return nullptr;
+    }
+}
+int mbsv_host_sorted_fragments(mbsv_host* h, int32_t* out) {
+    if (!h || !out || !h->packed) return hfail(MBSV_ERR_ARG, "mbsv_host_load first");
+    for (size_t i = 0; i < h->sorted_frag.size(); ++i) out[i] = h->sorted_frag[i];
+    return (int)h->sorted_frag.size();
+}
+
+int mbsv_host_set_results(mbsv_host* h, int32_t num_iters, int32_t burnin, const uint32_t* aln_count,
+                          const uint32_t* frag_err_count, const uint32_t* cluster_hist) {
+    if (!h || !h->packed || !aln_count || !frag_err_count || !cluster_hist) return hfail(MBSV_ERR_ARG, "bad argument");
+    h->num_iters = num_iters; h->burnin = burnin;
+    h->skip = std::max(1, num_iters / 1000);
+    h->r_aln.assign(aln_count, aln_count + h->aln_numerrors.size());
+    h->r_frag.assign(frag_err_count, frag_err_count + h->frag_order.size());
+    h->r_hist.assign(cluster_hist, cluster_hist + h->cluster_hist_ptr.back());
+    h->have_results = true;
+    h->have_trace = false;
+    return MBSV_OK;
+}
+
+int mbsv_host_run_mcmc(mbsv_host* h, int32_t num_iters, double perr, int32_t mode, int32_t device, int32_t save_space,
+                       const int32_t* init_assign, mbsv_results* results) {
+    mbsv_problem_desc d;
+    if (int rc = mbsv_host_desc(h, &d)) return rc;
+    if (num_iters < 0) return hfail(MBSV_ERR_ARG, "--numiterations must be a positive integer.");
+    if (!(perr >= 0 && perr <= 1)) return hfail(MBSV_ERR_ARG, "--perr must be a value between 0 and 1.");
+    // burnin / skip as the constructor derives them (MultiBreakSV.java:186-193)
+    h->num_iters = num_iters;
+    h->burnin = num_iters / 10 ? num_iters / 10 : 10;
+    h->skip = num_iters / 1000 ? num_iters / 1000 : 1;
+    mbsv_problem* prob = nullptr;
+    if (int rc = mbsv_problem_create(&d, device, &prob)) return hfail(rc, mbsv_last_error());
+    mbsv_run_params rp;
+    std::memset(&rp, 0, sizeof rp);
+    rp.mode = mode; rp.n_chains = 1; rp.num_iters = num_iters; rp.burnin = h->burnin; rp.perr = perr; rp.seed = 123456;
+    rp.device = device; rp.java_int_wrap = 1; rp.init_assign = init_assign; rp.trace = save_space ? 0 : 1; rp.memo_states = 256;
+    h->r_aln.assign(d.n_aln, 0); h->r_frag.assign(d.n_frag, 0); h->r_hist.assign(d.n_hist, 0); h->r_init.assign(d.n_frag, 0);
+    std::vector<int32_t> fin(d.n_frag, 0), errv(1, 0);
+    std::vector<double> flp(1, 0.0), ilp(1, 0.0);
+    std::vector<int64_t> counters(5, 0), totals(6, 0);
+    std::vector<uint64_t> rngs(1, 0);
+    if (!save_space) { h->r_trace_logprob.assign(num_iters, 0.0); h->r_trace_frag.assign(num_iters, -1); h->r_trace_assign.assign(num_iters, -1); }
+    mbsv_results r;
+    std::memset(&r, 0, sizeof r);
+    r.aln_count = h->r_aln.data(); r.frag_err_count = h->r_frag.data(); r.cluster_hist = h->r_hist.data();
+    r.final_assign = fin.data(); r.final_logprob = flp.data(); r.counters = counters.data(); r.rng_state = rngs.data();
+    r.error = errv.data(); r.initial_assign = h->r_init.data(); r.initial_logprob = ilp.data(); r.totals = totals.data();
+    if (!save_space) { r.trace_logprob = h->r_trace_logprob.data(); r.trace_move_frag = h->r_trace_frag.data(); r.trace_move_assign = h->r_trace_assign.data(); }
+    const int rc = mbsv_run(prob, &rp, &r);
+    mbsv_problem_destroy(prob);
+    if (rc) return hfail(rc, mbsv_last_error());
+    h->have_results = true;
+    h->have_trace = !save_space;
+    if (results) { *results = r; results->final_assign = nullptr; results->final_logprob = nullptr; results->counters = nullptr;
+                   results->rng_state = nullptr; results->error = nullptr; results->initial_logprob = nullptr; results->totals = nullptr; }
+    return MBSV_OK;
+}
+
+// MultiBreakSV.java:1754-1792
+int mbsv_host_write_final_files(mbsv_host* h, const char* prefix) {
+    if (!h || !prefix || !h->have_results) return hfail(MBSV_ERR_ARG, "no results to write");
+    const int C = (int)h->cl_order.size(), F = (int)h->frag_order.size();
+    {
+        std::ofstream w(std::string(prefix) + ".finalbreakpoints.longburnin");
+        if (!w) return hfail(MBSV_ERR_IO, "cannot write breakpoints file");
+        w << "ClusterID\tNumIters\tSupport0\tSupport1\tSupport2...\n";
+        for (int c = 0; c < C; ++c) {
+            w << h->cl_name[h->cl_order[c]] << "\t" << h->burnin;
+            const uint32_t* hist = h->r_hist.data() + h->cluster_hist_ptr[c];
+            const int bins = h->cluster_hist_ptr[c + 1] - h->cluster_hist_ptr[c];
+            double tot = 0;
+            for (int j = 1; j <= h->max_support; ++j) tot = tot + (j < bins ? (double)hist[j] : 0.0);
+            w << "\t" << java_double((double)h->burnin - tot);           // bin 0 is derived (:1766-1771)
+            for (int j = 1; j <= h->max_support; ++j) w << "\t" << java_double(j < bins ? (double)hist[j] : 0.0);
+            w << "\n";
+        }
+    }
+    {
+        std::ofstream w(std::string(prefix) + ".finalassignment.longburnin");
+        if (!w) return hfail(MBSV_ERR_IO, "cannot write assignment file");
+        w << "FragmentID\tAssignmentIndex\tAvgAssignment\tDiscordantPairs\n";
+        for (int k = 0; k < F; ++k) {
+            const int f = h->sorted_frag[k];
+            const std::string& id = h->frags[h->frag_order[f]].id;
+            w << id << "\t-1\t" << java_double((double)h->r_frag[f] / h->burnin) << "\terror\n";
+            for (int a = h->frag_aln_ptr[f]; a < h->frag_aln_ptr[f + 1]; ++a) {
+                w << id << "\t" << (a - h->frag_aln_ptr[f]) << "\t" << java_double((double)h->r_aln[a] / h->burnin) << "\t";
+                for (int j = h->aln_esp_ptr[a]; j < h->aln_esp_ptr[a + 1]; ++j)
+                    w << (j > h->aln_esp_ptr[a] ? "," : "") << h->esp_name[h->aln_esp_espid[j]];
+                w << "\n";
+            }
+        }
+    }
+    return MBSV_OK;
+}
+
+// runMCMC's writer (:779-828): Iteration, LogProb, NumBreakpoints (sum of supports.get(cID).size() = C*E every
+// `skip` iterations, else 0), MadeMove?
+int mbsv_host_write_mcmc_file(mbsv_host* h, const char* path) {
+    if (!h || !path || !h->have_trace) return hfail(MBSV_ERR_ARG, "no trace (run without --savespace)");
+    std::ofstream w(path);
+    if (!w) return hfail(MBSV_ERR_IO, "cannot write mcmc file");
+    w << "Iteration\tLogProb\tNumBreakpoints\tMadeMove?\n";
+    const long long numbps = (long long)h->cl_order.size() * (long long)h->pk_pseq.size();
+    for (int i = 0; i < h->num_iters; ++i)
+        w << i << "\t" << java_double(h->r_trace_logprob[i]) << "\t" << (i % h->skip == 0 ? numbps : 0) << "\t"
+          << (h->r_trace_frag[i] != -1 ? 1 : 0) << "\n";
+    return MBSV_OK;
+}
+
+// writeStateCounts (:1934-1949): counts/logprobs are keyed by the tab-joined assignment string in sorted-fragment
+// order (MultiBreakSVAssignmentMatrix.java:465-472) and iterated in HashMap order.
+int mbsv_host_write_state_counts(mbsv_host* h, const char* path) {
+    if (!h || !path || !h->have_trace) return hfail(MBSV_ERR_ARG, "no trace (run without --savespace)");
+    const int F = (int)h->frag_order.size();
+    std::vector<int32_t> cur = h->r_init;
+    JavaMapOrder counts;
+    std::unordered_map<std::string, int> id_of;
+    std::vector<std::string> keys;
+    std::vector<long long> cnt;
+    std::vector<double> lp;
+    for (int i = 0; i < h->num_iters; ++i) {
+        const int mf = h->r_trace_frag[i];
+        if (mf >= 0) cur[mf] = h->r_trace_assign[i];
+        else if (mf <= -2) {
+            const int k = -mf - 2;
+            for (int q = h->sv_frag_ptr[k]; q < h->sv_frag_ptr[k + 1]; ++q) cur[h->sv_frag[q]] = cur[h->sv_frag[q]] == -1 ? 0 : -1;
+        }
+        std::string key = std::to_string(cur[h->sorted_frag[0]]);
+        for (int k = 1; k < F; ++k) key += "\t" + std::to_string(cur[h->sorted_frag[k]]);
+        auto it = id_of.find(key);
+        if (it == id_of.end()) {
+            id_of.emplace(key, (int)keys.size());
+            keys.push_back(key); cnt.push_back(1); lp.push_back(h->r_trace_logprob[i]);
+            counts.put(key);
+        } else ++cnt[it->second];
+    }
+    std::ofstream w(path);
+    if (!w) return hfail(MBSV_ERR_IO, "cannot write state counts");
+    w << "SampledProb\tLogProb";
+    for (int k = 0; k < F; ++k) w << "\t" << h->frags[h->frag_order[h->sorted_frag[k]]].id;
+    w << "\n";
+    for (int id : counts.order()) w << java_double((double)cnt[id] / (double)h->num_iters) << "\t" << java_double(lp[id]) << "\t" << keys[id] << "\n";
+    return MBSV_OK;
+}
+
+int mbsv_host_batch_create(mbsv_host* const* hosts, int32_t n, mbsv_host_batch** out) {
+    if (!hosts || n < 1 || !out) return hfail(MBSV_ERR_ARG, "bad argument");
+    mbsv_host_batch* b = new (std::nothrow) mbsv_host_batch();
+    if (!b) return hfail(MBSV_ERR_OOM, "allocation failed");
+    auto fail_free = [&](int code, const std::string& m) { delete b; return hfail(code, m); };
+    b->n_exp = (int)hosts[0]->pk_pseq.size();
+    for (int i = 0; i < n; ++i) {
+        const mbsv_host* h = hosts[i];
+        if (!h || !h->packed || !h->priors || !h->sv_filled) return fail_free(MBSV_ERR_ARG, "every host must be loaded");
+        if (!h->unsupported.empty()) return fail_free(MBSV_ERR_UNSUPPORTED, h->unsupported);
+        if ((int)h->pk_pseq.size() != b->n_exp || h->pk_pseq != hosts[0]->pk_pseq || h->pk_lambda != hosts[0]->pk_lambda)
+            return fail_free(MBSV_ERR_ARG, "hosts of one batch must share the experiments file");
+        b->max_support = std::max(b->max_support, h->max_support);
+    }
+    b->pseq = hosts[0]->pk_pseq; b->lambda = hosts[0]->pk_lambda;
+    b->logprobcov.assign((size_t)b->n_exp * (b->max_support + 1), 0.0);
+    for (int x = 0; x < b->n_exp; ++x) mbsv_fill_logprobcov(b->lambda[x], b->max_support, b->logprobcov.data() + (size_t)x * (b->max_support + 1));
+    b->sub_frag_ptr = {0}; b->sub_cluster_ptr = {0}; b->sub_sv_ptr = {0}; b->frag_aln_ptr = {0}; b->aln_esp_ptr = {0};
+    b->cluster_hist_ptr = {0}; b->cluster_leaf_ptr = {0}; b->cluster_root_ptr = {0}; b->root_leaf_ptr = {0}; b->sv_frag_ptr = {0};
+    for (int i = 0; i < n; ++i) {
+        const mbsv_host* h = hosts[i];
+        const int f0 = b->sub_frag_ptr.back(), c0 = b->sub_cluster_ptr.back(), a0 = b->frag_aln_ptr.back(), k0 = b->aln_esp_ptr.back();
+        const int l0 = b->cluster_leaf_ptr.back(), r0 = b->cluster_root_ptr.back(), rl0 = b->root_leaf_ptr.back();
+        const int h0 = b->cluster_hist_ptr.back(), q0 = b->sv_frag_ptr.back();
+        const int F = (int)h->frag_order.size(), C = (int)h->cl_order.size();
+        for (int f = 1; f <= F; ++f) b->frag_aln_ptr.push_back(a0 + h->frag_aln_ptr[f]);
+        b->aln_numerrors.insert(b->aln_numerrors.end(), h->aln_numerrors.begin(), h->aln_numerrors.end());
+        b->aln_len.insert(b->aln_len.end(), h->aln_len.begin(), h->aln_len.end());
+        b->aln_exp.insert(b->aln_exp.end(), h->aln_exp.begin(), h->aln_exp.end());
+        for (size_t a = 1; a < h->aln_esp_ptr.size(); ++a) b->aln_esp_ptr.push_back(k0 + h->aln_esp_ptr[a]);
+        for (int c : h->aln_esp_cluster) b->aln_esp_cluster.push_back(c < 0 ? -1 : c0 + c);
+        b->aln_esp_leaf.insert(b->aln_esp_leaf.end(), h->aln_esp_leaf.begin(), h->aln_esp_leaf.end());
+        b->cluster_kind.insert(b->cluster_kind.end(), h->cluster_kind.begin(), h->cluster_kind.end());
+        for (int c : h->supports_order) b->supports_order.push_back(c0 + c);
+        for (int c = 1; c <= C; ++c) {
+            b->cluster_hist_ptr.push_back(h0 + h->cluster_hist_ptr[c]);
+            b->cluster_leaf_ptr.push_back(l0 + h->cluster_leaf_ptr[c]);
+            b->cluster_root_ptr.push_back(r0 + h->cluster_root_ptr[c]);
+        }
+        for (int o : h->leaf_owner) b->leaf_owner.push_back(o < 0 ? -1 : f0 + o);
+        for (size_t r = 1; r < h->root_leaf_ptr.size(); ++r) b->root_leaf_ptr.push_back(rl0 + h->root_leaf_ptr[r]);
+        b->root_leaf.insert(b->root_leaf.end(), h->root_leaf.begin(), h->root_leaf.end());
+        for (int c : h->sv_cluster) b->sv_cluster.push_back(c0 + c);
+        for (size_t k = 1; k < h->sv_frag_ptr.size(); ++k) b->sv_frag_ptr.push_back(q0 + h->sv_frag_ptr[k]);
+        for (int f : h->sv_frag) b->sv_frag.push_back(f0 + f);
+        b->sv_numchanged.insert(b->sv_numchanged.end(), h->sv_numchanged.begin(), h->sv_numchanged.end());
+        b->sub_frag_ptr.push_back(f0 + F); b->sub_cluster_ptr.push_back(c0 + C);
+        b->sub_sv_ptr.push_back(b->sub_sv_ptr.back() + (int)h->sv_cluster.size());
+    }
+    *out = b;
+    return MBSV_OK;
+}
+int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* d) {
+    if (!b || !d) return hfail(MBSV_ERR_ARG, "bad argument");
+    std::memset(d, 0, sizeof *d);
+    d->abi_version = MBSV_ABI_VERSION;
+    d->n_sub = (int)b->sub_frag_ptr.size() - 1;
+    d->n_frag = b->sub_frag_ptr.back(); d->n_aln = (int)b->aln_numerrors.size(); d->n_aln_esp = (int)b->aln_esp_cluster.size();
+    d->n_cluster = b->sub_cluster_ptr.back(); d->n_exp = b->n_exp; d->max_support = b->max_support;
+    d->n_sv = (int)b->sv_cluster.size(); d->n_sv_frag = (int)b->sv_frag.size(); d->n_leaf = (int)b->leaf_owner.size();
+    d->n_root = (int)b->root_leaf_ptr.size() - 1; d->n_root_leaf = (int)b->root_leaf.size(); d->n_hist = b->cluster_hist_ptr.back();
+    d->sub_frag_ptr = b->sub_frag_ptr.data(); d->sub_cluster_ptr = b->sub_cluster_ptr.data(); d->sub_sv_ptr = b->sub_sv_ptr.data();
+    d->frag_aln_ptr = b->frag_aln_ptr.data(); d->aln_numerrors = ptr_or_null(b->aln_numerrors); d->aln_len = ptr_or_null(b->aln_len);
+    d->aln_exp = ptr_or_null(b->aln_exp); d->aln_esp_ptr = b->aln_esp_ptr.data(); d->aln_esp_cluster = ptr_or_null(b->aln_esp_cluster);
+    d->aln_esp_leaf = ptr_or_null(b->aln_esp_leaf); d->cluster_kind = ptr_or_null(b->cluster_kind);
+    d->supports_order = ptr_or_null(b->supports_order); d->cluster_hist_ptr = b->cluster_hist_ptr.data();
+    d->cluster_leaf_ptr = b->cluster_leaf_ptr.data(); d->leaf_owner = ptr_or_null(b->leaf_owner);
+    d->cluster_root_ptr = b->cluster_root_ptr.data(); d->root_leaf_ptr = b->root_leaf_ptr.data(); d->root_leaf = ptr_or_null(b->root_leaf);
+    d->sv_cluster = ptr_or_null(b->sv_cluster); d->sv_frag_ptr = b->sv_frag_ptr.data(); d->sv_frag = ptr_or_null(b->sv_frag);
+    d->sv_numchanged = ptr_or_null(b->sv_numchanged); d->exp_pseq = b->pseq.data(); d->exp_lambda = b->lambda.data();
+    d->logprobcov = b->logprobcov.data();
+    return MBSV_OK;
+}
+int mbsv_host_batch_destroy(mbsv_host_batch* b) { delete b; return MBSV_OK; }
+
+int mbsv_java_double_to_string(double v, char* buf, int32_t buflen) {
+    const std::string s = java_double(v);
+    if (buf && buflen > 0) { std::strncpy(buf, s.c_str(), buflen - 1); buf[buflen - 1] = 0; }
+    return (int)s.size();
+}
+int mbsv_java_hashmap_order(const char* keys, int32_t n, int32_t* out_order, int32_t* out_capacity) {
+    JavaMapOrder m;
+    const char* p = keys;
+    for (int i = 0; i < n; ++i) { std::string k(p); p += k.size() + 1; m.put(k); }
+    int i = 0;
+    for (int id : m.order()) out_order[i++] = id;
+    if (out_capacity) *out_capacity = m.cap;
+    return m.tree_bin ? -1 : i;
+}
+
+}  // extern "C"

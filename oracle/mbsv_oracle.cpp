@@ -128,6 +128,7 @@ int orc_run(const orc_desc* d, const orc_params* p, orc_results* r, int nthreads
             rp.java_int_wrap = p->java_int_wrap;
             rp.memo_states = p->memo_states;
             rp.init_assign = p->init_assign ? p->init_assign + v.f0 : nullptr;
+            std::vector<double> lpcache;     // shared by the chains of this subproblem
             for (int c = 0; c < p->n_chains; ++c) {
                 size_t sc = (size_t)s * p->n_chains + c;
                 Trace tr, *trp = nullptr;
@@ -140,7 +141,7 @@ int orc_run(const orc_desc* d, const orc_params* p, orc_results* r, int nthreads
                 int32_t* fa = r->final_assign ? r->final_assign + (size_t)c * d->n_frag + v.f0 : nullptr;
                 int32_t* ia = r->initial_assign ? r->initial_assign + (size_t)c * d->n_frag + v.f0 : nullptr;
                 double* il = r->initial_logprob ? r->initial_logprob + sc : nullptr;
-                ChainResult cr = run_chain(v, rp, p->seed + c, r->aln_count, r->frag_err_count, r->cluster_hist, fa, trp, ia, il);
+                ChainResult cr = run_chain(v, rp, p->seed + c, r->aln_count, r->frag_err_count, r->cluster_hist, fa, trp, ia, il, &lpcache);
                 if (trp) for (int i = 0; i < p->num_iters; ++i) if (tr.move_frag[i] >= 0) tr.move_frag[i] += v.f0;
                 if (r->final_logprob) r->final_logprob[sc] = cr.final_logprob;
                 if (r->counters) {

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <stdexcept>
 #include <vector>
 
@@ -127,6 +128,11 @@ struct Chain {
     ChainResult res;
     int32_t win_base;                            // first iteration inside the long-burn-in window
     bool use_full = false;                       // evaluate proposals with full_logprob() (FAITHFUL, or memo-eligible)
+    // memo-eligible problems (INCREMENTAL): log-posterior of every joint state, filled on first use and shared by
+    // the chains of the problem — the reference's `logprobs` map (MultiBreakSV.java:58,1133-1137) as an array
+    std::vector<double>* lpcache = nullptr;
+    std::vector<int64_t> stride;
+    int64_t sidx = 0;
     // scratch reused across iterations (no heap traffic in the hot loop)
     std::vector<int> s_dirty, s_dd;
     std::vector<uint8_t> s_touched, s_tt;
@@ -161,6 +167,10 @@ struct Chain {
             int64_t nst = 1;
             for (int f = 0; f < v.F && nst <= rp.memo_states; ++f) nst *= (int64_t)nalign(f) + 1;
             use_full = !cc && nst <= rp.memo_states;
+            if (use_full) {
+                int64_t sp = 1;
+                for (int f = 0; f < v.F; ++f) { stride.push_back(sp); sp *= (int64_t)nalign(f) + 1; }
+            }
         }
     }
 
@@ -278,6 +288,7 @@ struct Chain {
         }
         rebuild_from_assign();
         logprob = full_logprob();
+        if (!stride.empty()) { sidx = 0; for (int f = 0; f < v.F; ++f) sidx += (assign[f] + 1) * stride[f]; }
     }
 
     // ---- proposals ------------------------------------------------------------------------------
@@ -460,8 +471,16 @@ struct Chain {
         // ---- acceptance ratio ----
         double newlogprob, arg;
         std::vector<double>& newLB = s_newLB; newLB = LB;
+        int64_t newidx = sidx;
         if (use_full) {
-            newlogprob = full_logprob();
+            if (lpcache && !stride.empty()) {
+                if (p.kind == 0) newidx += (int64_t)(p.now - p.prev) * stride[p.f];
+                else for (int q = v.sv_frag_ptr[p.sv], i = 0; q < v.sv_frag_ptr[p.sv + 1]; ++q, ++i)
+                    newidx += (sv_prev[i] == -1 ? 1 : -1) * stride[v.sv_frag[q] - v.f0];
+                double& c = (*lpcache)[newidx];
+                if (c != c) c = full_logprob();      // NaN = not computed yet
+                newlogprob = c;
+            } else newlogprob = full_logprob();
             arg = (newlogprob + p.Alogq) - (logprob + p.Anewlogq);               // :1146
         } else {
             double dlb = 0.0;
@@ -479,6 +498,7 @@ struct Chain {
         if (ratio > r) {
             if (p.kind == 0) ++res.naive_accepted; else ++res.sv_accepted;
             logprob = newlogprob;
+            sidx = newidx;
             LB.swap(newLB);
             if (rp.mode == 1) {
                 // difference tallies
@@ -566,8 +586,17 @@ struct Chain {
 // (callers zero them; several chains of one problem pool into the same arrays).
 static inline ChainResult run_chain(const View& v, const RunParams& rp, int64_t seed, uint32_t* aln_count,
                                     uint32_t* frag_err_count, uint32_t* cluster_hist, int32_t* final_assign,
-                                    Trace* tr, int32_t* initial_assign = nullptr, double* initial_logprob = nullptr) {
+                                    Trace* tr, int32_t* initial_assign = nullptr, double* initial_logprob = nullptr,
+                                    std::vector<double>* lpcache = nullptr) {
     Chain ch(v, rp, seed, aln_count, frag_err_count, cluster_hist);
+    if (lpcache && ch.use_full && !ch.stride.empty()) {
+        if (lpcache->empty()) {
+            int64_t nst = 1;
+            for (int f = 0; f < v.F; ++f) nst *= (int64_t)ch.nalign(f) + 1;
+            lpcache->assign((size_t)nst, std::numeric_limits<double>::quiet_NaN());
+        }
+        ch.lpcache = lpcache;
+    }
     ch.initialize();
     if (initial_assign) for (int f = 0; f < v.F; ++f) initial_assign[f] = ch.assign[f];
     if (initial_logprob) *initial_logprob = ch.logprob;

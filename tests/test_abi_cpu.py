@@ -12,15 +12,18 @@ from conftest import ROOT, to_packed
 
 
 def _declared_functions():
-    hdr = open(os.path.join(ROOT, "include", "mbsv_b200.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(mbsv_[a-z0-9_]+)\s*\(", hdr)))
+    names = set()
+    for h in ("mbsv_b200.h", "mbsv_host.h"):
+        hdr = open(os.path.join(ROOT, "include", h)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+        names |= set(re.findall(r"\b(mbsv_[a-z0-9_]+)\s*\(", hdr))
+    return sorted(names)
 
 
 def test_header_symbols_exported(mbsv):
     L = mbsv.load_library()
     names = _declared_functions()
-    assert "mbsv_run" in names and "mbsv_problem_create" in names
+    assert "mbsv_run" in names and "mbsv_problem_create" in names and "mbsv_host_run_mcmc" in names
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/mbsv_b200.h but not exported"
     assert L.mbsv_abi_version() == 1

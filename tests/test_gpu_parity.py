@@ -136,3 +136,51 @@ def test_device_math_matches_host(mbsv, oracle):
         assert L.mbsv_log(float(x)) == oracle.jlog(float(x))
     for x in np.linspace(-60, 10, 5001):
         assert L.mbsv_exp(float(x)) == oracle.jexp(float(x))
+
+
+def test_host_main_file_to_file(oracle, mbsv, example_problem, tmp_path):
+    """MultiBreakSV.main on the shipped example through the native host mirror: input files -> GPU -> the
+    reference's four output files, checked against the oracle's run of the same chain."""
+    import os
+    from conftest import EXAMPLE
+    from multibreak_sv_b200 import host
+    prefix = os.path.join(str(tmp_path), "out")
+    sv = host.main(["--clusterfile", os.path.join(EXAMPLE, "gasv.clusters"), "--assignmentfile",
+                    os.path.join(EXAMPLE, "assignments.txt"), "--experimentfile", os.path.join(EXAMPLE, "experiments.txt"),
+                    "--numiterations", "10000", "--perr", "0.001", "--prefix", prefix])
+    o = oracle.run(example_problem, "faithful", 10000, trace=True)
+    # expected long-burn-in files: same writer fed with the oracle's tallies
+    ref = host.MultiBreakSV(["--clusterfile", os.path.join(EXAMPLE, "gasv.clusters"), "--assignmentfile",
+                             os.path.join(EXAMPLE, "assignments.txt"), "--experimentfile",
+                             os.path.join(EXAMPLE, "experiments.txt"), "--numiterations", "10000", "--perr", "0.001",
+                             "--prefix", prefix + "_ref"]).load()
+    ref.setResults(o.aln_count, o.frag_err_count, o.cluster_hist)
+    ref.writeFinalFiles()
+    for ext in (".finalbreakpoints.longburnin", ".finalassignment.longburnin"):
+        assert open(prefix + ext).read() == open(prefix + "_ref" + ext).read()
+    # mcmc.txt: Iteration, LogProb, NumBreakpoints (C*E every skip=10 iterations), MadeMove?
+    lines = open(prefix + ".mcmc.txt").read().splitlines()
+    assert lines[0] == "Iteration\tLogProb\tNumBreakpoints\tMadeMove?" and len(lines) == 10001
+    for i in (0, 1, 2, 6, 21, 9999):
+        it, lp, nb, mv = lines[1 + i].split("\t")
+        assert int(it) == i and lp == host.java_double_to_string(o.trace_logprob[0, 0, i])
+        assert int(nb) == (27 if i % 10 == 0 else 0) and int(mv) == int(o.trace_move_frag[0, 0, i] != -1)
+    assert sum(int(l.split("\t")[3]) for l in lines[1:]) == 1174
+    # .samplingprobs: distinct states, SampledProb = count / numiters
+    st = oracle.replay_states(example_problem, o.initial_assign[0], o.trace_move_frag[0, 0], o.trace_move_assign[0, 0])
+    order = example_problem.names["sorted_frag"]
+    counts = {}
+    for row in st:
+        k = "\t".join(str(row[i]) for i in order)
+        counts[k] = counts.get(k, 0) + 1
+    sp = open(prefix + ".samplingprobs").read().splitlines()
+    assert sp[0] == "SampledProb\tLogProb\tlongread_118669\tlongread_118671\tlongread_118673\tlongread_118674"
+    got = {}
+    for l in sp[1:]:
+        f = l.split("\t")
+        got["\t".join(f[2:])] = f[0]
+    assert set(got) == set(counts)
+    assert all(got[k] == host.java_double_to_string(counts[k] / 10000) for k in counts)
+    # HashMap iteration order of the state strings
+    assert ["\t".join(l.split("\t")[2:]) for l in sp[1:]] == oracle.hashmap_order(list(dict.fromkeys(
+        "\t".join(str(row[i]) for i in order) for row in st)))[0]

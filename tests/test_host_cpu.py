@@ -1,0 +1,174 @@
+"""The native host mirror (include/mbsv_host.h, multibreak_sv_b200.host.MultiBreakSV) against the oracle's literal
+restatement of the reference parser: identical packed arrays (integer-exact, including the HashMap orders), identical
+rejection of malformed input, and output files in the reference's format (Double.toString)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import EXAMPLE
+
+ARGS = ["--numiterations", "10000", "--perr", "0.001"]
+
+
+def _host(mbsv, c, a, e, cf=False, extra=()):
+    from multibreak_sv_b200 import host
+    args = ["--clusterfile", c, "--assignmentfile", a, "--experimentfile", e] + ARGS + list(extra)
+    if cf:
+        args.append("--readclustersfirst")
+    return host.MultiBreakSV(args)
+
+
+def _same(p, q):
+    assert p.scalars == q.scalars
+    for k in p.arrays:
+        assert np.array_equal(p.arrays[k], q.arrays[k]), k
+
+
+def test_example_matches_oracle(mbsv, oracle, example_problem):
+    sv = _host(mbsv, os.path.join(EXAMPLE, "gasv.clusters"), os.path.join(EXAMPLE, "assignments.txt"),
+               os.path.join(EXAMPLE, "experiments.txt"))
+    sv.getFragmentAlignments(); sv.constructClusterDiagrams(); sv.precomputePriors(); sv.fillNonSingletonArray()
+    p = sv.packed()
+    _same(p, example_problem)
+    assert sv.names(0, 4) == example_problem.names["frag_id"]
+    assert sv.names(1, 27) == example_problem.names["cluster_id"]
+    assert sv.names(3, 86) == example_problem.names["aln_esp_name"]
+    assert sv.sortedFragments(4).tolist() == example_problem.names["sorted_frag"].tolist()
+    assert sv.burnin == 1000 and sv.rejected() == ""
+
+
+@pytest.mark.parametrize("cf", [False, True])
+@pytest.mark.parametrize("cfg,nfrag,cc", [("cfg4", 600, 0.4), ("cfg2", 1500, 0.0), ("cfg3", 300, 0.3)])
+def test_generated_files_match_oracle(mbsv, oracle, tmp_path, cf, cfg, nfrag, cc):
+    from multibreak_sv_b200 import synth
+    g = synth.generate(cfg, n_frag=nfrag, seed=31337, conncomp_frac=cc)
+    paths = synth.write_reference_files(g, str(tmp_path))
+    sv = _host(mbsv, paths["clusters"], paths["assignments"], paths["experiments"], cf).load()
+    q = oracle.load_files(paths["clusters"], paths["assignments"], paths["experiments"], clusters_first=cf)
+    p = sv.packed()
+    _same(p, q)
+    assert sv.names(0, p.scalars["n_frag"]) == q.names["frag_id"]
+    assert sv.names(1, p.scalars["n_cluster"]) == q.names["cluster_id"]
+    assert sv.names(2, p.scalars["n_exp"]) == q.names["exp_label"]
+    assert sv.warning() == q.names["warning"]
+
+
+def test_subset_of_clusters_with_readclustersfirst(mbsv, oracle, tmp_path):
+    """A subproblem file (a few rows of the clusters file) + --readclustersfirst: fragments outside it vanish."""
+    from multibreak_sv_b200 import host, synth
+    g = synth.generate("cfg4", n_frag=500, seed=5)
+    paths = synth.write_reference_files(g, str(tmp_path))
+    rows = open(paths["clusters"]).read().splitlines()
+    hosts = []
+    for k, chunk in enumerate((rows[:40], rows[40:45], rows[45:300])):
+        sub = os.path.join(str(tmp_path), f"subset-{k + 1}.clusters")
+        open(sub, "w").write("\n".join(chunk) + "\n")
+        sv = _host(mbsv, sub, paths["assignments"], paths["experiments"], cf=True).load()
+        _same(sv.packed(), oracle.load_files(sub, paths["assignments"], paths["experiments"], clusters_first=True))
+        hosts.append(sv)
+    b = host.batch(hosts)
+    assert b.scalars["n_sub"] == 3
+    assert b.scalars["n_frag"] == sum(h.packed().scalars["n_frag"] for h in hosts)
+    # the batch is the concatenation with re-based indices: running it on the oracle equals running the parts
+    ob = oracle.Problem(b.scalars, b.arrays)
+    rb = oracle.run(ob, "faithful", 500, n_chains=2)
+    off_a = 0
+    for s, h in enumerate(hosts):
+        ps = h.packed()
+        rs = oracle.run(oracle.Problem(ps.scalars, ps.arrays), "faithful", 500, n_chains=2)
+        n = ps.scalars["n_aln"]
+        assert np.array_equal(rb.aln_count[off_a:off_a + n], rs.aln_count)
+        assert np.array_equal(rb.counters[s], rs.counters[0])
+        off_a += n
+
+
+def test_malformed_inputs_rejected_like_the_oracle(mbsv, oracle, tmp_path):
+    from multibreak_sv_b200 import host
+
+    def w(name, text):
+        p = os.path.join(str(tmp_path), name)
+        open(p, "w").write(text)
+        return p
+    exp = w("e.txt", "ExperimentLabel\tPseq\tLambdaD\nx 0.1 3\n")
+    asg = ("FragmentID\tDiscordantPairs\tNumErrors\tBasesInAlignment\tExperimentLabel\n"
+           "longread_1\tlongread_1_0.0-1.0\t5\t100\tx\nlongread_1\tlongread_1_0.1-1.1\t7\t100\tx\n"
+           "longread_2\tlongread_2_0.0-1.0\t5\t100\tx\n")
+    good = "c1\t2\t10\tD\tlongread_1_0.0-1.0, longread_2_0.0-1.0\t1\t1\t1, 2\nc2\t1\t10\tD\tlongread_1_0.1-1.1\t1\t1\t1, 2\n"
+    a, c = w("a.txt", asg), w("c.txt", good)
+    _same(_host(mbsv, c, a, exp).load().packed(), oracle.load_files(c, a, exp))
+    with pytest.raises(mbsv.MbsvError, match="not in Experiments file") as e:
+        _host(mbsv, c, w("a2.txt", asg.replace("\tx\n", "\ty\n", 1)), exp).load()
+    assert e.value.status == -7
+    with pytest.raises(mbsv.MbsvError, match="ArrayIndexOutOfBounds"):
+        _host(mbsv, w("c2.txt", good.replace("\nc2", "\n\nc2")), a, exp).load()
+    dup = _host(mbsv, w("c3.txt", good + "c3\t1\t10\tD\tlongread_2_0.0-1.0\t1\t1\t1, 2\n"), a, exp).load()
+    assert "more than one cluster" in dup.rejected()
+    with pytest.raises(mbsv.MbsvError) as e:
+        dup.packed()
+    assert e.value.status == -6
+    with pytest.raises(mbsv.MbsvError, match="cannot open"):
+        _host(mbsv, "/nonexistent", a, exp).load()
+    for bad in (["--numiterations", "5"], ["--clusterfile", c, "--assignmentfile", a, "--experimentfile", exp, "--perr", "2",
+                                            "--numiterations", "5"], ["--bogus"]):
+        with pytest.raises(ValueError):
+            host.MultiBreakSV(bad)
+
+
+def test_hashmap_order_matches_oracle_including_collisions(mbsv, oracle):
+    from multibreak_sv_b200 import host
+    rng = np.random.default_rng(3)
+    for n in (1, 12, 13, 24, 25, 49, 97, 1000, 20000):
+        ks = [f"longread_{v}" for v in rng.choice(10 ** 7, n, replace=False)]
+        o_order, o_cap, o_tree = oracle.hashmap_order(ks)
+        h_order, h_cap = host.java_hashmap_order(ks)
+        assert not o_tree and h_order == o_order and h_cap == o_cap
+    # "Aa" and "BB" share a hashCode: 2^k colliding keys exercise treeifyBin()'s resize below capacity 64
+    coll = ["".join(p) for p in __import__("itertools").product(("Aa", "BB"), repeat=4)]      # 16 equal hashes
+    for n in (8, 9, 10):
+        o_order, o_cap, o_tree = oracle.hashmap_order(coll[:n])
+        assert not o_tree
+        h_order, h_cap = host.java_hashmap_order(coll[:n])
+        assert h_order == o_order and h_cap == o_cap
+    assert oracle.hashmap_order(coll[:10])[1] == 64                      # 9th and 10th entries doubled 16 -> 32 -> 64
+    assert oracle.hashmap_order(coll[:11])[2] is True                    # next one lands in a 10-entry bin at capacity 64
+    with pytest.raises(ValueError):
+        host.java_hashmap_order(coll[:11])
+
+
+def test_double_to_string(mbsv):
+    from multibreak_sv_b200 import host
+    want = {834.0: "834.0", 0.391: "0.391", 0.999: "0.999", 1e-4: "1.0E-4", 1e7: "1.0E7", 9999999.0: "9999999.0",
+            0.001: "0.001", 123456789.125: "1.23456789125E8", -35.263569332642774: "-35.263569332642774",
+            0.0: "0.0", 1 / 3: "0.3333333333333333", 100.0: "100.0", 1.5e-5: "1.5E-5", -2.5e10: "-2.5E10",
+            float("inf"): "Infinity", 608 / 1000: "0.608"}
+    for v, s in want.items():
+        assert host.java_double_to_string(v) == s, (v, s)
+    assert host.java_double_to_string(float("nan")) == "NaN"
+
+
+def test_write_final_files_format(mbsv, oracle, example_problem, tmp_path):
+    """writeFinalFiles (MultiBreakSV.java:1754-1792) from the oracle's tallies of the 10,000-iteration example run."""
+    sv = _host(mbsv, os.path.join(EXAMPLE, "gasv.clusters"), os.path.join(EXAMPLE, "assignments.txt"),
+               os.path.join(EXAMPLE, "experiments.txt"), extra=["--prefix", os.path.join(str(tmp_path), "out")]).load()
+    r = oracle.run(example_problem, "faithful", 10000)
+    sv.setResults(r.aln_count, r.frag_err_count, r.cluster_hist)
+    sv.writeFinalFiles()
+    bp = open(os.path.join(str(tmp_path), "out.finalbreakpoints.longburnin")).read().splitlines()
+    assert bp[0] == "ClusterID\tNumIters\tSupport0\tSupport1\tSupport2..."
+    assert [l.split("\t")[0] for l in bp[1:]] == example_problem.names["cluster_id"]          # breakpoints.keySet() order
+    row = dict((l.split("\t")[0], l.split("\t")) for l in bp[1:])["c4125"]
+    assert row[1] == "1000" and len(row) == 2 + 27
+    assert row[2:6] == ["1.0", "0.0", "165.0", "834.0"]       # bin 0 = burnin - sum(bins >= 1): 999 samples / 1000
+    asg = open(os.path.join(str(tmp_path), "out.finalassignment.longburnin")).read().splitlines()
+    assert asg[0] == "FragmentID\tAssignmentIndex\tAvgAssignment\tDiscordantPairs"
+    assert asg[1] == "longread_118669\t-1\t0.0\terror"
+    assert asg[2] == "longread_118669\t0\t0.325\tlongread_118669_0.0.0-0.1.0"
+    body = [l.split("\t") for l in asg[1:]]
+    assert [b[0] for b in body] == sorted(b[0] for b in body) and len(body) == 69 + 4
+    l74 = [b for b in body if b[0] == "longread_118674"]
+    assert [b[2] for b in l74] == ["0.0", "0.608", "0.391"]
+    l73 = [b for b in body if b[0] == "longread_118673" and b[1] == "-1"][0]
+    assert l73[2] == "0.999"
+    multi = [b for b in body if "," in b[3]]
+    assert len(multi) == 17 and all(", " not in b[3] for b in multi)
