@@ -72,6 +72,15 @@ int mbsv_host_batch_create(mbsv_host* const* hosts, int32_t n, mbsv_host_batch**
 int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* out);
 int mbsv_host_batch_destroy(mbsv_host_batch* b);
 
+/* generateIndependentSubproblems.pl (src/generateIndependentSubproblems.pl): connected components of the bipartite graph
+   long-read id (`longread_(\d+)` inside each ESP, :58) <-> cluster id over the non-dotted rows of a clusters file.
+   Subset k (1-based) is the component holding the numerically smallest long-read id not in subsets 1..k-1 (:85,107-113).
+   Writes <outdir>/subset-k.clusters (full lines, file order; dotted maximal-cluster rows are dropped exactly as the
+   script drops them) when outdir is not NULL; row_subset[i] (may be NULL, length max_rows) receives the subset of
+   physical line i of the file or 0 for dropped lines.  Returns the number of subsets or a negative status.
+   Union-find: O(rows * alpha) instead of the script's O(|subset|^2) scans (:130-141). */
+int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* row_subset, int32_t max_rows);
+
 /* Java's Double.toString (shortest repr, JDK 19+ behaviour) into buf; returns the length. */
 int mbsv_java_double_to_string(double v, char* buf, int32_t buflen);
 /* keySet() order of a java.util.HashMap<String,?> after inserting the n NUL-separated keys (test hook). */

@@ -843,6 +843,103 @@ int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* d) {
 }
 int mbsv_host_batch_destroy(mbsv_host_batch* b) { delete b; return MBSV_OK; }
 
+int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* row_subset, int32_t max_rows) {
+    if (!clusterfile) return hfail(MBSV_ERR_ARG, "clusters file is required");
+    std::string buf;
+    if (!slurp(clusterfile, buf)) return hfail(MBSV_ERR_IO, std::string("cannot open ") + clusterfile);
+    // physical lines (Perl: while (<CLUST>) { chomp; ... })
+    std::vector<std::string> lines;
+    for (size_t p = 0; p < buf.size();) {
+        size_t q = buf.find('\n', p);
+        if (q == std::string::npos) q = buf.size();
+        lines.push_back(buf.substr(p, q - p));
+        p = q + 1;
+    }
+    std::unordered_map<std::string, int> cid_last_line;      // $fulllines{$cid}: the last row of a cID wins
+    std::unordered_map<std::string, int> lr_node;            // long-read id string -> node
+    std::vector<long long> lr_value;                          // numeric value for the `<=>` sort
+    std::vector<int> parent;
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    auto node_of = [&](const std::string& lr) {
+        auto it = lr_node.find(lr);
+        if (it != lr_node.end()) return it->second;
+        const int id = (int)parent.size();
+        lr_node.emplace(lr, id);
+        parent.push_back(id);
+        lr_value.push_back(std::strtoll(lr.c_str(), nullptr, 10));
+        return id;
+    };
+    std::vector<int> line_node(lines.size(), -1);            // a long read of the row (all of them get united)
+    std::string last_lr;                                     // Perl's $1 keeps its previous value when the match fails
+    for (size_t i = 0; i < lines.size(); ++i) {
+        const std::vector<std::string> row = split(lines[i], "\t");
+        const std::string& cid = row[0];
+        if (cid.find('.') != std::string::npos) continue;    // maximal clusters are skipped (:52)
+        cid_last_line[cid] = (int)i;
+        if (row.size() < 5) continue;
+        int first = -1;
+        // split(/,\s*/, $row[4])
+        const std::string& list = row[4];
+        for (size_t p = 0; p <= list.size();) {
+            size_t q = list.find(',', p);
+            if (q == std::string::npos) q = list.size();
+            const std::string esp = list.substr(p, q - p);
+            p = q + 1;
+            while (p < list.size() && (list[p] == ' ' || list[p] == '\t')) ++p;
+            const size_t m = esp.find("longread_");
+            size_t d = m == std::string::npos ? std::string::npos : m + 9, e = d;
+            while (e != std::string::npos && e < esp.size() && esp[e] >= '0' && esp[e] <= '9') ++e;
+            if (d != std::string::npos && e > d) last_lr = esp.substr(d, e - d);
+            const int n = node_of(last_lr);
+            if (first < 0) first = n; else parent[find(n)] = find(first);
+            if (q == list.size()) break;
+        }
+        line_node[i] = first;
+    }
+    // a repeated cID only keeps its last row, but its long reads were linked through every row it appeared in
+    // (the script's %longreads accumulates over all rows while %clusters is overwritten): link rows of one cID
+    {
+        std::unordered_map<std::string, int> cid_first;
+        for (size_t i = 0; i < lines.size(); ++i) {
+            if (line_node[i] < 0) continue;
+            const std::string cid = split(lines[i], "\t")[0];
+            auto it = cid_first.find(cid);
+            if (it == cid_first.end()) cid_first.emplace(cid, line_node[i]);
+            else parent[find(line_node[i])] = find(it->second);
+        }
+    }
+    // subsets numbered by their numerically smallest long read
+    const int L = (int)parent.size();
+    std::vector<long long> comp_min(L, -1);
+    for (int n = 0; n < L; ++n) {
+        const int r = find(n);
+        if (comp_min[r] < 0 || lr_value[n] < comp_min[r]) comp_min[r] = lr_value[n];
+    }
+    std::vector<int> roots;
+    for (int n = 0; n < L; ++n) if (find(n) == n) roots.push_back(n);
+    std::sort(roots.begin(), roots.end(), [&](int a, int b) { return comp_min[a] < comp_min[b]; });
+    std::vector<int> subset_of_root(L, 0);
+    for (size_t k = 0; k < roots.size(); ++k) subset_of_root[roots[k]] = (int)k + 1;
+    std::vector<int> line_subset(lines.size(), 0);
+    for (const auto& kv : cid_last_line) {
+        const int i = kv.second;
+        if (line_node[i] >= 0) line_subset[i] = subset_of_root[find(line_node[i])];
+    }
+    if (row_subset) for (int i = 0; i < max_rows && i < (int)lines.size(); ++i) row_subset[i] = line_subset[i];
+    if (outdir) {
+        std::vector<std::ofstream> out;
+        // at most a few thousand files are kept open at once: write subset by subset
+        std::vector<std::vector<int>> members(roots.size() + 1);
+        for (size_t i = 0; i < lines.size(); ++i) if (line_subset[i] > 0) members[line_subset[i]].push_back((int)i);
+        for (size_t k = 1; k < members.size(); ++k) {
+            std::ofstream w(std::string(outdir) + "/subset-" + std::to_string(k) + ".clusters");
+            if (!w) return hfail(MBSV_ERR_IO, "cannot write subset file");
+            for (int i : members[k]) w << lines[i] << "\n";
+        }
+    }
+    return (int)roots.size();
+}
+
 int mbsv_java_double_to_string(double v, char* buf, int32_t buflen) {
     const std::string s = java_double(v);
     if (buf && buflen > 0) { std::strncpy(buf, s.c_str(), buflen - 1); buf[buflen - 1] = 0; }

@@ -37,6 +37,7 @@ def _bind(L):
     L.mbsv_host_batch_create.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(vp)]
     L.mbsv_host_batch_desc.argtypes = [vp, C.POINTER(ProblemDesc)]
     L.mbsv_host_batch_destroy.argtypes = [vp]
+    L.mbsv_host_partition.argtypes = [C.c_char_p, C.c_char_p, I32P, C.c_int32]
     L.mbsv_java_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int32]
     L.mbsv_java_hashmap_order.argtypes = [C.c_char_p, C.c_int32, I32P, I32P]
     L._host_bound = True
@@ -58,6 +59,17 @@ def java_hashmap_order(keys):
     if n < 0:
         raise ValueError("a HashMap bin would be treeified")
     return [keys[i] for i in out[:n]], cap.value
+
+
+def generateIndependentSubproblems(clusterfile: str, outdir: str | None = None):
+    """src/generateIndependentSubproblems.pl: returns (number of subsets, subset id of every physical line — 0 for
+    the dotted maximal-cluster rows the script drops) and writes <outdir>/subset-N.clusters when outdir is given."""
+    L = _bind(load_library())
+    nlines = sum(1 for _ in open(clusterfile))
+    rows = np.zeros(max(1, nlines), np.int32)
+    n = L.mbsv_host_partition(clusterfile.encode(), outdir.encode() if outdir else None, rows.ctypes.data_as(I32P), nlines)
+    check(min(n, 0))
+    return n, rows[:nlines]
 
 
 def _desc_to_packed(d: ProblemDesc) -> PackedProblem:

@@ -172,3 +172,55 @@ def test_write_final_files_format(mbsv, oracle, example_problem, tmp_path):
     assert l73[2] == "0.999"
     multi = [b for b in body if "," in b[3]]
     assert len(multi) == 17 and all(", " not in b[3] for b in multi)
+
+
+PERL_SPLITTER = "/root/reference/src/generateIndependentSubproblems.pl"
+
+
+@pytest.mark.skipif(not os.path.exists(PERL_SPLITTER), reason="the reference's Perl script is only present in the build container")
+@pytest.mark.parametrize("cfg,nfrag,cc", [("cfg4", 700, 0.3), ("cfg2", 2000, 0.0)])
+def test_partition_matches_the_reference_perl_script(mbsv, tmp_path, cfg, nfrag, cc):
+    """Live oracle for the partition: the unmodified generateIndependentSubproblems.pl (line order inside a subset
+    file is Perl-hash-random, so files are compared as sets of lines; the numbering must match exactly)."""
+    import subprocess
+    from multibreak_sv_b200 import host, synth
+    g = synth.generate(cfg, n_frag=nfrag, seed=2718, conncomp_frac=cc)
+    # long-read numbers in shuffled order so that "smallest unseen id" differs from file order
+    nums = np.random.default_rng(1).permutation(nfrag) * 3 + 1000
+    paths = synth.write_reference_files(g, str(tmp_path), frag_numbers=nums)
+    pdir, ndir = os.path.join(str(tmp_path), "perl"), os.path.join(str(tmp_path), "native")
+    os.makedirs(pdir); os.makedirs(ndir)
+    subprocess.run(["perl", PERL_SPLITTER, paths["clusters"], pdir], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    n, rows = host.generateIndependentSubproblems(paths["clusters"], ndir)
+    pfiles = sorted(os.listdir(pdir))
+    assert len(pfiles) == n >= g.scalars["n_sub"] and sorted(os.listdir(ndir)) == pfiles
+    for f in pfiles:
+        assert sorted(open(os.path.join(pdir, f)).read().splitlines()) == sorted(open(os.path.join(ndir, f)).read().splitlines()), f
+    lines = open(paths["clusters"]).read().splitlines()
+    assert all((r == 0) == ("." in l.split("\t")[0]) for r, l in zip(rows, lines))
+
+
+def test_partition_then_batch_refines_generator_subproblems(mbsv, oracle, tmp_path):
+    """partition -> one host per subset file (--readclustersfirst) -> batch: every fragment lands in exactly one
+    subproblem, and each connected component lies inside one generated subproblem (the generator does not force
+    its subproblems to be connected, so the partition may be finer)."""
+    from multibreak_sv_b200 import host, synth
+    g = synth.generate("cfg4", n_frag=300, seed=99)
+    paths = synth.write_reference_files(g, str(tmp_path))
+    sdir = os.path.join(str(tmp_path), "subs")
+    os.makedirs(sdir)
+    n, _ = host.generateIndependentSubproblems(paths["clusters"], sdir)
+    assert n >= g.scalars["n_sub"]
+    hosts = [_host(mbsv, os.path.join(sdir, f"subset-{k}.clusters"), paths["assignments"], paths["experiments"], cf=True).load()
+             for k in range(1, n + 1)]
+    b = host.batch(hosts)
+    assert b.scalars["n_sub"] == n and b.scalars["n_frag"] == 300 and b.scalars["n_aln"] == g.scalars["n_aln"]
+    fp = g.arrays["sub_frag_ptr"]
+    gen_sub = {f"longread_{(f + 1) * 7 + 100000}": s for s in range(g.scalars["n_sub"]) for f in range(fp[s], fp[s + 1])}
+    seen = set()
+    for h in hosts:
+        ids = h.names(0, h.packed().scalars["n_frag"])
+        assert len({gen_sub[i] for i in ids}) == 1 and not (seen & set(ids))
+        seen |= set(ids)
+    assert seen == set(gen_sub)
