@@ -184,3 +184,63 @@ def test_host_main_file_to_file(oracle, mbsv, example_problem, tmp_path):
     # HashMap iteration order of the state strings
     assert ["\t".join(l.split("\t")[2:]) for l in sp[1:]] == oracle.hashmap_order(list(dict.fromkeys(
         "\t".join(str(row[i]) for i in order) for row in st)))[0]
+
+
+def _exact_posterior(oracle, p):
+    """Exact marginals of a tiny single-subproblem PackedProblem by enumeration: per fragment P(assignment), per
+    cluster the distribution of the support value (sum over experiments of selected-ESP counts listed separately)."""
+    op = oracle.Problem(p.scalars, p.arrays)
+    lp = oracle.enumerate_logprobs(op, 0, 0.05)
+    w = np.exp(lp - lp.max()); w /= w.sum()
+    a = p.arrays
+    nal = np.diff(a["frag_aln_ptr"])
+    F, C, E = p.scalars["n_frag"], p.scalars["n_cluster"], p.scalars["n_exp"]
+    frag = [np.zeros(n + 1) for n in nal]
+    hist = np.zeros(p.scalars["n_hist"])
+    for s in range(len(w)):
+        t = s
+        cnt = np.zeros((C, E), int)
+        for f in range(F):
+            d = t % (nal[f] + 1); t //= (nal[f] + 1)
+            frag[f][d] += w[s]
+            if d > 0:
+                al = a["frag_aln_ptr"][f] + d - 1
+                for j in range(a["aln_esp_ptr"][al], a["aln_esp_ptr"][al + 1]):
+                    if a["aln_esp_cluster"][j] >= 0:
+                        cnt[a["aln_esp_cluster"][j], a["aln_exp"][al]] += 1
+        for c in range(C):
+            for x in range(E):
+                if cnt[c, x] > 0:
+                    hist[a["cluster_hist_ptr"][c] + cnt[c, x]] += w[s]
+    return frag, hist
+
+
+def test_multichain_posterior_within_monte_carlo_error(oracle, mbsv):
+    """Statistical tier: pooled multi-chain posteriors (fragment assignments and cluster-support histograms) agree
+    with the exactly enumerated posterior within 4 Monte-Carlo standard errors estimated from independent batches.
+    Fragments have <= 2 alignments so that the reference's biased 'other n-1' scan (quirk Q1) cannot bite."""
+    from multibreak_sv_b200 import synth
+    p = None
+    for seed in range(300):
+        q = synth.generate("cfg4", n_frag=6, seed=5000 + seed)
+        nal = np.diff(q.arrays["frag_aln_ptr"])
+        if q.scalars["n_sub"] == 1 and nal.max() == 2 and q.scalars["n_sv"] > 0:
+            p = q
+            break
+    assert p is not None
+    frag, hist = _exact_posterior(oracle, p)
+    dp = mbsv.DeviceProblem(p)
+    B, X, N = 12, 256, 6000
+    burn = N - 2000                                   # window = the last 1999 iterations
+    est_f, est_h = [], []
+    fp = p.arrays["frag_aln_ptr"]
+    for b in range(B):
+        g = dp.run(mbsv.MODE_FAST, N, n_chains=X, perr=0.05, seed=1000 * (b + 1), burnin=N - burn, per_chain=False,
+                   want_state=False)
+        nwin = (N - max(N - (N - burn) + 1, 0)) * X
+        est_f.append(np.concatenate([np.concatenate([[g.frag_err_count[f]], g.aln_count[fp[f]:fp[f + 1]]]) for f in range(6)]) / nwin)
+        est_h.append(g.cluster_hist / nwin)
+    for est, exact in ((np.array(est_f), np.concatenate(frag)), (np.array(est_h), hist)):
+        mean, se = est.mean(0), est.std(0, ddof=1) / np.sqrt(B)
+        z = np.abs(mean - exact) / np.maximum(se, 1e-4)
+        assert z.max() < 4.5, (z.max(), mean[z.argmax()], exact[z.argmax()])
