@@ -193,7 +193,7 @@ class DeviceProblem:
 
     def run(self, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 1, perr: float = 0.001,
             seed: int = 123456, burnin: int | None = None, java_int_wrap: bool | None = None, init_assign=None,
-            trace: bool = False, want_state: bool = True, per_chain: bool = True, memo_states: int = 256) -> RunOutput:
+            trace: bool = False, want_state: bool = True, per_chain: bool = True, memo_states: int = 65536) -> RunOutput:
         """MultiBreakSV.runMCMC (MultiBreakSV.java:773-877) for every (subproblem, chain), on the GPU."""
         s = self.packed.scalars
         S, F = s["n_sub"], s["n_frag"]
@@ -250,7 +250,7 @@ class DeviceProblem:
 
     def run_device(self, tensors: dict, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 1,
                    perr: float = 0.001, seed: int = 123456, burnin: int | None = None, java_int_wrap: bool = False,
-                   memo_states: int = 256):
+                   memo_states: int = 65536):
         """mbsv_run_device: `tensors` maps result-field names to DEVICE pointers (e.g. torch tensor.data_ptr()) on
         this problem's GPU; aln_count, frag_err_count, cluster_hist and totals are required.  Returns
         (status, kernel_ms)."""

@@ -6,8 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -77,7 +79,11 @@ struct mbsv_problem {
     int plan_memo = -1, plan_tab = -1;
     std::vector<int> sub_rows;    // tile rows of a warp of subproblem s (state + memo table)
     std::vector<int> sub_memo;    // joint states when the subproblem uses the memoised arithmetic, else 0
-    std::vector<char> sub_tab;    // 1: runs in the memoised kernel (table in shared memory)
+    std::vector<char> sub_tab;    // 1: runs in the memoised kernel
+    std::vector<long long> sub_tab_off;   // its table: offset (doubles) in the global table buffer, -1 = shared memory
+    long long memo_global_doubles = 0;
+    DevBuf<long long> d_sub_tab_off;
+    DevBuf<double> d_memo_global;
     std::vector<int> sub_order;   // memoised-kernel subproblems first, each group by ascending sub_rows (stable)
     int n_tab_subs = 0;
     int64_t csr_bytes = 0;
@@ -239,13 +245,24 @@ static int validate(const mbsv_problem_desc* d) {
 int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem** out) {
     if (!out) return fail(MBSV_ERR_ARG, "out is NULL");
     *out = nullptr;
+    static const bool dbg = std::getenv("MBSV_DEBUG_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mbsv create] %-10s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     int rc = validate(d);
     if (rc) return rc;
+    lap("validate");
     const int S = d->n_sub, F = d->n_frag, A = d->n_aln, K = d->n_aln_esp, C = d->n_cluster, E = d->n_exp;
     // Packing + per-subproblem checks, parallel over subproblems (they are independent and contiguous).
-    std::vector<int4> rec(A);
-    std::vector<int> slot(K, -1);
-    std::vector<int> sup_local(C);
+    // uninitialised buffers: the worker threads touch (and page in) their own parts
+    std::unique_ptr<int4[]> rec(new (std::nothrow) int4[(size_t)A]);
+    std::unique_ptr<int[]> slot(new (std::nothrow) int[(size_t)K + 1]);
+    std::unique_ptr<int[]> sup_local(new (std::nothrow) int[(size_t)C + 1]);
+    if (!rec || !slot || !sup_local) return fail(MBSV_ERR_OOM, "host allocation failed");
     int maxn = 1;
     {
         const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
@@ -278,6 +295,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                             rec[a] = make_int4(d->aln_numerrors[a], d->aln_len[a], j0, x | ((j1 - j0) << 8));
                             for (int j = j0; j < j1; ++j) {
                                 const int c = d->aln_esp_cluster[j];
+                                slot[j] = -1;
                                 if (c == -1) continue;
                                 if (c < c0 || c >= c1) { bad(MBSV_ERR_ARG, "aln_esp_cluster points outside the fragment's subproblem"); continue; }
                                 const int cl = c - c0;
@@ -323,6 +341,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
             maxn = std::max(maxn, t_maxn[t]);
         }
     }
+    lap("pack");
     std::vector<int> sub_sv_ptr(S + 1, 0), sv_frag_ptr(1, 0), sv_frag, sv_numchanged;
     if (d->n_sv > 0) {
         sub_sv_ptr.assign(d->sub_sv_ptr, d->sub_sv_ptr + S + 1);
@@ -352,6 +371,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     for (int n = 1; n <= maxn; ++n) logint[n] = mbsv::jm_log((double)n);
     for (int x = 0; x < E; ++x) { logp[x] = mbsv::jm_log(d->exp_pseq[x]); log1mp[x] = mbsv::jm_log(1 - d->exp_pseq[x]); }
 
+    lap("sv+logs");
     // every host-side check is done; from here on a CUDA device is required (no CPU fallback)
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -392,9 +412,9 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     chk(p->d_sub_cluster_ptr.upload_raw(d->sub_cluster_ptr, S + 1));
     chk(up(p->d_sub_sv_ptr, sub_sv_ptr));
     chk(p->d_frag_aln_ptr.upload_raw(d->frag_aln_ptr, F + 1));
-    chk(up(p->d_aln_rec, rec));
-    chk(up(p->d_aln_esp_slot, slot));
-    chk(up(p->d_supports_local, sup_local));
+    chk(p->d_aln_rec.upload_raw(rec.get(), A));
+    chk(p->d_aln_esp_slot.upload_raw(slot.get(), K));
+    chk(p->d_supports_local.upload_raw(sup_local.get(), C));
     if (C > 0) chk(p->d_cluster_hist_ptr.upload_raw(d->cluster_hist_ptr, C + 1)); else chk(up(p->d_cluster_hist_ptr, std::vector<int>(1, 0)));
     chk(up(p->d_sv_frag_ptr, sv_frag_ptr));
     chk(up(p->d_sv_frag, sv_frag));
@@ -493,19 +513,29 @@ KernelFn pick(int mode, bool trace, bool smem, int E) {
 // (Re)build the launch plan: which subproblems use the memoised arithmetic (memo_states), which of those run in the
 // memoised kernel (only when every warp holds chains of one subproblem, i.e. n_chains % 32 == 0, and the table fits
 // the largest shared-memory class), tile rows per warp, launch order.
-constexpr int MAX_SMEM_ROWS = 128;
+constexpr int SMEM_TABLE_ROWS = 48;   // tiles up to this many rows keep the table in shared memory
 int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
     if (p->plan_memo == memo_states && p->plan_tab == (int)tab_ok) return 0;
     const int S = p->n_sub;
     p->sub_rows.resize(S); p->sub_memo.assign(S, 0); p->sub_tab.assign(S, 0); p->sub_order.resize(S);
+    p->sub_tab_off.assign(S, -1);
     p->n_tab_subs = 0;
+    p->memo_global_doubles = 0;
     for (int s = 0; s < S; ++s) {
         int rows = p->sub_W[s];
         const int nst = p->sub_nstates[s];
         if (memo_states > 0 && nst > 0 && nst <= memo_states) {
             p->sub_memo[s] = nst;
-            const int with_table = rows + (2 * nst + p->sub_F[s] + 31) / 32;   // log-posterior table + fragment strides
-            if (tab_ok && with_table <= MAX_SMEM_ROWS) { p->sub_tab[s] = 1; rows = with_table; ++p->n_tab_subs; }
+            if (tab_ok) {
+                // fragment strides always sit after the state rows; the log-posterior table follows them when the
+                // whole tile still fits the small size classes, else it lives in the global table buffer
+                const int fr = (p->sub_F[s] + 1) & ~1;
+                const int with_table = rows + (fr + 2 * nst + 31) / 32;
+                p->sub_tab[s] = 1;
+                ++p->n_tab_subs;
+                if (with_table <= SMEM_TABLE_ROWS) rows = with_table;
+                else { rows += (fr + 31) / 32; p->sub_tab_off[s] = p->memo_global_doubles; p->memo_global_doubles += nst; }
+            }
         }
         p->sub_rows[s] = rows;
     }
@@ -516,6 +546,8 @@ int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
     });
     CUDA_TRY(p->d_sub_order.upload(p->sub_order));
     CUDA_TRY(p->d_sub_memo.upload(p->sub_memo));
+    CUDA_TRY(p->d_sub_tab_off.upload(p->sub_tab_off));
+    CUDA_TRY(p->d_memo_global.alloc((size_t)p->memo_global_doubles));
     p->plan_memo = memo_states;
     p->plan_tab = (int)tab_ok;
     return 0;
@@ -560,6 +592,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     dr.java_int_wrap = rp->java_int_wrap; dr.perr = rp->perr; dr.logperr = mbsv::jm_log(rp->perr);
     dr.log1mperr = mbsv::jm_log(1 - rp->perr); dr.seed = rp->seed;
     dr.sub_order = p->d_sub_order.p; dr.sub_W = p->d_sub_W.p; dr.sub_memo = p->d_sub_memo.p; dr.n_items = n_items;
+    dr.sub_tab_off = p->d_sub_tab_off.p; dr.memo_global = p->d_memo_global.p;
 
     if (rp->init_assign) {
         if (results_on_device) dr.init_assign = rp->init_assign;

@@ -657,7 +657,7 @@ int mbsv_host_run_mcmc(mbsv_host* h, int32_t num_iters, double perr, int32_t mod
     mbsv_run_params rp;
     std::memset(&rp, 0, sizeof rp);
     rp.mode = mode; rp.n_chains = 1; rp.num_iters = num_iters; rp.burnin = h->burnin; rp.perr = perr; rp.seed = 123456;
-    rp.device = device; rp.java_int_wrap = 1; rp.init_assign = init_assign; rp.trace = save_space ? 0 : 1; rp.memo_states = 256;
+    rp.device = device; rp.java_int_wrap = 1; rp.init_assign = init_assign; rp.trace = save_space ? 0 : 1; rp.memo_states = 65536;
     h->r_aln.assign(d.n_aln, 0); h->r_frag.assign(d.n_frag, 0); h->r_hist.assign(d.n_hist, 0); h->r_init.assign(d.n_frag, 0);
     std::vector<int32_t> fin(d.n_frag, 0), errv(1, 0);
     std::vector<double> flp(1, 0.0), ilp(1, 0.0);

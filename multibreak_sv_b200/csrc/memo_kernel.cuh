@@ -43,8 +43,12 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     const int N = alive ? R.num_iters : 0;
     const int W = R.sub_W[sub];
     const int nst = R.sub_memo[sub];
-    double* tab = reinterpret_cast<double*>(smem_tile + ((size_t)wic * R.rows_per_warp + W) * 32);
-    int* strides = reinterpret_cast<int*>(tab + nst);
+    // after the state rows: fragment strides, then the table — in shared memory when it fits the size classes,
+    // otherwise in a global buffer (one region per subproblem; both warps of a subproblem fill it with the same
+    // values and each reads only after its own complete build)
+    int* strides = smem_tile + ((size_t)wic * R.rows_per_warp + W) * 32;
+    const long long tab_off = R.sub_tab_off[sub];
+    double* tab = tab_off >= 0 ? R.memo_global + tab_off : reinterpret_cast<double*>(strides + ((F + 1) & ~1));
     const double logperr = R.logperr;
     const int win_base = R.win_base;
 

@@ -48,6 +48,8 @@ struct DevRun {
     const int* sub_order;            // subproblems by ascending state size
     const int* sub_W;                // state rows per chain of each subproblem
     const int* sub_memo;             // per subproblem: joint states if it takes the memoised path, else 0 (or NULL)
+    const long long* sub_tab_off;    // memoised kernel: offset of the subproblem's table in memo_global, -1 = shared memory
+    double* memo_global;
     long long n_items;               // n_sub * n_chains
     const long long* warp_row_off;   // [warp - global_warp0] row offset into workspace (global class)
     int* workspace;

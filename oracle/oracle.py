@@ -305,7 +305,7 @@ def alloc_results(prob: Problem, n_chains: int, num_iters: int, trace: bool, res
 
 def run(prob: Problem, mode: str = "faithful", num_iters: int = 10000, n_chains: int = 1, perr: float = 0.001,
         seed: int = 123456, burnin: int | None = None, java_int_wrap: bool = True, init_assign=None,
-        trace: bool = False, nthreads: int = 1, memo_states: int = 256) -> RunResult:
+        trace: bool = False, nthreads: int = 1, memo_states: int = 65536) -> RunResult:
     """MultiBreakSV.runMCMC (MultiBreakSV.java:773-877) on every (subproblem, chain) of `prob`, on the CPU."""
     d = prob.desc(OrcDesc)
     p = OrcParams()
