@@ -155,6 +155,25 @@ struct JavaRandom {
         s = s * MULT + ADD;
         return (uint32_t)((s & MASK) >> (48 - bits));
     }
+    // advance by m steps without producing values (draws whose value cannot influence the chain)
+    template <int M_STEPS> JM_HD void skip() { s = s * jump_mul(M_STEPS) + jump_add(M_STEPS); }
+    // the 53-bit integer of nextDouble(): nextDouble() == bits53() * 2^-53, so `nextDouble() < p` is the integer
+    // comparison bits53() < ceil(p * 2^53)
+    JM_HD uint64_t bits53() {
+        uint64_t s1 = s * MULT + ADD;
+        uint64_t s2 = s * MULT2 + ADD2;
+        s = s2;
+        return (((s1 & MASK) >> 22) << 27) + ((s2 & MASK) >> 21);
+    }
+    static JM_HD double to_double(uint64_t m53) {
+#if defined(__CUDA_ARCH__)
+        const double da = __hiloint2double(0x43300000, (int)(m53 >> 27)) - 4503599627370496.0;
+        const double db = __hiloint2double(0x43300000, (int)(m53 & 0x7FFFFFFu)) - 4503599627370496.0;
+        return da * 0x1.0p-26 + db * 0x1.0p-53;
+#else
+        return (double)(int64_t)m53 * 0x1.0p-53;
+#endif
+    }
     JM_HD double nextDouble() {
         uint64_t s1 = s * MULT + ADD;      // independent of s2: both multiplies issue back to back
         uint64_t s2 = s * MULT2 + ADD2;

@@ -74,6 +74,7 @@ struct mbsv_problem {
     int n_sub = 0, n_frag = 0, n_aln = 0, n_cluster = 0, n_exp = 0, n_hist = 0;
     std::vector<int> sub_W;       // state rows of a chain of subproblem s (F_s + C_s*E + conn-comp blocks)
     std::vector<int> sub_F;       // fragments of subproblem s
+    std::vector<int> sub_nsv;     // AlterSV candidates of subproblem s
     std::vector<int> sub_nstates; // joint state space prod(n_f + 1), saturated at 2^30; 0 when it has a conn-comp
     // launch plan, depends on mbsv_run_params.memo_states (cached for the last value used)
     int plan_memo = -1, plan_tab = -1;
@@ -403,6 +404,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
             nst *= (long long)(d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]) + 1;
         p->sub_nstates.push_back((int)std::min<long long>(nst, 1LL << 30));
         p->sub_F.push_back(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]);
+        p->sub_nsv.push_back(sub_sv_ptr[s + 1] - sub_sv_ptr[s]);
     }
 
     auto up = [&](auto& buf, const auto& vec) -> cudaError_t { return buf.upload(vec); };
@@ -530,7 +532,9 @@ int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
                 // fragment strides always sit after the state rows; the log-posterior table follows them when the
                 // whole tile still fits the small size classes, else it lives in the global table buffer
                 const int fr = (p->sub_F[s] + 1) & ~1;
-                const int with_table = rows + (fr + 2 * nst + 31) / 32;
+                // one-fragment subproblems without AlterSV candidates also tabulate the acceptance ratios (nst^2)
+                const int ratio_words = (p->sub_F[s] == 1 && p->sub_nsv[s] == 0) ? 2 * nst * nst : 0;
+                const int with_table = rows + (fr + 2 * nst + ratio_words + 31) / 32;
                 p->sub_tab[s] = 1;
                 ++p->n_tab_subs;
                 if (with_table <= SMEM_TABLE_ROWS) rows = with_table;

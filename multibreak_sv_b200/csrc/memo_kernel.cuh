@@ -51,6 +51,11 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     double* tab = tab_off >= 0 ? R.memo_global + tab_off : reinterpret_cast<double*>(strides + ((F + 1) & ~1));
     const double logperr = R.logperr;
     const int win_base = R.win_base;
+    const double neglogF = -P.sub_logF[sub];
+    // One-fragment subproblems without AlterSV candidates (the bulk of a power-law batch): the whole acceptance
+    // ratio min(1, exp(..)) of every (previous, proposed) pair is tabulated too, so a proposal needs no exp.
+    const bool f1 = (F == 1) && (nsv == 0) && (tab_off < 0);
+    double* rtab = tab + nst;
 
     // ---------------- table: log-posterior of every joint state (fragment 0 = least significant digit) ----------------
     {
@@ -97,6 +102,21 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
             if (lane == 0) {
                 int sprod = 1;
                 for (int f = 0; f < F; ++f) { strides[f] = sprod; sprod *= P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f] + 1; }
+            }
+        }
+        __syncwarp();
+        if (f1 && alive) {
+            const int n = nst - 1;                      // alignments of the only fragment
+            for (int idx = lane; idx < nst * nst; idx += nalive) {
+                const int pv = idx / nst - 1, nw = idx % nst - 1;
+                double ratio = 0.0;
+                if (pv != nw) {
+                    double Alogq, Anewlogq;
+                    naive_logq(n, pv, nw, neglogF, logperr, R.log1mperr, P.logint, Alogq, Anewlogq);
+                    const double e = exp_dev((tab[nw + 1] + Alogq) - (tab[pv + 1] + Anewlogq));   // :1146
+                    ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);
+                }
+                rtab[idx] = ratio;
             }
         }
         __syncwarp();
@@ -174,8 +194,9 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     };
 
     // ---------------- iterations (MultiBreakSV.java:796-837, 1101-1182) ----------------
-    const double neglogF = -P.sub_logF[sub];
     const double neglogNsv = P.sub_neglogNsv[sub];
+    const unsigned long long perr_thr = prob_threshold53(R.perr);
+    constexpr unsigned long long NAIVE_THR = 0x1CCCCCCCCCCCCDULL;   // 0.9 * 2^53: nextDouble() < 0.9
     int n_naive_prop = 0, n_naive_acc = 0, n_sv_prop = 0, n_sv_acc = 0;
     long long n_sv_reassign = 0;
     int err = 0;
@@ -201,39 +222,55 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
         if (__all_sync(0xffffffffu, done)) break;
         if (!live) continue;
         const int t = iter;
-        double r = rng.nextDouble();
-        const bool naive = (r < 0.9) || (nsv == 0);
-        const double u = rng.nextDouble();
-        int f = -1, a0 = 0, prev = -1, now = -1, svk = -1, q0 = 0, nmoves = 1;
-        double Alogq, Anewlogq;
+        bool naive = true;
+        int f = 0, a0 = 0, prev = -1, now = -1, svk = -1, q0 = 0, nmoves = 1;
         int newidx = sidx;
-        if (naive) {
+        double newlogprob, ratio;
+        if (f1) {
+            // move-type coin and fragment pick are consumed but cannot matter (no AlterSV candidate, one fragment)
+            rng.skip<4>();
             ++n_naive_prop;
-            f = (int)(u * (double)F);
-            a0 = P.frag_aln_ptr[f0 + f];
-            const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
-            prev = MBSV_ST(f);
-            naive_pick(rng, n, prev, neglogF, R.perr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
+            a0 = P.frag_aln_ptr[f0];
+            prev = sidx - 1;
+            now = naive_draw(rng, nst - 1, prev, perr_thr);
             if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
-            newidx += (now - prev) * strides[f];
+            newidx = now + 1;
+            newlogprob = tab[newidx];
+            ratio = rtab[sidx * nst + newidx];
         } else {
-            ++n_sv_prop;
-            svk = (int)(u * (double)nsv);
-            n_sv_reassign += P.sv_numchanged[sv0 + svk];
-            q0 = P.sv_frag_ptr[sv0 + svk];
-            nmoves = P.sv_frag_ptr[sv0 + svk + 1] - q0;
-            Alogq = neglogNsv;
-            Anewlogq = neglogNsv;
-            for (int q = 0; q < nmoves; ++q) {
-                const int g = P.sv_frag[q0 + q] - f0;
-                const int from = MBSV_ST(g);
-                newidx += ((from == -1) ? 1 : -1) * strides[g];
+            if (nsv == 0) rng.skip<2>(); else naive = rng.bits53() < NAIVE_THR;
+            double u = 0.0;
+            if (naive && F == 1) rng.skip<2>(); else u = rng.nextDouble();
+            double Alogq, Anewlogq;
+            if (naive) {
+                ++n_naive_prop;
+                f = (int)(u * (double)F);
+                a0 = P.frag_aln_ptr[f0 + f];
+                const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
+                prev = MBSV_ST(f);
+                naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
+                if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
+                newidx += (now - prev) * strides[f];
+            } else {
+                ++n_sv_prop;
+                svk = (int)(u * (double)nsv);
+                n_sv_reassign += P.sv_numchanged[sv0 + svk];
+                q0 = P.sv_frag_ptr[sv0 + svk];
+                nmoves = P.sv_frag_ptr[sv0 + svk + 1] - q0;
+                Alogq = neglogNsv;
+                Anewlogq = neglogNsv;
+                for (int q = 0; q < nmoves; ++q) {
+                    const int g = P.sv_frag[q0 + q] - f0;
+                    const int from = MBSV_ST(g);
+                    newidx += ((from == -1) ? 1 : -1) * strides[g];
+                }
             }
+            newlogprob = tab[newidx];
+            const double arg = (newlogprob + Alogq) - (logprob + Anewlogq);      // :1146
+            const double e = exp_dev(arg);
+            ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);                          // Math.min(1, e)
         }
-        const double newlogprob = tab[newidx];
-        const double arg = (newlogprob + Alogq) - (logprob + Anewlogq);      // :1146
-        const double e = exp_dev(arg);
-        const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);             // Math.min(1, e)
+        double r;
         r = rng.nextDouble();
         const bool accept = ratio > r;
         if (accept) {

@@ -83,35 +83,53 @@ __device__ __forceinline__ void lazy_skip(JavaRandom& rng, int& iter, const int 
 // naiveMove (MultiBreakSV.java:1198-1272): new assignment of a fragment with n alignments currently at `prev`, and the
 // proposal log-probabilities of the reverse (Alogq) and forward (Anewlogq) moves.  Includes quirk Q1: the scan over
 // "the other n-1" is biased when prev == 0.  The cumulative sums are accumulated exactly as the reference does.
-__device__ __forceinline__ void naive_pick(JavaRandom& rng, const int n, const int prev, const double neglogF,
-                                           const double perr, const double logperr, const double log1mperr,
-                                           const double* __restrict__ logint, int& now, double& Alogq, double& Anewlogq) {
-    double r = rng.nextDouble();
+// ceil(p * 2^53) as an integer threshold: nextDouble() < p  <=>  bits53() < threshold  (p * 2^53 is exact)
+__device__ __forceinline__ unsigned long long prob_threshold53(double p) {
+    const double x = p * 9007199254740992.0;
+    if (!(x > 0.0)) return 0ULL;
+    if (x >= 9007199254740992.0) return 1ULL << 53;
+    return __double2ull_ru(x);
+}
+
+// which alignment naiveMove draws (MultiBreakSV.java:1198-1256); `now` = -1 for "unmapped".  Consumes one or two
+// nextDouble()s exactly as the reference does.
+__device__ __forceinline__ int naive_draw(JavaRandom& rng, const int n, const int prev, const unsigned long long perr_thr) {
+    const unsigned long long m = rng.bits53();
     if (prev == -1) {
+        const double r = JavaRandom::to_double(m);
         int thisassign = 0;
         const double inc = (double)1 / n;
         double sum = inc;
         while (thisassign < n - 1 && r > sum) { ++thisassign; sum += inc; }
-        now = thisassign;
-        if (n == 1) { Alogq = neglogF + 0.0; Anewlogq = neglogF + 0.0; }
-        else { Alogq = neglogF + logperr; Anewlogq = neglogF - logint[n]; }
-    } else if (r < perr || n == 1) {
-        now = -1;
-        if (n == 1) { Alogq = neglogF + 0.0; Anewlogq = neglogF + 0.0; }
-        else { Alogq = neglogF - logint[n]; Anewlogq = neglogF + logperr; }
-    } else {
-        int thisassign = 0;
-        r = rng.nextDouble();
-        const double inc = (double)1 / (n - 1);
-        double sum = inc;
-        while (thisassign < n - 1 && (thisassign == prev || r > sum)) {
-            ++thisassign;
-            if (thisassign != prev) sum += inc;
-        }
-        now = thisassign;
-        Anewlogq = neglogF + log1mperr - logint[n - 1];
-        Alogq = Anewlogq;
+        return thisassign;
     }
+    if (m < perr_thr || n == 1) return -1;
+    const double r = rng.nextDouble();
+    int thisassign = 0;
+    const double inc = (double)1 / (n - 1);
+    double sum = inc;
+    while (thisassign < n - 1 && (thisassign == prev || r > sum)) {
+        ++thisassign;
+        if (thisassign != prev) sum += inc;
+    }
+    return thisassign;
+}
+
+// proposal log-probabilities of the reverse (Alogq) and forward (Anewlogq) Naive moves (:1218-1271)
+__device__ __forceinline__ void naive_logq(const int n, const int prev, const int now, const double neglogF,
+                                           const double logperr, const double log1mperr,
+                                           const double* __restrict__ logint, double& Alogq, double& Anewlogq) {
+    if (n == 1 && (prev == -1 || now == -1)) { Alogq = neglogF + 0.0; Anewlogq = neglogF + 0.0; }
+    else if (prev == -1) { Alogq = neglogF + logperr; Anewlogq = neglogF - logint[n]; }
+    else if (now == -1) { Alogq = neglogF - logint[n]; Anewlogq = neglogF + logperr; }
+    else { Anewlogq = neglogF + log1mperr - logint[n - 1]; Alogq = Anewlogq; }
+}
+
+__device__ __forceinline__ void naive_pick(JavaRandom& rng, const int n, const int prev, const double neglogF,
+                                           const unsigned long long perr_thr, const double logperr, const double log1mperr,
+                                           const double* __restrict__ logint, int& now, double& Alogq, double& Anewlogq) {
+    now = naive_draw(rng, n, prev, perr_thr);
+    naive_logq(n, prev, now, neglogF, logperr, log1mperr, logint, Alogq, Anewlogq);
 }
 
 // One atomic per counter per converged group of lanes.

@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
     const double neglogF = -logF;
     const double perr = R.perr, logperr = R.logperr;
     const double dF = (double)F;
+    const unsigned long long perr_thr = prob_threshold53(perr);
+    constexpr unsigned long long NAIVE_THR = 0x1CCCCCCCCCCCCDULL;   // 0.9 * 2^53 exactly: nextDouble() < 0.9
 
     JavaRandom rng;
     rng.seed(R.seed + chain);
@@ -344,13 +346,16 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
         if (__all_sync(0xffffffffu, done)) break;
         if (!live) continue;
         const int t = iter;
-        r = rng.nextDouble();
-        const bool naive = (r < 0.9) || (nsv == 0);
+        // Move-type coin (:1115-1118): its value cannot matter when there is no AlterSV candidate; the fragment pick
+        // (:1400) cannot matter for a one-fragment problem.  The draws are still consumed.
+        bool naive = true;
+        if (nsv == 0) rng.skip<2>(); else naive = rng.bits53() < NAIVE_THR;
         // A proposal is a list of single-fragment moves: one for Naive, the cluster's single-alignment
         // fragments for AlterSV.  Both kinds run through the same code below.
         int f = -1, a0 = 0, prev = -1, now = -1, svk = -1, q0 = 0, nmoves = 1;
         double Alogq, Anewlogq;
-        const double u = rng.nextDouble();
+        double u = 0.0;
+        if (naive && F == 1) rng.skip<2>(); else u = rng.nextDouble();
         if (naive) {
             // ---- naiveMove (:1184-1273) ----
             ++n_naive_prop; ++n_reassign;
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
             a0 = P.frag_aln_ptr[f0 + f];
             const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
             prev = MBSV_ST(f);
-            naive_pick(rng, n, prev, neglogF, perr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
+            naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
             if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
         } else {
             // ---- svMove (:1291-1343) ----
