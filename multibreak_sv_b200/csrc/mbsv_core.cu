@@ -83,7 +83,12 @@ struct mbsv_problem {
     std::vector<char> sub_tab;    // 1: runs in the memoised kernel
     std::vector<long long> sub_tab_off;   // its table: offset (doubles) in the global table buffer, -1 = shared memory
     long long memo_global_doubles = 0;
-    DevBuf<long long> d_sub_tab_off;
+    std::vector<long long> tab_state_ptr;  // device-memory tables: first global state of each such subproblem (+ total)
+    std::vector<int> tab_sub;              // ... and the subproblem
+    int tab_scratch_rows = 0;              // max clusters x experiments among them
+    DevBuf<long long> d_sub_tab_off, d_tab_state_ptr;
+    DevBuf<int> d_tab_sub;
+    cudaEvent_t ev_built = nullptr;
     DevBuf<double> d_memo_global;
     std::vector<int> sub_order;   // memoised-kernel subproblems first, each group by ascending sub_rows (stable)
     int n_tab_subs = 0;
@@ -466,6 +471,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         chk(cudaEventCreate(&p->ev_cls0[i]));
         chk(cudaEventCreate(&p->ev_cls1[i]));
     }
+    chk(cudaEventCreateWithFlags(&p->ev_built, cudaEventDisableTiming));
     chk(cudaEventCreate(&p->ev_start));
     chk(cudaEventCreate(&p->ev_stop));
     if (e != cudaSuccess) { delete p; return fail(MBSV_ERR_CUDA, std::string("stream setup: ") + cudaGetErrorString(e)); }
@@ -482,6 +488,7 @@ int mbsv_problem_destroy(mbsv_problem* p) {
             cudaStreamDestroy(p->streams[i]); cudaEventDestroy(p->ev_done[i]);
             cudaEventDestroy(p->ev_cls0[i]); cudaEventDestroy(p->ev_cls1[i]);
         }
+        cudaEventDestroy(p->ev_built);
         cudaEventDestroy(p->ev_start);
         cudaEventDestroy(p->ev_stop);
     }
@@ -523,6 +530,7 @@ int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
     p->sub_tab_off.assign(S, -1);
     p->n_tab_subs = 0;
     p->memo_global_doubles = 0;
+    p->tab_state_ptr.clear(); p->tab_sub.clear(); p->tab_scratch_rows = 1;
     for (int s = 0; s < S; ++s) {
         int rows = p->sub_W[s];
         const int nst = p->sub_nstates[s];
@@ -538,7 +546,14 @@ int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
                 p->sub_tab[s] = 1;
                 ++p->n_tab_subs;
                 if (with_table <= SMEM_TABLE_ROWS) rows = with_table;
-                else { rows += (fr + 31) / 32; p->sub_tab_off[s] = p->memo_global_doubles; p->memo_global_doubles += nst; }
+                else {
+                    rows += (fr + 31) / 32;
+                    p->sub_tab_off[s] = p->memo_global_doubles;
+                    p->tab_state_ptr.push_back(p->memo_global_doubles);
+                    p->tab_sub.push_back(s);
+                    p->tab_scratch_rows = std::max(p->tab_scratch_rows, p->sub_W[s] - p->sub_F[s]);
+                    p->memo_global_doubles += nst;
+                }
             }
         }
         p->sub_rows[s] = rows;
@@ -552,6 +567,9 @@ int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
     CUDA_TRY(p->d_sub_memo.upload(p->sub_memo));
     CUDA_TRY(p->d_sub_tab_off.upload(p->sub_tab_off));
     CUDA_TRY(p->d_memo_global.alloc((size_t)p->memo_global_doubles));
+    p->tab_state_ptr.push_back(p->memo_global_doubles);
+    CUDA_TRY(p->d_tab_state_ptr.upload(p->tab_state_ptr));
+    CUDA_TRY(p->d_tab_sub.upload(p->tab_sub));
     p->plan_memo = memo_states;
     p->plan_tab = (int)tab_ok;
     return 0;
@@ -691,6 +709,16 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     if ((int)launches.size() > NSTREAM - 1) return fail(MBSV_ERR_ARG, "too many size classes");
 
     CUDA_TRY(cudaEventRecord(p->ev_start, s0));
+    // device-memory memo tables are filled once per run by a fully parallel kernel; only the launches that read them
+    // wait for it
+    const bool have_global_tables = !p->tab_sub.empty();
+    if (have_global_tables) {
+        mbsv::DevRun rb = dr;
+        CUDA_TRY(mbsv::launch_memo_build(p->dp, rb, (int)p->tab_sub.size(), p->d_tab_state_ptr.p, p->d_tab_sub.p,
+                                         p->memo_global_doubles, p->tab_scratch_rows, s0));
+        ++g_launches;
+        CUDA_TRY(cudaEventRecord(p->ev_built, s0));
+    }
     int nstream = 0;
     for (const Launch& l : launches) {
         mbsv::DevRun r = dr;
@@ -707,7 +735,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         // MBSV_SERIAL_LAUNCHES=1 (tuning aid): run the size classes back to back on one stream
         static const bool serial = std::getenv("MBSV_SERIAL_LAUNCHES") != nullptr;
         cudaStream_t st = serial ? p->streams[1] : p->streams[1 + nstream];
-        CUDA_TRY(cudaStreamWaitEvent(st, p->ev_start, 0));
+        CUDA_TRY(cudaStreamWaitEvent(st, (l.memo && have_global_tables) ? p->ev_built : p->ev_start, 0));
         const int grid = (l.we - l.wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         CUDA_TRY(cudaEventRecord(p->ev_cls0[1 + nstream], st));
         fn<<<grid, WARPS_PER_CTA * 32, shm, st>>>(p->dp, r);

@@ -20,6 +20,64 @@ namespace mbsv {
 #define MBSV_MEMO_MIN_BLOCKS 8
 #endif
 
+// Fills the device-memory tables: one thread per joint state of every subproblem whose table does not fit the
+// shared-memory classes.  state_ptr[k] is the first global state of the k-th such subproblem (ascending), so a thread
+// finds its (subproblem, state) by binary search; the counts of the state live in a [slot][thread] shared-memory
+// scratch (one column per thread, bank-conflict free).
+__global__ void __launch_bounds__(128) mbsv_memo_build_kernel(const __grid_constant__ DevProblem P,
+                                                              const __grid_constant__ DevRun R, const int n_tab,
+                                                              const long long* __restrict__ state_ptr,
+                                                              const int* __restrict__ tab_sub, const int scratch_rows) {
+    extern __shared__ int smem_tile[];
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= state_ptr[n_tab]) return;
+    int lo = 0, hi = n_tab - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (state_ptr[mid] <= g) lo = mid; else hi = mid - 1; }
+    const int sub = tab_sub[lo];
+    const int idx = (int)(g - state_ptr[lo]);
+    int* cnt = smem_tile + threadIdx.x;                 // cnt[slot * 128]
+    const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
+    const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
+    const int E = P.n_exp, Tstride = P.max_support + 1;
+    if (C * E > scratch_rows) return;                   // cannot happen: the host sizes the scratch
+    for (int i = 0; i < C * E; ++i) cnt[i * 128] = 0;
+    long long Et[MBSV_MAX_EXP], Lt[MBSV_MAX_EXP];
+    for (int x = 0; x < MBSV_MAX_EXP; ++x) { Et[x] = 0; Lt[x] = 0; }
+    int nerr = 0, rem = idx;
+    for (int f = 0; f < F; ++f) {
+        const int a0 = P.frag_aln_ptr[f0 + f];
+        const int n1 = P.frag_aln_ptr[f0 + f + 1] - a0 + 1;
+        const int a = rem % n1 - 1;
+        rem /= n1;
+        if (a == -1) { ++nerr; continue; }
+        const int4 rec = P.aln_rec[a0 + a];
+        const int x = rec.w & 0xff, ne = rec.w >> 8;
+        for (int j = 0; j < ne; ++j) {
+            const int slot = P.aln_esp_slot[rec.z + j];
+            if (slot >= 0) cnt[slot * 128] += 1;
+        }
+        Et[x] += rec.x; Lt[x] += rec.y;
+    }
+    double lp = 0;
+    for (int i = 0; i < C; ++i) {
+        const int cl = P.supports_order_local[c0 + i];
+        double lpc = 0.0;
+        for (int x = 0; x < E; ++x) {
+            const int n = cnt[(cl * E + x) * 128];
+            if (n > 0) lpc = lpc + P.T[(size_t)x * Tstride + n];
+        }
+        lp += lpc;
+    }
+    lp += 0.0;
+    lp += (double)nerr * R.logperr;
+    for (int x = 0; x < E; ++x) {
+        long long e = Et[x], l = Lt[x];
+        if (R.java_int_wrap) { e = (long long)(int)(unsigned)(unsigned long long)e; l = (long long)(int)(unsigned)(unsigned long long)l; }
+        lp += log_binomial_dev(e, l, P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi, P.logint, P.maxn);
+    }
+    R.memo_global[R.sub_tab_off[sub] + idx] = lp;
+}
+
 template <bool TRACE>
 __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(const __grid_constant__ DevProblem P,
                                                                               const __grid_constant__ DevRun R) {
@@ -61,7 +119,8 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     {
         const int nalive = __popc(__ballot_sync(0xffffffffu, alive));
         if (alive) {
-            for (int idx = lane; idx < nst; idx += nalive) {
+            // tables in device memory were filled by mbsv_memo_build_kernel before this launch
+            for (int idx = lane; idx < (tab_off >= 0 ? 0 : nst); idx += nalive) {
                 for (int i = F; i < F + C * E; ++i) MBSV_ST(i) = 0;
                 long long Et[MBSV_MAX_EXP], Lt[MBSV_MAX_EXP];
                 for (int x = 0; x < MBSV_MAX_EXP; ++x) { Et[x] = 0; Lt[x] = 0; }

@@ -80,5 +80,8 @@ KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_E
 KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
 KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with connected-component clusters
 KernelFn get_kernel_memo(bool trace);                           // memoised subproblems (memo_kernel.cuh)
+// fills the device-memory log-posterior tables of the memoised subproblems listed in tab_sub
+cudaError_t launch_memo_build(const DevProblem& P, const DevRun& R, int n_tab, const long long* state_ptr, const int* tab_sub,
+                              long long n_states, int scratch_rows, cudaStream_t stream);
 
 }  // namespace mbsv
