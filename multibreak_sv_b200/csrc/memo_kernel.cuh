@@ -198,20 +198,29 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
             }
             MBSV_ST(f) = a;
             sidx += (a + 1) * strides[f];
-            if (a != -1) {
-                const int4 rec = P.aln_rec[a0 + a];
-                const int ne = rec.w >> 8;
-                for (int j = 0; j < ne; ++j) {
-                    const int slot = P.aln_esp_slot[rec.z + j];
-                    if (slot >= 0) MBSV_ST(F + slot) += 1;
-                }
-            }
             if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
         }
     }
     double logprob = alive ? tab[sidx] : 0.0;
     if (alive && R.initial_logprob) R.initial_logprob[sc] = logprob;
 
+    // The selected-ESP counts only feed the support tallies, so they are rebuilt from the assignments when a chain first
+    // needs them (its first accepted move inside the long-burn-in window, or the epilogue) and maintained from then on.
+    bool counts_live = false;
+    auto rebuild_counts = [&]() {
+        for (int i = F; i < F + C * E; ++i) MBSV_ST(i) = 0;
+        for (int f = 0; f < F; ++f) {
+            const int a = MBSV_ST(f);
+            if (a == -1) continue;
+            const int4 rec = P.aln_rec[P.frag_aln_ptr[f0 + f] + a];
+            const int ne = rec.w >> 8;
+            for (int j = 0; j < ne; ++j) {
+                const int slot = P.aln_esp_slot[rec.z + j];
+                if (slot >= 0) MBSV_ST(F + slot) += 1;
+            }
+        }
+        counts_live = true;
+    };
     // Counts follow an accepted single-fragment move; inside the long-burn-in window every unit step also emits
     // the support-histogram difference tallies (value n leaves: +d, value n' enters: -d).
     auto apply_move = [&](int g, int a0, int from, int to, unsigned d) {
@@ -336,12 +345,18 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
             logprob = newlogprob;
             sidx = newidx;
             const unsigned d = t > win_base ? (unsigned)(t - win_base) : 0u;
-            if (naive) {
-                ++n_naive_acc;
-                apply_move(f, a0, prev, now, d);
+            if (naive) ++n_naive_acc; else ++n_sv_acc;
+            if (d == 0u && !counts_live) {
+                // before the window only the assignments move
+                if (naive) MBSV_ST(f) = now;
+                else for (int q = 0; q < nmoves; ++q) {
+                    const int g = P.sv_frag[q0 + q] - f0;
+                    MBSV_ST(g) = (MBSV_ST(g) == -1) ? 0 : -1;
+                }
             } else {
-                ++n_sv_acc;
-                for (int q = 0; q < nmoves; ++q) {
+                if (!counts_live) rebuild_counts();
+                if (naive) apply_move(f, a0, prev, now, d);
+                else for (int q = 0; q < nmoves; ++q) {
                     const int g = P.sv_frag[q0 + q] - f0;
                     const int from = MBSV_ST(g);
                     apply_move(g, P.frag_aln_ptr[f0 + g], from, (from == -1) ? 0 : -1, d);
@@ -362,6 +377,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
         const long long nwin = (long long)N - win_base;
         if (nwin > 0) {
             const unsigned d = (unsigned)nwin;
+            if (!counts_live) rebuild_counts();
             for (int f = 0; f < F; ++f) {
                 const int a = MBSV_ST(f);
                 if (a == -1) atomicAdd(&R.frag_err_count[f0 + f], d);
