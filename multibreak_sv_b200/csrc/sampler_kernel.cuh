@@ -434,12 +434,21 @@ __global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const 
         } else {
             double dlb = 0.0;
 #pragma unroll
-            for (int x = 0; x < MAXE; ++x) {
-                newLB[x] = LB[x];
-                if (x < E && ((touched >> x) & 1u)) {
-                    newLB[x] = lb_of(x, Etot[x], Ltot[x]);
-                    dlb = dlb + (newLB[x] - LB[x]);
-                }
+            for (int x = 0; x < MAXE; ++x) newLB[x] = LB[x];
+            // Each lane walks ITS touched experiments in ascending order (same summation order as before), so lanes
+            // whose proposals touch different platforms evaluate logBinomial together instead of one platform at a time.
+            unsigned mask = touched & ((1u << E) - 1u);
+            while (mask) {
+                const int x = __ffs(mask) - 1;
+                mask &= mask - 1;
+                long long ex = 0, lx = 0;
+                double old = 0.0;
+#pragma unroll
+                for (int y = 0; y < MAXE; ++y) if (y == x) { ex = Etot[y]; lx = Ltot[y]; old = LB[y]; }
+                const double nl = lb_of(x, ex, lx);
+#pragma unroll
+                for (int y = 0; y < MAXE; ++y) if (y == x) newLB[y] = nl;
+                dlb = dlb + (nl - old);
             }
             const double delta = (dcov + derr) + dlb;
             newlogprob = logprob + delta;
