@@ -24,11 +24,16 @@ namespace mbsv {
 #ifndef MBSV_MIN_BLOCKS
 #define MBSV_MIN_BLOCKS 5
 #endif
+// Launch bounds of the global-workspace class (large subproblems).  Measured on B200: 8 blocks/SM (64 registers, spills)
+// is slower than 5 (96 registers) both alone (289 vs 267 ms) and next to the other classes.
+#ifndef MBSV_MIN_BLOCKS_GLOBAL
+#define MBSV_MIN_BLOCKS_GLOBAL 5
+#endif
 
 // CC = the batch contains connected-component clusters (GASV localization -1): their support is the sorted
 // multiset of a greedy set cover (MultiBreakSVAssignmentMatrix.java:337-409) kept per chain next to the counts.
 template <int MODE, bool TRACE, bool SMEM, int MAXE, bool CC = false>
-__global__ void __launch_bounds__(128, MBSV_MIN_BLOCKS) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
+__global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_GLOBAL) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
                                                          const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
