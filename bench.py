@@ -207,7 +207,8 @@ def main():
     ap.add_argument("--config", default="cfg4")
     ap.add_argument("--n-frag", type=int, default=0, help="fragments per GPU (default: the config's)")
     ap.add_argument("--chains", type=int, default=0)
-    ap.add_argument("--iters", type=int, default=2000, help="MH iterations per chain per step")
+    ap.add_argument("--iters", type=int, default=5000,
+                    help="MH iterations per chain per step (a full reference run is 1e5; setup costs amortise with it)")
     ap.add_argument("--mode", default="fast", choices=["fast", "replay"])
     ap.add_argument("--cpu-iterations", type=float, default=2.0e9,
                     help="chain-iterations in the bounded CPU sample (about 10-30 s on the host cores)")

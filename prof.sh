@@ -1,6 +1,9 @@
 set -x
 mkdir -p gpurun_out
-SMALL="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --n-frag 1000000 --iters 500"
+SMALL="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --n-frag 1000000 --iters 1000"
+python bench.py > gpurun_out/bench_default.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01.csv python bench.py > gpurun_out/ncu_launches.log 2>&1
 $SMALL > gpurun_out/plain_small.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:mbsv_ -s 12 -c 12 -o gpurun_out/prof_r01d $SMALL > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_full.log | cut -c1-300
+ncu --set full --clock-control none --import-source on -k regex:mbsv_ -s 13 -c 13 -o gpurun_out/prof_r01_final $SMALL > gpurun_out/ncu_full.log 2>&1
+tail -1 gpurun_out/bench_default.log | cut -c1-400
+tail -2 gpurun_out/ncu_full.log | cut -c1-200
