@@ -345,7 +345,7 @@ def main():
             issue = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_reduced_config": traffic_other, "peak_source": peak_src,
-                "kernel": "mbsv_chain_kernel<FAST> (all size classes, one launch per state-size class)",
+                "kernel": "mbsv_memo_kernel + mbsv_chain_kernel<FAST> (one launch per state-size class, concurrent streams)",
                 "kernel_ms_per_step": kernel_ms / args.steps, "algorithmic_bytes_per_step": alg,
                 "binding": issue,
                 "note": "algorithmic bytes are served from shared memory / L1 / L2 (chain state is SM-resident), so "
