@@ -154,6 +154,10 @@ def build_workload(args, rank, world):
     from multibreak_sv_b200 import sharding, synth
     cfg = synth.CONFIGS[args.config]
     per_gpu = args.n_frag if args.n_frag else cfg.n_frag
+    if cfg.sub_sizes == "single":
+        # giant component (BASELINE configs[4]): cannot be split spatially; every rank holds the same subproblem and
+        # runs its share of the chains (sharding.split_chains), tallies are summed with one reduce
+        return cfg, synth.generate(cfg, n_frag=per_gpu)
     sk = synth.draw_skeleton(cfg, n_frag=per_gpu * world)
     if world > 1:
         part = sharding.lpt_shard(sk.weights * args.chains, world)
@@ -250,8 +254,18 @@ def main():
             "totals": torch.zeros(6, dtype=torch.int64, device=dev)}
     ptrs = {k: v.data_ptr() for k, v in bufs.items()}
 
+    giant = cfg.sub_sizes == "single"
+    my_first, my_chains = 0, args.chains
+    if giant:
+        from multibreak_sv_b200 import sharding
+        my_first, my_chains = sharding.split_chains(args.chains, world, rank)
+
     def step():
-        st, ms = dp.run_device(ptrs, mode=mode, num_iters=args.iters, n_chains=args.chains)
+        st, ms = dp.run_device(ptrs, mode=mode, num_iters=args.iters, n_chains=my_chains, seed=123456 + my_first)
+        if giant and world > 1:
+            # one reduce of the integer tallies onto rank 0 (NCCL over NVLink)
+            for k in ("aln_count", "frag_err_count", "cluster_hist"):
+                dist.reduce(bufs[k], dst=0, op=dist.ReduceOp.SUM)
         return ms
 
     for _ in range(args.warmup):
@@ -297,7 +311,7 @@ def main():
         e2e_launches = 0
         for _ in range(args.steps):
             d2 = mbsv.DeviceProblem(p, device=local_rank)
-            out = d2.run(mode, args.iters, n_chains=args.chains, want_state=False, per_chain=False)
+            out = d2.run(mode, args.iters, n_chains=my_chains, seed=123456 + my_first, want_state=False, per_chain=False)
             e2e_launches += out.launches
             d2h = out.result_bytes
             if int(out.totals[5]) != 0:
@@ -370,7 +384,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg.name, "fragments_per_gpu": sc["n_frag"] if world == 1 else args.n_frag or cfg.n_frag,
                        "subproblems_rank0": sc["n_sub"], "alignments_rank0": sc["n_aln"], "chains": args.chains,
-                       "iters_per_step": args.iters, "mode": args.mode, "sharding": "lpt" if world > 1 else "none",
+                       "iters_per_step": args.iters, "mode": args.mode,
+                       "sharding": ("chains split + reduce" if giant else "lpt") if world > 1 else "none",
                        "l2": "inputs larger than L2 (CSR + chain state >> 126 MB); no flush"},
             "iterations_per_s": (sc["n_sub"] * args.chains * args.iters) * args.steps / dt_max if world == 1 else None,
             "accepted_per_s": acc_all * args.steps / dt_max, "proposals_per_s": prop_all * args.steps / dt_max,

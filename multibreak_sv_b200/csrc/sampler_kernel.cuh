@@ -220,21 +220,43 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
         }
     };
 
-    // MultiBreakSVAssignmentMatrix.java:130-246 in the reference's summation order.
+    // MultiBreakSVAssignmentMatrix.java:130-246 in the reference's summation order.  Clusters are taken four at a time so
+    // that the index / count / table loads of a batch are in flight together (the chain state of a large subproblem lives
+    // in device memory); the additions keep the reference's order: per cluster over experiments, then cluster by cluster.
     auto full_logprob = [&]() -> double {
         double lp = 0;
-        for (int i = 0; i < C; ++i) {
-            const int cl = P.supports_order_local[c0 + i];
-            double lpc = 0.0;
-            if (CC && P.cluster_cc_off[c0 + cl] >= 0) {
-                lpc = cc_lpc(cl);
+        constexpr int B = 4;
+        for (int i = 0; i < C; i += B) {
+            int cl[B];
+            double lpc[B];
+            bool any_cc = false;
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                cl[k] = (i + k < C) ? P.supports_order_local[c0 + i + k] : -1;
+                lpc[k] = 0.0;
+                if (CC && cl[k] >= 0 && P.cluster_cc_off[c0 + cl[k]] >= 0) any_cc = true;
+            }
+            if (CC && any_cc) {
+#pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    if (cl[k] < 0) continue;
+                    if (P.cluster_cc_off[c0 + cl[k]] >= 0) lpc[k] = cc_lpc(cl[k]);
+                    else for (int x = 0; x < E; ++x) {
+                        const int n = MBSV_ST(F + cl[k] * E + x);
+                        if (n > 0) lpc[k] = lpc[k] + P.T[(size_t)x * Tstride + n];
+                    }
+                }
             } else {
                 for (int x = 0; x < E; ++x) {
-                    const int n = MBSV_ST(F + cl * E + x);
-                    if (n > 0) lpc = lpc + P.T[(size_t)x * Tstride + n];
+                    int n[B];
+#pragma unroll
+                    for (int k = 0; k < B; ++k) n[k] = cl[k] >= 0 ? MBSV_ST(F + cl[k] * E + x) : 0;
+#pragma unroll
+                    for (int k = 0; k < B; ++k) if (n[k] > 0) lpc[k] = lpc[k] + P.T[(size_t)x * Tstride + n[k]];
                 }
             }
-            lp += lpc;
+#pragma unroll
+            for (int k = 0; k < B; ++k) if (cl[k] >= 0) lp += lpc[k];
         }
         lp += 0.0;
         lp += (double)nerr * logperr;
@@ -298,21 +320,44 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
     {
         const int W = alive ? R.sub_W[sub] : 0;
         for (int i = 0; i < W; ++i) MBSV_ST(i) = 0;
-        double dc = 0.0, de = 0.0;
-        unsigned tch = 0;
-        nerr = F;   // move_counts(-1 -> a) decrements
+        // phase A: the draws of :999-1015 (serial RNG); the assignment goes straight to the state tile
         for (int f = 0; f < F; ++f) {
-            const int a0 = P.frag_aln_ptr[f0 + f];
-            const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
             int a;
             if (R.init_assign) a = R.init_assign[f0 + f];
             else {
                 if (rng.nextDouble() < perr) a = -1;
-                else a = rng.nextInt(n);
+                else a = rng.nextInt(P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f]);
             }
             MBSV_ST(f) = a;
-            if (a != -1) move_counts(a0, -1, a, dc, de, tch);
             if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
+        }
+        // phase B: counts and per-experiment totals, eight fragments at a time so that the dependent loads
+        // (assignment -> alignment record -> ESP slots) of a batch overlap; counts in a device-memory tile are
+        // bumped with fire-and-forget atomics (only this lane touches its column)
+        nerr = 0;
+        constexpr int IB = 8;
+        for (int fb = 0; fb < F; fb += IB) {
+            int a[IB], al[IB];
+#pragma unroll
+            for (int k = 0; k < IB; ++k) a[k] = (fb + k < F) ? MBSV_ST(fb + k) : -2;
+#pragma unroll
+            for (int k = 0; k < IB; ++k) al[k] = a[k] >= 0 ? P.frag_aln_ptr[f0 + fb + k] + a[k] : 0;
+            int4 rec[IB];
+#pragma unroll
+            for (int k = 0; k < IB; ++k) rec[k] = a[k] >= 0 ? P.aln_rec[al[k]] : make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < IB; ++k) {
+                if (a[k] == -1) ++nerr;
+                if (a[k] < 0) continue;
+                const int x = rec[k].w & 0xff, ne = rec[k].w >> 8;
+                for (int j = 0; j < ne; ++j) {
+                    const int slot = P.aln_esp_slot[rec[k].z + j];
+                    if (slot < 0) continue;
+                    if (SMEM) MBSV_ST(F + slot) += 1; else atomicAdd(&MBSV_ST(F + slot), 1);
+                }
+#pragma unroll
+                for (int y = 0; y < MAXE; ++y) if (y == x) { Etot[y] += rec[k].x; Ltot[y] += rec[k].y; }
+            }
         }
 #pragma unroll
         for (int x = 0; x < MAXE; ++x) if (x < E) LB[x] = lb_of(x, Etot[x], Ltot[x]);
@@ -578,19 +623,34 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
         const long long nwin = (long long)N - win_base;
         if (nwin > 0) {
             const unsigned d = (unsigned)nwin;
-            for (int f = 0; f < F; ++f) {
-                const int a = MBSV_ST(f);
-                if (a == -1) atomicAdd(&R.frag_err_count[f0 + f], d);
-                else atomicAdd(&R.aln_count[P.frag_aln_ptr[f0 + f] + a], d);
-            }
-            for (int cl = 0; cl < C; ++cl) {
-                if (CC && P.cluster_cc_off[c0 + cl] >= 0) { cc_hist(cl, 0, d); continue; }
-                unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + cl];
-                for (int x = 0; x < E; ++x) {
-                    const int n = MBSV_ST(F + cl * E + x);
-                    if (n > 0) atomicAdd(&h[n], d);
+            // eight loads in flight per batch: the state of a large subproblem is in device memory
+            constexpr int EB = 8;
+            for (int fb = 0; fb < F; fb += EB) {
+                int a[EB], a0[EB];
+#pragma unroll
+                for (int k = 0; k < EB; ++k) a[k] = (fb + k < F) ? MBSV_ST(fb + k) : -2;
+#pragma unroll
+                for (int k = 0; k < EB; ++k) a0[k] = a[k] >= 0 ? P.frag_aln_ptr[f0 + fb + k] : 0;
+#pragma unroll
+                for (int k = 0; k < EB; ++k) {
+                    if (a[k] == -1) atomicAdd(&R.frag_err_count[f0 + fb + k], d);
+                    else if (a[k] >= 0) atomicAdd(&R.aln_count[a0[k] + a[k]], d);
                 }
             }
+            const int nslot = C * E;
+            for (int sb = 0; sb < nslot; sb += EB) {
+                int n[EB], hp[EB];
+#pragma unroll
+                for (int k = 0; k < EB; ++k) {
+                    const bool ok = sb + k < nslot && !(CC && P.cluster_cc_off[c0 + (sb + k) / E] >= 0);
+                    n[k] = ok ? MBSV_ST(F + sb + k) : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < EB; ++k) hp[k] = n[k] > 0 ? P.cluster_hist_ptr[c0 + (sb + k) / E] : 0;
+#pragma unroll
+                for (int k = 0; k < EB; ++k) if (n[k] > 0) atomicAdd(&R.cluster_hist[hp[k] + n[k]], d);
+            }
+            if (CC) for (int cl = 0; cl < C; ++cl) if (P.cluster_cc_off[c0 + cl] >= 0) cc_hist(cl, 0, d);
         }
     }
     if (R.final_assign)

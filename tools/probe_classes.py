@@ -1,4 +1,5 @@
-import sys, time, os; sys.path.insert(0,'.')
+"""Tuning aid: device time of every launch (size class) of one sampler step on the 5M-fragment mixed config.\nMBSV_SERIAL_LAUNCHES=1 runs the classes back to back so that each time is the standalone cost."""
+import sys, time, os; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np
 import multibreak_sv_b200 as m
 from multibreak_sv_b200 import synth

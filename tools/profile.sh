@@ -1,3 +1,5 @@
+# Profiling recipe used for profiles/ (run under gpurun from the repo root): default bench, ncu launch list of the same
+# command, then ncu --set full on a reduced size; summaries: python profiles/summarize_ncu.py gpurun_out/prof_r01_final.ncu-rep profiles/<name>
 set -x
 mkdir -p gpurun_out
 SMALL="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --n-frag 1000000 --iters 1000"
