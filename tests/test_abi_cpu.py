@@ -48,6 +48,16 @@ def test_struct_layouts_match_header(mbsv):
     want = [C.sizeof(_abi.ProblemDesc), C.sizeof(_abi.RunParams), C.sizeof(_abi.Results),
             _abi.ProblemDesc.sub_frag_ptr.offset, _abi.RunParams.init_assign.offset, _abi.Results.kernel_ms.offset]
     assert got == want
+    # the literal offsets integration/java/MultiBreakSVGpu.java writes through (Panama FFM MemorySegment.set)
+    assert _abi.ProblemDesc.sub_frag_ptr.offset == 56 and C.sizeof(_abi.ProblemDesc) == 14 * 4 + 25 * 8
+    assert (_abi.RunParams.perr.offset, _abi.RunParams.seed.offset, _abi.RunParams.device.offset,
+            _abi.RunParams.init_assign.offset, _abi.RunParams.trace.offset, _abi.RunParams.memo_states.offset,
+            C.sizeof(_abi.RunParams)) == (16, 24, 32, 40, 48, 52, 56)
+    assert _abi.Results.kernel_ms.offset == 14 * 8 and C.sizeof(_abi.Results) == 14 * 8 + 8
+    java = open(os.path.join(ROOT, "integration", "java", "MultiBreakSVGpu.java")).read()
+    for needle in ("arena.allocate(14 * 4 + 25 * 8, 8)", "56L + 8L * i", "arena.allocate(56, 8)", "rp.set(JAVA_INT, 52, 65536)",
+                   "arena.allocate(14 * 8 + 8, 8)"):
+        assert needle in java
 
 
 def test_no_cpu_fallback(mbsv, example_problem):

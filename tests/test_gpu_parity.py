@@ -244,3 +244,38 @@ def test_multichain_posterior_within_monte_carlo_error(oracle, mbsv):
         mean, se = est.mean(0), est.std(0, ddof=1) / np.sqrt(B)
         z = np.abs(mean - exact) / np.maximum(se, 1e-4)
         assert z.max() < 4.5, (z.max(), mean[z.argmax()], exact[z.argmax()])
+
+
+def test_full_size_invariants(mbsv):
+    """BASELINE-size batch (mixed config, 64 chains): properties that do not need the oracle.
+    (1) every fragment's tallies sum to window x chains; (2) every (cluster, experiment) contributes at most one bin
+    per sample, so a cluster's histogram mass is <= E x window x chains; (3) proposals + lazy iterations = iterations,
+    with the lazy share near 1/2; (4) a second run reproduces the first bit for bit (no race in the atomics' sums);
+    (5) REPLAY_EXACT and FAST agree on every integer output of a sub-batch."""
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg4", n_frag=2_000_000)
+    dp = mbsv.DeviceProblem(p)
+    X, N = 64, 400
+    g = dp.run(mbsv.MODE_FAST, N, n_chains=X, want_state=False, per_chain=False)
+    burnin = mbsv.reference_burnin(N)
+    nwin = N - max(N - burnin + 1, 0)
+    a = p.arrays
+    per_frag = np.add.reduceat(g.aln_count.astype(np.int64), a["frag_aln_ptr"][:-1]) + g.frag_err_count
+    assert (per_frag == nwin * X).all()
+    hp = a["cluster_hist_ptr"]
+    mass = np.add.reduceat(g.cluster_hist.astype(np.int64), hp[:-1])
+    assert (g.cluster_hist[hp[:-1]] == 0).all()                         # bin 0 is derived by the host
+    assert (mass <= p.scalars["n_exp"] * nwin * X).all() and mass.sum() > 0
+    chains = p.scalars["n_sub"] * X
+    props = int(g.totals[0] + g.totals[2])
+    assert abs(props / (chains * N) - 0.5) < 0.002 and int(g.totals[5]) == 0
+    assert int(g.totals[1]) <= int(g.totals[0]) and int(g.totals[4]) >= props - int(g.totals[2])
+    g2 = dp.run(mbsv.MODE_FAST, N, n_chains=X, want_state=False, per_chain=False)
+    assert np.array_equal(g.aln_count, g2.aln_count) and np.array_equal(g.cluster_hist, g2.cluster_hist)
+    assert np.array_equal(g.totals, g2.totals)
+    small = synth.generate("cfg4", n_frag=60_000, seed=4)
+    ds = mbsv.DeviceProblem(small)
+    f = ds.run(mbsv.MODE_FAST, N, n_chains=X)
+    r = ds.run(mbsv.MODE_REPLAY_EXACT, N, n_chains=X, java_int_wrap=False)
+    for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "counters", "rng_state"):
+        assert np.array_equal(getattr(f, k), getattr(r, k)), k
