@@ -279,3 +279,17 @@ def test_full_size_invariants(mbsv):
     r = ds.run(mbsv.MODE_REPLAY_EXACT, N, n_chains=X, java_int_wrap=False)
     for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "counters", "rng_state"):
         assert np.array_equal(getattr(f, k), getattr(r, k)), k
+
+
+@pytest.mark.parametrize("n_chains", [1, 32, 64])
+def test_tiny_iteration_counts_without_trace(oracle, mbsv, example_problem, n_chains):
+    """The look-ahead lazy skip (non-trace kernels) at the end of a chain: every small N, generic and memoised kernels."""
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg4", n_frag=300, seed=12)
+    op = oracle.Problem(p.scalars, p.arrays)
+    dp, de = mbsv.DeviceProblem(p), mbsv.DeviceProblem(to_packed(mbsv, example_problem))
+    for n in (0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 16, 33):
+        for prob, oprob in ((dp, op), (de, example_problem)):
+            g = prob.run(mbsv.MODE_FAST, n, n_chains=n_chains)
+            o = oracle.run(oprob, "incremental", n, n_chains=n_chains, java_int_wrap=False)
+            assert_same(o, g)
