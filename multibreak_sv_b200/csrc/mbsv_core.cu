@@ -599,11 +599,21 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         return fail(MBSV_ERR_ARG, "trace requested without trace buffers");
     if (rp->memo_states < 0) return fail(MBSV_ERR_ARG, "memo_states must be >= 0");
     CUDA_TRY(cudaSetDevice(p->device));
-    if (int prc = ensure_plan(p, rp->memo_states, rp->n_chains % 32 == 0)) return prc;
-
     const int S = p->n_sub, X = rp->n_chains;
     const int64_t n_items = (int64_t)S * X;
-    const int64_t n_warps64 = (n_items + 31) / 32;
+    // Small batches run fewer chains per warp: one warp per scheduler issues an instruction only every ~8 cycles
+    // (each chain is one long dependency chain), so until the GPU holds its ~20 resident warps per SM more warps
+    // with idle lanes are faster than full warps.  L = chains per warp, a power of two.
+    int L = 32;
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+        const int64_t resident_warps = (int64_t)sms * 20;
+        while (L > 1 && (n_items + L / 2 - 1) / (L / 2) <= resident_warps) L /= 2;
+        if (const char* env = std::getenv("MBSV_LANES_PER_WARP")) L = std::max(1, std::min(32, std::atoi(env)));
+    }
+    if (int prc = ensure_plan(p, rp->memo_states, rp->n_chains % 32 == 0 && L == 32)) return prc;
+    const int64_t n_warps64 = (n_items + L - 1) / L;
     if (n_warps64 > 0x7fffffff / 32) return fail(MBSV_ERR_ARG, "too many chains for one launch");
     const int n_warps = (int)n_warps64;
     const int64_t sc_total = n_items;
@@ -615,6 +625,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     dr.log1mperr = mbsv::jm_log(1 - rp->perr); dr.seed = rp->seed;
     dr.sub_order = p->d_sub_order.p; dr.sub_W = p->d_sub_W.p; dr.sub_memo = p->d_sub_memo.p; dr.n_items = n_items;
     dr.sub_tab_off = p->d_sub_tab_off.p; dr.memo_global = p->d_memo_global.p;
+    dr.lanes_per_warp = L;
 
     if (rp->init_assign) {
         if (results_on_device) dr.init_assign = rp->init_assign;
@@ -665,12 +676,12 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         for (const char* q = env; *q;) { cls.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
     }
     auto warp_rows = [&](int w) -> int {
-        const int64_t last = std::min<int64_t>((int64_t)w * 32 + 31, n_items - 1);
+        const int64_t last = std::min<int64_t>((int64_t)w * L + L - 1, n_items - 1);
         return std::max(1, p->sub_rows[p->sub_order[last / X]]);
     };
     // Two groups of warps, each sorted by rows: [0, wsplit) memoised-kernel subproblems, [wsplit, n_warps) the rest.
     // (n_chains % 32 == 0 whenever the first group is non-empty, so the split falls on a warp boundary.)
-    const int wsplit = (int)(((int64_t)p->n_tab_subs * X) / 32);
+    const int wsplit = (int)(((int64_t)p->n_tab_subs * X) / L);   // n_tab_subs > 0 only when L == 32
     struct Launch { int wb, we, rows; bool smem, memo; };
     std::vector<Launch> launches;
     auto add_group = [&](int g0, int g1, bool memo) {

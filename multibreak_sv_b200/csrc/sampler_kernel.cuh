@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
     if (warp >= R.warp_end) return;
     // Lanes beyond the last item stay in the warp as idle passengers (zero-sized problem, no iterations, no
     // writes): the main loop below synchronises the full warp.
-    const long long item_raw = (long long)warp * 32 + lane;
-    const bool alive = item_raw < R.n_items;
+    const long long item_raw = (long long)warp * R.lanes_per_warp + lane;
+    const bool alive = lane < R.lanes_per_warp && item_raw < R.n_items;
     const long long item = alive ? item_raw : R.n_items - 1;
     const int sub = R.sub_order[item / R.n_chains];
     const int chain = (int)(item % R.n_chains);

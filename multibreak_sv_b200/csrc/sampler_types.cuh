@@ -44,13 +44,15 @@ struct DevRun {
     double perr, logperr, log1mperr;
     long long seed;
     const int* init_assign;
-    // plan: item g = warp*32 + lane is chain (g % n_chains) of subproblem sub_order[g / n_chains]
+    // plan: item g = warp*lanes_per_warp + lane is chain (g % n_chains) of subproblem sub_order[g / n_chains]
     const int* sub_order;            // subproblems by ascending state size
     const int* sub_W;                // state rows per chain of each subproblem
     const int* sub_memo;             // per subproblem: joint states if it takes the memoised path, else 0 (or NULL)
     const long long* sub_tab_off;    // memoised kernel: offset of the subproblem's table in memo_global, -1 = shared memory
     double* memo_global;
     long long n_items;               // n_sub * n_chains
+    int lanes_per_warp;              // chains per warp: 32, or fewer for small batches (more warps hide the serial
+                                     // dependency chain of a chain better than full warps do when the GPU is not full)
     const long long* warp_row_off;   // [warp - global_warp0] row offset into workspace (global class)
     int* workspace;
     int warp_begin, warp_end, rows_per_warp, global_warp0;
