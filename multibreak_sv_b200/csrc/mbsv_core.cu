@@ -612,8 +612,13 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         while (L > 1 && (n_items + L / 2 - 1) / (L / 2) <= resident_warps) L /= 2;
         if (const char* env = std::getenv("MBSV_LANES_PER_WARP")) L = std::max(1, std::min(32, std::atoi(env)));
     }
-    if (int prc = ensure_plan(p, rp->memo_states, rp->n_chains % 32 == 0 && L == 32)) return prc;
-    const int64_t n_warps64 = (n_items + L - 1) / L;
+    // The memoised kernel needs warps that hold chains of ONE subproblem: full warps when n_chains is a multiple of 32,
+    // half / quarter warps for 16 / 8 chains (it is ~3x cheaper per chain than the general kernel, so idle lanes pay off).
+    const int Lm = X % 32 == 0 ? 32 : (X == 16 || X == 8) ? X : 0;
+    if (int prc = ensure_plan(p, rp->memo_states, Lm > 0 && L == 32)) return prc;
+    const int64_t tab_items = (int64_t)p->n_tab_subs * X;
+    const int64_t memo_warps = Lm > 0 ? tab_items / Lm : 0;
+    const int64_t n_warps64 = memo_warps + (n_items - tab_items + L - 1) / L;
     if (n_warps64 > 0x7fffffff / 32) return fail(MBSV_ERR_ARG, "too many chains for one launch");
     const int n_warps = (int)n_warps64;
     const int64_t sc_total = n_items;
@@ -676,12 +681,13 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         for (const char* q = env; *q;) { cls.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
     }
     auto warp_rows = [&](int w) -> int {
-        const int64_t last = std::min<int64_t>((int64_t)w * L + L - 1, n_items - 1);
+        const int64_t last = w < memo_warps ? (int64_t)w * Lm + Lm - 1
+                                            : std::min<int64_t>(tab_items + (int64_t)(w - memo_warps) * L + L - 1, n_items - 1);
         return std::max(1, p->sub_rows[p->sub_order[last / X]]);
     };
     // Two groups of warps, each sorted by rows: [0, wsplit) memoised-kernel subproblems, [wsplit, n_warps) the rest.
     // (n_chains % 32 == 0 whenever the first group is non-empty, so the split falls on a warp boundary.)
-    const int wsplit = (int)(((int64_t)p->n_tab_subs * X) / L);   // n_tab_subs > 0 only when L == 32
+    const int wsplit = (int)memo_warps;
     struct Launch { int wb, we, rows; bool smem, memo; };
     std::vector<Launch> launches;
     auto add_group = [&](int g0, int g1, bool memo) {
@@ -725,6 +731,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     const bool have_global_tables = !p->tab_sub.empty();
     if (have_global_tables) {
         mbsv::DevRun rb = dr;
+        rb.warp_base = 0; rb.item_base = 0;
         CUDA_TRY(mbsv::launch_memo_build(p->dp, rb, (int)p->tab_sub.size(), p->d_tab_state_ptr.p, p->d_tab_sub.p,
                                          p->memo_global_doubles, p->tab_scratch_rows, s0));
         ++g_launches;
@@ -738,6 +745,9 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.warp_row_off = l.smem ? nullptr : ob.row_off.p;
         r.workspace = l.smem ? nullptr : ob.workspace.p;
         r.global_warp0 = g0;
+        r.warp_base = l.memo ? 0 : wsplit;
+        r.item_base = l.memo ? 0 : tab_items;
+        r.lanes_per_warp = l.memo ? Lm : L;
         KernelFn fn = l.memo ? mbsv::get_kernel_memo(rp->trace != 0)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
                                  : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);

@@ -85,10 +85,11 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const int warp = R.warp_begin + blockIdx.x * 4 + wic;
     if (warp >= R.warp_end) return;
-    const long long item_raw = (long long)warp * 32 + lane;
-    const bool alive = item_raw < R.n_items;
-    const long long item = alive ? item_raw : R.n_items - 1;
-    const int sub = R.sub_order[item / R.n_chains];          // warp-uniform (n_chains % 32 == 0)
+    const long long item_raw = R.item_base + (long long)(warp - R.warp_base) * R.lanes_per_warp + lane;
+    const bool alive = lane < R.lanes_per_warp && item_raw < R.n_items;
+    // idle lanes mirror the warp's first item, so that every per-subproblem quantity stays warp-uniform
+    const long long item = alive ? item_raw : R.item_base + (long long)(warp - R.warp_base) * R.lanes_per_warp;
+    const int sub = R.sub_order[item / R.n_chains];          // warp-uniform: lanes_per_warp divides n_chains
     const int chain = (int)(item % R.n_chains);
     int* st = smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane;
 

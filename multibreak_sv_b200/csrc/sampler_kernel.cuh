@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
     if (warp >= R.warp_end) return;
     // Lanes beyond the last item stay in the warp as idle passengers (zero-sized problem, no iterations, no
     // writes): the main loop below synchronises the full warp.
-    const long long item_raw = (long long)warp * R.lanes_per_warp + lane;
+    const long long item_raw = R.item_base + (long long)(warp - R.warp_base) * R.lanes_per_warp + lane;
     const bool alive = lane < R.lanes_per_warp && item_raw < R.n_items;
     const long long item = alive ? item_raw : R.n_items - 1;
     const int sub = R.sub_order[item / R.n_chains];

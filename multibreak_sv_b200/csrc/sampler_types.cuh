@@ -44,7 +44,8 @@ struct DevRun {
     double perr, logperr, log1mperr;
     long long seed;
     const int* init_assign;
-    // plan: item g = warp*lanes_per_warp + lane is chain (g % n_chains) of subproblem sub_order[g / n_chains]
+    // plan: item g = item_base + (warp - warp_base)*lanes_per_warp + lane is chain (g % n_chains) of subproblem
+    // sub_order[g / n_chains]; the memoised group and the general group of a run have their own (base, lanes)
     const int* sub_order;            // subproblems by ascending state size
     const int* sub_W;                // state rows per chain of each subproblem
     const int* sub_memo;             // per subproblem: joint states if it takes the memoised path, else 0 (or NULL)
@@ -56,6 +57,8 @@ struct DevRun {
     const long long* warp_row_off;   // [warp - global_warp0] row offset into workspace (global class)
     int* workspace;
     int warp_begin, warp_end, rows_per_warp, global_warp0;
+    int warp_base;                   // first warp of the group this launch belongs to
+    long long item_base;             // first item of that group
     // outputs (device)
     unsigned int* aln_count;
     unsigned int* frag_err_count;

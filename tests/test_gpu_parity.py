@@ -281,6 +281,21 @@ def test_full_size_invariants(mbsv):
         assert np.array_equal(getattr(f, k), getattr(r, k)), k
 
 
+@pytest.mark.parametrize("n_chains", [8, 16, 24, 48])
+def test_memo_kernel_with_partial_warps(oracle, mbsv, n_chains):
+    """8 / 16 chains run the memoised kernel with quarter / half warps; other counts fall back to the general kernel."""
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg3", n_frag=1200, seed=21)
+    op = oracle.Problem(p.scalars, p.arrays)
+    dp = mbsv.DeviceProblem(p)
+    o = oracle.run(op, "incremental", 1500, n_chains=n_chains, nthreads=8, java_int_wrap=False, trace=True)
+    g = dp.run(mbsv.MODE_FAST, 1500, n_chains=n_chains, trace=True)
+    assert_same(o, g, trace=True)
+    g = dp.run(mbsv.MODE_FAST, 1500, n_chains=n_chains)
+    assert np.array_equal(o.aln_count, g.aln_count) and np.array_equal(o.rng_state, g.rng_state)
+    assert np.array_equal(o.final_logprob, g.final_logprob)
+
+
 @pytest.mark.parametrize("n_chains", [1, 32, 64])
 def test_tiny_iteration_counts_without_trace(oracle, mbsv, example_problem, n_chains):
     """The look-ahead lazy skip (non-trace kernels) at the end of a chain: every small N, generic and memoised kernels."""
