@@ -91,28 +91,25 @@ __device__ __forceinline__ unsigned long long prob_threshold53(double p) {
     return __double2ull_ru(x);
 }
 
-// which alignment naiveMove draws (MultiBreakSV.java:1198-1256); `now` = -1 for "unmapped".  Consumes one or two
-// nextDouble()s exactly as the reference does.
+// which alignment naiveMove draws (MultiBreakSV.java:1198-1256); -1 = "unmapped".  Consumes one or two nextDouble()s
+// exactly as the reference does.
 __device__ __forceinline__ int naive_draw(JavaRandom& rng, const int n, const int prev, const unsigned long long perr_thr) {
-    const unsigned long long m = rng.bits53();
-    if (prev == -1) {
-        const double r = JavaRandom::to_double(m);
-        int thisassign = 0;
-        const double inc = (double)1 / n;
-        double sum = inc;
-        while (thisassign < n - 1 && r > sum) { ++thisassign; sum += inc; }
-        return thisassign;
-    }
-    if (m < perr_thr || n == 1) return -1;
-    const double r = rng.nextDouble();
-    int thisassign = 0;
-    const double inc = (double)1 / (n - 1);
+    // The reference has two scans (:1205-1209 from "unmapped": thresholds k/n, no index skipped; :1251-1256 to another
+    // alignment: thresholds k/(n-1), index `prev` skipped).  With prev == -1 the second loop never skips, so ONE loop with
+    // m = n or n-1 reproduces both, and lanes taking different branches stay converged.
+    const unsigned long long m53 = rng.bits53();
+    const bool from_err = prev == -1;
+    const bool to_err = !from_err && (m53 < perr_thr || n == 1);
+    double r = JavaRandom::to_double(m53);
+    if (!from_err && !to_err) r = rng.nextDouble();          // the second draw of :1248
+    const double inc = (double)1 / (from_err ? n : n - 1);
     double sum = inc;
-    while (thisassign < n - 1 && (thisassign == prev || r > sum)) {
+    int thisassign = 0;
+    while (!to_err && thisassign < n - 1 && (thisassign == prev || r > sum)) {
         ++thisassign;
         if (thisassign != prev) sum += inc;
     }
-    return thisassign;
+    return to_err ? -1 : thisassign;
 }
 
 // proposal log-probabilities of the reverse (Alogq) and forward (Anewlogq) Naive moves (:1218-1271)

@@ -224,3 +224,26 @@ def test_partition_then_batch_refines_generator_subproblems(mbsv, oracle, tmp_pa
         assert len({gen_sub[i] for i in ids}) == 1 and not (seen & set(ids))
         seen |= set(ids)
     assert seen == set(gen_sub)
+
+
+def test_matchfile_initial_state(mbsv, tmp_path):
+    """--matchfile (MultiBreakSV.java:1030-1085): the shipped initialset.txt never matches (its IDs lack `longread_`), so
+    every fragment starts unassigned; a matching single-ESP alignment is set, a two-ESP alignment never is (thisval <= 1)."""
+    from multibreak_sv_b200 import host
+    sv = _host(mbsv, os.path.join(EXAMPLE, "gasv.clusters"), os.path.join(EXAMPLE, "assignments.txt"),
+               os.path.join(EXAMPLE, "experiments.txt"), extra=["--matchfile", os.path.join(EXAMPLE, "initialset.txt")]).load()
+    p = sv.packed()
+    assert sv.initialAssignmentFromMatchfile(p).tolist() == [-1, -1, -1, -1]
+    names = sv.names(3, p.scalars["n_aln_esp"])
+    a = p.arrays
+    # pick a single-ESP alignment of fragment 2 and a two-ESP alignment of fragment 0
+    single = next(al for al in range(a["frag_aln_ptr"][2], a["frag_aln_ptr"][3]) if a["aln_esp_ptr"][al + 1] - a["aln_esp_ptr"][al] == 1)
+    double = next(al for al in range(a["frag_aln_ptr"][0], a["frag_aln_ptr"][1]) if a["aln_esp_ptr"][al + 1] - a["aln_esp_ptr"][al] == 2)
+    mf = os.path.join(str(tmp_path), "match.txt")
+    open(mf, "w").write(names[a["aln_esp_ptr"][single]] + "\n" + names[a["aln_esp_ptr"][double]] + "\n" + names[a["aln_esp_ptr"][double] + 1] + "\n")
+    sv.matchfile = mf
+    init = sv.initialAssignmentFromMatchfile(p)
+    assert init[2] == single - a["frag_aln_ptr"][2]
+    # the first alignment of fragment 0 that contains a listed ESP and has exactly one ESP wins, two-ESP ones never do
+    al0 = a["frag_aln_ptr"][0] + init[0] if init[0] >= 0 else None
+    assert al0 is None or a["aln_esp_ptr"][al0 + 1] - a["aln_esp_ptr"][al0] == 1
