@@ -93,6 +93,9 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     const int chain = (int)(item % R.n_chains);
     int* st = smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane;
 
+#ifdef MBSV_BOUNDS_CHECK
+    const int st_rows = min(R.sub_W[sub], R.rows_per_warp);
+#endif
     const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
     const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
     const int E = P.n_exp;
@@ -115,6 +118,15 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     // ratio min(1, exp(..)) of every (previous, proposed) pair is tabulated too, so a proposal needs no exp.
     const bool f1 = (F == 1) && (nsv == 0) && (tab_off < 0);
     double* rtab = tab + nst;
+#ifdef MBSV_BOUNDS_CHECK
+    {   // strides, table and ratio table must end inside this warp's rows of the tile
+        const int* end = tab_off >= 0 ? strides + ((F + 1) & ~1) : reinterpret_cast<const int*>(rtab + (f1 ? nst * nst : 0));
+        if (end > smem_tile + (size_t)(wic + 1) * R.rows_per_warp * 32) {
+            printf("memo tables of subproblem %d overrun the %d-row tile\n", sub, R.rows_per_warp);
+            __trap();
+        }
+    }
+#endif
 
     // ---------------- table: log-posterior of every joint state (fragment 0 = least significant digit) ----------------
     {

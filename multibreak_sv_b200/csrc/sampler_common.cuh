@@ -1,6 +1,7 @@
 // Device helpers shared by the sampler kernels (sampler_kernel.cuh: generic MH kernel; memo_kernel.cuh: memoised
 // kernel): Java-compatible math wrappers, the lazy-iteration look-ahead, the Naive proposal draw, counter reduction.
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -40,7 +41,20 @@ static __device__ MBSV_MATH_INLINE double log_binomial_dev(long long k, long lon
 
 static __device__ MBSV_MATH_INLINE double exp_dev(double x) { return jm_exp(x); }
 
+// Row i of this chain's column of the [rows][32] state tile.  The checked build (make check) traps on a row outside
+// the subproblem's rows instead of corrupting a neighbour's state; `st_rows` is defined next to `st` in each kernel.
+#ifdef MBSV_BOUNDS_CHECK
+static __device__ __noinline__ int& mbsv_st_checked(int* st, long long i, int rows, int line) {
+    if (i < 0 || i >= rows) {
+        printf("MBSV_ST: row %lld outside [0,%d) at line %d (block %d thread %d)\n", i, rows, line, blockIdx.x, threadIdx.x);
+        __trap();
+    }
+    return st[(size_t)i << 5];
+}
+#define MBSV_ST(i) mbsv_st_checked(st, (i), st_rows, __LINE__)
+#else
 #define MBSV_ST(i) st[(size_t)(i) << 5]
+#endif
 
 
 // Lazy chain (MultiBreakSV.java:1106-1113): with probability 1/2 an iteration only consumes one nextDouble().

@@ -49,6 +49,9 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
     int* st = SMEM ? (smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane)
                    : (R.workspace + (size_t)R.warp_row_off[warp - R.global_warp0] * 32 + lane);
 
+#ifdef MBSV_BOUNDS_CHECK
+    const int st_rows = !alive ? 0 : SMEM ? min(R.sub_W[sub], R.rows_per_warp) : R.sub_W[sub];
+#endif
     const int f0 = P.sub_frag_ptr[sub], F = alive ? P.sub_frag_ptr[sub + 1] - f0 : 0;
     const int c0 = P.sub_cluster_ptr[sub], C = alive ? P.sub_cluster_ptr[sub + 1] - c0 : 0;
     const int E = P.n_exp;

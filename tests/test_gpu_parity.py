@@ -308,3 +308,20 @@ def test_tiny_iteration_counts_without_trace(oracle, mbsv, example_problem, n_ch
             g = prob.run(mbsv.MODE_FAST, n, n_chains=n_chains)
             o = oracle.run(oprob, "incremental", n, n_chains=n_chains, java_int_wrap=False)
             assert_same(o, g)
+
+
+@pytest.mark.gpu
+def test_bounds_checked_build():
+    """The parity cases again on libmbsv_b200_check.so (`make check`): every access to a chain's state tile and the
+    memo tables' extent are range-checked on the device and trap instead of corrupting a neighbouring chain.  (This
+    pool runs no compute-sanitizer; these are the kernels' own checks.)"""
+    import subprocess
+    import sys
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multibreak_sv_b200",
+                       "libmbsv_b200_check.so")
+    assert os.path.exists(lib), "libmbsv_b200_check.so missing: run `make -C multibreak_sv_b200/csrc check`"
+    env = dict(os.environ, MBSV_B200_LIB=lib)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "not bounds_checked and not full_size and not posterior_within"],
+                       env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
