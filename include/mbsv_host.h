@@ -9,6 +9,7 @@
  *   mbsv_host_construct_cluster_diagrams constructClusterDiagrams :658-739 (+ MultiBreakSVDiagram.java:56-139)
  *   mbsv_host_precompute_priors         precomputePriors :604-656   (logprobcov tables)
  *   mbsv_host_fill_non_singleton_array  fillNonSingletonArray :748-771
+ *   mbsv_host_matchfile_initial         initializeMatrix's --matchfile branch :1030-1085
  *   mbsv_host_run_mcmc                  runMCMC :773-877             (-> mbsv_problem_create + mbsv_run)
  *   mbsv_host_write_final_files         writeFinalFiles :1712-1859   (.finalbreakpoints.longburnin, .finalassignment.longburnin)
  *   mbsv_host_write_mcmc_file           the per-iteration mcmc.txt of runMCMC :779-828
@@ -59,6 +60,12 @@ int mbsv_host_sorted_fragments(mbsv_host* h, int32_t* out);
    params is given.  Results are kept inside the host for the writers; `results` (may be NULL) receives a view. */
 int mbsv_host_run_mcmc(mbsv_host* h, int32_t num_iters, double perr, int32_t mode, int32_t device, int32_t save_space,
                        const int32_t* init_assign, mbsv_results* results);
+/* After mbsv_host_run_mcmc: counters[5] = {naive proposals, naive accepted, AlterSV proposals, AlterSV accepted,
+   fragment reassignments} (proposalCounts/moveCounts, MultiBreakSV.java:842-843) and the initial / final logprob (:839). */
+int mbsv_host_run_summary(mbsv_host* h, int64_t* counters, double* initial_logprob, double* final_logprob);
+/* --matchfile (MultiBreakSV.java:1030-1085): initial assignment per fragment (keySet() order, n_frag entries) from a
+   file of ESPs; counts (may be NULL) = {fragments set, set to error, with a listed ESP but not set, ESPs read}. */
+int mbsv_host_matchfile_initial(mbsv_host* h, const char* matchfile, int32_t* init_assign, int32_t* counts);
 /* Inject results computed elsewhere (tests without a GPU; batched runs): counts are copied. */
 int mbsv_host_set_results(mbsv_host* h, int32_t num_iters, int32_t burnin, const uint32_t* aln_count,
                           const uint32_t* frag_err_count, const uint32_t* cluster_hist);

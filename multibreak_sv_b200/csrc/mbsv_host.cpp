@@ -207,6 +207,8 @@ struct mbsv_host {
     std::vector<uint32_t> r_aln, r_frag, r_hist;
     std::vector<int32_t> r_init, r_trace_frag, r_trace_assign;
     std::vector<double> r_trace_logprob;
+    int64_t r_counters[5] = {0, 0, 0, 0, 0};
+    double r_final_logprob = 0.0, r_initial_logprob = 0.0;
     bool have_results = false, have_trace = false;
 
     int esp(const std::string& name) {
@@ -673,10 +675,52 @@ int mbsv_host_run_mcmc(mbsv_host* h, int32_t num_iters, double perr, int32_t mod
     const int rc = mbsv_run(prob, &rp, &r);
     mbsv_problem_destroy(prob);
     if (rc) return hfail(rc, mbsv_last_error());
+    if (errv[0]) return hfail(MBSV_ERR_INVARIANT, "the chain stopped on one of the reference's Error conditions (MultiBreakSV.java:1122-1144)");
+    for (int i = 0; i < 5; ++i) h->r_counters[i] = counters[i];
+    h->r_final_logprob = flp[0]; h->r_initial_logprob = ilp[0];
     h->have_results = true;
     h->have_trace = !save_space;
     if (results) { *results = r; results->final_assign = nullptr; results->final_logprob = nullptr; results->counters = nullptr;
                    results->rng_state = nullptr; results->error = nullptr; results->initial_logprob = nullptr; results->totals = nullptr; }
+    return MBSV_OK;
+}
+
+int mbsv_host_run_summary(mbsv_host* h, int64_t* counters, double* initial_logprob, double* final_logprob) {
+    if (!h || !h->have_results) return hfail(MBSV_ERR_ARG, "no results: mbsv_host_run_mcmc first");
+    if (counters) for (int i = 0; i < 5; ++i) counters[i] = h->r_counters[i];
+    if (initial_logprob) *initial_logprob = h->r_initial_logprob;
+    if (final_logprob) *final_logprob = h->r_final_logprob;
+    return MBSV_OK;
+}
+
+// The --matchfile branch of initializeMatrix (MultiBreakSV.java:1030-1085): the file is whitespace-separated ESPs.
+// Per fragment, the first alignment with `thisval == alignments.size()` is set, where thisval counts at most ONE
+// listed ESP (the inner loop breaks at the first hit, :1058-1063) -- so only single-ESP alignments can ever be set;
+// every other fragment starts "unmapped".  counts = {numset, numerr, numbad, ESPs read} as the reference prints them.
+int mbsv_host_matchfile_initial(mbsv_host* h, const char* matchfile, int32_t* init_assign, int32_t* counts) {
+    if (!h || !h->packed || !matchfile || !init_assign) return hfail(MBSV_ERR_ARG, "mbsv_host_load first");
+    Scanner sc;
+    if (!slurp(matchfile, sc.buf)) return hfail(MBSV_ERR_IO, std::string("cannot open ") + matchfile);
+    std::unordered_map<std::string, char> listed;
+    int nread = 0;
+    while (sc.hasNext()) { listed.emplace(sc.next(), 1); ++nread; }
+    int numset = 0, numerr = 0, numbad = 0;
+    const int F = (int)h->frag_order.size();
+    for (int f = 0; f < F; ++f) {
+        init_assign[f] = -1;
+        bool foundall = false, foundany = false;
+        for (int a = h->frag_aln_ptr[f]; a < h->frag_aln_ptr[f + 1] && !foundall; ++a) {
+            int thisval = 0;
+            // FragmentAlignment.contains(esp) is membership of the alignment's ESP list; which listed ESP hits first
+            // does not matter, only whether any does
+            for (int j = h->aln_esp_ptr[a]; j < h->aln_esp_ptr[a + 1]; ++j)
+                if (listed.count(h->esp_name[h->aln_esp_espid[j]])) { thisval = 1; foundany = true; break; }
+            if (thisval == h->aln_esp_ptr[a + 1] - h->aln_esp_ptr[a]) { init_assign[f] = a - h->frag_aln_ptr[f]; ++numset; foundall = true; }
+        }
+        if (!foundany && !foundall) ++numerr;
+        if (foundany && !foundall) ++numbad;
+    }
+    if (counts) { counts[0] = numset; counts[1] = numerr; counts[2] = numbad; counts[3] = nread; }
     return MBSV_OK;
 }
 

@@ -12,7 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._abi import (DESC_ARRAYS, DESC_SCALARS, I32P, MODE_REPLAY_EXACT, U32P, PackedProblem, ProblemDesc, Results, check,
+from ._abi import (DESC_ARRAYS, DESC_SCALARS, F64P, I32P, I64P, MODE_REPLAY_EXACT, U32P, PackedProblem, ProblemDesc, Results, check,
                    load_library, reference_burnin)
 
 
@@ -30,6 +30,8 @@ def _bind(L):
     L.mbsv_host_name.argtypes = [vp, C.c_int32, C.c_int32]; L.mbsv_host_name.restype = C.c_char_p
     L.mbsv_host_sorted_fragments.argtypes = [vp, I32P]
     L.mbsv_host_run_mcmc.argtypes = [vp, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32, I32P, C.POINTER(Results)]
+    L.mbsv_host_run_summary.argtypes = [vp, I64P, F64P, F64P]
+    L.mbsv_host_matchfile_initial.argtypes = [vp, C.c_char_p, I32P, I32P]
     L.mbsv_host_set_results.argtypes = [vp, C.c_int32, C.c_int32, U32P, U32P, U32P]
     L.mbsv_host_write_final_files.argtypes = [vp, C.c_char_p]
     L.mbsv_host_write_mcmc_file.argtypes = [vp, C.c_char_p]
@@ -182,22 +184,18 @@ class MultiBreakSV:
         self.lib.mbsv_host_sorted_fragments(self.h, out.ctypes.data_as(I32P))
         return out
 
-    def initialAssignmentFromMatchfile(self, p: PackedProblem):
+    def initialAssignmentFromMatchfile(self, p: PackedProblem = None):
         """The --matchfile path (MultiBreakSV.java:1030-1085) reduced to "initial state supplied by the host": an
         alignment is set when it has exactly one ESP and that ESP is listed (the loop `break`s after the first hit,
         so thisval <= 1, :1058-1065); every other fragment starts unassigned."""
-        esps = set(open(self.matchfile).read().split())
-        a = p.arrays
-        init = np.full(p.scalars["n_frag"], -1, np.int32)
-        names = self.names(3, p.scalars["n_aln_esp"])
-        for f in range(p.scalars["n_frag"]):
-            for al in range(a["frag_aln_ptr"][f], a["frag_aln_ptr"][f + 1]):
-                j0, j1 = a["aln_esp_ptr"][al], a["aln_esp_ptr"][al + 1]
-                hit = any(names[j] in esps for j in range(j0, j1))
-                if (1 if hit else 0) == j1 - j0:
-                    init[f] = al - a["frag_aln_ptr"][f]
-                    break
-        return init
+        d = ProblemDesc()
+        check(self.lib.mbsv_host_desc(self.h, C.byref(d)))
+        init = np.full(max(1, d.n_frag), -1, np.int32)
+        counts = np.zeros(4, np.int32)
+        check(self.lib.mbsv_host_matchfile_initial(self.h, self.matchfile.encode(), init.ctypes.data_as(I32P),
+                                                   counts.ctypes.data_as(I32P)))
+        self.matchfile_counts = dict(zip(("numset", "numerr", "numbad", "esps"), (int(v) for v in counts)))
+        return init[:d.n_frag]
 
     def runMCMC(self, file=None):
         """MultiBreakSV.runMCMC (:773-877) on the GPU; results stay in the host object for the writers."""

@@ -304,7 +304,7 @@ def write_reference_files(p: PackedProblem, outdir: str, frag_numbers: np.ndarra
             if a["cluster_kind"][c] == 0:
                 fh.write(f"c{c + 1}\t{len(names)}\t100.0\tD\t{', '.join(names)}\t1\t1\t1, 2, 3, 4\n")
             else:
-                fh.write(f"c{c + 1}\t{len(names)}\t-1\tD\t{', '.join(names)}\t1\t1\t\n")
+                fh.write(f"c{c + 1}\t{len(names)}\t-1\tD\t{', '.join(names)}\t1\t1\t1, 2, 3, 4\n")
                 for k, r in enumerate(range(a["cluster_root_ptr"][c], a["cluster_root_ptr"][c + 1])):
                     sub = [names[int(l)] for l in a["root_leaf"][a["root_leaf_ptr"][r]:a["root_leaf_ptr"][r + 1]]]
                     fh.write(f"c{c + 1}.{k + 1}\t{len(sub)}\t90.0\tD\t{', '.join(sub)}\t1\t1\t1, 2, 3, 4\n")

@@ -2,6 +2,7 @@
 tallies, counters, RNG state, final state — must be bit-exact; log-probabilities must be bit-exact too because
 both sides run the same individually-rounded fdlibm arithmetic."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -158,6 +159,18 @@ def test_host_main_file_to_file(oracle, mbsv, example_problem, tmp_path):
     ref.writeFinalFiles()
     for ext in (".finalbreakpoints.longburnin", ".finalassignment.longburnin"):
         assert open(prefix + ext).read() == open(prefix + "_ref" + ext).read()
+    # the C++ command-line driver (what replaces `java -jar MultiBreakSV.jar`) writes the same four files
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.abspath(host.__file__)), "mbsv_cli")
+    r = subprocess.run([cli, "--clusterfile", os.path.join(EXAMPLE, "gasv.clusters"), "--assignmentfile",
+                        os.path.join(EXAMPLE, "assignments.txt"), "--experimentfile", os.path.join(EXAMPLE, "experiments.txt"),
+                        "--numiterations", "10000", "--perr", "0.001", "--prefix", prefix + "_cli"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "1174 of 5006(" + host.java_double_to_string(1174 / 5006) + ") Naive Moves" in r.stdout      # KAT-6, :842
+    assert "0 of 0(NaN) AlterSV Moves" in r.stdout
+    assert "After 10000 iterations, probability is " + host.java_double_to_string(float(o.final_logprob.ravel()[0])) in r.stdout
+    for ext in (".finalbreakpoints.longburnin", ".finalassignment.longburnin", ".mcmc.txt", ".samplingprobs"):
+        assert open(prefix + ext).read() == open(prefix + "_cli" + ext).read(), ext
     # mcmc.txt: Iteration, LogProb, NumBreakpoints (C*E every skip=10 iterations), MadeMove?
     lines = open(prefix + ".mcmc.txt").read().splitlines()
     assert lines[0] == "Iteration\tLogProb\tNumBreakpoints\tMadeMove?" and len(lines) == 10001

@@ -247,3 +247,37 @@ def test_matchfile_initial_state(mbsv, tmp_path):
     # the first alignment of fragment 0 that contains a listed ESP and has exactly one ESP wins, two-ESP ones never do
     al0 = a["frag_aln_ptr"][0] + init[0] if init[0] >= 0 else None
     assert al0 is None or a["aln_esp_ptr"][al0 + 1] - a["aln_esp_ptr"][al0] == 1
+    c = sv.matchfile_counts
+    assert c["esps"] == 3 and c["numset"] == int((init >= 0).sum()) and c["numset"] + c["numerr"] + c["numbad"] == 4
+    # the same rule, restated: first alignment whose ESP count equals min(1, listed ESPs it contains)
+    listed = set(open(mf).read().split())
+    for f in range(4):
+        want = -1
+        for al in range(a["frag_aln_ptr"][f], a["frag_aln_ptr"][f + 1]):
+            j0, j1 = a["aln_esp_ptr"][al], a["aln_esp_ptr"][al + 1]
+            if int(any(names[j] in listed for j in range(j0, j1))) == j1 - j0:
+                want = al - a["frag_aln_ptr"][f]
+                break
+        assert init[f] == want
+
+
+def test_cli_usage_and_loud_failure_without_gpu(mbsv):
+    """mbsv_cli mirrors the reference's option checks (MultiBreakSV.java:211-267) and never falls back to a CPU path."""
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multibreak_sv_b200", "mbsv_cli")
+    assert os.path.exists(cli), "run make -C multibreak_sv_b200/csrc"
+    files = ["--clusterfile", os.path.join(EXAMPLE, "gasv.clusters"), "--assignmentfile", os.path.join(EXAMPLE, "assignments.txt"),
+             "--experimentfile", os.path.join(EXAMPLE, "experiments.txt")]
+    for args, msg in ((["--clusterfile", "x"], "Assignment file is required."),
+                      (files, "Number of iterations is required to sample."),
+                      (files + ["--numiterations", "10"], "Mapping error probability (perr) is required."),
+                      (files + ["--numiterations", "10", "--perr", "1.5"], "--perr must be a value between 0 and 1."),
+                      (files + ["--numiterations", "ten", "--perr", "0.1"], "--numiterations must be a positive integer."),
+                      (files + ["--bogus"], "--bogus is not a valid option."),
+                      (files + ["--enumerate"], "--enumerate is outside the sampler path")):
+        r = subprocess.run([cli] + args, capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([cli] + files + ["--numiterations", "10", "--perr", "0.001", "--prefix", "/tmp/never"], capture_output=True, text=True)
+        assert r.returncode == 2 and "runMCMC:" in r.stderr and not os.path.exists("/tmp/never.finalassignment.longburnin")
