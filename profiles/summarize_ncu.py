@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn an .ncu-rep (ncu --set full) into the small text summaries kept under profiles/.
 
-    python profiles/summarize_ncu.py gpurun_out/prof_r01b.ncu-rep profiles/r01_ncu_full
+    python profiles/summarize_ncu.py gpurun_out/prof_r01b.ncu-rep profiles/r01_ncu_full [launch-index]
 
 writes <out>_metrics.csv (one row per captured launch), <out>_lines.txt (CUDA source lines ranked by executed
 warp-instructions with their average active lanes) and prints the dominant kernel's DRAM traffic per launch.
@@ -47,6 +47,8 @@ def main():
     # dominant launch = the one that executed the most warp-instructions (the bulk of the chains)
     inst = [float(r[idx["smsp__inst_executed.sum"]]) for r in data]
     k = max(range(len(data)), key=lambda i: inst[i])
+    if len(sys.argv) > 3:          # source lines of another captured launch (e.g. one of the general-kernel classes)
+        k = int(sys.argv[3])
 
     def to_bytes(v, u):
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
@@ -85,7 +87,7 @@ def main():
     tott = sum(a[1] for a in agg.values())
     tots = sum(a[2] for a in agg.values()) or 1
     with open(out + "_lines.txt", "w") as fh:
-        fh.write(f"dominant launch #{k}: {data[k][idx['Kernel Name']]} grid {data[k][idx['launch__grid_size']]}\n")
+        fh.write(f"{'dominant ' if len(sys.argv) <= 3 else ''}launch #{k}: {data[k][idx['Kernel Name']]} grid {data[k][idx['launch__grid_size']]}\n")
         fh.write(f"warp-instructions {tot}  thread-instructions {tott}  avg active lanes {tott / tot:.2f}\n")
         fh.write("share-of-warp-inst  share-of-stall-samples  avg-active-lanes  file:line  source\n")
         for (f, l), (e, t, s, sline) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:60]:

@@ -10,7 +10,8 @@ for cfg, T in (("cfg2", 100000), ("cfg3", 20000)):
     c = synth.CONFIGS[cfg]
     p = synth.generate(cfg)
     dp = m.DeviceProblem(p)
-    for it in range(2):
-        g = dp.run(m.MODE_FAST, T, n_chains=c.n_chains, want_state=False, per_chain=False)
-    print(cfg, p.scalars["n_sub"], "subs x", c.n_chains, "chains x", T, "iters: kernel %.1f ms" % g.kernel_ms,
-          "reassign/s %.3e" % (g.totals[4] / (g.kernel_ms / 1e3)), [(li["rows"], li["warps"], round(li["ms"], 1)) for li in dp.launch_info()])
+    for memo in (65536, 0):
+        for it in range(2):
+            g = dp.run(m.MODE_FAST, T, n_chains=c.n_chains, want_state=False, per_chain=False, memo_states=memo)
+        print(cfg, "memo_states", memo, p.scalars["n_sub"], "subs x", c.n_chains, "chains x", T, "iters: kernel %.1f ms" % g.kernel_ms,
+              "reassign/s %.3e" % (g.totals[4] / (g.kernel_ms / 1e3)), [(li["rows"], li["warps"], round(li["ms"], 1)) for li in dp.launch_info()])
