@@ -30,6 +30,10 @@ import sys
 import threading
 import time
 
+# the sampler overlaps one kernel per state-size class: more hardware queues than CUDA's default 8 (see mbsv_core.cu);
+# must be in the environment before torch creates the CUDA context
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -3,6 +3,12 @@
 Only the sampler hot path lives here: the C-ABI library `libmbsv_b200.so` (csrc/), its ctypes
 binding (`_abi`), and the host-side mirror of the reference's `MultiBreakSV` driver.
 """
+import os as _os
+
+# A run overlaps one kernel per state-size class (up to 19 streams); with CUDA's default of 8 hardware queues the 9th
+# stream would silently wait for the 1st (csrc/mbsv_core.cu).  Read at CUDA context creation, so set it on import.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from ._abi import (MODE_FAST, MODE_REPLAY_EXACT, DeviceProblem, MbsvError, PackedProblem, RunOutput, load_library,
                    reference_burnin)
 

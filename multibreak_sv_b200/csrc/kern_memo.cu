@@ -1,7 +1,10 @@
 // Memoised kernels (memo_kernel.cuh): one instantiation without and one with the per-iteration trace.
 #include "memo_kernel.cuh"
 namespace mbsv {
-KernelFn get_kernel_memo(bool trace) { return trace ? mbsv_memo_kernel<true> : mbsv_memo_kernel<false>; }
+KernelFn get_kernel_memo(bool trace, bool mixed) {
+    return mixed ? (trace ? mbsv_memo_kernel<true, true> : mbsv_memo_kernel<false, true>)
+                 : (trace ? mbsv_memo_kernel<true, false> : mbsv_memo_kernel<false, false>);
+}
 cudaError_t launch_memo_build(const DevProblem& P, const DevRun& R, int n_tab, const long long* state_ptr, const int* tab_sub,
                               long long n_states, int scratch_rows, cudaStream_t stream) {
     if (n_tab <= 0 || n_states <= 0) return cudaSuccess;

@@ -22,6 +22,12 @@ namespace {
 
 thread_local std::string g_err;
 thread_local int64_t g_launches = 0;
+// One run launches up to NSTREAM - 1 kernels (one per state-size class) that must overlap.  With the default of 8
+// hardware work queues, the 9th stream shares a queue with the 1st and its kernel silently waits for that one to finish
+// (measured: a 200 ms tail on a latency-bound batch).  The variable is read when the CUDA context is created, so it is set
+// when the library is loaded; a host that initialises CUDA earlier sets it itself (bench.py, the Python package do).
+__attribute__((constructor)) static void mbsv_more_hardware_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 struct LaunchInfo { int rows; int warps; int grid; int smem_bytes; float ms; int memo; };
 thread_local std::vector<LaunchInfo> g_launch_info;
 
@@ -522,32 +528,46 @@ KernelFn pick(int mode, bool trace, bool smem, int E) {
 // (Re)build the launch plan: which subproblems use the memoised arithmetic (memo_states), which of those run in the
 // memoised kernel (only when every warp holds chains of one subproblem, i.e. n_chains % 32 == 0, and the table fits
 // the largest shared-memory class), tile rows per warp, launch order.
+constexpr int MAX_SMEM_ROWS = 128;     // largest shared-memory size class (rows per chain)
 constexpr int SMEM_TABLE_ROWS = 48;   // tiles up to this many rows keep the table in shared memory
-int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
-    if (p->plan_memo == memo_states && p->plan_tab == (int)tab_ok) return 0;
+// tab_mode: 0 = no memoised kernel (memo-eligible subproblems re-sum the posterior per proposal in the general kernel),
+// 1 = warps of one subproblem (strides and, when small, the table in the warp's shared memory), 2 = mixed warps (every
+// lane its own subproblem: strides in the lane's column, every table in device memory).  The arithmetic is the same in
+// all three, so the choice may depend on the batch shape and on free memory.
+int ensure_plan(mbsv_problem* p, int memo_states, int tab_mode) {
+    if (p->plan_memo == memo_states && p->plan_tab == tab_mode) return 0;
     const int S = p->n_sub;
     p->sub_rows.resize(S); p->sub_memo.assign(S, 0); p->sub_tab.assign(S, 0); p->sub_order.resize(S);
     p->sub_tab_off.assign(S, -1);
     p->n_tab_subs = 0;
     p->memo_global_doubles = 0;
     p->tab_state_ptr.clear(); p->tab_sub.clear(); p->tab_scratch_rows = 1;
+    // device-memory tables may take a quarter of what is free now (the chain-state workspace needs the rest)
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const long long table_budget = (long long)(free_b / 4 / sizeof(double));
     for (int s = 0; s < S; ++s) {
         int rows = p->sub_W[s];
         const int nst = p->sub_nstates[s];
         if (memo_states > 0 && nst > 0 && nst <= memo_states) {
             p->sub_memo[s] = nst;
-            if (tab_ok) {
-                // fragment strides always sit after the state rows; the log-posterior table follows them when the
-                // whole tile still fits the small size classes, else it lives in the global table buffer
-                const int fr = (p->sub_F[s] + 1) & ~1;
-                // one-fragment subproblems without AlterSV candidates also tabulate the acceptance ratios (nst^2)
-                const int ratio_words = (p->sub_F[s] == 1 && p->sub_nsv[s] == 0) ? 2 * nst * nst : 0;
-                const int with_table = rows + (fr + 2 * nst + ratio_words + 31) / 32;
+            // fragment strides always sit after the state rows; the log-posterior table follows them when the
+            // whole tile still fits the small size classes, else it lives in the global table buffer
+            const int fr = (p->sub_F[s] + 1) & ~1;
+            // one-fragment subproblems without AlterSV candidates also tabulate the acceptance ratios (nst^2)
+            const int ratio_words = (p->sub_F[s] == 1 && p->sub_nsv[s] == 0) ? 2 * nst * nst : 0;
+            const int with_table = rows + (fr + 2 * nst + ratio_words + 31) / 32;
+            int trows = 0;
+            bool global_table = true;
+            if (tab_mode == 1 && with_table <= SMEM_TABLE_ROWS) { trows = with_table; global_table = false; }
+            else if (tab_mode == 1) trows = rows + (fr + 31) / 32;
+            else if (tab_mode == 2) trows = rows + p->sub_F[s];
+            // the memoised kernel keeps its state in shared memory: larger tiles (many clusters) stay in the general kernel
+            if (tab_mode != 0 && trows <= MAX_SMEM_ROWS && (!global_table || p->memo_global_doubles + nst <= table_budget)) {
+                rows = trows;
                 p->sub_tab[s] = 1;
                 ++p->n_tab_subs;
-                if (with_table <= SMEM_TABLE_ROWS) rows = with_table;
-                else {
-                    rows += (fr + 31) / 32;
+                if (global_table) {
                     p->sub_tab_off[s] = p->memo_global_doubles;
                     p->tab_state_ptr.push_back(p->memo_global_doubles);
                     p->tab_sub.push_back(s);
@@ -571,7 +591,7 @@ int ensure_plan(mbsv_problem* p, int memo_states, bool tab_ok) {
     CUDA_TRY(p->d_tab_state_ptr.upload(p->tab_state_ptr));
     CUDA_TRY(p->d_tab_sub.upload(p->tab_sub));
     p->plan_memo = memo_states;
-    p->plan_tab = (int)tab_ok;
+    p->plan_tab = tab_mode;
     return 0;
 }
 
@@ -614,10 +634,14 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     }
     // The memoised kernel needs warps that hold chains of ONE subproblem: full warps when n_chains is a multiple of 32,
     // half / quarter warps for 16 / 8 chains (it is ~3x cheaper per chain than the general kernel, so idle lanes pay off).
-    const int Lm = X % 32 == 0 ? 32 : (X == 16 || X == 8) ? X : 0;
-    if (int prc = ensure_plan(p, rp->memo_states, Lm > 0 && L == 32)) return prc;
+    // Any other chain count, and small batches, run it with mixed warps: every lane its own (subproblem, chain), tables in
+    // device memory.
+    const int Lu = X % 32 == 0 ? 32 : (X == 16 || X == 8) ? X : 0;
+    const bool mixed = !(Lu > 0 && L == 32);
+    const int Lm = mixed ? L : Lu;
+    if (int prc = ensure_plan(p, rp->memo_states, mixed ? 2 : 1)) return prc;
     const int64_t tab_items = (int64_t)p->n_tab_subs * X;
-    const int64_t memo_warps = Lm > 0 ? tab_items / Lm : 0;
+    const int64_t memo_warps = (tab_items + Lm - 1) / Lm;
     const int64_t n_warps64 = memo_warps + (n_items - tab_items + L - 1) / L;
     if (n_warps64 > 0x7fffffff / 32) return fail(MBSV_ERR_ARG, "too many chains for one launch");
     const int n_warps = (int)n_warps64;
@@ -681,7 +705,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         for (const char* q = env; *q;) { cls.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
     }
     auto warp_rows = [&](int w) -> int {
-        const int64_t last = w < memo_warps ? (int64_t)w * Lm + Lm - 1
+        const int64_t last = w < memo_warps ? std::min<int64_t>((int64_t)w * Lm + Lm - 1, tab_items - 1)
                                             : std::min<int64_t>(tab_items + (int64_t)(w - memo_warps) * L + L - 1, n_items - 1);
         return std::max(1, p->sub_rows[p->sub_order[last / X]]);
     };
@@ -736,6 +760,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
                                          p->memo_global_doubles, p->tab_scratch_rows, s0));
         ++g_launches;
         CUDA_TRY(cudaEventRecord(p->ev_built, s0));
+        CUDA_TRY(cudaEventRecord(p->ev_cls0[0], s0));      // (timing of the build, MBSV_DEBUG_TIMING)
     }
     int nstream = 0;
     for (const Launch& l : launches) {
@@ -748,7 +773,9 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.warp_base = l.memo ? 0 : wsplit;
         r.item_base = l.memo ? 0 : tab_items;
         r.lanes_per_warp = l.memo ? Lm : L;
-        KernelFn fn = l.memo ? mbsv::get_kernel_memo(rp->trace != 0)
+        r.memo_mixed = mixed ? 1 : 0;
+        if (l.memo) r.n_items = tab_items;      // the last warp of the memoised group may be partly filled
+        KernelFn fn = l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
                                  : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);
         const size_t shm = l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
@@ -775,6 +802,20 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     res->kernel_ms = ms;
     for (size_t i = 0; i < g_launch_info.size(); ++i)
         cudaEventElapsedTime(&g_launch_info[i].ms, p->ev_cls0[1 + i], p->ev_cls1[1 + i]);
+    if (std::getenv("MBSV_DEBUG_TIMING"))
+        for (size_t i = 0; i < g_launch_info.size(); ++i) {
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, p->ev_start, p->ev_cls0[1 + i]);
+            cudaEventElapsedTime(&t1, p->ev_start, p->ev_cls1[1 + i]);
+            std::fprintf(stderr, "[mbsv run] class rows %d%s warps %d: start %.1f end %.1f ms\n", g_launch_info[i].rows,
+                         g_launch_info[i].memo ? " (memo)" : "", g_launch_info[i].warps, t0, t1);
+        }
+    if (have_global_tables && std::getenv("MBSV_DEBUG_TIMING")) {
+        float bms = 0;
+        cudaEventElapsedTime(&bms, p->ev_start, p->ev_cls0[0]);
+        std::fprintf(stderr, "[mbsv run] table build: %zu subproblems, %lld states, %.3f ms; lanes/warp %d (memo %d%s)\n",
+                     p->tab_sub.size(), p->memo_global_doubles, bms, L, Lm, mixed ? ", mixed" : "");
+    }
 
     // chain status
     long long htot[6] = {0, 0, 0, 0, 0, 0};

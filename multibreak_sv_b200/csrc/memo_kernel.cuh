@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) mbsv_memo_build_kernel(const __grid_const
     R.memo_global[R.sub_tab_off[sub] + idx] = lp;
 }
 
-template <bool TRACE>
+template <bool TRACE, bool MIXED>
 __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(const __grid_constant__ DevProblem P,
                                                                               const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
@@ -89,12 +89,14 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     const bool alive = lane < R.lanes_per_warp && item_raw < R.n_items;
     // idle lanes mirror the warp's first item, so that every per-subproblem quantity stays warp-uniform
     const long long item = alive ? item_raw : R.item_base + (long long)(warp - R.warp_base) * R.lanes_per_warp;
-    const int sub = R.sub_order[item / R.n_chains];          // warp-uniform: lanes_per_warp divides n_chains
+    // warp-uniform unless R.memo_mixed (then lanes_per_warp need not divide n_chains and nothing below relies on it)
+    const int sub = R.sub_order[item / R.n_chains];
+    constexpr bool mixed = MIXED;     // (DevRun.memo_mixed says the same; compile-time here so full warps pay nothing)
     const int chain = (int)(item % R.n_chains);
     int* st = smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane;
 
 #ifdef MBSV_BOUNDS_CHECK
-    const int st_rows = min(R.sub_W[sub], R.rows_per_warp);
+    const int st_rows = min(R.sub_W[sub] + (MIXED ? P.sub_frag_ptr[sub + 1] - P.sub_frag_ptr[sub] : 0), R.rows_per_warp);
 #endif
     const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
     const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
@@ -108,7 +110,9 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     // after the state rows: fragment strides, then the table — in shared memory when it fits the size classes,
     // otherwise in a global buffer (one region per subproblem; both warps of a subproblem fill it with the same
     // values and each reads only after its own complete build)
-    int* strides = smem_tile + ((size_t)wic * R.rows_per_warp + W) * 32;
+    // (mixed warps: the strides sit in the lane's own column, rows W .. W+F-1, and every table is in the global buffer)
+    int* strides = mixed ? st + (size_t)W * 32 : smem_tile + ((size_t)wic * R.rows_per_warp + W) * 32;
+    constexpr int sstr = MIXED ? 32 : 1;
     const long long tab_off = R.sub_tab_off[sub];
     double* tab = tab_off >= 0 ? R.memo_global + tab_off : reinterpret_cast<double*>(strides + ((F + 1) & ~1));
     const double logperr = R.logperr;
@@ -120,8 +124,8 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     double* rtab = tab + nst;
 #ifdef MBSV_BOUNDS_CHECK
     {   // strides, table and ratio table must end inside this warp's rows of the tile
-        const int* end = tab_off >= 0 ? strides + ((F + 1) & ~1) : reinterpret_cast<const int*>(rtab + (f1 ? nst * nst : 0));
-        if (end > smem_tile + (size_t)(wic + 1) * R.rows_per_warp * 32) {
+        const int* end = mixed ? smem_tile : tab_off >= 0 ? strides + ((F + 1) & ~1) : reinterpret_cast<const int*>(rtab + (f1 ? nst * nst : 0));
+        if ((mixed && tab_off < 0) || end > smem_tile + (size_t)(wic + 1) * R.rows_per_warp * 32) {
             printf("memo tables of subproblem %d overrun the %d-row tile\n", sub, R.rows_per_warp);
             __trap();
         }
@@ -171,9 +175,9 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
                 }
                 tab[idx] = lp;
             }
-            if (lane == 0) {
+            if (lane == 0 || mixed) {
                 int sprod = 1;
-                for (int f = 0; f < F; ++f) { strides[f] = sprod; sprod *= P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f] + 1; }
+                for (int f = 0; f < F; ++f) { strides[f * sstr] = sprod; sprod *= P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f] + 1; }
             }
         }
         __syncwarp();
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
                 else a = rng.nextInt(n);
             }
             MBSV_ST(f) = a;
-            sidx += (a + 1) * strides[f];
+            sidx += (a + 1) * strides[f * sstr];
             if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
         }
     }
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
                 prev = MBSV_ST(f);
                 naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
                 if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
-                newidx += (now - prev) * strides[f];
+                newidx += (now - prev) * strides[f * sstr];
             } else {
                 ++n_sv_prop;
                 svk = (int)(u * (double)nsv);
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
                 for (int q = 0; q < nmoves; ++q) {
                     const int g = P.sv_frag[q0 + q] - f0;
                     const int from = MBSV_ST(g);
-                    newidx += ((from == -1) ? 1 : -1) * strides[g];
+                    newidx += ((from == -1) ? 1 : -1) * strides[g * sstr];
                 }
             }
             newlogprob = tab[newidx];

@@ -52,6 +52,9 @@ struct DevRun {
     const long long* sub_tab_off;    // memoised kernel: offset of the subproblem's table in memo_global, -1 = shared memory
     double* memo_global;
     long long n_items;               // n_sub * n_chains
+    int memo_mixed;                  // memoised kernel: 0 = a warp holds chains of ONE subproblem (strides/tables shared by
+                                     // the warp), 1 = every lane may hold another subproblem (strides in the lane's own
+                                     // column after its state rows, all tables in memo_global)
     int lanes_per_warp;              // chains per warp: 32, or fewer for small batches (more warps hide the serial
                                      // dependency chain of a chain better than full warps do when the GPU is not full)
     const long long* warp_row_off;   // [warp - global_warp0] row offset into workspace (global class)
@@ -84,7 +87,7 @@ KernelFn get_kernel_fast(bool smem, int n_exp);                 // MODE_FAST, no
 KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_EXACT, no trace
 KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
 KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with connected-component clusters
-KernelFn get_kernel_memo(bool trace);                           // memoised subproblems (memo_kernel.cuh)
+KernelFn get_kernel_memo(bool trace, bool mixed);               // memoised subproblems (memo_kernel.cuh)
 // fills the device-memory log-posterior tables of the memoised subproblems listed in tab_sub
 cudaError_t launch_memo_build(const DevProblem& P, const DevRun& R, int n_tab, const long long* state_ptr, const int* tab_sub,
                               long long n_states, int scratch_rows, cudaStream_t stream);

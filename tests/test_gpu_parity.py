@@ -294,9 +294,10 @@ def test_full_size_invariants(mbsv):
         assert np.array_equal(getattr(f, k), getattr(r, k)), k
 
 
-@pytest.mark.parametrize("n_chains", [8, 16, 24, 48])
+@pytest.mark.parametrize("n_chains", [1, 3, 8, 16, 24, 48])
 def test_memo_kernel_with_partial_warps(oracle, mbsv, n_chains):
-    """8 / 16 chains run the memoised kernel with quarter / half warps; other counts fall back to the general kernel."""
+    """8 / 16 chains run the memoised kernel with quarter / half warps of one subproblem; other counts (and small
+    batches) run it with mixed warps: every lane its own subproblem, strides in the lane's column, tables in device memory."""
     from multibreak_sv_b200 import synth
     p = synth.generate("cfg3", n_frag=1200, seed=21)
     op = oracle.Problem(p.scalars, p.arrays)
@@ -307,6 +308,49 @@ def test_memo_kernel_with_partial_warps(oracle, mbsv, n_chains):
     g = dp.run(mbsv.MODE_FAST, 1500, n_chains=n_chains)
     assert np.array_equal(o.aln_count, g.aln_count) and np.array_equal(o.rng_state, g.rng_state)
     assert np.array_equal(o.final_logprob, g.final_logprob)
+
+
+@pytest.mark.parametrize("n_chains,mode_rows", [(32, -1), (5, -1), (64, -1)])
+def test_memoised_subproblem_wider_than_shared_memory(oracle, mbsv, n_chains, mode_rows):
+    """A one-fragment subproblem with 300 alignments in 300 clusters is memo-eligible (301 states) but its counts do not
+    fit the shared-memory classes: it must run (general kernel, same full-sum arithmetic) next to small memoised ones."""
+    from multibreak_sv_b200 import synth
+    g = synth.generate("cfg2", n_frag=40, seed=5)
+    a, sc = {k: v.copy() for k, v in g.arrays.items()}, dict(g.scalars)
+    nA, nC = 300, 300
+    F0, A0, K0, C0, S0 = sc["n_frag"], sc["n_aln"], sc["n_aln_esp"], sc["n_cluster"], sc["n_sub"]
+    cat = np.concatenate
+    a["sub_frag_ptr"] = cat([a["sub_frag_ptr"], [F0 + 1]]).astype(np.int32)
+    a["sub_cluster_ptr"] = cat([a["sub_cluster_ptr"], [C0 + nC]]).astype(np.int32)
+    a["sub_sv_ptr"] = cat([a["sub_sv_ptr"], [a["sub_sv_ptr"][-1]]]).astype(np.int32)
+    a["frag_aln_ptr"] = cat([a["frag_aln_ptr"], [A0 + nA]]).astype(np.int32)
+    rng = np.random.default_rng(8)
+    a["aln_numerrors"] = cat([a["aln_numerrors"], rng.integers(0, 6, nA)]).astype(np.int32)
+    a["aln_len"] = cat([a["aln_len"], np.full(nA, 200)]).astype(np.int32)
+    a["aln_exp"] = cat([a["aln_exp"], np.zeros(nA)]).astype(np.int32)
+    a["aln_esp_ptr"] = cat([a["aln_esp_ptr"], K0 + 1 + np.arange(nA)]).astype(np.int32)
+    a["aln_esp_cluster"] = cat([a["aln_esp_cluster"], C0 + np.arange(nA)]).astype(np.int32)
+    a["aln_esp_leaf"] = cat([a["aln_esp_leaf"], np.zeros(nA)]).astype(np.int32)
+    a["cluster_kind"] = cat([a["cluster_kind"], np.zeros(nC)]).astype(np.uint8)
+    a["supports_order"] = cat([a["supports_order"], C0 + rng.permutation(nC)]).astype(np.int32)
+    one = 1 + np.arange(nC)
+    a["cluster_hist_ptr"] = cat([a["cluster_hist_ptr"], a["cluster_hist_ptr"][-1] + 2 * one]).astype(np.int32)   # supports 0..1
+    a["cluster_leaf_ptr"] = cat([a["cluster_leaf_ptr"], a["cluster_leaf_ptr"][-1] + one]).astype(np.int32)
+    a["leaf_owner"] = cat([a["leaf_owner"], np.full(nC, F0)]).astype(np.int32)
+    a["cluster_root_ptr"] = cat([a["cluster_root_ptr"], a["cluster_root_ptr"][-1] + one]).astype(np.int32)
+    a["root_leaf_ptr"] = cat([a["root_leaf_ptr"], a["root_leaf_ptr"][-1] + one]).astype(np.int32)
+    a["root_leaf"] = cat([a["root_leaf"], np.zeros(nC)]).astype(np.int32)
+    sc.update(n_sub=S0 + 1, n_frag=F0 + 1, n_aln=A0 + nA, n_aln_esp=K0 + nA, n_cluster=C0 + nC,
+              n_hist=int(a["cluster_hist_ptr"][-1]), n_leaf=sc["n_leaf"] + nC, n_root=sc["n_root"] + nC,
+              n_root_leaf=sc["n_root_leaf"] + nC)
+    p = mbsv.PackedProblem(sc, a)
+    op = oracle.Problem(sc, a)
+    dp = mbsv.DeviceProblem(p)
+    o = oracle.run(op, "incremental", 1200, n_chains=n_chains, nthreads=8, java_int_wrap=False)
+    gr = dp.run(mbsv.MODE_FAST, 1200, n_chains=n_chains)
+    assert_same(o, gr)
+    rows = [li["rows"] for li in dp.launch_info()]
+    assert 0 in rows                                      # the wide subproblem went to the global-workspace class
 
 
 @pytest.mark.parametrize("n_chains", [1, 32, 64])
