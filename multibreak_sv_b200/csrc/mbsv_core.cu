@@ -625,10 +625,11 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     // (each chain is one long dependency chain), so until the GPU holds its ~20 resident warps per SM more warps
     // with idle lanes are faster than full warps.  L = chains per warp, a power of two.
     int L = 32;
+    int64_t resident_warps = 148 * 20;
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-        const int64_t resident_warps = (int64_t)sms * 20;
+        resident_warps = (int64_t)sms * 20;
         while (L > 1 && (n_items + L / 2 - 1) / (L / 2) <= resident_warps) L /= 2;
         if (const char* env = std::getenv("MBSV_LANES_PER_WARP")) L = std::max(1, std::min(32, std::atoi(env)));
     }
@@ -641,10 +642,6 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     const int Lm = mixed ? L : Lu;
     if (int prc = ensure_plan(p, rp->memo_states, mixed ? 2 : 1)) return prc;
     const int64_t tab_items = (int64_t)p->n_tab_subs * X;
-    const int64_t memo_warps = (tab_items + Lm - 1) / Lm;
-    const int64_t n_warps64 = memo_warps + (n_items - tab_items + L - 1) / L;
-    if (n_warps64 > 0x7fffffff / 32) return fail(MBSV_ERR_ARG, "too many chains for one launch");
-    const int n_warps = (int)n_warps64;
     const int64_t sc_total = n_items;
 
     OutBufs ob;
@@ -704,49 +701,70 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         cls.clear();
         for (const char* q = env; *q;) { cls.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
     }
-    auto warp_rows = [&](int w) -> int {
-        const int64_t last = w < memo_warps ? std::min<int64_t>((int64_t)w * Lm + Lm - 1, tab_items - 1)
-                                            : std::min<int64_t>(tab_items + (int64_t)(w - memo_warps) * L + L - 1, n_items - 1);
-        return std::max(1, p->sub_rows[p->sub_order[last / X]]);
-    };
-    // Two groups of warps, each sorted by rows: [0, wsplit) memoised-kernel subproblems, [wsplit, n_warps) the rest.
-    // (n_chains % 32 == 0 whenever the first group is non-empty, so the split falls on a warp boundary.)
-    const int wsplit = (int)memo_warps;
-    struct Launch { int wb, we, rows; bool smem, memo; };
+    // Classes are cut in (sorted subproblem) space, separately for the memoised group [0, n_tab_subs) and the rest; every
+    // class then picks its own chains-per-warp.  Starting from the batch-wide L, classes are revisited from the largest
+    // state down and their L halved while the GPU still has unfilled warp slots: the few chains of the big classes are the
+    // critical path of a small batch, and a warp of k diverged chains runs each of them ~k times slower.
+    struct Launch { int wb, we, rows; bool smem, memo; int64_t i0, i1; int lanes; };
     std::vector<Launch> launches;
-    auto add_group = [&](int g0, int g1, bool memo) {
-        int lo = g0;
-        for (size_t k = 0; k < cls.size() && lo < g1; ++k) {
-            int a = lo, b = g1;
-            while (a < b) { int m = a + (b - a) / 2; if (warp_rows(m) <= cls[k]) a = m + 1; else b = m; }
-            if (a > lo) launches.push_back({lo, a, cls[k], true, memo});
+    auto add_group = [&](int k0, int k1, bool memo) {
+        int lo = k0;
+        auto rows_of = [&](int k) { return std::max(1, p->sub_rows[p->sub_order[k]]); };
+        for (size_t c = 0; c < cls.size() && lo < k1; ++c) {
+            int a = lo, b = k1;
+            while (a < b) { int m = a + (b - a) / 2; if (rows_of(m) <= cls[c]) a = m + 1; else b = m; }
+            if (a > lo) launches.push_back({0, 0, cls[c], true, memo, (int64_t)lo * X, (int64_t)a * X, memo ? Lm : L});
             lo = a;
         }
-        if (lo < g1) launches.push_back({lo, g1, 0, false, memo});
+        if (lo < k1) launches.push_back({0, 0, 0, false, memo, (int64_t)lo * X, (int64_t)k1 * X, memo ? Lm : L});
     };
-    add_group(0, wsplit, true);
-    add_group(wsplit, n_warps, false);
-    int g0 = n_warps;
+    add_group(0, p->n_tab_subs, true);
+    add_group(p->n_tab_subs, S, false);
+    // largest state first: the global-workspace class (few, slow chains) starts before the bulk of small chains
+    std::stable_sort(launches.begin(), launches.end(), [](const Launch& a, const Launch& b) {
+        const int ra = a.smem ? a.rows : 1 << 30, rb = b.smem ? b.rows : 1 << 30;
+        return ra > rb;
+    });
+    {
+        auto warps_of = [](const Launch& l, int lanes) { return (l.i1 - l.i0 + lanes - 1) / lanes; };
+        int64_t total = 0;
+        for (const Launch& l : launches) total += warps_of(l, l.lanes);
+        int64_t spare = resident_warps - total;
+        for (Launch& l : launches) {
+            if (l.memo && !mixed) continue;                  // warps of one subproblem keep their fixed width
+            while (l.lanes > 1) {
+                const int64_t extra = warps_of(l, l.lanes / 2) - warps_of(l, l.lanes);
+                if (extra > spare) break;
+                spare -= extra;
+                l.lanes /= 2;
+            }
+        }
+        if (std::getenv("MBSV_LANES_PER_WARP")) for (Launch& l : launches) l.lanes = l.memo ? Lm : L;
+        int64_t w = 0;
+        for (Launch& l : launches) {
+            if (l.memo && !l.smem) return fail(MBSV_ERR_ARG, "internal: memoised subproblem does not fit the shared-memory classes");
+            l.wb = (int)w;
+            w += warps_of(l, l.lanes);
+            if (w > 0x7fffffff / 32) return fail(MBSV_ERR_ARG, "too many chains for one launch");
+            l.we = (int)w;
+        }
+    }
+    // the global-workspace class: one row range per warp (rows of its largest = last subproblem)
     for (const Launch& l : launches) {
         if (l.smem) continue;
-        if (l.memo) return fail(MBSV_ERR_ARG, "internal: memoised subproblem does not fit the shared-memory classes");
-        g0 = l.wb;
-    }
-    if (g0 < n_warps) {
-        std::vector<long long> off(n_warps - g0);
+        std::vector<long long> off(l.we - l.wb);
         long long acc = 0;
-        for (int w = g0; w < n_warps; ++w) { off[w - g0] = acc; acc += warp_rows(w); }
+        for (int w = l.wb; w < l.we; ++w) {
+            const int64_t last = std::min<int64_t>(l.i0 + (int64_t)(w - l.wb) * l.lanes + l.lanes - 1, l.i1 - 1);
+            off[w - l.wb] = acc;
+            acc += std::max(1, p->sub_rows[p->sub_order[last / X]]);
+        }
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         if ((size_t)acc * 128 > free_b) return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory");
         CUDA_TRY(ob.workspace.alloc((size_t)acc * 32));
         CUDA_TRY(ob.row_off.upload(off));
     }
-    // largest state first: the global-workspace class (few, slow chains) starts before the bulk of small chains
-    std::stable_sort(launches.begin(), launches.end(), [](const Launch& a, const Launch& b) {
-        const int ra = a.smem ? a.rows : 1 << 30, rb = b.smem ? b.rows : 1 << 30;
-        return ra > rb;
-    });
     if ((int)launches.size() > NSTREAM - 1) return fail(MBSV_ERR_ARG, "too many size classes");
 
     CUDA_TRY(cudaEventRecord(p->ev_start, s0));
@@ -769,12 +787,12 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.rows_per_warp = l.smem ? l.rows : 0;
         r.warp_row_off = l.smem ? nullptr : ob.row_off.p;
         r.workspace = l.smem ? nullptr : ob.workspace.p;
-        r.global_warp0 = g0;
-        r.warp_base = l.memo ? 0 : wsplit;
-        r.item_base = l.memo ? 0 : tab_items;
-        r.lanes_per_warp = l.memo ? Lm : L;
+        r.global_warp0 = l.wb;
+        r.warp_base = l.wb;
+        r.item_base = l.i0;
+        r.n_items = l.i1;                       // the last warp of a class may be partly filled
+        r.lanes_per_warp = l.lanes;
         r.memo_mixed = mixed ? 1 : 0;
-        if (l.memo) r.n_items = tab_items;      // the last warp of the memoised group may be partly filled
         KernelFn fn = l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
                                  : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);
