@@ -761,8 +761,9 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         }
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        if ((size_t)acc * 128 > free_b) return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory");
-        CUDA_TRY(ob.workspace.alloc((size_t)acc * 32));
+        if ((size_t)acc * 128 > free_b && !(l.lanes == 1 && !rp->trace && (size_t)acc * 4 <= free_b)) return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory");
+        const bool packed = l.lanes == 1 && !rp->trace;     // one chain per warp: contiguous columns (kern_packed.cu)
+        CUDA_TRY(ob.workspace.alloc((size_t)acc * (packed ? 1 : 32)));
         CUDA_TRY(ob.row_off.upload(off));
     }
     if ((int)launches.size() > NSTREAM - 1) return fail(MBSV_ERR_ARG, "too many size classes");
@@ -794,6 +795,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.lanes_per_warp = l.lanes;
         r.memo_mixed = mixed ? 1 : 0;
         KernelFn fn = l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
+                     : (!l.smem && l.lanes == 1 && !rp->trace) ? mbsv::get_kernel_packed(rp->mode, p->has_cc)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
                                  : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);
         const size_t shm = l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;

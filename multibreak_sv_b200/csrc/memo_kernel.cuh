@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     constexpr bool mixed = MIXED;     // (DevRun.memo_mixed says the same; compile-time here so full warps pay nothing)
     const int chain = (int)(item % R.n_chains);
     int* st = smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane;
+    constexpr int st_stride = 32;
 
 #ifdef MBSV_BOUNDS_CHECK
     const int st_rows = min(R.sub_W[sub] + (MIXED ? P.sub_frag_ptr[sub + 1] - P.sub_frag_ptr[sub] : 0), R.rows_per_warp);

@@ -41,19 +41,20 @@ static __device__ MBSV_MATH_INLINE double log_binomial_dev(long long k, long lon
 
 static __device__ MBSV_MATH_INLINE double exp_dev(double x) { return jm_exp(x); }
 
-// Row i of this chain's column of the [rows][32] state tile.  The checked build (make check) traps on a row outside
+// Row i of this chain's column of the [rows][st_stride] state tile (32 in shared memory: one bank per lane; the global
+// workspace packs the rows of narrow warps, st_stride = chains per warp).  The checked build (make check) traps on a row outside
 // the subproblem's rows instead of corrupting a neighbour's state; `st_rows` is defined next to `st` in each kernel.
 #ifdef MBSV_BOUNDS_CHECK
-static __device__ __noinline__ int& mbsv_st_checked(int* st, long long i, int rows, int line) {
+static __device__ __noinline__ int& mbsv_st_checked(int* st, long long i, int rows, int line, int stride) {
     if (i < 0 || i >= rows) {
         printf("MBSV_ST: row %lld outside [0,%d) at line %d (block %d thread %d)\n", i, rows, line, blockIdx.x, threadIdx.x);
         __trap();
     }
-    return st[(size_t)i << 5];
+    return st[i * (long long)stride];
 }
-#define MBSV_ST(i) mbsv_st_checked(st, (i), st_rows, __LINE__)
+#define MBSV_ST(i) mbsv_st_checked(st, (i), st_rows, __LINE__, st_stride)
 #else
-#define MBSV_ST(i) st[(size_t)(i) << 5]
+#define MBSV_ST(i) st[(long long)(int)(i) * (long long)st_stride]      // one IMAD.WIDE
 #endif
 
 

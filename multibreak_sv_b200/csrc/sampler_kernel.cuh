@@ -32,7 +32,7 @@ namespace mbsv {
 
 // CC = the batch contains connected-component clusters (GASV localization -1): their support is the sorted
 // multiset of a greedy set cover (MultiBreakSVAssignmentMatrix.java:337-409) kept per chain next to the counts.
-template <int MODE, bool TRACE, bool SMEM, int MAXE, bool CC = false>
+template <int MODE, bool TRACE, bool SMEM, int MAXE, bool CC = false, bool PACKED = false>
 __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_GLOBAL) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
                                                          const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
@@ -46,8 +46,12 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
     const long long item = alive ? item_raw : R.n_items - 1;
     const int sub = R.sub_order[item / R.n_chains];
     const int chain = (int)(item % R.n_chains);
+    // A chain's state is a column of a [rows][32] tile (conflict-free banks in shared memory, coalesced rows in the global
+    // workspace).  PACKED (one chain per warp, global workspace): the column is stored contiguously, so that the few
+    // chains of a giant component take 4 bytes per row instead of a 128-byte row each and stay L2-resident.
+    constexpr int st_stride = (!SMEM && PACKED) ? 1 : 32;
     int* st = SMEM ? (smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane)
-                   : (R.workspace + (size_t)R.warp_row_off[warp - R.global_warp0] * 32 + lane);
+                   : (R.workspace + (size_t)R.warp_row_off[warp - R.global_warp0] * st_stride + (PACKED ? 0 : lane));
 
 #ifdef MBSV_BOUNDS_CHECK
     const int st_rows = !alive ? 0 : SMEM ? min(R.sub_W[sub], R.rows_per_warp) : R.sub_W[sub];

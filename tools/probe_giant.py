@@ -6,7 +6,7 @@ from multibreak_sv_b200 import synth
 p = synth.generate("cfg5")
 print(p.scalars)
 dp = m.DeviceProblem(p)
-for X in (64, 1024):
-    for T in (0, 20000, 40000):
+for X in (8, 64, 1024):
+    for T in (0, 20000, 100000):
         o = dp.run(m.MODE_FAST, T, n_chains=X, want_state=False, per_chain=False)
         print('X', X, 'T', T, 'kernel %.1f ms'%o.kernel_ms, 'reassign', int(o.totals[4]))
