@@ -141,7 +141,9 @@ typedef struct mbsv_run_params {
                                 prod(n_f + 1) is at most memo_states evaluate a proposal with the full log-posterior
                                 of the proposed state, i.e. REPLAY arithmetic — the reference's own memo of state
                                 log-probabilities (MultiBreakSV.java:58,1133-1137); the device keeps one table per
-                                subproblem (shared memory when small, else device memory).  0 disables; 65536 is the tuned default. */
+                                subproblem (shared memory when small, else device memory, at most a quarter of the free
+                                device memory in total).  The arithmetic depends only on this value, never on the chain
+                                count or the GPU.  0 disables; 65536 is the tuned default. */
 } mbsv_run_params;
 
 /* Output buffers (caller-allocated host memory; NULL pointers are skipped). */
