@@ -6,6 +6,6 @@ from multibreak_sv_b200 import synth
 p = synth.generate("cfg4", skeleton=synth.draw_skeleton("cfg4"))
 dp = m.DeviceProblem(p)
 for it in range(2):
-    o = dp.run(m.MODE_FAST, 2000, n_chains=64, want_state=False, per_chain=False)
+    o = dp.run(m.MODE_FAST, int(os.environ.get('ITERS', 2000)), n_chains=64, want_state=False, per_chain=False, memo_states=int(os.environ.get('MEMO', 65536)))
 print('kernel %.1f ms'%o.kernel_ms, 'reassign/s %.3e'%(o.totals[4]/(o.kernel_ms/1e3)))
 for li in dp.launch_info(): print('  rows %4d warps %8d ms %7.1f'%(li['rows'], li['warps'], li['ms']))
