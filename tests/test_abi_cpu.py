@@ -105,6 +105,18 @@ def test_descriptor_validation(mbsv, example_problem):
     assert create(bad) == -6
     assert L.mbsv_problem_create(None, 0, C.byref(h)) == -1
     assert L.mbsv_status_string(-5) == b"reference invariant violated"
+    # an empty problem (no subproblem / fragment / alignment) is an argument error: the reference cannot run it either
+    # (nextInt(0) and an index into an empty fragment list throw, MultiBreakSV.java:1013,1198)
+    for key in ("n_sub", "n_frag", "n_aln"):
+        bad = to_packed(mbsv, example_problem)
+        bad.scalars[key] = 0
+        assert create(bad) == -1 and b"out of range" in L.mbsv_last_error()
+    # a fragment without any alignment is ragged input the packer rejects too
+    bad = to_packed(mbsv, example_problem)
+    fp = p.arrays["frag_aln_ptr"].copy()
+    fp[1] = fp[0]
+    bad.arrays["frag_aln_ptr"] = fp
+    assert create(bad) == -1
 
 
 def test_host_math_matches_oracle(mbsv, oracle):

@@ -382,3 +382,53 @@ def test_bounds_checked_build():
                         "not bounds_checked and not full_size and not posterior_within"],
                        env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def _with_experiments(mbsv, g, n_exp, seed):
+    """The generated problem with its alignments spread over n_exp sequencing experiments (1..4 on the device)."""
+    import ctypes as C_
+    a, sc = {k: v.copy() for k, v in g.arrays.items()}, dict(g.scalars)
+    rng = np.random.default_rng(seed)
+    a["aln_exp"] = rng.integers(0, n_exp, sc["n_aln"]).astype(np.int32)
+    a["exp_pseq"] = np.array([0.01, 0.15, 0.05, 0.10][:n_exp])
+    a["exp_lambda"] = np.array([10.0, 3.0, 5.0, 2.0][:n_exp])
+    T = np.zeros((n_exp, sc["max_support"] + 1))
+    L = mbsv.load_library()
+    for x in range(n_exp):
+        L.mbsv_fill_logprobcov(float(a["exp_lambda"][x]), sc["max_support"], T[x].ctypes.data_as(C_.POINTER(C_.c_double)))
+    a["logprobcov"] = T.ravel()
+    sc["n_exp"] = n_exp
+    return mbsv.PackedProblem(sc, a)
+
+
+@pytest.mark.parametrize("n_exp,cc", [(3, 0.0), (4, 0.0), (4, 0.4)])
+def test_three_and_four_experiments(oracle, mbsv, n_exp, cc):
+    """MBSV_MAX_EXP = 4: per-experiment totals, logBinomial terms and count slots for every experiment count."""
+    from multibreak_sv_b200 import synth
+    p = _with_experiments(mbsv, synth.generate("cfg4", n_frag=1500, seed=31, conncomp_frac=cc), n_exp, 7)
+    op = oracle.Problem(p.scalars, p.arrays)
+    dp = mbsv.DeviceProblem(p)
+    for mode, omode in ((mbsv.MODE_FAST, "incremental"), (mbsv.MODE_REPLAY_EXACT, "faithful")):
+        o = oracle.run(op, omode, 1500, n_chains=32, nthreads=8, java_int_wrap=False, trace=True)
+        g = dp.run(mode, 1500, n_chains=32, java_int_wrap=False, trace=True)
+        assert_same(o, g, trace=True)
+        g = dp.run(mode, 1500, n_chains=32, java_int_wrap=False)
+        assert_same(o, g)
+
+
+@pytest.mark.parametrize("perr", [0.0, 1.0, 0.5, 1e-300])
+def test_error_probability_extremes(oracle, mbsv, example_problem, perr):
+    """perr = 0 makes log(perr) = -inf (0 * -inf = NaN log-posteriors, never accepted: Math.min(1, NaN) > u is false);
+    perr = 1 makes every draw propose "unmapped"; both must follow the reference's arithmetic, not trap."""
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg4", n_frag=400, seed=77)
+    op = oracle.Problem(p.scalars, p.arrays)
+    for prob, oprob in ((mbsv.DeviceProblem(p), op), (mbsv.DeviceProblem(to_packed(mbsv, example_problem)), example_problem)):
+        for mode, omode in ((mbsv.MODE_FAST, "incremental"), (mbsv.MODE_REPLAY_EXACT, "faithful")):
+            o = oracle.run(oprob, omode, 800, n_chains=32, perr=perr, nthreads=8, java_int_wrap=False)
+            g = prob.run(mode, 800, n_chains=32, perr=perr, java_int_wrap=False)
+            assert np.array_equal(o.counters, g.counters) and np.array_equal(o.rng_state, g.rng_state)
+            assert np.array_equal(o.final_assign, g.final_assign) and np.array_equal(o.aln_count, g.aln_count)
+            assert np.array_equal(o.cluster_hist, g.cluster_hist) and np.array_equal(o.frag_err_count, g.frag_err_count)
+            # NaN log-posteriors compare by bit pattern
+            assert np.array_equal(o.final_logprob.view(np.uint64), g.final_logprob.view(np.uint64))
