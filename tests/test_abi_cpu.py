@@ -126,6 +126,14 @@ def test_host_math_matches_oracle(mbsv, oracle):
         assert L.mbsv_log(float(x)) == oracle.jlog(float(x))
     for x in rng.uniform(-750, 710, 20000):
         assert L.mbsv_exp(float(x)) == oracle.jexp(float(x))
+    # the selected (formerly early-return) cases of e_exp.c: thresholds, subnormal results, tiny arguments, non-finite
+    bits = lambda v: np.float64(v).view(np.uint64)
+    special = [0.0, -0.0, 1e-10, -1e-10, 2.0 ** -28, 2.0 ** -29, -2.0 ** -29, 709.782712893384, 709.7827128933841, 709.79,
+               -745.1332191019411, -745.1332191019412, -745.14, -708.0, -708.4, -720.0, -744.9, 1e300, -1e300, 5e3, -5e3,
+               float("inf"), float("-inf"), float("nan"), 0.5 * np.log(2.0), 1.5 * np.log(2.0), -0.34, 0.35, 1.04]
+    special += list(rng.uniform(-746, -707, 2000)) + list(rng.uniform(-1e-7, 1e-7, 2000)) + list(rng.uniform(-1e5, 1e5, 2000))
+    for x in special:
+        assert bits(L.mbsv_exp(float(x))) == bits(oracle.jexp(float(x))), x
     t = np.zeros(27)
     assert L.mbsv_fill_logprobcov(3.0, 26, t.ctypes.data_as(C.POINTER(C.c_double))) == 0
     assert t[0] == 0.0 and abs(t[3] - (-3 + 3 * np.log(3) - np.log(6))) < 1e-12
