@@ -633,12 +633,12 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         while (L > 1 && (n_items + L / 2 - 1) / (L / 2) <= resident_warps) L /= 2;
         if (const char* env = std::getenv("MBSV_LANES_PER_WARP")) L = std::max(1, std::min(32, std::atoi(env)));
     }
-    // The memoised kernel needs warps that hold chains of ONE subproblem: full warps when n_chains is a multiple of 32,
-    // half / quarter warps for 16 / 8 chains (it is ~3x cheaper per chain than the general kernel, so idle lanes pay off).
-    // Any other chain count, and small batches, run it with mixed warps: every lane its own (subproblem, chain), tables in
-    // device memory.
-    const int Lu = X % 32 == 0 ? 32 : (X == 16 || X == 8) ? X : 0;
-    const bool mixed = !(Lu > 0 && L == 32);
+    // The memoised kernel runs either full warps of ONE subproblem (n_chains a multiple of 32: strides and small tables in
+    // the warp's shared memory) or mixed warps where every lane holds its own (subproblem, chain) with the tables in device
+    // memory — any other chain count, and small batches.  (Half / quarter warps of one subproblem for 16 / 8 chains were
+    // measured 35 % slower than mixed full warps on the 16-chain long-read config.)
+    const int Lu = X % 32 == 0 ? 32 : 0;
+    const bool mixed = !(Lu > 0 && L == 32) || std::getenv("MBSV_FORCE_MIXED") != nullptr;   // (env: tuning aid)
     const int Lm = mixed ? L : Lu;
     if (int prc = ensure_plan(p, rp->memo_states, mixed ? 2 : 1)) return prc;
     const int64_t tab_items = (int64_t)p->n_tab_subs * X;

@@ -296,8 +296,8 @@ def test_full_size_invariants(mbsv):
 
 @pytest.mark.parametrize("n_chains", [1, 3, 8, 16, 24, 48])
 def test_memo_kernel_with_partial_warps(oracle, mbsv, n_chains):
-    """8 / 16 chains run the memoised kernel with quarter / half warps of one subproblem; other counts (and small
-    batches) run it with mixed warps: every lane its own subproblem, strides in the lane's column, tables in device memory."""
+    """Chain counts that are not a multiple of 32 (and small batches) run the memoised kernel with mixed warps: every lane
+    its own subproblem, strides in the lane's column, tables in device memory."""
     from multibreak_sv_b200 import synth
     p = synth.generate("cfg3", n_frag=1200, seed=21)
     op = oracle.Problem(p.scalars, p.arrays)
