@@ -7,10 +7,12 @@
 #include <charconv>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -25,7 +27,7 @@ int hfail(int code, const std::string& msg) { mbsv_internal_set_error(msg.c_str(
 // ---------------------------------------------------------------------------------------------------------
 // Java semantics
 // ---------------------------------------------------------------------------------------------------------
-uint32_t java_hash(const std::string& s) {            // String.hashCode then HashMap.hash spreading
+uint32_t java_hash(std::string_view s) {               // String.hashCode then HashMap.hash spreading
     uint32_t h = 0;
     for (unsigned char c : s) h = 31u * h + c;
     return h ^ (h >> 16);
@@ -49,7 +51,7 @@ struct JavaMapOrder {
         bin.assign(cap, 0);
         for (size_t i = 0; i < hash.size(); ++i) if (alive[i]) ++bin[hash[i] & (cap - 1)];
     }
-    int put(const std::string& key) {                 // key must be new
+    int put(std::string_view key) {                   // key must be new
         if (cap == 0) resize();
         const uint32_t h = java_hash(key);
         hash.push_back(h);
@@ -87,32 +89,107 @@ struct Scanner {                                      // java.util.Scanner over 
         while (pos < buf.size() && !java_ws((unsigned char)buf[pos])) ++pos;
         return buf.substr(a, pos - a);
     }
-    std::string nextLine() {
+    std::string nextLine() { return std::string(nextLineView()); }
+    // the same tokens as views into `buf` (no allocation; valid while the Scanner lives)
+    std::string_view nextView() {
+        while (pos < buf.size() && java_ws((unsigned char)buf[pos])) ++pos;
+        const size_t a = pos;
+        while (pos < buf.size() && !java_ws((unsigned char)buf[pos])) ++pos;
+        return std::string_view(buf).substr(a, pos - a);
+    }
+    std::string_view nextLineView() {
         const size_t a = pos;
         while (pos < buf.size() && buf[pos] != '\n' && buf[pos] != '\r') ++pos;
-        std::string line = buf.substr(a, pos - a);
+        const std::string_view line = std::string_view(buf).substr(a, pos - a);
         if (pos < buf.size()) pos += (buf[pos] == '\r' && pos + 1 < buf.size() && buf[pos + 1] == '\n') ? 2 : 1;
         return line;
     }
 };
 
-std::vector<std::string> split(const std::string& s, const std::string& sep) {   // String.split(literal)
-    std::vector<std::string> out;
+// String.split(literal) into views (trailing empty strings removed; no separator -> the string itself)
+void split_views(std::string_view s, std::string_view sep, std::vector<std::string_view>& out) {
+    out.clear();
     size_t p = 0, q;
     bool any = false;
-    while ((q = s.find(sep, p)) != std::string::npos) { any = true; out.push_back(s.substr(p, q - p)); p = q + sep.size(); }
-    if (!any) return {s};
+    while ((q = s.find(sep, p)) != std::string_view::npos) { any = true; out.push_back(s.substr(p, q - p)); p = q + sep.size(); }
+    if (!any) { out.push_back(s); return; }
     out.push_back(s.substr(p));
     while (!out.empty() && out.back().empty()) out.pop_back();
-    return out;
 }
-std::string trim(const std::string& s) {
+std::string_view trim_view(std::string_view s) {
     size_t a = 0, b = s.size();
     while (a < b && (unsigned char)s[a] <= ' ') ++a;
     while (b > a && (unsigned char)s[b - 1] <= ' ') --b;
     return s.substr(a, b - a);
 }
-bool parse_int(const std::string& s, int& out) {
+
+// Interned strings (ESP names, fragment ids: millions at the 5M-fragment scale): NUL-terminated in one arena, found
+// through an open-addressing index.  Ids are dense in insertion order.
+struct StrTable {
+    struct Entry { uint64_t off; uint32_t len; uint32_t tag; };
+    std::vector<char> pool;
+    std::vector<Entry> ent;
+    std::vector<uint64_t> slot;         // open addressing: (tag << 32) | (id + 1), 0 = empty; the tag spares a visit to
+                                        // `ent` and `pool` (two more cache misses) for probes that cannot match
+    static uint64_t hash(std::string_view s) {
+        uint64_t h = 1469598103934665603ULL;
+        for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+        return h ^ (h >> 29);
+    }
+    int size() const { return (int)ent.size(); }
+    std::string_view view(int id) const { return std::string_view(pool.data() + ent[id].off, ent[id].len); }
+    const char* c_str(int id) const { return pool.data() + ent[id].off; }
+    std::string str(int id) const { return std::string(view(id)); }
+    bool same(int id, std::string_view s) const {
+        return ent[id].len == s.size() && std::memcmp(pool.data() + ent[id].off, s.data(), s.size()) == 0;
+    }
+    int find(std::string_view s) const {
+        if (slot.empty()) return -1;
+        const size_t mask = slot.size() - 1;
+        const uint64_t h = hash(s);
+        const uint32_t tag = (uint32_t)(h >> 32);
+        for (size_t i = h & mask;; i = (i + 1) & mask) {
+            const uint64_t v = slot[i];
+            if (v == 0) return -1;
+            if ((uint32_t)(v >> 32) == tag && same((int)(uint32_t)v - 1, s)) return (int)(uint32_t)v - 1;
+        }
+    }
+    int intern(std::string_view s, bool* added = nullptr) {
+        if ((ent.size() + 1) * 2 > slot.size()) grow();
+        const size_t mask = slot.size() - 1;
+        const uint64_t h = hash(s);
+        const uint32_t tag = (uint32_t)(h >> 32);
+        size_t i = h & mask;
+        for (;; i = (i + 1) & mask) {
+            const uint64_t v = slot[i];
+            if (v == 0) break;
+            if ((uint32_t)(v >> 32) == tag && same((int)(uint32_t)v - 1, s)) { if (added) *added = false; return (int)(uint32_t)v - 1; }
+        }
+        const int id = (int)ent.size();
+        slot[i] = ((uint64_t)tag << 32) | (uint32_t)(id + 1);
+        ent.push_back(Entry{pool.size(), (uint32_t)s.size(), tag});
+        pool.insert(pool.end(), s.begin(), s.end());
+        pool.push_back(0);
+        if (added) *added = true;
+        return id;
+    }
+    void grow() {
+        const size_t n = slot.empty() ? 1024 : slot.size() * 2;
+        slot.assign(n, 0);
+        for (int id = 0; id < (int)ent.size(); ++id) {
+            const uint64_t h = hash(view(id));
+            size_t i = h & (n - 1);
+            while (slot[i] != 0) i = (i + 1) & (n - 1);
+            slot[i] = ((uint64_t)ent[id].tag << 32) | (uint32_t)(id + 1);
+        }
+    }
+};
+std::vector<std::string> split(const std::string& s, const std::string& sep) {   // String.split(literal), owning copies
+    std::vector<std::string_view> v;
+    split_views(s, sep, v);
+    return std::vector<std::string>(v.begin(), v.end());
+}
+bool parse_int(std::string_view s, int& out) {
     if (s.empty()) return false;
     size_t i = (s[0] == '-' || s[0] == '+') ? 1 : 0;
     if (i >= s.size()) return false;
@@ -133,12 +210,20 @@ bool parse_double(const std::string& s, double& out) {
     return end != s.c_str() && *end == 0;
 }
 bool slurp(const std::string& path, std::string& out) {
-    std::ifstream in(path, std::ios::binary);
-    if (!in) return false;
-    std::stringstream ss;
-    ss << in.rdbuf();
-    out = ss.str();
-    return true;
+    std::FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    out.clear();
+    if (std::fseek(f, 0, SEEK_END) == 0) {
+        const long n = std::ftell(f);
+        std::rewind(f);
+        if (n > 0) out.reserve((size_t)n);
+    }
+    char buf[1 << 16];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, got);
+    const bool ok = !std::ferror(f);
+    std::fclose(f);
+    return ok;
 }
 
 // Double.toString: shortest digits that round-trip, decimal for 1e-3 <= |v| < 1e7, else d.dddE[-]n
@@ -182,12 +267,12 @@ struct mbsv_host {
     // ---- parsed state (field names follow the reference) ----
     std::vector<std::string> exp_label; std::vector<double> exp_pseq, exp_lambda;   // by experiment id
     std::unordered_map<std::string, int> exp_id; JavaMapOrder experiments;
-    std::vector<std::string> esp_name; std::unordered_map<std::string, int> esp_id_of;
-    std::vector<Fragment> frags; std::unordered_map<std::string, int> frag_id_of; JavaMapOrder fragments;
+    StrTable esp_name;                        // ESP id <-> name
+    std::vector<Fragment> frags; StrTable frag_id_of; JavaMapOrder fragments;   // fragment id == its index in frag_id_of
     std::vector<int> esp2fragment;            // ESP id -> fragment id (last writer), -1
     std::vector<char> in_allesps;
     std::vector<int> esp2cid;                 // ESP id -> cluster id (as in `clust`), -1
-    std::vector<std::string> cl_name; std::unordered_map<std::string, int> cl_id_of; std::vector<char> cl_is_cluster;
+    std::vector<std::string> cl_name; StrTable cl_id_of; std::vector<char> cl_is_cluster;   // cluster id == index in cl_id_of
     JavaMapOrder clust, breakpoints;          // cluster id == insertion id in `clust`
     std::vector<int> bp_of_cl, cl_of_bp;      // cluster id <-> breakpoints entry id (-1: none)
     int max_support = 0;
@@ -211,13 +296,10 @@ struct mbsv_host {
     double r_final_logprob = 0.0, r_initial_logprob = 0.0;
     bool have_results = false, have_trace = false;
 
-    int esp(const std::string& name) {
-        auto it = esp_id_of.find(name);
-        if (it != esp_id_of.end()) return it->second;
-        const int id = (int)esp_name.size();
-        esp_id_of.emplace(name, id);
-        esp_name.push_back(name);
-        esp2fragment.push_back(-1); in_allesps.push_back(0); esp2cid.push_back(-1);
+    int esp(std::string_view name) {
+        bool added;
+        const int id = esp_name.intern(name, &added);
+        if (added) { esp2fragment.push_back(-1); in_allesps.push_back(0); esp2cid.push_back(-1); }
         return id;
     }
     void clear() { *this = mbsv_host(); }
@@ -260,35 +342,35 @@ int read_assignment_file(mbsv_host* h) {
     Scanner sc;
     if (!slurp(h->assignmentfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->assignmentfile);
     if (!sc.hasNextLine()) return hfail(MBSV_ERR_IO, "empty assignment file");
-    sc.nextLine();
+    sc.nextLineView();
+    std::vector<std::string_view> esps;
+    std::vector<int> ids;
     while (sc.hasNext()) {
-        const std::string fragmentID = sc.next();
+        const std::string_view fragmentID = sc.nextView();
         if (!sc.hasNext()) return hfail(MBSV_ERR_IO, "Error parsing line. Check assignmentfile format.");
-        const std::vector<std::string> esps = split(sc.next(), ",");
+        split_views(sc.nextView(), ",", esps);
         int numerrors, length;
-        if (!sc.hasNext() || !parse_int(sc.next(), numerrors) || !sc.hasNext() || !parse_int(sc.next(), length) || !sc.hasNext())
+        if (!sc.hasNext() || !parse_int(sc.nextView(), numerrors) || !sc.hasNext() || !parse_int(sc.nextView(), length) || !sc.hasNext())
             return hfail(MBSV_ERR_IO, "Error parsing line. Check assignmentfile format.");
-        const std::string explabel = sc.next();
+        const std::string explabel(sc.nextView());
         auto ex = h->exp_id.find(explabel);
         if (ex == h->exp_id.end()) return hfail(MBSV_ERR_IO, "ERROR: Experiment Label " + explabel + " not in Experiments file.");
-        std::vector<int> ids;
+        ids.clear();
         for (const auto& e : esps) ids.push_back(h->esp(e));
         if (h->clusters_first) {
             bool any = false;
             for (int id : ids) if (h->in_allesps[id]) { any = true; break; }
             if (!any) continue;
         }
-        auto it = h->frag_id_of.find(fragmentID);
-        int fid;
-        if (it == h->frag_id_of.end()) {
-            fid = (int)h->frags.size();
-            h->frag_id_of.emplace(fragmentID, fid);
-            h->frags.push_back(Fragment{fragmentID, {}});
+        bool added;
+        const int fid = h->frag_id_of.intern(fragmentID, &added);
+        if (added) {
+            h->frags.push_back(Fragment{std::string(fragmentID), {}});
             h->fragments.put(fragmentID);
-        } else fid = it->second;
+        }
         Alignment al;
         al.esps = ids; al.numerrors = numerrors; al.len = length; al.exp = ex->second;
-        h->frags[fid].alns.push_back(al);
+        h->frags[fid].alns.push_back(std::move(al));
         for (int id : ids) { h->in_allesps[id] = 1; h->esp2fragment[id] = fid; }
     }
     return 0;
@@ -300,29 +382,30 @@ int read_clusters_file(mbsv_host* h) {
     if (!slurp(h->clusterfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->clusterfile);
     h->max_support = 0;
     bool warn = false;
+    std::vector<std::string_view> row, names;
     while (sc.hasNext()) {
-        const std::vector<std::string> row = split(sc.nextLine(), "\t");
+        split_views(sc.nextLineView(), "\t", row);
         if (row[0] == "cID") continue;
-        const std::string& cID = row[0];
+        const std::string cID(row[0]);
         if (cID.find('.') != std::string::npos) continue;
         int n;
         if (row.size() < 2) return hfail(MBSV_ERR_IO, "ArrayIndexOutOfBounds: clusters row has < 2 columns");
-        if (!parse_int(row[1], n)) return hfail(MBSV_ERR_IO, "NumberFormatException: " + row[1]);
+        if (!parse_int(row[1], n)) return hfail(MBSV_ERR_IO, "NumberFormatException: " + std::string(row[1]));
         if (h->max_support < n) h->max_support = n;
         if (row.size() < 5) return hfail(MBSV_ERR_IO, "ArrayIndexOutOfBounds: clusters row has < 5 columns");
-        auto it = h->cl_id_of.find(cID);
-        int cid = it == h->cl_id_of.end() ? -1 : it->second;
+        int cid = h->cl_id_of.find(cID);
         auto ensure = [&]() {                       // clust.put(cID, ...) — a repeated cID keeps its slot
             if (cid >= 0) return;
             cid = (int)h->cl_name.size();
-            h->cl_id_of.emplace(cID, cid);
+            h->cl_id_of.intern(cID);
             h->cl_name.push_back(cID); h->cl_is_cluster.push_back(1); h->bp_of_cl.push_back(-1);
             h->diagrams.emplace_back();
             h->clust.put(cID);
         };
         bool some = false;
-        for (const auto& raw : split(row[4], ",")) {
-            const int id = h->esp(trim(raw));
+        split_views(row[4], ",", names);
+        for (const auto& raw : names) {
+            const int id = h->esp(trim_view(raw));
             if (!h->clusters_first && !h->in_allesps[id]) { warn = true; continue; }
             some = true;
             ensure();
@@ -367,29 +450,34 @@ void intersect_clusters_and_fragments(mbsv_host* h) {
 int construct_cluster_diagrams(mbsv_host* h) {
     Scanner sc;
     if (!slurp(h->clusterfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->clusterfile);
-    std::vector<std::string> row;
-    auto advance = [&]() -> bool { if (!sc.hasNext()) return false; row = split(sc.nextLine(), "\t"); return true; };
+    std::vector<std::string_view> row, list_items;
+    auto advance = [&]() -> bool { if (!sc.hasNext()) return false; split_views(sc.nextLineView(), "\t", row); return true; };
     bool have = advance();
+    std::vector<int> seen_stamp;              // ESP id -> last cluster row group that listed it (leaves are a set)
+    int stamp = 0;
     while (have) {
         if (row[0] == "cID") { have = advance(); continue; }
         if (row.size() < 5) return hfail(MBSV_ERR_IO, "ArrayIndexOutOfBounds: clusters row has < 5 columns");
-        const std::string cID = row[0], local = row[2], names = row[4];
-        auto it = h->cl_id_of.find(cID);
-        if (it == h->cl_id_of.end() || h->bp_of_cl[it->second] < 0) { have = advance(); continue; }
-        const int cid = it->second;
+        const std::string cID(row[0]);
+        const bool simple = row[2] != "-1";
+        const std::string_view names = row[4];
+        const int cid = h->cl_id_of.find(cID);
+        if (cid < 0 || h->bp_of_cl[cid] < 0) { have = advance(); continue; }
         Diagram d;
         d.built = true;
-        std::unordered_set<int> seen;
-        auto add_root = [&](const std::string& list) {
+        ++stamp;
+        auto add_root = [&](std::string_view list) {
             std::vector<int> r;
-            for (const auto& e : split(list, ", ")) {
+            split_views(list, ", ", list_items);
+            for (const auto& e : list_items) {
                 const int id = h->esp(e);
                 r.push_back(id);
-                if (seen.insert(id).second) d.leaves.push_back(id);
+                if ((size_t)id >= seen_stamp.size()) seen_stamp.resize(std::max<size_t>(h->esp_name.size(), (size_t)id + 1), 0);
+                if (seen_stamp[id] != stamp) { seen_stamp[id] = stamp; d.leaves.push_back(id); }
             }
-            d.roots.push_back(r);
+            d.roots.push_back(std::move(r));
         };
-        if (local != "-1") {
+        if (simple) {
             d.is_cluster = true;
             add_root(names);
             have = advance();
@@ -403,7 +491,7 @@ int construct_cluster_diagrams(mbsv_host* h) {
             }
         }
         for (int e : d.leaves) if (h->esp2cid[e] >= 0) h->esp2cid[e] = cid;
-        h->diagrams[cid] = d;
+        h->diagrams[cid] = std::move(d);
     }
     for (int be : h->breakpoints.order())
         if (!h->diagrams[h->cl_of_bp[be]].built) return hfail(MBSV_ERR_IO, "NullPointerException: no diagram for " + h->cl_name[h->cl_of_bp[be]]);
@@ -440,23 +528,29 @@ int pack(mbsv_host* h) {
     // leaves / roots
     h->cluster_leaf_ptr.assign(1, 0); h->leaf_owner.clear(); h->cluster_root_ptr.assign(1, 0); h->root_leaf_ptr.assign(1, 0);
     h->root_leaf.clear();
-    std::vector<int> leaf_count(h->esp_name.size(), 0);
-    std::vector<std::unordered_map<int, int>> slot_of(C);
+    // An ESP is a leaf of at most one cluster in accepted input (anything else is flagged below), so "slot of ESP e among
+    // the leaves of cluster i" is two flat arrays instead of a map per cluster; `mark` detects repeats within one list.
+    const size_t nesp = h->esp_name.size();
+    std::vector<int> leaf_count(nesp, 0), leaf_cluster(nesp, -1), leaf_slot(nesp, -1), mark(nesp, 0);
+    int stamp = 0;
     for (int i = 0; i < C; ++i) {
         const Diagram& d = h->diagrams[h->cl_order[i]];
         if (d.is_cluster != (h->cluster_kind[i] == 0)) h->unsupported = "cluster kind mismatch for " + h->cl_name[h->cl_order[i]];
         for (int e : d.leaves) {
-            slot_of[i][e] = (int)h->leaf_owner.size() - h->cluster_leaf_ptr[i];
+            leaf_cluster[e] = i;
+            leaf_slot[e] = (int)h->leaf_owner.size() - h->cluster_leaf_ptr[i];
             ++leaf_count[e];
             const int fe = h->esp2fragment[e];
             h->leaf_owner.push_back(fe >= 0 && h->fragments.alive[fe] ? frag_idx[fe] : -1);
         }
         h->cluster_leaf_ptr.push_back((int)h->leaf_owner.size());
         for (const auto& r : d.roots) {
-            std::unordered_set<int> seen;
+            ++stamp;
             for (int e : r) {
-                if (!seen.insert(e).second) h->unsupported = "ESP " + h->esp_name[e] + " listed twice in one row of cluster " + h->cl_name[h->cl_order[i]];
-                h->root_leaf.push_back(slot_of[i].at(e));
+                if (mark[e] == stamp) h->unsupported = "ESP " + h->esp_name.str(e) + " listed twice in one row of cluster " + h->cl_name[h->cl_order[i]];
+                mark[e] = stamp;
+                // (every ESP of a root was added to this diagram's leaves; leaf_cluster[e] != i only for rejected input)
+                h->root_leaf.push_back(leaf_cluster[e] == i ? leaf_slot[e] : 0);
             }
             h->root_leaf_ptr.push_back((int)h->root_leaf.size());
         }
@@ -465,23 +559,25 @@ int pack(mbsv_host* h) {
             h->unsupported = "cluster " + h->cl_name[h->cl_order[i]] + " has more ESPs than its declared count (logprobcov overflow)";
     }
     for (size_t e = 0; e < leaf_count.size(); ++e)
-        if (leaf_count[e] > 1) h->unsupported = "ESP " + h->esp_name[e] + " is a leaf of more than one cluster";
+        if (leaf_count[e] > 1) h->unsupported = "ESP " + h->esp_name.str((int)e) + " is a leaf of more than one cluster";
     // alignments
     h->frag_aln_ptr.assign(1, 0); h->aln_esp_ptr.assign(1, 0);
     h->aln_numerrors.clear(); h->aln_len.clear(); h->aln_exp.clear(); h->aln_esp_cluster.clear(); h->aln_esp_leaf.clear();
     h->aln_esp_espid.clear();
+    h->aln_esp_cluster.reserve(nesp); h->aln_esp_leaf.reserve(nesp); h->aln_esp_espid.reserve(nesp);
     for (int i = 0; i < F; ++i) {
         const Fragment& fr = h->frags[h->frag_order[i]];
         for (const Alignment& al : fr.alns) {
             h->aln_numerrors.push_back(al.numerrors); h->aln_len.push_back(al.len); h->aln_exp.push_back(exp_idx[al.exp]);
-            std::unordered_set<int> seen;
+            ++stamp;
             for (int e : al.esps) {
-                if (!seen.insert(e).second) h->unsupported = "ESP " + h->esp_name[e] + " listed twice in one alignment of " + fr.id;
+                if (mark[e] == stamp) h->unsupported = "ESP " + h->esp_name.str(e) + " listed twice in one alignment of " + fr.id;
+                mark[e] = stamp;
                 const int c = cl_idx[h->esp2cid[e]];
-                auto ls = slot_of[c].find(e);
-                const bool contributes = ls != slot_of[c].end() && h->leaf_owner[h->cluster_leaf_ptr[c] + ls->second] == i;
+                const bool is_leaf = c >= 0 && leaf_cluster[e] == c;
+                const bool contributes = is_leaf && h->leaf_owner[h->cluster_leaf_ptr[c] + leaf_slot[e]] == i;
                 h->aln_esp_cluster.push_back(contributes ? c : -1);
-                h->aln_esp_leaf.push_back(contributes ? ls->second : -1);
+                h->aln_esp_leaf.push_back(contributes ? leaf_slot[e] : -1);
                 h->aln_esp_espid.push_back(e);
             }
             h->aln_esp_ptr.push_back((int)h->aln_esp_cluster.size());
@@ -558,19 +654,46 @@ int mbsv_host_set_files(mbsv_host* h, const char* clusterfile, const char* assig
     return MBSV_OK;
 }
 
+namespace {
+struct Lap {   // MBSV_DEBUG_TIMING=1: phase times of the host mirror on stderr
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void operator()(const char* what) {
+        static const bool on = std::getenv("MBSV_DEBUG_TIMING") != nullptr;
+        const auto n = std::chrono::steady_clock::now();
+        if (on) std::fprintf(stderr, "[mbsv host] %-28s %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+        t = n;
+    }
+};
+}  // namespace
+
 int mbsv_host_get_fragment_alignments(mbsv_host* h) {
     if (!h) return hfail(MBSV_ERR_ARG, "host is NULL");
     int rc;
+    Lap lap;
     if ((rc = read_experiment_file(h))) return rc;
-    if (h->clusters_first) { if ((rc = read_clusters_file(h)) || (rc = read_assignment_file(h))) return rc; }
-    else { if ((rc = read_assignment_file(h)) || (rc = read_clusters_file(h))) return rc; }
+    if (h->clusters_first) {
+        if ((rc = read_clusters_file(h))) return rc;
+        lap("readClustersFile");
+        if ((rc = read_assignment_file(h))) return rc;
+        lap("readAssignmentFile");
+    } else {
+        if ((rc = read_assignment_file(h))) return rc;
+        lap("readAssignmentFile");
+        if ((rc = read_clusters_file(h))) return rc;
+        lap("readClustersFile");
+    }
     intersect_clusters_and_fragments(h);
+    lap("intersectClustersAndFragments");
     return MBSV_OK;
 }
 int mbsv_host_construct_cluster_diagrams(mbsv_host* h) {
     if (!h) return hfail(MBSV_ERR_ARG, "host is NULL");
+    Lap lap;
     if (int rc = construct_cluster_diagrams(h)) return rc;
-    return pack(h);
+    lap("constructClusterDiagrams");
+    const int rc = pack(h);
+    lap("pack");
+    return rc;
 }
 int mbsv_host_precompute_priors(mbsv_host* h) {
     if (!h || !h->packed) return hfail(MBSV_ERR_ARG, "construct the cluster diagrams first");
@@ -619,7 +742,7 @@ const char* mbsv_host_name(mbsv_host* h, int32_t kind, int32_t i) {
         case 0: return (i >= 0 && i < (int)h->frag_order.size()) ? h->frags[h->frag_order[i]].id.c_str() : nullptr;
         case 1: return (i >= 0 && i < (int)h->cl_order.size()) ? h->cl_name[h->cl_order[i]].c_str() : nullptr;
         case 2: { const auto o = h->experiments.order(); return (i >= 0 && i < (int)o.size()) ? h->exp_label[o[i]].c_str() : nullptr; }
-        case 3: return (i >= 0 && i < (int)h->aln_esp_espid.size()) ? h->esp_name[h->aln_esp_espid[i]].c_str() : nullptr;
+        case 3: return (i >= 0 && i < (int)h->aln_esp_espid.size()) ? h->esp_name.c_str(h->aln_esp_espid[i]) : nullptr;
         case 4: return h->warning.c_str();
         case 5: return h->unsupported.c_str();
         default: return nullptr;
@@ -714,7 +837,7 @@ int mbsv_host_matchfile_initial(mbsv_host* h, const char* matchfile, int32_t* in
             // FragmentAlignment.contains(esp) is membership of the alignment's ESP list; which listed ESP hits first
             // does not matter, only whether any does
             for (int j = h->aln_esp_ptr[a]; j < h->aln_esp_ptr[a + 1]; ++j)
-                if (listed.count(h->esp_name[h->aln_esp_espid[j]])) { thisval = 1; foundany = true; break; }
+                if (listed.count(h->esp_name.str(h->aln_esp_espid[j]))) { thisval = 1; foundany = true; break; }
             if (thisval == h->aln_esp_ptr[a + 1] - h->aln_esp_ptr[a]) { init_assign[f] = a - h->frag_aln_ptr[f]; ++numset; foundall = true; }
         }
         if (!foundany && !foundall) ++numerr;
@@ -754,7 +877,7 @@ int mbsv_host_write_final_files(mbsv_host* h, const char* prefix) {
             for (int a = h->frag_aln_ptr[f]; a < h->frag_aln_ptr[f + 1]; ++a) {
                 w << id << "\t" << (a - h->frag_aln_ptr[f]) << "\t" << java_double((double)h->r_aln[a] / h->burnin) << "\t";
                 for (int j = h->aln_esp_ptr[a]; j < h->aln_esp_ptr[a + 1]; ++j)
-                    w << (j > h->aln_esp_ptr[a] ? "," : "") << h->esp_name[h->aln_esp_espid[j]];
+                    w << (j > h->aln_esp_ptr[a] ? "," : "") << h->esp_name.view(h->aln_esp_espid[j]);
                 w << "\n";
             }
         }
