@@ -184,11 +184,6 @@ struct StrTable {
         }
     }
 };
-std::vector<std::string> split(const std::string& s, const std::string& sep) {   // String.split(literal), owning copies
-    std::vector<std::string_view> v;
-    split_views(s, sep, v);
-    return std::vector<std::string>(v.begin(), v.end());
-}
 bool parse_int(std::string_view s, int& out) {
     if (s.empty()) return false;
     size_t i = (s[0] == '-' || s[0] == '+') ? 1 : 0;
@@ -1014,65 +1009,68 @@ int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* ro
     if (!clusterfile) return hfail(MBSV_ERR_ARG, "clusters file is required");
     std::string buf;
     if (!slurp(clusterfile, buf)) return hfail(MBSV_ERR_IO, std::string("cannot open ") + clusterfile);
-    // physical lines (Perl: while (<CLUST>) { chomp; ... })
-    std::vector<std::string> lines;
+    // physical lines (Perl: while (<CLUST>) { chomp; ... }), as views into buf
+    std::vector<std::string_view> lines;
     for (size_t p = 0; p < buf.size();) {
         size_t q = buf.find('\n', p);
         if (q == std::string::npos) q = buf.size();
-        lines.push_back(buf.substr(p, q - p));
+        lines.push_back(std::string_view(buf).substr(p, q - p));
         p = q + 1;
     }
-    std::unordered_map<std::string, int> cid_last_line;      // $fulllines{$cid}: the last row of a cID wins
-    std::unordered_map<std::string, int> lr_node;            // long-read id string -> node
+    StrTable cids;                                            // cluster ids in order of first appearance
+    std::vector<int> cid_last_line;                           // $fulllines{$cid}: the last row of a cID wins
+    std::vector<int> cid_first_node;                          // a long read of the first row of the cID
+    StrTable lr_node;                                         // long-read id string -> node
     std::vector<long long> lr_value;                          // numeric value for the `<=>` sort
     std::vector<int> parent;
     auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-    auto node_of = [&](const std::string& lr) {
-        auto it = lr_node.find(lr);
-        if (it != lr_node.end()) return it->second;
-        const int id = (int)parent.size();
-        lr_node.emplace(lr, id);
-        parent.push_back(id);
-        lr_value.push_back(std::strtoll(lr.c_str(), nullptr, 10));
+    auto node_of = [&](std::string_view lr) {
+        bool added;
+        const int id = lr_node.intern(lr, &added);
+        if (added) {
+            parent.push_back(id);
+            long long v = 0;                                  // strtoll of a digit string (empty: 0)
+            for (char ch : lr) v = v * 10 + (ch - '0');
+            lr_value.push_back(v);
+        }
         return id;
     };
     std::vector<int> line_node(lines.size(), -1);            // a long read of the row (all of them get united)
+    std::vector<int> line_cid(lines.size(), -1);
     std::string last_lr;                                     // Perl's $1 keeps its previous value when the match fails
+    std::vector<std::string_view> row;
     for (size_t i = 0; i < lines.size(); ++i) {
-        const std::vector<std::string> row = split(lines[i], "\t");
-        const std::string& cid = row[0];
-        if (cid.find('.') != std::string::npos) continue;    // maximal clusters are skipped (:52)
-        cid_last_line[cid] = (int)i;
+        split_views(lines[i], "\t", row);
+        const std::string_view cid = row[0];
+        if (cid.find('.') != std::string_view::npos) continue;    // maximal clusters are skipped (:52)
+        bool added;
+        const int ci = cids.intern(cid, &added);
+        if (added) { cid_last_line.push_back((int)i); cid_first_node.push_back(-1); } else cid_last_line[ci] = (int)i;
         if (row.size() < 5) continue;
         int first = -1;
         // split(/,\s*/, $row[4])
-        const std::string& list = row[4];
+        const std::string_view list = row[4];
         for (size_t p = 0; p <= list.size();) {
             size_t q = list.find(',', p);
-            if (q == std::string::npos) q = list.size();
-            const std::string esp = list.substr(p, q - p);
+            if (q == std::string_view::npos) q = list.size();
+            const std::string_view esp = list.substr(p, q - p);
             p = q + 1;
             while (p < list.size() && (list[p] == ' ' || list[p] == '\t')) ++p;
             const size_t m = esp.find("longread_");
-            size_t d = m == std::string::npos ? std::string::npos : m + 9, e = d;
-            while (e != std::string::npos && e < esp.size() && esp[e] >= '0' && esp[e] <= '9') ++e;
-            if (d != std::string::npos && e > d) last_lr = esp.substr(d, e - d);
+            size_t d = m == std::string_view::npos ? std::string_view::npos : m + 9, e = d;
+            while (e != std::string_view::npos && e < esp.size() && esp[e] >= '0' && esp[e] <= '9') ++e;
+            if (d != std::string_view::npos && e > d) last_lr.assign(esp.substr(d, e - d));
             const int n = node_of(last_lr);
             if (first < 0) first = n; else parent[find(n)] = find(first);
             if (q == list.size()) break;
         }
         line_node[i] = first;
-    }
-    // a repeated cID only keeps its last row, but its long reads were linked through every row it appeared in
-    // (the script's %longreads accumulates over all rows while %clusters is overwritten): link rows of one cID
-    {
-        std::unordered_map<std::string, int> cid_first;
-        for (size_t i = 0; i < lines.size(); ++i) {
-            if (line_node[i] < 0) continue;
-            const std::string cid = split(lines[i], "\t")[0];
-            auto it = cid_first.find(cid);
-            if (it == cid_first.end()) cid_first.emplace(cid, line_node[i]);
-            else parent[find(line_node[i])] = find(it->second);
+        line_cid[i] = ci;
+        // a repeated cID only keeps its last row, but its long reads were linked through every row it appeared in
+        // (the script's %longreads accumulates over all rows while %clusters is overwritten): link rows of one cID
+        if (first >= 0) {
+            if (cid_first_node[ci] < 0) cid_first_node[ci] = first;
+            else parent[find(first)] = find(cid_first_node[ci]);
         }
     }
     // subsets numbered by their numerically smallest long read
@@ -1088,10 +1086,8 @@ int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* ro
     std::vector<int> subset_of_root(L, 0);
     for (size_t k = 0; k < roots.size(); ++k) subset_of_root[roots[k]] = (int)k + 1;
     std::vector<int> line_subset(lines.size(), 0);
-    for (const auto& kv : cid_last_line) {
-        const int i = kv.second;
+    for (const int i : cid_last_line)
         if (line_node[i] >= 0) line_subset[i] = subset_of_root[find(line_node[i])];
-    }
     if (row_subset) for (int i = 0; i < max_rows && i < (int)lines.size(); ++i) row_subset[i] = line_subset[i];
     if (outdir) {
         std::vector<std::ofstream> out;
