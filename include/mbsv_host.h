@@ -19,7 +19,8 @@
  * (fragments, breakpoints, supports, experiments), Double.toString.
  *
  * A host object holds ONE problem (what one JVM run of the reference sees).  mbsv_host_batch_* concatenates several
- * hosts (e.g. one per subset-N.clusters file of generateIndependentSubproblems.pl) into one mbsv_problem_desc.
+ * hosts (e.g. one per subset-N.clusters file of generateIndependentSubproblems.pl) into one mbsv_problem_desc;
+ * mbsv_host_load_partitioned does partition + per-subset loading in memory and in parallel, reading each file once.
  */
 #ifndef MBSV_HOST_H
 #define MBSV_HOST_H
@@ -78,6 +79,16 @@ int mbsv_host_write_state_counts(mbsv_host* h, const char* path);
 int mbsv_host_batch_create(mbsv_host* const* hosts, int32_t n, mbsv_host_batch** out);
 int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* out);
 int mbsv_host_batch_destroy(mbsv_host_batch* b);
+
+/* Partition + load in one call, in memory: the batch holds one subproblem per subset of generateIndependentSubproblems.pl,
+   each packed exactly as a reference run on `subset-k.clusters --readclustersfirst` with the full assignments file would
+   see it (doc/MultiBreakSV-Manual.txt:464-473) -- but the assignments file is read once, not once per subset, and no
+   subset file is written.  Subsets without any fragment are skipped.  flags bit 0: a subset whose HashMap order cannot be
+   reproduced (a bin Java would treeify, see MBSV_ERR_UNSUPPORTED) keeps the plain-list order instead of failing the load
+   -- its chain is valid but not the trajectory a JVM would produce.  info (may be NULL) = {skipped subsets, subsets with
+   such an order}.  Returns the number of subproblems (> 0) or a negative status. */
+int mbsv_host_load_partitioned(const char* clusterfile, const char* assignmentfile, const char* experimentfile,
+                               int32_t flags, mbsv_host_batch** out, int32_t* info);
 
 /* generateIndependentSubproblems.pl (src/generateIndependentSubproblems.pl): connected components of the bipartite graph
    long-read id (`longread_(\d+)` inside each ESP, :58) <-> cluster id over the non-dotted rows of a clusters file.

@@ -13,6 +13,7 @@
 #include <sstream>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -174,7 +175,7 @@ struct StrTable {
         return id;
     }
     void grow() {
-        const size_t n = slot.empty() ? 1024 : slot.size() * 2;
+        const size_t n = slot.empty() ? 16 : slot.size() * 2;
         slot.assign(n, 0);
         for (int id = 0; id < (int)ent.size(); ++id) {
             const uint64_t h = hash(view(id));
@@ -259,6 +260,8 @@ struct Diagram { bool is_cluster = true; std::vector<int> leaves; std::vector<st
 struct mbsv_host {
     std::string clusterfile, assignmentfile, experimentfile;
     bool clusters_first = false;
+    // in-memory text instead of the files (mbsv_host_load_partitioned feeds every subset through the same readers)
+    const std::string* text_clusters = nullptr; const std::string* text_assignments = nullptr; const std::string* text_experiments = nullptr;
     // ---- parsed state (field names follow the reference) ----
     std::vector<std::string> exp_label; std::vector<double> exp_pseq, exp_lambda;   // by experiment id
     std::unordered_map<std::string, int> exp_id; JavaMapOrder experiments;
@@ -311,10 +314,15 @@ struct mbsv_host_batch {
 
 namespace {
 
+bool fetch(const std::string* text, const std::string& path, std::string& out) {
+    if (text) { out = *text; return true; }
+    return slurp(path, out);
+}
+
 // MultiBreakSV.java:319-331
 int read_experiment_file(mbsv_host* h) {
     Scanner sc;
-    if (!slurp(h->experimentfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->experimentfile);
+    if (!fetch(h->text_experiments, h->experimentfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->experimentfile);
     if (!sc.hasNextLine()) return hfail(MBSV_ERR_IO, "empty experiment file");
     sc.nextLine();
     while (sc.hasNext()) {
@@ -335,7 +343,7 @@ int read_experiment_file(mbsv_host* h) {
 // MultiBreakSV.java:333-400
 int read_assignment_file(mbsv_host* h) {
     Scanner sc;
-    if (!slurp(h->assignmentfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->assignmentfile);
+    if (!fetch(h->text_assignments, h->assignmentfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->assignmentfile);
     if (!sc.hasNextLine()) return hfail(MBSV_ERR_IO, "empty assignment file");
     sc.nextLineView();
     std::vector<std::string_view> esps;
@@ -374,7 +382,7 @@ int read_assignment_file(mbsv_host* h) {
 // MultiBreakSV.java:402-473
 int read_clusters_file(mbsv_host* h) {
     Scanner sc;
-    if (!slurp(h->clusterfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->clusterfile);
+    if (!fetch(h->text_clusters, h->clusterfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->clusterfile);
     h->max_support = 0;
     bool warn = false;
     std::vector<std::string_view> row, names;
@@ -444,7 +452,7 @@ void intersect_clusters_and_fragments(mbsv_host* h) {
 // MultiBreakSV.java:658-746 + MultiBreakSVDiagram.java:56-139
 int construct_cluster_diagrams(mbsv_host* h) {
     Scanner sc;
-    if (!slurp(h->clusterfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->clusterfile);
+    if (!fetch(h->text_clusters, h->clusterfile, sc.buf)) return hfail(MBSV_ERR_IO, "cannot open " + h->clusterfile);
     std::vector<std::string_view> row, list_items;
     auto advance = [&]() -> bool { if (!sc.hasNext()) return false; split_views(sc.nextLineView(), "\t", row); return true; };
     bool have = advance();
@@ -655,7 +663,8 @@ struct Lap {   // MBSV_DEBUG_TIMING=1: phase times of the host mirror on stderr
     void operator()(const char* what) {
         static const bool on = std::getenv("MBSV_DEBUG_TIMING") != nullptr;
         const auto n = std::chrono::steady_clock::now();
-        if (on) std::fprintf(stderr, "[mbsv host] %-28s %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+        const double dt = std::chrono::duration<double>(n - t).count();
+        if (on && dt >= 0.005) std::fprintf(stderr, "[mbsv host] %-28s %.3f s\n", what, dt);   // (not for the many tiny subsets)
         t = n;
     }
 };
@@ -930,57 +939,243 @@ int mbsv_host_write_state_counts(mbsv_host* h, const char* path) {
     return MBSV_OK;
 }
 
+static int partition_lines(const std::string& buf, std::vector<std::string_view>& lines, std::vector<int>& line_subset);
+
+// one more subproblem at the end of the batch (the host may be reused or destroyed afterwards)
+static int batch_append(mbsv_host_batch* b, const mbsv_host* h) {
+    if (!h || !h->packed || !h->priors || !h->sv_filled) return hfail(MBSV_ERR_ARG, "every host must be loaded");
+    if (!h->unsupported.empty()) return hfail(MBSV_ERR_UNSUPPORTED, h->unsupported);
+    if (b->sub_frag_ptr.empty()) {
+        b->n_exp = (int)h->pk_pseq.size();
+        b->pseq = h->pk_pseq; b->lambda = h->pk_lambda;
+        b->sub_frag_ptr = {0}; b->sub_cluster_ptr = {0}; b->sub_sv_ptr = {0}; b->frag_aln_ptr = {0}; b->aln_esp_ptr = {0};
+        b->cluster_hist_ptr = {0}; b->cluster_leaf_ptr = {0}; b->cluster_root_ptr = {0}; b->root_leaf_ptr = {0}; b->sv_frag_ptr = {0};
+    } else if (h->pk_pseq != b->pseq || h->pk_lambda != b->lambda) {
+        return hfail(MBSV_ERR_ARG, "hosts of one batch must share the experiments file");
+    }
+    b->max_support = std::max(b->max_support, h->max_support);
+    const int f0 = b->sub_frag_ptr.back(), c0 = b->sub_cluster_ptr.back(), a0 = b->frag_aln_ptr.back(), k0 = b->aln_esp_ptr.back();
+    const int l0 = b->cluster_leaf_ptr.back(), r0 = b->cluster_root_ptr.back(), rl0 = b->root_leaf_ptr.back();
+    const int h0 = b->cluster_hist_ptr.back(), q0 = b->sv_frag_ptr.back();
+    const int F = (int)h->frag_order.size(), C = (int)h->cl_order.size();
+    for (int f = 1; f <= F; ++f) b->frag_aln_ptr.push_back(a0 + h->frag_aln_ptr[f]);
+    b->aln_numerrors.insert(b->aln_numerrors.end(), h->aln_numerrors.begin(), h->aln_numerrors.end());
+    b->aln_len.insert(b->aln_len.end(), h->aln_len.begin(), h->aln_len.end());
+    b->aln_exp.insert(b->aln_exp.end(), h->aln_exp.begin(), h->aln_exp.end());
+    for (size_t a = 1; a < h->aln_esp_ptr.size(); ++a) b->aln_esp_ptr.push_back(k0 + h->aln_esp_ptr[a]);
+    for (int c : h->aln_esp_cluster) b->aln_esp_cluster.push_back(c < 0 ? -1 : c0 + c);
+    b->aln_esp_leaf.insert(b->aln_esp_leaf.end(), h->aln_esp_leaf.begin(), h->aln_esp_leaf.end());
+    b->cluster_kind.insert(b->cluster_kind.end(), h->cluster_kind.begin(), h->cluster_kind.end());
+    for (int c : h->supports_order) b->supports_order.push_back(c0 + c);
+    for (int c = 1; c <= C; ++c) {
+        b->cluster_hist_ptr.push_back(h0 + h->cluster_hist_ptr[c]);
+        b->cluster_leaf_ptr.push_back(l0 + h->cluster_leaf_ptr[c]);
+        b->cluster_root_ptr.push_back(r0 + h->cluster_root_ptr[c]);
+    }
+    for (int o : h->leaf_owner) b->leaf_owner.push_back(o < 0 ? -1 : f0 + o);
+    for (size_t r = 1; r < h->root_leaf_ptr.size(); ++r) b->root_leaf_ptr.push_back(rl0 + h->root_leaf_ptr[r]);
+    b->root_leaf.insert(b->root_leaf.end(), h->root_leaf.begin(), h->root_leaf.end());
+    for (int c : h->sv_cluster) b->sv_cluster.push_back(c0 + c);
+    for (size_t k = 1; k < h->sv_frag_ptr.size(); ++k) b->sv_frag_ptr.push_back(q0 + h->sv_frag_ptr[k]);
+    for (int f : h->sv_frag) b->sv_frag.push_back(f0 + f);
+    b->sv_numchanged.insert(b->sv_numchanged.end(), h->sv_numchanged.begin(), h->sv_numchanged.end());
+    b->sub_frag_ptr.push_back(f0 + F); b->sub_cluster_ptr.push_back(c0 + C);
+    b->sub_sv_ptr.push_back(b->sub_sv_ptr.back() + (int)h->sv_cluster.size());
+    return MBSV_OK;
+}
+// logprobcov is shared by the batch: one table up to the largest maxSupport (values do not depend on the table length)
+static void batch_finish(mbsv_host_batch* b) {
+    b->logprobcov.assign((size_t)b->n_exp * (b->max_support + 1), 0.0);
+    for (int x = 0; x < b->n_exp; ++x) mbsv_fill_logprobcov(b->lambda[x], b->max_support, b->logprobcov.data() + (size_t)x * (b->max_support + 1));
+}
+
+// dst += src (all subproblems of src, in order)
+static int batch_merge(mbsv_host_batch* d, const mbsv_host_batch* s) {
+    if (s->sub_frag_ptr.size() < 2) return MBSV_OK;
+    if (d->sub_frag_ptr.empty()) { *d = *s; return MBSV_OK; }
+    if (s->pseq != d->pseq || s->lambda != d->lambda) return hfail(MBSV_ERR_ARG, "hosts of one batch must share the experiments file");
+    d->max_support = std::max(d->max_support, s->max_support);
+    const int f0 = d->sub_frag_ptr.back(), c0 = d->sub_cluster_ptr.back(), a0 = d->frag_aln_ptr.back(), k0 = d->aln_esp_ptr.back();
+    const int l0 = d->cluster_leaf_ptr.back(), r0 = d->cluster_root_ptr.back(), rl0 = d->root_leaf_ptr.back();
+    const int h0 = d->cluster_hist_ptr.back(), q0 = d->sv_frag_ptr.back(), v0 = d->sub_sv_ptr.back();
+    auto cat = [](std::vector<int32_t>& a, const std::vector<int32_t>& b, int add, size_t skip, bool keep_neg) {
+        a.reserve(a.size() + b.size());
+        for (size_t i = skip; i < b.size(); ++i) a.push_back(keep_neg && b[i] < 0 ? b[i] : b[i] + add);
+    };
+    cat(d->sub_frag_ptr, s->sub_frag_ptr, f0, 1, false); cat(d->sub_cluster_ptr, s->sub_cluster_ptr, c0, 1, false);
+    cat(d->sub_sv_ptr, s->sub_sv_ptr, v0, 1, false); cat(d->frag_aln_ptr, s->frag_aln_ptr, a0, 1, false);
+    cat(d->aln_numerrors, s->aln_numerrors, 0, 0, false); cat(d->aln_len, s->aln_len, 0, 0, false); cat(d->aln_exp, s->aln_exp, 0, 0, false);
+    cat(d->aln_esp_ptr, s->aln_esp_ptr, k0, 1, false); cat(d->aln_esp_cluster, s->aln_esp_cluster, c0, 0, true);
+    cat(d->aln_esp_leaf, s->aln_esp_leaf, 0, 0, false);
+    d->cluster_kind.insert(d->cluster_kind.end(), s->cluster_kind.begin(), s->cluster_kind.end());
+    cat(d->supports_order, s->supports_order, c0, 0, false); cat(d->cluster_hist_ptr, s->cluster_hist_ptr, h0, 1, false);
+    cat(d->cluster_leaf_ptr, s->cluster_leaf_ptr, l0, 1, false); cat(d->leaf_owner, s->leaf_owner, f0, 0, true);
+    cat(d->cluster_root_ptr, s->cluster_root_ptr, r0, 1, false); cat(d->root_leaf_ptr, s->root_leaf_ptr, rl0, 1, false);
+    cat(d->root_leaf, s->root_leaf, 0, 0, false); cat(d->sv_cluster, s->sv_cluster, c0, 0, false);
+    cat(d->sv_frag_ptr, s->sv_frag_ptr, q0, 1, false); cat(d->sv_frag, s->sv_frag, f0, 0, false);
+    cat(d->sv_numchanged, s->sv_numchanged, 0, 0, false);
+    return MBSV_OK;
+}
+
 int mbsv_host_batch_create(mbsv_host* const* hosts, int32_t n, mbsv_host_batch** out) {
     if (!hosts || n < 1 || !out) return hfail(MBSV_ERR_ARG, "bad argument");
     mbsv_host_batch* b = new (std::nothrow) mbsv_host_batch();
     if (!b) return hfail(MBSV_ERR_OOM, "allocation failed");
-    auto fail_free = [&](int code, const std::string& m) { delete b; return hfail(code, m); };
-    b->n_exp = (int)hosts[0]->pk_pseq.size();
-    for (int i = 0; i < n; ++i) {
-        const mbsv_host* h = hosts[i];
-        if (!h || !h->packed || !h->priors || !h->sv_filled) return fail_free(MBSV_ERR_ARG, "every host must be loaded");
-        if (!h->unsupported.empty()) return fail_free(MBSV_ERR_UNSUPPORTED, h->unsupported);
-        if ((int)h->pk_pseq.size() != b->n_exp || h->pk_pseq != hosts[0]->pk_pseq || h->pk_lambda != hosts[0]->pk_lambda)
-            return fail_free(MBSV_ERR_ARG, "hosts of one batch must share the experiments file");
-        b->max_support = std::max(b->max_support, h->max_support);
-    }
-    b->pseq = hosts[0]->pk_pseq; b->lambda = hosts[0]->pk_lambda;
-    b->logprobcov.assign((size_t)b->n_exp * (b->max_support + 1), 0.0);
-    for (int x = 0; x < b->n_exp; ++x) mbsv_fill_logprobcov(b->lambda[x], b->max_support, b->logprobcov.data() + (size_t)x * (b->max_support + 1));
-    b->sub_frag_ptr = {0}; b->sub_cluster_ptr = {0}; b->sub_sv_ptr = {0}; b->frag_aln_ptr = {0}; b->aln_esp_ptr = {0};
-    b->cluster_hist_ptr = {0}; b->cluster_leaf_ptr = {0}; b->cluster_root_ptr = {0}; b->root_leaf_ptr = {0}; b->sv_frag_ptr = {0};
-    for (int i = 0; i < n; ++i) {
-        const mbsv_host* h = hosts[i];
-        const int f0 = b->sub_frag_ptr.back(), c0 = b->sub_cluster_ptr.back(), a0 = b->frag_aln_ptr.back(), k0 = b->aln_esp_ptr.back();
-        const int l0 = b->cluster_leaf_ptr.back(), r0 = b->cluster_root_ptr.back(), rl0 = b->root_leaf_ptr.back();
-        const int h0 = b->cluster_hist_ptr.back(), q0 = b->sv_frag_ptr.back();
-        const int F = (int)h->frag_order.size(), C = (int)h->cl_order.size();
-        for (int f = 1; f <= F; ++f) b->frag_aln_ptr.push_back(a0 + h->frag_aln_ptr[f]);
-        b->aln_numerrors.insert(b->aln_numerrors.end(), h->aln_numerrors.begin(), h->aln_numerrors.end());
-        b->aln_len.insert(b->aln_len.end(), h->aln_len.begin(), h->aln_len.end());
-        b->aln_exp.insert(b->aln_exp.end(), h->aln_exp.begin(), h->aln_exp.end());
-        for (size_t a = 1; a < h->aln_esp_ptr.size(); ++a) b->aln_esp_ptr.push_back(k0 + h->aln_esp_ptr[a]);
-        for (int c : h->aln_esp_cluster) b->aln_esp_cluster.push_back(c < 0 ? -1 : c0 + c);
-        b->aln_esp_leaf.insert(b->aln_esp_leaf.end(), h->aln_esp_leaf.begin(), h->aln_esp_leaf.end());
-        b->cluster_kind.insert(b->cluster_kind.end(), h->cluster_kind.begin(), h->cluster_kind.end());
-        for (int c : h->supports_order) b->supports_order.push_back(c0 + c);
-        for (int c = 1; c <= C; ++c) {
-            b->cluster_hist_ptr.push_back(h0 + h->cluster_hist_ptr[c]);
-            b->cluster_leaf_ptr.push_back(l0 + h->cluster_leaf_ptr[c]);
-            b->cluster_root_ptr.push_back(r0 + h->cluster_root_ptr[c]);
-        }
-        for (int o : h->leaf_owner) b->leaf_owner.push_back(o < 0 ? -1 : f0 + o);
-        for (size_t r = 1; r < h->root_leaf_ptr.size(); ++r) b->root_leaf_ptr.push_back(rl0 + h->root_leaf_ptr[r]);
-        b->root_leaf.insert(b->root_leaf.end(), h->root_leaf.begin(), h->root_leaf.end());
-        for (int c : h->sv_cluster) b->sv_cluster.push_back(c0 + c);
-        for (size_t k = 1; k < h->sv_frag_ptr.size(); ++k) b->sv_frag_ptr.push_back(q0 + h->sv_frag_ptr[k]);
-        for (int f : h->sv_frag) b->sv_frag.push_back(f0 + f);
-        b->sv_numchanged.insert(b->sv_numchanged.end(), h->sv_numchanged.begin(), h->sv_numchanged.end());
-        b->sub_frag_ptr.push_back(f0 + F); b->sub_cluster_ptr.push_back(c0 + C);
-        b->sub_sv_ptr.push_back(b->sub_sv_ptr.back() + (int)h->sv_cluster.size());
-    }
+    for (int i = 0; i < n; ++i)
+        if (const int rc = batch_append(b, hosts[i])) { delete b; return rc; }
+    batch_finish(b);
     *out = b;
     return MBSV_OK;
+}
+
+// The large-scale workflow in one call: partition the clusters file (generateIndependentSubproblems.pl), then load every
+// subset exactly as one reference run on `subset-k.clusters --readclustersfirst` would see it -- without writing the subset
+// files and without re-reading the assignments file once per subset (doc/MultiBreakSV-Manual.txt:464-473 does both).
+// Every assignments tuple is routed to the subset(s) that list one of its ESPs; each subset then goes through the same
+// readers on its own slice of text, so orders, filtering and quirks are those of the per-file path (tested equal).
+// Subsets left without any fragment are skipped (n_skipped).  Returns the number of subproblems in the batch.
+int mbsv_host_load_partitioned(const char* clusterfile, const char* assignmentfile, const char* experimentfile,
+                               int32_t flags, mbsv_host_batch** out, int32_t* info) {
+    if (!clusterfile || !assignmentfile || !experimentfile || !out) return hfail(MBSV_ERR_ARG, "bad argument");
+    std::string cbuf, abuf, ebuf;
+    if (!slurp(clusterfile, cbuf)) return hfail(MBSV_ERR_IO, std::string("cannot open ") + clusterfile);
+    if (!slurp(assignmentfile, abuf)) return hfail(MBSV_ERR_IO, std::string("cannot open ") + assignmentfile);
+    if (!slurp(experimentfile, ebuf)) return hfail(MBSV_ERR_IO, std::string("cannot open ") + experimentfile);
+    Lap lap;
+    std::vector<std::string_view> lines;
+    std::vector<int> line_subset;
+    const int S = partition_lines(cbuf, lines, line_subset);
+    lap("partition");
+    // subset texts of the clusters file (file order) and ESP -> subset (names as readClustersFile splits them: "," + trim)
+    std::vector<std::string> ctext((size_t)S + 1), atext((size_t)S + 1);
+    // allesps of every subset, as one table: ESP -> the subset whose allesps holds it (a second, third ... subset goes to
+    // `more`; that needs an ESP shared by unlinked rows and does not happen with long-read-named ESPs)
+    StrTable esps;
+    std::vector<int> esp_subset;
+    std::unordered_map<int, std::vector<int>> more;
+    auto add_member = [&](std::string_view name, int k) {
+        bool added;
+        const int id = esps.intern(name, &added);
+        if (added) { esp_subset.push_back(k); return; }
+        if (esp_subset[id] == k) return;
+        std::vector<int>& v = more[id];
+        if (std::find(v.begin(), v.end(), k) == v.end()) v.push_back(k);
+    };
+    std::vector<std::string_view> row, names;
+    for (size_t i = 0; i < lines.size(); ++i) {
+        const int k = line_subset[i];
+        if (k <= 0) continue;
+        ctext[k].append(lines[i]); ctext[k].push_back('\n');
+        split_views(lines[i], "\t", row);
+        if (row.size() < 5) continue;
+        split_views(row[4], ",", names);
+        for (const auto& raw : names) add_member(trim_view(raw), k);
+    }
+    lap("subset cluster texts");
+    // route the assignments tuples (token-based, like readAssignmentFile :342-373): a tuple is kept by a subset when one of
+    // its ESPs is in that subset's allesps -- and a kept tuple adds ALL its ESPs to allesps (:386), so a later tuple can be
+    // kept through an ESP no cluster lists; one forward pass in file order reproduces that
+    Scanner sc;
+    sc.buf.swap(abuf);
+    if (!sc.hasNextLine()) return hfail(MBSV_ERR_IO, "empty assignment file");
+    const std::string header = std::string(sc.nextLineView()) + "\n";
+    std::vector<std::string_view> tuple_esps;
+    std::vector<int> targets;
+    while (sc.hasNext()) {
+        const std::string_view frag = sc.nextView();
+        if (!sc.hasNext()) return hfail(MBSV_ERR_IO, "Error parsing line. Check assignmentfile format.");
+        const std::string_view list = sc.nextView();
+        if (!sc.hasNext()) return hfail(MBSV_ERR_IO, "Error parsing line. Check assignmentfile format.");
+        const std::string_view nerr = sc.nextView();
+        if (!sc.hasNext()) return hfail(MBSV_ERR_IO, "Error parsing line. Check assignmentfile format.");
+        const std::string_view len = sc.nextView();
+        if (!sc.hasNext()) return hfail(MBSV_ERR_IO, "Error parsing line. Check assignmentfile format.");
+        const std::string_view label = sc.nextView();
+        split_views(list, ",", tuple_esps);
+        targets.clear();
+        auto want = [&](int k) { if (std::find(targets.begin(), targets.end(), k) == targets.end()) targets.push_back(k); };
+        for (const auto& e : tuple_esps) {
+            const int id = esps.find(e);
+            if (id < 0) continue;
+            want(esp_subset[id]);
+            if (!more.empty()) { auto it = more.find(id); if (it != more.end()) for (int k : it->second) want(k); }
+        }
+        for (int k : targets) {
+            std::string& t = atext[k];
+            if (t.empty()) t = header;
+            t.append(frag); t.push_back('\t'); t.append(list); t.push_back('\t'); t.append(nerr); t.push_back('\t');
+            t.append(len); t.push_back('\t'); t.append(label); t.push_back('\n');
+            for (const auto& e : tuple_esps) add_member(e, k);
+        }
+    }
+    lap("route assignments");
+    // the subsets are independent: worker threads load contiguous ranges into partial batches, merged in subset order
+    mbsv_host_batch* b = new (std::nothrow) mbsv_host_batch();
+    if (!b) return hfail(MBSV_ERR_OOM, "allocation failed");
+    int nthreads = (int)std::max(1u, std::min({std::thread::hardware_concurrency(), 32u, (unsigned)((S + 255) / 256)}));
+    if (const char* env = std::getenv("MBSV_HOST_THREADS")) nthreads = std::max(1, std::min(64, std::atoi(env)));   // (tests)
+    std::vector<mbsv_host_batch> part(nthreads);
+    std::vector<int> t_skipped(nthreads, 0), t_approx(nthreads, 0), t_rc(nthreads, MBSV_OK);
+    std::vector<std::string> t_msg(nthreads);
+    // ranges balanced by text size (a few subsets hold most of the data)
+    std::vector<int> bound(nthreads + 1, S + 1);
+    {
+        size_t total = 0;
+        for (int k = 1; k <= S; ++k) total += atext[k].size() + ctext[k].size();
+        size_t acc = 0;
+        int t = 0;
+        bound[0] = 1;
+        for (int k = 1; k <= S; ++k) {
+            acc += atext[k].size() + ctext[k].size();
+            while (t + 1 < nthreads && acc * nthreads >= total * (size_t)(t + 1)) bound[++t] = k + 1;
+        }
+        for (int u = t + 1; u <= nthreads; ++u) bound[u] = S + 1;
+    }
+    auto worker = [&](int t) {
+        mbsv_host* h = new (std::nothrow) mbsv_host();
+        if (!h) { t_rc[t] = MBSV_ERR_OOM; t_msg[t] = "allocation failed"; return; }
+        for (int k = bound[t]; k < bound[t + 1] && t_rc[t] == MBSV_OK; ++k) {
+            if (atext[k].empty()) { ++t_skipped[t]; continue; }
+            h->clear();
+            h->clusterfile = "subset-" + std::to_string(k) + ".clusters"; h->assignmentfile = assignmentfile; h->experimentfile = experimentfile;
+            h->clusters_first = true;
+            h->text_clusters = &ctext[k]; h->text_assignments = &atext[k]; h->text_experiments = &ebuf;
+            int rc = mbsv_host_load(h);
+            if (rc == MBSV_OK && (flags & 1) && (h->experiments.tree_bin || h->fragments.tree_bin || h->breakpoints.tree_bin) &&
+                h->unsupported.rfind("a java.util.HashMap bin", 0) == 0) {
+                // a bin Java would treeify: keep the plain-list iteration order (a valid chain, but not the trajectory a
+                // JVM would produce for this subset) and count it
+                h->unsupported.clear();
+                ++t_approx[t];
+            }
+            if (rc == MBSV_OK && h->frag_order.empty()) { ++t_skipped[t]; continue; }
+            if (rc == MBSV_OK) rc = batch_append(&part[t], h);
+            if (rc != MBSV_OK) { t_rc[t] = rc; t_msg[t] = "subset " + std::to_string(k) + ": " + mbsv_last_error(); }
+            std::string().swap(ctext[k]); std::string().swap(atext[k]);
+        }
+        delete h;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
+        worker(0);
+        for (auto& x : th) x.join();
+    }
+    lap("load subsets");
+    int skipped = 0, approx = 0, rc = MBSV_OK;
+    for (int t = 0; t < nthreads && rc == MBSV_OK; ++t) {
+        if (t_rc[t] != MBSV_OK) { rc = hfail(t_rc[t], t_msg[t]); break; }
+        skipped += t_skipped[t]; approx += t_approx[t];
+        rc = batch_merge(b, &part[t]);
+        part[t] = mbsv_host_batch();
+    }
+    lap("merge");
+    if (rc != MBSV_OK) { delete b; return rc; }
+    if (b->sub_frag_ptr.size() < 2) { delete b; return hfail(MBSV_ERR_ARG, "no subset has any fragment"); }
+    batch_finish(b);
+    if (info) { info[0] = skipped; info[1] = approx; }
+    *out = b;
+    return (int)b->sub_frag_ptr.size() - 1;
 }
 int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* d) {
     if (!b || !d) return hfail(MBSV_ERR_ARG, "bad argument");
@@ -1005,12 +1200,11 @@ int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* d) {
 }
 int mbsv_host_batch_destroy(mbsv_host_batch* b) { delete b; return MBSV_OK; }
 
-int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* row_subset, int32_t max_rows) {
-    if (!clusterfile) return hfail(MBSV_ERR_ARG, "clusters file is required");
-    std::string buf;
-    if (!slurp(clusterfile, buf)) return hfail(MBSV_ERR_IO, std::string("cannot open ") + clusterfile);
+// Connected components of the clusters file as generateIndependentSubproblems.pl finds them: lines = the physical lines
+// of buf, line_subset[i] = 1-based subset of line i (0: dropped).  Returns the number of subsets.
+static int partition_lines(const std::string& buf, std::vector<std::string_view>& lines, std::vector<int>& line_subset) {
     // physical lines (Perl: while (<CLUST>) { chomp; ... }), as views into buf
-    std::vector<std::string_view> lines;
+    lines.clear();
     for (size_t p = 0; p < buf.size();) {
         size_t q = buf.find('\n', p);
         if (q == std::string::npos) q = buf.size();
@@ -1085,14 +1279,24 @@ int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* ro
     std::sort(roots.begin(), roots.end(), [&](int a, int b) { return comp_min[a] < comp_min[b]; });
     std::vector<int> subset_of_root(L, 0);
     for (size_t k = 0; k < roots.size(); ++k) subset_of_root[roots[k]] = (int)k + 1;
-    std::vector<int> line_subset(lines.size(), 0);
+    line_subset.assign(lines.size(), 0);
     for (const int i : cid_last_line)
         if (line_node[i] >= 0) line_subset[i] = subset_of_root[find(line_node[i])];
+    return (int)roots.size();
+}
+
+int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* row_subset, int32_t max_rows) {
+    if (!clusterfile) return hfail(MBSV_ERR_ARG, "clusters file is required");
+    std::string buf;
+    if (!slurp(clusterfile, buf)) return hfail(MBSV_ERR_IO, std::string("cannot open ") + clusterfile);
+    std::vector<std::string_view> lines;
+    std::vector<int> line_subset;
+    const int n_subsets = partition_lines(buf, lines, line_subset);
     if (row_subset) for (int i = 0; i < max_rows && i < (int)lines.size(); ++i) row_subset[i] = line_subset[i];
     if (outdir) {
         std::vector<std::ofstream> out;
         // at most a few thousand files are kept open at once: write subset by subset
-        std::vector<std::vector<int>> members(roots.size() + 1);
+        std::vector<std::vector<int>> members((size_t)n_subsets + 1);
         for (size_t i = 0; i < lines.size(); ++i) if (line_subset[i] > 0) members[line_subset[i]].push_back((int)i);
         for (size_t k = 1; k < members.size(); ++k) {
             std::ofstream w(std::string(outdir) + "/subset-" + std::to_string(k) + ".clusters");
@@ -1100,7 +1304,7 @@ int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* ro
             for (int i : members[k]) w << lines[i] << "\n";
         }
     }
-    return (int)roots.size();
+    return n_subsets;
 }
 
 int mbsv_java_double_to_string(double v, char* buf, int32_t buflen) {

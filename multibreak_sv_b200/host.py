@@ -39,6 +39,7 @@ def _bind(L):
     L.mbsv_host_batch_create.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(vp)]
     L.mbsv_host_batch_desc.argtypes = [vp, C.POINTER(ProblemDesc)]
     L.mbsv_host_batch_destroy.argtypes = [vp]
+    L.mbsv_host_load_partitioned.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(vp), I32P]
     L.mbsv_host_partition.argtypes = [C.c_char_p, C.c_char_p, I32P, C.c_int32]
     L.mbsv_java_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int32]
     L.mbsv_java_hashmap_order.argtypes = [C.c_char_p, C.c_int32, I32P, I32P]
@@ -242,6 +243,28 @@ def batch(hosts) -> PackedProblem:
         d = ProblemDesc()
         check(L.mbsv_host_batch_desc(b, C.byref(d)))
         return _desc_to_packed(d)
+    finally:
+        L.mbsv_host_batch_destroy(b)
+
+
+def load_partitioned(clusterfile: str, assignmentfile: str, experimentfile: str, tolerate_tree_bins: bool = False, info=None):
+    """Partition + load in memory (mbsv_host_load_partitioned): one subproblem per subset of
+    generateIndependentSubproblems.pl, each packed as a run on `subset-k.clusters --readclustersfirst` would see it; the
+    assignments file is read once.  Returns (PackedProblem, number of skipped empty subsets); `info` (a dict) also receives
+    the number of subsets whose HashMap order could not be reproduced (only with tolerate_tree_bins)."""
+    L = _bind(load_library())
+    b = C.c_void_p()
+    skipped = np.zeros(2, np.int32)
+    n = L.mbsv_host_load_partitioned(clusterfile.encode(), assignmentfile.encode(), experimentfile.encode(),
+                                     int(tolerate_tree_bins), C.byref(b), skipped.ctypes.data_as(I32P))
+    if info is not None:
+        info.update(skipped=int(skipped[0]), unreproducible_order=int(skipped[1]))
+    if n < 0:
+        check(n)
+    try:
+        d = ProblemDesc()
+        check(L.mbsv_host_batch_desc(b, C.byref(d)))
+        return _desc_to_packed(d), int(skipped[0])
     finally:
         L.mbsv_host_batch_destroy(b)
 

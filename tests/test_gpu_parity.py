@@ -432,3 +432,19 @@ def test_error_probability_extremes(oracle, mbsv, example_problem, perr):
             assert np.array_equal(o.cluster_hist, g.cluster_hist) and np.array_equal(o.frag_err_count, g.frag_err_count)
             # NaN log-posteriors compare by bit pattern
             assert np.array_equal(o.final_logprob.view(np.uint64), g.final_logprob.view(np.uint64))
+
+
+def test_partitioned_files_to_gpu(oracle, mbsv, tmp_path):
+    """Reference-format files -> mbsv_host_load_partitioned (in-memory partition + per-subset packing) -> GPU batch; the
+    oracle runs the same packed batch."""
+    from multibreak_sv_b200 import host, synth
+    g = synth.generate("cfg4", n_frag=900, seed=123, conncomp_frac=0.2)
+    paths = synth.write_reference_files(g, str(tmp_path), frag_numbers=np.random.default_rng(9).permutation(900) * 5 + 77)
+    p, skipped = host.load_partitioned(paths["clusters"], paths["assignments"], paths["experiments"])
+    assert skipped == 0 and p.scalars["n_frag"] == 900 and p.scalars["n_sub"] >= g.scalars["n_sub"]
+    op = oracle.Problem(p.scalars, p.arrays)
+    dp = mbsv.DeviceProblem(p)
+    o = oracle.run(op, "incremental", 2000, n_chains=32, nthreads=8, java_int_wrap=False)
+    assert_same(o, dp.run(mbsv.MODE_FAST, 2000, n_chains=32))
+    o = oracle.run(op, "faithful", 500, n_chains=2, nthreads=8, java_int_wrap=True, trace=True)
+    assert_same(o, dp.run(mbsv.MODE_REPLAY_EXACT, 500, n_chains=2, trace=True), trace=True)

@@ -226,6 +226,46 @@ def test_partition_then_batch_refines_generator_subproblems(mbsv, oracle, tmp_pa
     assert seen == set(gen_sub)
 
 
+@pytest.mark.parametrize("cfg,nfrag,cc,seed", [("cfg4", 400, 0.3, 99), ("cfg2", 900, 0.0, 5), ("cfg3", 250, 0.4, 17)])
+def test_load_partitioned_equals_one_host_per_subset_file(mbsv, tmp_path, cfg, nfrag, cc, seed):
+    """mbsv_host_load_partitioned (partition + load in memory, assignments file read once) must give exactly the batch
+    of: generateIndependentSubproblems -> subset-k.clusters files -> one --readclustersfirst host per file -> batch."""
+    from multibreak_sv_b200 import host, synth
+    g = synth.generate(cfg, n_frag=nfrag, seed=seed, conncomp_frac=cc)
+    nums = np.random.default_rng(seed).permutation(nfrag) * 3 + 1000          # subset numbering != file order
+    paths = synth.write_reference_files(g, str(tmp_path), frag_numbers=nums)
+    sdir = os.path.join(str(tmp_path), "subs")
+    os.makedirs(sdir)
+    n, _ = host.generateIndependentSubproblems(paths["clusters"], sdir)
+    hosts = [_host(mbsv, os.path.join(sdir, f"subset-{k}.clusters"), paths["assignments"], paths["experiments"], cf=True).load()
+             for k in range(1, n + 1)]
+    want = host.batch([h for h in hosts if h.packed().scalars["n_frag"] > 0])
+    for threads in ("1", "3", "7"):                  # worker threads load ranges of subsets, merged in subset order
+        os.environ["MBSV_HOST_THREADS"] = threads
+        try:
+            got, skipped = host.load_partitioned(paths["clusters"], paths["assignments"], paths["experiments"])
+        finally:
+            del os.environ["MBSV_HOST_THREADS"]
+        assert skipped == sum(1 for h in hosts if h.packed().scalars["n_frag"] == 0)
+        _same(got, want)
+        assert got.scalars["n_sub"] == n - skipped and got.scalars["n_frag"] == nfrag
+
+
+def test_load_partitioned_on_the_shipped_second_data_set(mbsv, oracle):
+    """Ten independent clusters: each subproblem equals the oracle's load of the shipped iterK.clusters file."""
+    from conftest import GOLDEN
+    from multibreak_sv_b200 import host
+    pre = os.path.join(GOLDEN, "preproc_infiles")
+    files = [os.path.join(pre, "gasv.in.clusters"), os.path.join(pre, "assignments.txt"), os.path.join(pre, "experiments.txt")]
+    got, skipped = host.load_partitioned(*files)
+    assert (got.scalars["n_sub"], skipped, got.scalars["n_frag"], got.scalars["n_cluster"]) == (10, 0, 16, 10)
+    # subset 1 is c7 (longread_1, two alignments): iter6.clusters in the shipped numbering
+    q = oracle.load_files(os.path.join(pre, "cluster-subproblems", "iter6.clusters"), files[1], files[2], clusters_first=True)
+    a = got.arrays
+    assert a["sub_frag_ptr"][1] == 1 and a["frag_aln_ptr"][1] == 2 and q.scalars["n_frag"] == 1 and q.scalars["n_aln"] == 2
+    assert a["aln_numerrors"][:2].tolist() == q.arrays["aln_numerrors"].tolist() == [1007, 1002]
+
+
 def test_matchfile_initial_state(mbsv, tmp_path):
     """--matchfile (MultiBreakSV.java:1030-1085): the shipped initialset.txt never matches (its IDs lack `longread_`), so
     every fragment starts unassigned; a matching single-ESP alignment is set, a two-ESP alignment never is (thisval <= 1)."""

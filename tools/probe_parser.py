@@ -20,3 +20,8 @@ for cf in (False, True):
 t0 = time.time()
 n, rows = host.generateIndependentSubproblems(paths["clusters"], None)
 print("partition %.2f s -> %d subsets" % (time.time() - t0, n))
+t0 = time.time()
+info = {}
+p, skipped = host.load_partitioned(paths["clusters"], paths["assignments"], paths["experiments"], tolerate_tree_bins=True, info=info)
+print(info)
+print("load_partitioned %.2f s -> %d subproblems (%d skipped), %d fragments" % (time.time() - t0, p.scalars["n_sub"], skipped, p.scalars["n_frag"]))
