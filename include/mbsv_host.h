@@ -79,13 +79,22 @@ int mbsv_host_write_state_counts(mbsv_host* h, const char* path);
 int mbsv_host_batch_create(mbsv_host* const* hosts, int32_t n, mbsv_host_batch** out);
 int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* out);
 int mbsv_host_batch_destroy(mbsv_host_batch* b);
+/* writeFinalFiles (MultiBreakSV.java:1712-1859) for a batch whose names were kept: <prefix>.finalbreakpoints.longburnin and
+   <prefix>.finalassignment.longburnin with one header and the rows of every subproblem in batch order, i.e. the
+   concatenation of the per-subset outputs of the reference workflow (rows are ragged across subproblems: each prints
+   its own maxSupport columns).  The tallies are those of mbsv_run on the batch descriptor; burnin = the window length. */
+int mbsv_host_batch_write_final_files(mbsv_host_batch* b, int32_t burnin, const uint32_t* aln_count,
+                                      const uint32_t* frag_err_count, const uint32_t* cluster_hist, const char* prefix);
+/* out[i] = subset number (mbsv_host_load_partitioned) or running index (mbsv_host_batch_create) of subproblem i */
+int mbsv_host_batch_numbers(mbsv_host_batch* b, int32_t* out);
 
 /* Partition + load in one call, in memory: the batch holds one subproblem per subset of generateIndependentSubproblems.pl,
    each packed exactly as a reference run on `subset-k.clusters --readclustersfirst` with the full assignments file would
    see it (doc/MultiBreakSV-Manual.txt:464-473) -- but the assignments file is read once, not once per subset, and no
    subset file is written.  Subsets without any fragment are skipped.  flags bit 0: a subset whose HashMap order cannot be
    reproduced (a bin Java would treeify, see MBSV_ERR_UNSUPPORTED) keeps the plain-list order instead of failing the load
-   -- its chain is valid but not the trajectory a JVM would produce.  info (may be NULL) = {skipped subsets, subsets with
+   -- its chain is valid but not the trajectory a JVM would produce; bit 1: keep the names (fragment, cluster, ESP) for
+   mbsv_host_batch_write_final_files.  info (may be NULL) = {skipped subsets, subsets with
    such an order}.  Returns the number of subproblems (> 0) or a negative status. */
 int mbsv_host_load_partitioned(const char* clusterfile, const char* assignmentfile, const char* experimentfile,
                                int32_t flags, mbsv_host_batch** out, int32_t* info);

@@ -310,6 +310,12 @@ struct mbsv_host_batch {
     std::vector<uint8_t> cluster_kind;
     std::vector<double> pseq, lambda, logprobcov;
     int max_support = 0, n_exp = 0;
+    // for the writers (every host appended so far contributed them; mbsv_host_load_partitioned: flags bit 1)
+    bool have_names = true;
+    std::vector<char> name_pool;                               // NUL-terminated strings
+    std::vector<uint64_t> frag_name, cl_name, esp_name;        // offsets: per fragment / cluster / alignment-ESP entry
+    std::vector<int32_t> sorted_frag;                          // per subproblem: its fragments in getFragmentIDs() order (global index)
+    std::vector<int32_t> sub_max_support, sub_number;          // the subset's own maxSupport; its subset number (or running index)
 };
 
 namespace {
@@ -942,7 +948,7 @@ int mbsv_host_write_state_counts(mbsv_host* h, const char* path) {
 static int partition_lines(const std::string& buf, std::vector<std::string_view>& lines, std::vector<int>& line_subset);
 
 // one more subproblem at the end of the batch (the host may be reused or destroyed afterwards)
-static int batch_append(mbsv_host_batch* b, const mbsv_host* h) {
+static int batch_append(mbsv_host_batch* b, const mbsv_host* h, bool keep_names = true, int number = 0) {
     if (!h || !h->packed || !h->priors || !h->sv_filled) return hfail(MBSV_ERR_ARG, "every host must be loaded");
     if (!h->unsupported.empty()) return hfail(MBSV_ERR_UNSUPPORTED, h->unsupported);
     if (b->sub_frag_ptr.empty()) {
@@ -981,6 +987,16 @@ static int batch_append(mbsv_host_batch* b, const mbsv_host* h) {
     b->sv_numchanged.insert(b->sv_numchanged.end(), h->sv_numchanged.begin(), h->sv_numchanged.end());
     b->sub_frag_ptr.push_back(f0 + F); b->sub_cluster_ptr.push_back(c0 + C);
     b->sub_sv_ptr.push_back(b->sub_sv_ptr.back() + (int)h->sv_cluster.size());
+    b->sub_max_support.push_back(h->max_support);
+    b->sub_number.push_back(number > 0 ? number : (int)b->sub_max_support.size());
+    if (!keep_names) b->have_names = false;
+    if (b->have_names) {
+        auto put = [&](std::string_view v) { const uint64_t o = b->name_pool.size(); b->name_pool.insert(b->name_pool.end(), v.begin(), v.end()); b->name_pool.push_back(0); return o; };
+        for (int f = 0; f < F; ++f) b->frag_name.push_back(put(h->frags[h->frag_order[f]].id));
+        for (int c = 0; c < C; ++c) b->cl_name.push_back(put(h->cl_name[h->cl_order[c]]));
+        for (int e : h->aln_esp_espid) b->esp_name.push_back(put(h->esp_name.view(e)));
+        for (int f : h->sorted_frag) b->sorted_frag.push_back(f0 + f);
+    }
     return MBSV_OK;
 }
 // logprobcov is shared by the batch: one table up to the largest maxSupport (values do not depend on the table length)
@@ -1014,6 +1030,16 @@ static int batch_merge(mbsv_host_batch* d, const mbsv_host_batch* s) {
     cat(d->root_leaf, s->root_leaf, 0, 0, false); cat(d->sv_cluster, s->sv_cluster, c0, 0, false);
     cat(d->sv_frag_ptr, s->sv_frag_ptr, q0, 1, false); cat(d->sv_frag, s->sv_frag, f0, 0, false);
     cat(d->sv_numchanged, s->sv_numchanged, 0, 0, false);
+    cat(d->sub_max_support, s->sub_max_support, 0, 0, false); cat(d->sub_number, s->sub_number, 0, 0, false);
+    if (!s->have_names) d->have_names = false;
+    if (d->have_names) {
+        const uint64_t p0 = d->name_pool.size();
+        d->name_pool.insert(d->name_pool.end(), s->name_pool.begin(), s->name_pool.end());
+        for (uint64_t o : s->frag_name) d->frag_name.push_back(p0 + o);
+        for (uint64_t o : s->cl_name) d->cl_name.push_back(p0 + o);
+        for (uint64_t o : s->esp_name) d->esp_name.push_back(p0 + o);
+        cat(d->sorted_frag, s->sorted_frag, f0, 0, false);
+    }
     return MBSV_OK;
 }
 
@@ -1149,7 +1175,7 @@ int mbsv_host_load_partitioned(const char* clusterfile, const char* assignmentfi
                 ++t_approx[t];
             }
             if (rc == MBSV_OK && h->frag_order.empty()) { ++t_skipped[t]; continue; }
-            if (rc == MBSV_OK) rc = batch_append(&part[t], h);
+            if (rc == MBSV_OK) rc = batch_append(&part[t], h, (flags & 2) != 0, k);
             if (rc != MBSV_OK) { t_rc[t] = rc; t_msg[t] = "subset " + std::to_string(k) + ": " + mbsv_last_error(); }
             std::string().swap(ctext[k]); std::string().swap(atext[k]);
         }
@@ -1199,6 +1225,57 @@ int mbsv_host_batch_desc(mbsv_host_batch* b, mbsv_problem_desc* d) {
     return MBSV_OK;
 }
 int mbsv_host_batch_destroy(mbsv_host_batch* b) { delete b; return MBSV_OK; }
+
+// writeFinalFiles (:1712-1859) for a whole batch: one pair of files, one header, the rows of every subproblem in batch
+// order -- what concatenating the per-subset outputs of the reference workflow gives.  Each subproblem prints its own
+// number of Support columns (its maxSupport), so rows are ragged across subproblems, as those per-subset files are.
+int mbsv_host_batch_write_final_files(mbsv_host_batch* b, int32_t burnin, const uint32_t* aln_count,
+                                      const uint32_t* frag_err_count, const uint32_t* cluster_hist, const char* prefix) {
+    if (!b || !aln_count || !frag_err_count || !cluster_hist || !prefix || burnin <= 0) return hfail(MBSV_ERR_ARG, "bad argument");
+    if (!b->have_names || b->frag_name.size() != (size_t)b->sub_frag_ptr.back())
+        return hfail(MBSV_ERR_ARG, "the batch was built without names (mbsv_host_load_partitioned flags bit 1)");
+    const int S = (int)b->sub_frag_ptr.size() - 1;
+    const char* pool = b->name_pool.data();
+    {
+        std::ofstream w(std::string(prefix) + ".finalbreakpoints.longburnin");
+        if (!w) return hfail(MBSV_ERR_IO, "cannot write breakpoints file");
+        w << "ClusterID\tNumIters\tSupport0\tSupport1\tSupport2...\n";
+        for (int s = 0; s < S; ++s)
+            for (int c = b->sub_cluster_ptr[s]; c < b->sub_cluster_ptr[s + 1]; ++c) {
+                w << (pool + b->cl_name[c]) << "\t" << burnin;
+                const uint32_t* hist = cluster_hist + b->cluster_hist_ptr[c];
+                const int bins = b->cluster_hist_ptr[c + 1] - b->cluster_hist_ptr[c];
+                const int ms = b->sub_max_support[s];
+                double tot = 0;
+                for (int j = 1; j <= ms; ++j) tot = tot + (j < bins ? (double)hist[j] : 0.0);
+                w << "\t" << java_double((double)burnin - tot);
+                for (int j = 1; j <= ms; ++j) w << "\t" << java_double(j < bins ? (double)hist[j] : 0.0);
+                w << "\n";
+            }
+    }
+    {
+        std::ofstream w(std::string(prefix) + ".finalassignment.longburnin");
+        if (!w) return hfail(MBSV_ERR_IO, "cannot write assignment file");
+        w << "FragmentID\tAssignmentIndex\tAvgAssignment\tDiscordantPairs\n";
+        for (size_t k = 0; k < b->sorted_frag.size(); ++k) {
+            const int f = b->sorted_frag[k];
+            const char* id = pool + b->frag_name[f];
+            w << id << "\t-1\t" << java_double((double)frag_err_count[f] / burnin) << "\terror\n";
+            for (int a = b->frag_aln_ptr[f]; a < b->frag_aln_ptr[f + 1]; ++a) {
+                w << id << "\t" << (a - b->frag_aln_ptr[f]) << "\t" << java_double((double)aln_count[a] / burnin) << "\t";
+                for (int j = b->aln_esp_ptr[a]; j < b->aln_esp_ptr[a + 1]; ++j) w << (j > b->aln_esp_ptr[a] ? "," : "") << (pool + b->esp_name[j]);
+                w << "\n";
+            }
+        }
+    }
+    return MBSV_OK;
+}
+/* subset number (mbsv_host_load_partitioned) or running index of every subproblem of the batch */
+int mbsv_host_batch_numbers(mbsv_host_batch* b, int32_t* out) {
+    if (!b || !out) return hfail(MBSV_ERR_ARG, "bad argument");
+    for (size_t i = 0; i < b->sub_number.size(); ++i) out[i] = b->sub_number[i];
+    return (int)b->sub_number.size();
+}
 
 // Connected components of the clusters file as generateIndependentSubproblems.pl finds them: lines = the physical lines
 // of buf, line_subset[i] = 1-based subset of line i (0: dropped).  Returns the number of subsets.

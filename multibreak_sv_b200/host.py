@@ -40,6 +40,8 @@ def _bind(L):
     L.mbsv_host_batch_desc.argtypes = [vp, C.POINTER(ProblemDesc)]
     L.mbsv_host_batch_destroy.argtypes = [vp]
     L.mbsv_host_load_partitioned.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(vp), I32P]
+    L.mbsv_host_batch_write_final_files.argtypes = [vp, C.c_int32, U32P, U32P, U32P, C.c_char_p]
+    L.mbsv_host_batch_numbers.argtypes = [vp, I32P]
     L.mbsv_host_partition.argtypes = [C.c_char_p, C.c_char_p, I32P, C.c_int32]
     L.mbsv_java_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int32]
     L.mbsv_java_hashmap_order.argtypes = [C.c_char_p, C.c_int32, I32P, I32P]
@@ -267,6 +269,42 @@ def load_partitioned(clusterfile: str, assignmentfile: str, experimentfile: str,
         return _desc_to_packed(d), int(skipped[0])
     finally:
         L.mbsv_host_batch_destroy(b)
+
+
+class PartitionedBatch:
+    """Files -> partition -> one batched problem that remembers its names, so that the reference's output files can be
+    written for the whole batch (mbsv_host_load_partitioned with names + mbsv_host_batch_write_final_files)."""
+
+    def __init__(self, clusterfile: str, assignmentfile: str, experimentfile: str, tolerate_tree_bins: bool = False):
+        self.lib = _bind(load_library())
+        self.h = C.c_void_p()
+        info = np.zeros(2, np.int32)
+        n = self.lib.mbsv_host_load_partitioned(clusterfile.encode(), assignmentfile.encode(), experimentfile.encode(),
+                                                2 | int(tolerate_tree_bins), C.byref(self.h), info.ctypes.data_as(I32P))
+        if n < 0:
+            check(n)
+        self.skipped, self.unreproducible_order = int(info[0]), int(info[1])
+        d = ProblemDesc()
+        check(self.lib.mbsv_host_batch_desc(self.h, C.byref(d)))
+        self.packed = _desc_to_packed(d)
+        self.numbers = np.zeros(n, np.int32)                 # subset number of every subproblem
+        self.lib.mbsv_host_batch_numbers(self.h, self.numbers.ctypes.data_as(I32P))
+
+    def writeFinalFiles(self, prefix: str, burnin: int, aln_count, frag_err_count, cluster_hist):
+        a, f, h = (np.ascontiguousarray(x, np.uint32) for x in (aln_count, frag_err_count, cluster_hist))
+        check(self.lib.mbsv_host_batch_write_final_files(self.h, burnin, a.ctypes.data_as(U32P), f.ctypes.data_as(U32P),
+                                                         h.ctypes.data_as(U32P), prefix.encode()))
+
+    def close(self):
+        if self.h:
+            self.lib.mbsv_host_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def main(argv):

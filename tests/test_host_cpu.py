@@ -251,6 +251,41 @@ def test_load_partitioned_equals_one_host_per_subset_file(mbsv, tmp_path, cfg, n
         assert got.scalars["n_sub"] == n - skipped and got.scalars["n_frag"] == nfrag
 
 
+def test_batch_final_files_are_the_concatenated_per_subset_outputs(mbsv, oracle, tmp_path):
+    """PartitionedBatch.writeFinalFiles == header + the rows of every `subset-k` run's own output files, in subset order."""
+    from multibreak_sv_b200 import host, synth
+    g = synth.generate("cfg4", n_frag=300, seed=41, conncomp_frac=0.25)
+    paths = synth.write_reference_files(g, str(tmp_path), frag_numbers=np.random.default_rng(2).permutation(300) * 3 + 500)
+    b = host.PartitionedBatch(paths["clusters"], paths["assignments"], paths["experiments"])
+    p = b.packed
+    r = oracle.run(oracle.Problem(p.scalars, p.arrays), "incremental", 2000, n_chains=4, nthreads=4, java_int_wrap=False)
+    burnin = 4 * 200                                            # pooled over the 4 chains: window length x chains
+    prefix = os.path.join(str(tmp_path), "batch")
+    b.writeFinalFiles(prefix, burnin, r.aln_count, r.frag_err_count, r.cluster_hist)
+    sdir = os.path.join(str(tmp_path), "subs")
+    os.makedirs(sdir)
+    n, _ = host.generateIndependentSubproblems(paths["clusters"], sdir)
+    assert b.numbers.tolist() == list(range(1, n + 1)) and b.skipped == 0
+    a = p.arrays
+    bp, asg = [], []
+    for i, k in enumerate(b.numbers):
+        sv = _host(mbsv, os.path.join(sdir, f"subset-{k}.clusters"), paths["assignments"], paths["experiments"], cf=True,
+                   extra=["--prefix", os.path.join(sdir, f"out-{k}")]).load()
+        f0, f1 = a["sub_frag_ptr"][i], a["sub_frag_ptr"][i + 1]
+        c0, c1 = a["sub_cluster_ptr"][i], a["sub_cluster_ptr"][i + 1]
+        sv.setResults(r.aln_count[a["frag_aln_ptr"][f0]:a["frag_aln_ptr"][f1]], r.frag_err_count[f0:f1],
+                      r.cluster_hist[a["cluster_hist_ptr"][c0]:a["cluster_hist_ptr"][c1]], numiters=8000)     # burnin 800
+        assert sv.burnin == burnin
+        sv.writeFinalFiles()
+        bp += open(os.path.join(sdir, f"out-{k}.finalbreakpoints.longburnin")).read().splitlines()[1:]
+        asg += open(os.path.join(sdir, f"out-{k}.finalassignment.longburnin")).read().splitlines()[1:]
+    got_bp = open(prefix + ".finalbreakpoints.longburnin").read().splitlines()
+    got_asg = open(prefix + ".finalassignment.longburnin").read().splitlines()
+    assert got_bp[0] == "ClusterID\tNumIters\tSupport0\tSupport1\tSupport2..." and got_bp[1:] == bp
+    assert got_asg[0] == "FragmentID\tAssignmentIndex\tAvgAssignment\tDiscordantPairs" and got_asg[1:] == asg
+    b.close()
+
+
 def test_load_partitioned_on_the_shipped_second_data_set(mbsv, oracle):
     """Ten independent clusters: each subproblem equals the oracle's load of the shipped iterK.clusters file."""
     from conftest import GOLDEN

@@ -16,8 +16,8 @@ t0 = time.time()
 paths = synth.write_reference_files(g, out)
 print("wrote files %.1f s: %s MB" % (time.time() - t0, {k: os.path.getsize(v) >> 20 for k, v in paths.items()}), flush=True)
 t0 = time.time()
-info = {}
-p, skipped = host.load_partitioned(paths["clusters"], paths["assignments"], paths["experiments"], tolerate_tree_bins=True, info=info)
+b = host.PartitionedBatch(paths["clusters"], paths["assignments"], paths["experiments"], tolerate_tree_bins=True)
+p, info = b.packed, {"skipped": b.skipped, "unreproducible_order": b.unreproducible_order}
 t_load = time.time() - t0
 print("partition + load: %.2f s -> %d subproblems, %d fragments, %d alignments %s" % (t_load, p.scalars["n_sub"], p.scalars["n_frag"], p.scalars["n_aln"], info), flush=True)
 t0 = time.time()
@@ -28,3 +28,7 @@ r = dp.run(m.MODE_FAST, iters, n_chains=chains, want_state=False, per_chain=Fals
 t_run = time.time() - t0
 print("create %.2f s, run %.2f s (kernel %.0f ms): %d chains x %d iterations, %.3e reassignments -> %.3e /s end to end from files"
       % (t_create, t_run, r.kernel_ms, chains, iters, float(r.totals[4]), float(r.totals[4]) / (t_load + t_create + t_run)))
+t0 = time.time()
+burnin = chains * m.reference_burnin(iters)
+b.writeFinalFiles(os.path.join(out, "batch"), burnin, r.aln_count, r.frag_err_count, r.cluster_hist)
+print("wrote %s.final{breakpoints,assignment}.longburnin in %.2f s" % (os.path.join(out, "batch"), time.time() - t0))
