@@ -5,6 +5,10 @@
 // reference's writers.  Extra options of this driver: --device N, --mode replay|fast (default replay = the
 // reference's arithmetic).  --enumerate is outside the sampler path and is refused.
 //
+// --partition [--chains N]: the whole multi-subproblem workflow of the manual (IV: generateIndependentSubproblems.pl, then
+// one run per subset-k.clusters with --readclustersfirst) in one process: partition + load in memory, one GPU batch, and
+// the concatenated .final*.longburnin files.  Implies --savespace.
+//
 // Exit codes: 0 ok; 1 bad usage (the reference prints its usage and exits); 2 the library reported an error.
 #include <chrono>
 #include <cstdio>
@@ -22,7 +26,7 @@ void usage(const char* why) {
                  "ERROR: %s\n\n"
                  "Usage: mbsv_cli --clusterfile F --assignmentfile F --experimentfile F --numiterations N --perr P\n"
                  "                [--prefix OUT] [--matchfile F] [--savespace] [--readclustersfirst]\n"
-                 "                [--device N] [--mode replay|fast]\n",
+                 "                [--device N] [--mode replay|fast] [--partition [--chains N]]\n",
                  why);
 }
 
@@ -44,17 +48,18 @@ int main(int argc, char** argv) {
     std::string clusterfile, assignmentfile, experimentfile, matchfile, prefix = "out";
     long numiters = -1;
     double perr = -1;
-    bool save_space = false, clusters_first = false;
-    int device = 0, mode = MBSV_MODE_REPLAY_EXACT;
+    bool save_space = false, clusters_first = false, partition = false;
+    int device = 0, mode = MBSV_MODE_REPLAY_EXACT, chains = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto value = [&]() -> const char* { return i + 1 < argc ? argv[++i] : nullptr; };
         const char* v = nullptr;
         if (a == "--savespace") { save_space = true; continue; }
         if (a == "--readclustersfirst") { clusters_first = true; continue; }
+        if (a == "--partition") { partition = true; continue; }
         if (a == "--enumerate") { usage("--enumerate is outside the sampler path"); return 1; }
         if (a != "--clusterfile" && a != "--assignmentfile" && a != "--experimentfile" && a != "--matchfile" && a != "--prefix" &&
-            a != "--numiterations" && a != "--perr" && a != "--device" && a != "--mode") {
+            a != "--numiterations" && a != "--perr" && a != "--device" && a != "--mode" && a != "--chains") {
             usage((a + " is not a valid option.").c_str());
             return 1;
         }
@@ -68,6 +73,7 @@ int main(int argc, char** argv) {
         else if (a == "--numiterations") { numiters = std::strtol(v, &end, 10); if (*end || numiters < 0 || numiters > 2147483647L) { usage("--numiterations must be a positive integer."); return 1; } }
         else if (a == "--perr") { perr = std::strtod(v, &end); if (*end) { usage("--perr must be a float between 0 and 1."); return 1; } }
         else if (a == "--device") device = std::atoi(v);
+        else if (a == "--chains") { chains = std::atoi(v); if (chains < 1) { usage("--chains must be a positive integer."); return 1; } }
         else if (a == "--mode") {
             if (!std::strcmp(v, "replay")) mode = MBSV_MODE_REPLAY_EXACT;
             else if (!std::strcmp(v, "fast")) mode = MBSV_MODE_FAST;
@@ -81,6 +87,39 @@ int main(int argc, char** argv) {
     if (perr == -1) { usage("Mapping error probability (perr) is required."); return 1; }
     if (perr < 0 || perr > 1) { usage("--perr must be a value between 0 and 1."); return 1; }
 
+    if (partition) {
+        if (!matchfile.empty()) { usage("--matchfile cannot be combined with --partition"); return 1; }
+        mbsv_host_batch* b = nullptr;
+        int32_t info[2] = {0, 0};
+        const int S = mbsv_host_load_partitioned(clusterfile.c_str(), assignmentfile.c_str(), experimentfile.c_str(), 2, &b, info);
+        if (S < 0) return fail_lib("partition + load");
+        mbsv_problem_desc d;
+        if (mbsv_host_batch_desc(b, &d)) return fail_lib("batch");
+        std::printf("%d independent subproblems (%d empty skipped): %d fragments, %d alignments, %d clusters\n", S, info[0], d.n_frag,
+                    d.n_aln, d.n_cluster);
+        mbsv_problem* prob = nullptr;
+        if (mbsv_problem_create(&d, device, &prob)) return fail_lib("create");
+        mbsv_run_params rp;
+        std::memset(&rp, 0, sizeof rp);
+        const int burnin = numiters / 10 ? (int)(numiters / 10) : 10;          // :186-193
+        rp.mode = mode; rp.n_chains = chains; rp.num_iters = (int32_t)numiters; rp.burnin = burnin; rp.perr = perr; rp.seed = 123456;
+        rp.device = device; rp.java_int_wrap = 1; rp.memo_states = 65536;
+        std::vector<uint32_t> aln(d.n_aln), fe(d.n_frag), hist(d.n_hist > 0 ? d.n_hist : 1);
+        std::vector<int64_t> totals(6, 0);
+        mbsv_results r;
+        std::memset(&r, 0, sizeof r);
+        r.aln_count = aln.data(); r.frag_err_count = fe.data(); r.cluster_hist = hist.data(); r.totals = totals.data();
+        if (mbsv_run(prob, &rp, &r)) return fail_lib("runMCMC");
+        mbsv_problem_destroy(prob);
+        std::printf("%lld of %lld(%s) Naive Moves\n", (long long)totals[1], (long long)totals[0], jd((double)totals[1] / (double)totals[0]).c_str());
+        std::printf("%lld of %lld(%s) AlterSV Moves\n", (long long)totals[3], (long long)totals[2], jd((double)totals[3] / (double)totals[2]).c_str());
+        // tallies are pooled over the chains: the window length is chains x burnin samples
+        if (mbsv_host_batch_write_final_files(b, burnin * chains, aln.data(), fe.data(), hist.data(), prefix.c_str())) return fail_lib("writeFinalFiles");
+        mbsv_host_batch_destroy(b);
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("SAMPLING TIME %s\n", jd(secs).c_str());
+        return 0;
+    }
     mbsv_host* h = nullptr;
     if (mbsv_host_create(&h)) return fail_lib("create");
     if (mbsv_host_set_files(h, clusterfile.c_str(), assignmentfile.c_str(), experimentfile.c_str(), clusters_first)) return fail_lib("files");

@@ -116,3 +116,25 @@ def test_cli_file_to_file(mbsv, oracle, preproc_problem, tmp_path):
     ref.writeFinalFiles()
     for ext in (".finalbreakpoints.longburnin", ".finalassignment.longburnin"):
         assert open(prefix + ext).read() == open(prefix + "_ref" + ext).read()
+
+
+@pytest.mark.gpu
+def test_cli_partition_mode(mbsv, oracle, tmp_path):
+    """mbsv_cli --partition: partition + load in memory, one GPU batch over the ten subproblems, concatenated output files;
+    expected = the oracle's run of the same batch through the same batch writer."""
+    from multibreak_sv_b200 import host
+    prefix = os.path.join(str(tmp_path), "part")
+    cli = os.path.join(os.path.dirname(os.path.abspath(host.__file__)), "mbsv_cli")
+    r = subprocess.run([cli, "--clusterfile", FILES[0], "--assignmentfile", FILES[1], "--experimentfile", FILES[2],
+                        "--numiterations", "10000", "--perr", "0.001", "--prefix", prefix, "--partition"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "10 independent subproblems (0 empty skipped): 16 fragments, 17 alignments, 10 clusters" in r.stdout
+    b = host.PartitionedBatch(*FILES)
+    p = b.packed
+    o = oracle.run(oracle.Problem(p.scalars, p.arrays), "faithful", 10000)
+    assert f"{int(o.counters[:, :, 1].sum())} of {int(o.counters[:, :, 0].sum())}(" in r.stdout
+    b.writeFinalFiles(prefix + "_ref", 1000, o.aln_count, o.frag_err_count, o.cluster_hist)
+    for ext in (".finalbreakpoints.longburnin", ".finalassignment.longburnin"):
+        assert open(prefix + ext).read() == open(prefix + "_ref" + ext).read()
+    assert len(open(prefix + ".finalbreakpoints.longburnin").read().splitlines()) == 11
