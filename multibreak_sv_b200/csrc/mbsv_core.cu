@@ -730,14 +730,30 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         int64_t total = 0;
         for (const Launch& l : launches) total += warps_of(l, l.lanes);
         int64_t spare = resident_warps - total;
-        for (Launch& l : launches) {
-            if (l.memo && !mixed) continue;                  // warps of one subproblem keep their fixed width
-            while (l.lanes > 1) {
-                const int64_t extra = warps_of(l, l.lanes / 2) - warps_of(l, l.lanes);
-                if (extra > spare) break;
-                spare -= extra;
-                l.lanes /= 2;
-            }
+        // Small batches only (spare > 0): the step ends when the slowest class ends, and a class's time grows with its
+        // chains per warp (measured on the 100k-fragment single-chain config: general kernel 190 / 211 / 305 ms at 1-2 / 4 /
+        // 8 chains per warp, memoised kernel about half of that).  So: narrow the class with the largest estimate while
+        // warp slots are left; when they run out, widen the class that stays cheapest after widening to free some.
+        auto est = [&](const Launch& l, int lanes) { return (l.memo ? 0.5 : 1.0) * (1.0 + 0.1 * (lanes - 1)); };
+        auto movable = [&](const Launch& l) { return !(l.memo && !mixed); };     // warps of one subproblem keep their width
+        for (int guard = 0; spare >= 0 && guard < 256; ++guard) {
+            Launch* worst = nullptr;
+            for (Launch& l : launches)
+                if (movable(l) && l.lanes > 1 && (!worst || est(l, l.lanes) > est(*worst, worst->lanes))) worst = &l;
+            if (!worst) break;
+            double top = 0;
+            for (const Launch& l : launches) top = std::max(top, est(l, l.lanes));
+            if (est(*worst, worst->lanes) < top) break;                          // the slowest class cannot be narrowed further
+            const int64_t extra = warps_of(*worst, worst->lanes / 2) - warps_of(*worst, worst->lanes);
+            if (extra <= spare) { spare -= extra; worst->lanes /= 2; continue; }
+            Launch* give = nullptr;                                              // free slots: widen the cheapest class
+            for (Launch& l : launches)
+                if (movable(l) && &l != worst && l.lanes < 32 && est(l, l.lanes * 2) < est(*worst, worst->lanes) &&
+                    warps_of(l, l.lanes) > warps_of(l, l.lanes * 2) &&
+                    (!give || est(l, l.lanes * 2) < est(*give, give->lanes * 2))) give = &l;
+            if (!give) break;
+            spare += warps_of(*give, give->lanes) - warps_of(*give, give->lanes * 2);
+            give->lanes *= 2;
         }
         if (std::getenv("MBSV_LANES_PER_WARP")) for (Launch& l : launches) l.lanes = l.memo ? Lm : L;
         int64_t w = 0;
