@@ -9,8 +9,8 @@ import os as _os
 # stream would silently wait for the 1st (csrc/mbsv_core.cu).  Read at CUDA context creation, so set it on import.
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
-from ._abi import (MODE_FAST, MODE_REPLAY_EXACT, DeviceProblem, MbsvError, PackedProblem, RunOutput, load_library,
+from ._abi import (MODE_FAST, MODE_GIBBS, MODE_REPLAY_EXACT, DeviceProblem, MbsvError, PackedProblem, RunOutput, load_library,
                    reference_burnin)
 
-__all__ = ["MODE_FAST", "MODE_REPLAY_EXACT", "DeviceProblem", "MbsvError", "PackedProblem", "RunOutput",
+__all__ = ["MODE_FAST", "MODE_GIBBS", "MODE_REPLAY_EXACT", "DeviceProblem", "MbsvError", "PackedProblem", "RunOutput",
            "load_library", "reference_burnin"]

@@ -26,6 +26,7 @@ F64P = C.POINTER(C.c_double)
 MBSV_ABI_VERSION = 1
 MODE_REPLAY_EXACT = 0
 MODE_FAST = 1
+MODE_GIBBS = 2          # heat-bath sampler of the statistical tier (not the reference's chain)
 
 STATUS = {0: "MBSV_OK", -1: "MBSV_ERR_ARG", -2: "MBSV_ERR_CUDA", -3: "MBSV_ERR_NCCL", -4: "MBSV_ERR_OOM",
           -5: "MBSV_ERR_INVARIANT", -6: "MBSV_ERR_UNSUPPORTED", -7: "MBSV_ERR_IO"}

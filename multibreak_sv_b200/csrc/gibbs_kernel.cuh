@@ -1,0 +1,240 @@
+// Heat-bath (Gibbs) sampler, SURVEY.md section 8 row f-4: NOT the reference's chain.  The reference is Metropolis-Hastings
+// (MultiBreakSV.java:1101-1182) and only that replays its trajectory; this kernel samples the SAME posterior
+// (MultiBreakSVAssignmentMatrix.computeLogProb, :130-246) with exact conditionals, for the statistical tier: random-scan
+// Gibbs, one fragment per iteration redrawn from P(assignment | everything else).  No proposal is ever rejected, so it
+// mixes faster per iteration than the lazy MH chain (half of whose iterations do nothing and ~83 % of whose proposals are
+// rejected on the 5M config); it does not reproduce quirk Q1 of naiveMove (the asymmetric proposal), which is why the
+// two samplers agree on the posterior only where the reference's own chain is unbiased.
+//
+// Mapping: one WARP per (subproblem, chain).  The chain's state (assignments, selected-ESP counts) lives in the warp's
+// shared memory; the candidate alignments of the chosen fragment are spread over the lanes: every lane evaluates the
+// log-posterior change of "its" option, a warp max / sum normalises, and the categorical draw is an inclusive
+// __shfl_up prefix scan followed by a __ballot for the first lane whose cumulative weight passes u.  All lanes carry the
+// same RNG state and the same per-experiment totals (uniform registers), so nothing needs broadcasting.
+// Connected-component clusters are not supported here (MBSV_ERR_UNSUPPORTED).
+#pragma once
+#include "sampler_common.cuh"
+
+namespace mbsv {
+
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ DevRun R) {
+    extern __shared__ int smem_tile[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int warp = R.warp_begin + blockIdx.x * 4 + wic;
+    if (warp >= R.warp_end) return;
+    const long long item = R.item_base + (warp - R.warp_base);
+    const int sub = R.sub_order[item / R.n_chains];
+    const int chain = (int)(item % R.n_chains);
+    int* st = smem_tile + (size_t)wic * R.rows_per_warp;          // [F] assignments, [C*E] counts, then the option weights
+    const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
+    const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
+    const int E = P.n_exp, Tstride = P.max_support + 1;
+    double* wopt = reinterpret_cast<double*>(st + ((F + C * E + 1) & ~1));
+    const long long sc = (long long)sub * R.n_chains + chain;
+    const int N = R.num_iters, win_base = R.win_base;
+    const double logperr = R.logperr;
+
+    JavaRandom rng;
+    rng.seed(R.seed + chain);
+    long long Et[MBSV_MAX_EXP], Lt[MBSV_MAX_EXP];
+    double LB[MBSV_MAX_EXP];
+#pragma unroll
+    for (int x = 0; x < MBSV_MAX_EXP; ++x) { Et[x] = 0; Lt[x] = 0; LB[x] = 0.0; }
+    int nerr = 0;
+    auto lb_of = [&](int x, long long e, long long l) {
+        return log_binomial_dev(e, l, P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi, P.logint, P.maxn);
+    };
+    auto bump_totals = [&](int x, long long de, long long dl) {
+#pragma unroll
+        for (int y = 0; y < MBSV_MAX_EXP; ++y) if (y == x) { Et[y] += de; Lt[y] += dl; }
+    };
+    auto get_E = [&](int x) { long long v = 0;
+#pragma unroll
+        for (int y = 0; y < MBSV_MAX_EXP; ++y) if (y == x) v = Et[y]; return v; };
+    auto get_L = [&](int x) { long long v = 0;
+#pragma unroll
+        for (int y = 0; y < MBSV_MAX_EXP; ++y) if (y == x) v = Lt[y]; return v; };
+    auto get_LB = [&](int x) { double v = 0;
+#pragma unroll
+        for (int y = 0; y < MBSV_MAX_EXP; ++y) if (y == x) v = LB[y]; return v; };
+    auto set_LB = [&](int x, double v) {
+#pragma unroll
+        for (int y = 0; y < MBSV_MAX_EXP; ++y) if (y == x) LB[y] = v; };
+    // lane 0 moves the counts of one alignment by `sgn`; inside the long-burn-in window (d != 0) every unit step emits the
+    // support-histogram difference tallies, exactly as the MH kernels do (value n leaves: +d, value n' enters: -d)
+    auto move_counts = [&](int al, int sgn, unsigned d) {
+        const int4 rec = P.aln_rec[al];
+        const int ne = rec.w >> 8;
+        for (int j = 0; j < ne; ++j) {
+            const int slot = P.aln_esp_slot[rec.z + j];
+            if (slot < 0) continue;
+            const int n = st[F + slot];
+            if (d) {
+                unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                if (n > 0) atomicAdd(&h[n], d);
+                if (n + sgn > 0) atomicAdd(&h[n + sgn], 0u - d);
+            }
+            st[F + slot] = n + sgn;
+        }
+    };
+    auto full_logprob = [&]() {
+        double lp = 0.0;
+        for (int i = lane; i < C * E; i += 32) {
+            const int n = st[F + i];
+            if (n > 0) lp += P.T[(size_t)(i % E) * Tstride + n];
+        }
+        lp = warp_sum(lp);
+        lp += (double)nerr * logperr;
+        for (int x = 0; x < E; ++x) lp += get_LB(x);
+        return lp;
+    };
+
+    // ---------------- initial state: the reference's draws (MultiBreakSV.java:999-1015) or the supplied one ----------------
+    for (int i = lane; i < F + C * E; i += 32) st[i] = 0;
+    __syncwarp();
+    for (int f = 0; f < F; ++f) {
+        const int a0 = P.frag_aln_ptr[f0 + f];
+        const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
+        int a;
+        if (R.init_assign) a = R.init_assign[f0 + f];
+        else if (rng.nextDouble() < R.perr) a = -1;
+        else a = rng.nextInt(n);
+        if (a == -1) ++nerr;
+        else {
+            const int4 rec = P.aln_rec[a0 + a];
+            bump_totals(rec.w & 0xff, rec.x, rec.y);
+            if (lane == 0) move_counts(a0 + a, +1, 0u);
+        }
+        if (lane == 0) {
+            st[f] = a;
+            if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
+        }
+    }
+    __syncwarp();
+    for (int x = 0; x < E; ++x) set_LB(x, lb_of(x, get_E(x), get_L(x)));
+    if (R.initial_logprob) { const double lp = full_logprob(); if (lane == 0) R.initial_logprob[sc] = lp; }
+
+    // ---------------- iterations: redraw one fragment from its conditional ----------------
+    long long n_changed = 0;
+    for (int t = 0; t < N; ++t) {
+        const int f = F > 1 ? rng.nextInt(F) : 0;
+        const int a0 = P.frag_aln_ptr[f0 + f];
+        const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
+        const int cur = st[f];
+        // state R = everything else: take the current assignment out
+        int xcur = -1;
+        if (cur != -1) {
+            const int4 rec = P.aln_rec[a0 + cur];
+            xcur = rec.w & 0xff;
+            bump_totals(xcur, -(long long)rec.x, -(long long)rec.y);
+            if (lane == 0) move_counts(a0 + cur, -1, 0u);
+        } else --nerr;
+        __syncwarp();
+        const double lb_cur_removed = xcur >= 0 ? lb_of(xcur, get_E(xcur), get_L(xcur)) : 0.0;
+        // log P(option | rest) up to a constant: option 0 = "unmapped", option k = alignment k-1
+        const int nopt = n + 1;
+        double m = -1.7976931348623157e308;
+        for (int o = lane; o < nopt; o += 32) {
+            double dl;
+            if (o == 0) dl = logperr;
+            else {
+                const int4 rec = P.aln_rec[a0 + o - 1];
+                const int x = rec.w & 0xff, ne = rec.w >> 8;
+                double dcov = 0.0;
+                for (int j = 0; j < ne; ++j) {
+                    const int slot = P.aln_esp_slot[rec.z + j];
+                    if (slot < 0) continue;
+                    int nn = st[F + slot];
+                    for (int i = 0; i < j; ++i) if (P.aln_esp_slot[rec.z + i] == slot) ++nn;     // the same cluster twice in one alignment
+                    dcov += P.T[(size_t)x * Tstride + nn + 1] - (nn > 0 ? P.T[(size_t)x * Tstride + nn] : 0.0);
+                }
+                const double base = x == xcur ? lb_cur_removed : get_LB(x);
+                dl = dcov + (lb_of(x, get_E(x) + rec.x, get_L(x) + rec.y) - base);
+            }
+            wopt[o] = dl;
+            m = dl > m ? dl : m;
+        }
+        m = warp_max(m);
+        __syncwarp();
+        double s = 0.0;
+        for (int o = lane; o < nopt; o += 32) { const double w = exp_dev(wopt[o] - m); wopt[o] = w; s += w; }
+        s = warp_sum(s);
+        __syncwarp();
+        const double u = rng.nextDouble() * s;
+        // categorical draw: inclusive prefix scan of the weights across lanes, ballot for the first lane past u
+        int pick = nopt - 1;
+        double run = 0.0;
+        for (int o0 = 0; o0 < nopt; o0 += 32) {
+            const int o = o0 + lane;
+            double c = o < nopt ? wopt[o] : 0.0;
+            for (int k = 1; k < 32; k <<= 1) { const double v = __shfl_up_sync(0xffffffffu, c, k); if (lane >= k) c += v; }
+            c += run;
+            const unsigned hit = __ballot_sync(0xffffffffu, o < nopt && c > u);
+            if (hit) { pick = o0 + __ffs(hit) - 1; break; }
+            run = __shfl_sync(0xffffffffu, c, 31);
+        }
+        __syncwarp();
+        const int now = pick - 1;
+        // put the drawn assignment in; tallies only when the state changed
+        if (xcur >= 0) set_LB(xcur, lb_cur_removed);
+        const unsigned d = (now != cur && t > win_base) ? (unsigned)(t - win_base) : 0u;
+        if (lane == 0) {
+            if (now == cur) { if (cur != -1) move_counts(a0 + cur, +1, 0u); }
+            else {
+                if (cur != -1) { move_counts(a0 + cur, +1, 0u); move_counts(a0 + cur, -1, d); }      // leave with tallies
+                if (now != -1) move_counts(a0 + now, +1, d);
+                if (d) {
+                    if (cur == -1) atomicAdd(&R.frag_err_count[f0 + f], d); else atomicAdd(&R.aln_count[a0 + cur], d);
+                    if (now == -1) atomicAdd(&R.frag_err_count[f0 + f], 0u - d); else atomicAdd(&R.aln_count[a0 + now], 0u - d);
+                }
+                st[f] = now;
+            }
+        }
+        if (now != -1) {
+            const int4 rec = P.aln_rec[a0 + now];
+            const int x = rec.w & 0xff;
+            bump_totals(x, rec.x, rec.y);
+            set_LB(x, lb_of(x, get_E(x), get_L(x)));
+        } else ++nerr;
+        if (now != cur) ++n_changed;
+        __syncwarp();
+    }
+
+    // ---------------- epilogue: the final state stays until the end of the window ----------------
+    const long long nwin = (long long)N - win_base;
+    if (nwin > 0) {
+        const unsigned d = (unsigned)nwin;
+        for (int f = lane; f < F; f += 32) {
+            const int a = st[f];
+            if (a == -1) atomicAdd(&R.frag_err_count[f0 + f], d);
+            else atomicAdd(&R.aln_count[P.frag_aln_ptr[f0 + f] + a], d);
+        }
+        for (int i = lane; i < C * E; i += 32) {
+            const int nn = st[F + i];
+            if (nn > 0) atomicAdd(&(R.cluster_hist + P.cluster_hist_ptr[c0 + i / E])[nn], d);
+        }
+    }
+    if (R.final_assign) for (int f = lane; f < F; f += 32) R.final_assign[(size_t)chain * P.n_frag + f0 + f] = st[f];
+    const double lpf = full_logprob();
+    if (lane == 0) {
+        if (R.final_logprob) R.final_logprob[sc] = lpf;
+        if (R.counters) { long long* k = R.counters + sc * 5; k[0] = N; k[1] = n_changed; k[2] = 0; k[3] = 0; k[4] = N; }
+        if (R.rng_state) R.rng_state[sc] = rng.state();
+        if (R.error) R.error[sc] = 0;
+        if (R.totals) {
+            atomicAdd(&R.totals[0], (unsigned long long)N); atomicAdd(&R.totals[1], (unsigned long long)n_changed);
+            atomicAdd(&R.totals[4], (unsigned long long)N);
+        }
+    }
+}
+
+}  // namespace mbsv

@@ -608,7 +608,10 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     g_launches = 0;
     g_launch_info.clear();
     if (!p || !rp || !res) return fail(MBSV_ERR_ARG, "mbsv_run: NULL argument");
-    if (rp->mode != MBSV_MODE_REPLAY_EXACT && rp->mode != MBSV_MODE_FAST) return fail(MBSV_ERR_ARG, "unknown mode");
+    if (rp->mode != MBSV_MODE_REPLAY_EXACT && rp->mode != MBSV_MODE_FAST && rp->mode != MBSV_MODE_GIBBS) return fail(MBSV_ERR_ARG, "unknown mode");
+    const bool gibbs = rp->mode == MBSV_MODE_GIBBS;
+    if (gibbs && rp->trace) return fail(MBSV_ERR_ARG, "MBSV_MODE_GIBBS has no per-iteration trace");
+    if (gibbs && p->has_cc) return fail(MBSV_ERR_UNSUPPORTED, "MBSV_MODE_GIBBS does not support connected-component clusters");
     if (rp->n_chains < 1 || rp->num_iters < 0 || rp->burnin < 0) return fail(MBSV_ERR_ARG, "bad run parameters");
     if (!(rp->perr >= 0 && rp->perr <= 1)) return fail(MBSV_ERR_ARG, "--perr must be a value between 0 and 1.");
     if (rp->device != p->device) return fail(MBSV_ERR_ARG, "run device differs from the problem's device");
@@ -640,7 +643,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     const int Lu = X % 32 == 0 ? 32 : 0;
     const bool mixed = !(Lu > 0 && L == 32) || std::getenv("MBSV_FORCE_MIXED") != nullptr;   // (env: tuning aid)
     const int Lm = mixed ? L : Lu;
-    if (int prc = ensure_plan(p, rp->memo_states, mixed ? 2 : 1)) return prc;
+    if (int prc = gibbs ? ensure_plan(p, 0, 0) : ensure_plan(p, rp->memo_states, mixed ? 2 : 1)) return prc;
     const int64_t tab_items = (int64_t)p->n_tab_subs * X;
     const int64_t sc_total = n_items;
 
@@ -718,8 +721,22 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         }
         if (lo < k1) launches.push_back({0, 0, 0, false, memo, (int64_t)lo * X, (int64_t)k1 * X, memo ? Lm : L});
     };
-    add_group(0, p->n_tab_subs, true);
-    add_group(p->n_tab_subs, S, false);
+    if (gibbs) {
+        // one warp per (subproblem, chain); a class = the ints of shared memory a warp needs: state + one double per option
+        const int extra = 2 * (p->dp.maxn + 2);
+        static const int gcls[] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288};
+        int lo = 0;
+        for (int c : gcls) {
+            int a = lo, b = S;
+            while (a < b) { const int m = a + (b - a) / 2; if (p->sub_W[p->sub_order[m]] + extra <= c) a = m + 1; else b = m; }
+            if (a > lo) launches.push_back({0, 0, c, true, false, (int64_t)lo * X, (int64_t)a * X, 1});
+            lo = a;
+        }
+        if (lo < S) return fail(MBSV_ERR_UNSUPPORTED, "MBSV_MODE_GIBBS keeps a chain's state in shared memory: a subproblem is too large");
+    } else {
+        add_group(0, p->n_tab_subs, true);
+        add_group(p->n_tab_subs, S, false);
+    }
     // largest state first: the global-workspace class (few, slow chains) starts before the bulk of small chains
     std::stable_sort(launches.begin(), launches.end(), [](const Launch& a, const Launch& b) {
         const int ra = a.smem ? a.rows : 1 << 30, rb = b.smem ? b.rows : 1 << 30;
@@ -736,7 +753,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         // warp slots are left; when they run out, widen the class that stays cheapest after widening to free some.
         auto est = [&](const Launch& l, int lanes) { return (l.memo ? 0.5 : 1.0) * (1.0 + 0.1 * (lanes - 1)); };
         auto movable = [&](const Launch& l) { return !(l.memo && !mixed); };     // warps of one subproblem keep their width
-        for (int guard = 0; spare >= 0 && guard < 256; ++guard) {
+        for (int guard = 0; !gibbs && spare >= 0 && guard < 256; ++guard) {
             Launch* worst = nullptr;
             for (Launch& l : launches)
                 if (movable(l) && l.lanes > 1 && (!worst || est(l, l.lanes) > est(*worst, worst->lanes))) worst = &l;
@@ -755,7 +772,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             spare += warps_of(*give, give->lanes) - warps_of(*give, give->lanes * 2);
             give->lanes *= 2;
         }
-        if (std::getenv("MBSV_LANES_PER_WARP")) for (Launch& l : launches) l.lanes = l.memo ? Lm : L;
+        if (!gibbs && std::getenv("MBSV_LANES_PER_WARP")) for (Launch& l : launches) l.lanes = l.memo ? Lm : L;
         int64_t w = 0;
         for (Launch& l : launches) {
             if (l.memo && !l.smem) return fail(MBSV_ERR_ARG, "internal: memoised subproblem does not fit the shared-memory classes");
@@ -810,11 +827,12 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.n_items = l.i1;                       // the last warp of a class may be partly filled
         r.lanes_per_warp = l.lanes;
         r.memo_mixed = mixed ? 1 : 0;
-        KernelFn fn = l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
+        KernelFn fn = gibbs ? mbsv::get_kernel_gibbs()
+                     : l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : (!l.smem && l.lanes == 1 && !rp->trace) ? mbsv::get_kernel_packed(rp->mode, p->has_cc)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
                                  : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);
-        const size_t shm = l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
+        const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * l.rows * sizeof(int) : l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
         if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         // MBSV_SERIAL_LAUNCHES=1 (tuning aid): run the size classes back to back on one stream
         static const bool serial = std::getenv("MBSV_SERIAL_LAUNCHES") != nullptr;

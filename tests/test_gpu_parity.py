@@ -448,3 +448,75 @@ def test_partitioned_files_to_gpu(oracle, mbsv, tmp_path):
     assert_same(o, dp.run(mbsv.MODE_FAST, 2000, n_chains=32))
     o = oracle.run(op, "faithful", 500, n_chains=2, nthreads=8, java_int_wrap=True, trace=True)
     assert_same(o, dp.run(mbsv.MODE_REPLAY_EXACT, 500, n_chains=2, trace=True), trace=True)
+
+
+@pytest.mark.parametrize("max_aln", [2, 9])
+def test_gibbs_mode_samples_the_exact_posterior(oracle, mbsv, max_aln):
+    """MBSV_MODE_GIBBS (statistical tier): pooled heat-bath chains against the exactly enumerated posterior,
+    within 4.5 Monte-Carlo standard errors from independent batches.  Unlike the reference's MH chain the Gibbs kernel has
+    no proposal asymmetry (quirk Q1), so fragments with many alignments are fair game too (max_aln = 9)."""
+    from multibreak_sv_b200 import synth
+    p = None
+    for seed in range(600):
+        q = synth.generate("cfg4", n_frag=5, seed=9000 + seed)
+        nal = np.diff(q.arrays["frag_aln_ptr"])
+        if q.scalars["n_sub"] == 1 and nal.max() == max_aln and np.prod(nal + 1.0) < 3000:
+            p = q
+            break
+    assert p is not None
+    frag, hist = _exact_posterior(oracle, p)
+    dp = mbsv.DeviceProblem(p)
+    # single-site updates cross between the modes of coupled fragments slowly: a long burn-in (measured: 1000 iterations
+    # leave a visible trace of the random initial state, 10000 do not)
+    B, X, N = 12, 256, 20000
+    win = 10000
+    est_f, est_h = [], []
+    fp = p.arrays["frag_aln_ptr"]
+    F = p.scalars["n_frag"]
+    for b in range(B):
+        g = dp.run(mbsv.MODE_GIBBS, N, n_chains=X, perr=0.05, seed=777 * (b + 1), burnin=win, per_chain=False, want_state=False)
+        assert int(g.totals[0]) == N * X and int(g.totals[5]) == 0 and 0 < int(g.totals[1]) < N * X
+        nwin = (N - max(N - win + 1, 0)) * X
+        est_f.append(np.concatenate([np.concatenate([[g.frag_err_count[f]], g.aln_count[fp[f]:fp[f + 1]]]) for f in range(F)]) / nwin)
+        est_h.append(g.cluster_hist / nwin)
+        # every sample of the window has every fragment in exactly one state
+        assert all(int(g.frag_err_count[f]) + int(g.aln_count[fp[f]:fp[f + 1]].sum()) == nwin for f in range(F))
+    for est, exact in ((np.array(est_f), np.concatenate(frag)), (np.array(est_h), hist)):
+        mean, se = est.mean(0), est.std(0, ddof=1) / np.sqrt(B)
+        z = np.abs(mean - exact) / np.maximum(se, 1e-4)
+        assert z.max() < 4.5, (z.max(), mean[z.argmax()], exact[z.argmax()])
+
+
+def test_gibbs_mode_limits_and_determinism(mbsv, example_problem):
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg4", n_frag=2000, seed=3)
+    dp = mbsv.DeviceProblem(p)
+    a = dp.run(mbsv.MODE_GIBBS, 500, n_chains=8)
+    b = dp.run(mbsv.MODE_GIBBS, 500, n_chains=8)
+    for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "counters", "rng_state", "final_logprob"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert (a.counters[:, :, 0] == 500).all() and (a.counters[:, :, 1] <= 500).all()
+    # the shipped example has a fragment with 32 alignments: 33 options, two lane chunks
+    de = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
+    g = de.run(mbsv.MODE_GIBBS, 4000, n_chains=64)
+    assert int(g.totals[0]) == 4000 * 64 and np.isfinite(g.final_logprob).all()
+    with pytest.raises(mbsv.MbsvError) as e:
+        de.run(mbsv.MODE_GIBBS, 10, trace=True)
+    assert e.value.status == -1
+    cc = mbsv.DeviceProblem(synth.generate("cfg4", n_frag=200, seed=3, conncomp_frac=0.5))
+    with pytest.raises(mbsv.MbsvError) as e:
+        cc.run(mbsv.MODE_GIBBS, 10)
+    assert e.value.status == -6
+
+
+def test_rhat_across_chain_groups(mbsv):
+    """diagnostics.rhat on the device: groups of Gibbs chains agree (R-hat ~ 1) after a long run and visibly disagree when
+    the run is far too short for the random initial states to be forgotten."""
+    from multibreak_sv_b200 import diagnostics, synth
+    dp = mbsv.DeviceProblem(synth.generate("cfg4", n_frag=300, seed=8))
+    good = diagnostics.rhat(dp, mbsv.MODE_GIBBS, 20000, chains_per_group=32, groups=4, burnin=10000, perr=0.05)
+    assert good["samples_per_group"] == 9999 * 32 and 0.99 < good["max"] < 1.05
+    mh = diagnostics.rhat(dp, mbsv.MODE_FAST, 20000, chains_per_group=32, groups=4, burnin=10000, perr=0.05)
+    assert 0.99 < mh["max"] < 1.1
+    short = diagnostics.rhat(dp, mbsv.MODE_GIBBS, 12, chains_per_group=2, groups=4, burnin=10, perr=0.05)
+    assert short["max"] > 1.2
