@@ -49,8 +49,8 @@ typedef enum mbsv_mode {
                                    log-posterior in the reference's order (supports.keySet(), experiments.keySet()) */
     MBSV_MODE_FAST = 1,         /* same RNG stream and proposals; Delta-log-posterior; difference tallies */
     MBSV_MODE_GIBBS = 2         /* NOT the reference's chain (statistical tier only): random-scan heat-bath
-                                   Gibbs on the same posterior, one warp per (subproblem, chain), the candidate alignments of
-                                   the redrawn fragment across the lanes.  One iteration = one fragment redrawn from its exact
+                                   Gibbs on the same posterior, 4 / 8 / 32 lanes per (subproblem, chain), the candidate alignments of
+                                   the redrawn fragment across those lanes.  One iteration = one fragment redrawn from its exact
                                    conditional (counters: [0] = [4] = updates, [1] = updates that changed the state).  Same
                                    outputs; no trace; no connected-component clusters; subproblem state must fit shared
                                    memory (else MBSV_ERR_UNSUPPORTED) */

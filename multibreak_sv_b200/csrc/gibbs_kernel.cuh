@@ -6,35 +6,44 @@
 // rejected on the 5M config); it does not reproduce quirk Q1 of naiveMove (the asymmetric proposal), which is why the
 // two samplers agree on the posterior only where the reference's own chain is unbiased.
 //
-// Mapping: one WARP per (subproblem, chain).  The chain's state (assignments, selected-ESP counts) lives in the warp's
-// shared memory; the candidate alignments of the chosen fragment are spread over the lanes: every lane evaluates the
-// log-posterior change of "its" option, a warp max / sum normalises, and the categorical draw is an inclusive
-// __shfl_up prefix scan followed by a __ballot for the first lane whose cumulative weight passes u.  All lanes carry the
-// same RNG state and the same per-experiment totals (uniform registers), so nothing needs broadcasting.
+// Mapping: one GROUP of G lanes (G = 4, 8 or 32, a template parameter chosen per size class) per (subproblem, chain).
+// The chain's state (assignments, selected-ESP counts) lives in the group's shared memory; the candidate alignments of
+// the chosen fragment are spread over the group's lanes: every lane evaluates the log-posterior change of "its" option, a
+// group max / sum normalises, and the categorical draw is an inclusive __shfl_up prefix scan followed by a __ballot for
+// the first lane whose cumulative weight passes u.  All lanes of a group carry the same RNG state and the same
+// per-experiment totals (uniform registers), so nothing needs broadcasting; the groups of a warp run independent chains
+// and only ever synchronise within their own lane mask.  Small subproblems (two or three candidates) use G = 4.
 // Connected-component clusters are not supported here (MBSV_ERR_UNSUPPORTED).
 #pragma once
 #include "sampler_common.cuh"
 
 namespace mbsv {
 
-__device__ __forceinline__ double warp_max(double v) {
-    for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+template <int G> __device__ __forceinline__ double group_max(unsigned mask, double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) { const double w = __shfl_xor_sync(mask, v, o); v = w > v ? w : v; }
     return v;
 }
-__device__ __forceinline__ double warp_sum(double v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+template <int G> __device__ __forceinline__ double group_sum(unsigned mask, double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
 }
 
+template <int G>
 __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
-    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    constexpr int GPW = 32 / G;                                    // groups (chains) per warp
+    const int wlane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int lane = wlane % G, grp = wlane / G;                   // `lane` = position inside the group from here on
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     const int warp = R.warp_begin + blockIdx.x * 4 + wic;
     if (warp >= R.warp_end) return;
-    const long long item = R.item_base + (warp - R.warp_base);
+    const long long item = R.item_base + (long long)(warp - R.warp_base) * GPW + grp;
+    if (item >= R.n_items) return;                                 // (the other groups never name these lanes in a mask)
     const int sub = R.sub_order[item / R.n_chains];
     const int chain = (int)(item % R.n_chains);
-    int* st = smem_tile + (size_t)wic * R.rows_per_warp;          // [F] assignments, [C*E] counts, then the option weights
+    int* st = smem_tile + ((size_t)wic * GPW + grp) * R.rows_per_warp;   // [F] assignments, [C*E] counts, then the option weights
     const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
     const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
     const int E = P.n_exp, Tstride = P.max_support + 1;
@@ -88,19 +97,19 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
     };
     auto full_logprob = [&]() {
         double lp = 0.0;
-        for (int i = lane; i < C * E; i += 32) {
+        for (int i = lane; i < C * E; i += G) {
             const int n = st[F + i];
             if (n > 0) lp += P.T[(size_t)(i % E) * Tstride + n];
         }
-        lp = warp_sum(lp);
+        lp = group_sum<G>(gmask, lp);
         lp += (double)nerr * logperr;
         for (int x = 0; x < E; ++x) lp += get_LB(x);
         return lp;
     };
 
     // ---------------- initial state: the reference's draws (MultiBreakSV.java:999-1015) or the supplied one ----------------
-    for (int i = lane; i < F + C * E; i += 32) st[i] = 0;
-    __syncwarp();
+    for (int i = lane; i < F + C * E; i += G) st[i] = 0;
+    __syncwarp(gmask);
     for (int f = 0; f < F; ++f) {
         const int a0 = P.frag_aln_ptr[f0 + f];
         const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
@@ -119,7 +128,7 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
             if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
         }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     for (int x = 0; x < E; ++x) set_LB(x, lb_of(x, get_E(x), get_L(x)));
     if (R.initial_logprob) { const double lp = full_logprob(); if (lane == 0) R.initial_logprob[sc] = lp; }
 
@@ -138,12 +147,12 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
             bump_totals(xcur, -(long long)rec.x, -(long long)rec.y);
             if (lane == 0) move_counts(a0 + cur, -1, 0u);
         } else --nerr;
-        __syncwarp();
+        __syncwarp(gmask);
         const double lb_cur_removed = xcur >= 0 ? lb_of(xcur, get_E(xcur), get_L(xcur)) : 0.0;
         // log P(option | rest) up to a constant: option 0 = "unmapped", option k = alignment k-1
         const int nopt = n + 1;
         double m = -1.7976931348623157e308;
-        for (int o = lane; o < nopt; o += 32) {
+        for (int o = lane; o < nopt; o += G) {
             double dl;
             if (o == 0) dl = logperr;
             else {
@@ -163,26 +172,27 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
             wopt[o] = dl;
             m = dl > m ? dl : m;
         }
-        m = warp_max(m);
-        __syncwarp();
+        m = group_max<G>(gmask, m);
+        __syncwarp(gmask);
         double s = 0.0;
-        for (int o = lane; o < nopt; o += 32) { const double w = exp_dev(wopt[o] - m); wopt[o] = w; s += w; }
-        s = warp_sum(s);
-        __syncwarp();
+        for (int o = lane; o < nopt; o += G) { const double w = exp_dev(wopt[o] - m); wopt[o] = w; s += w; }
+        s = group_sum<G>(gmask, s);
+        __syncwarp(gmask);
         const double u = rng.nextDouble() * s;
         // categorical draw: inclusive prefix scan of the weights across lanes, ballot for the first lane past u
         int pick = nopt - 1;
         double run = 0.0;
-        for (int o0 = 0; o0 < nopt; o0 += 32) {
+        for (int o0 = 0; o0 < nopt; o0 += G) {
             const int o = o0 + lane;
             double c = o < nopt ? wopt[o] : 0.0;
-            for (int k = 1; k < 32; k <<= 1) { const double v = __shfl_up_sync(0xffffffffu, c, k); if (lane >= k) c += v; }
+#pragma unroll
+            for (int k = 1; k < G; k <<= 1) { const double v = __shfl_up_sync(gmask, c, k, G); if (lane >= k) c += v; }
             c += run;
-            const unsigned hit = __ballot_sync(0xffffffffu, o < nopt && c > u);
+            const unsigned hit = __ballot_sync(gmask, o < nopt && c > u) >> (grp * G);
             if (hit) { pick = o0 + __ffs(hit) - 1; break; }
-            run = __shfl_sync(0xffffffffu, c, 31);
+            run = __shfl_sync(gmask, c, G - 1, G);
         }
-        __syncwarp();
+        __syncwarp(gmask);
         const int now = pick - 1;
         // put the drawn assignment in; tallies only when the state changed
         if (xcur >= 0) set_LB(xcur, lb_cur_removed);
@@ -206,24 +216,24 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
             set_LB(x, lb_of(x, get_E(x), get_L(x)));
         } else ++nerr;
         if (now != cur) ++n_changed;
-        __syncwarp();
+        __syncwarp(gmask);
     }
 
     // ---------------- epilogue: the final state stays until the end of the window ----------------
     const long long nwin = (long long)N - win_base;
     if (nwin > 0) {
         const unsigned d = (unsigned)nwin;
-        for (int f = lane; f < F; f += 32) {
+        for (int f = lane; f < F; f += G) {
             const int a = st[f];
             if (a == -1) atomicAdd(&R.frag_err_count[f0 + f], d);
             else atomicAdd(&R.aln_count[P.frag_aln_ptr[f0 + f] + a], d);
         }
-        for (int i = lane; i < C * E; i += 32) {
+        for (int i = lane; i < C * E; i += G) {
             const int nn = st[F + i];
             if (nn > 0) atomicAdd(&(R.cluster_hist + P.cluster_hist_ptr[c0 + i / E])[nn], d);
         }
     }
-    if (R.final_assign) for (int f = lane; f < F; f += 32) R.final_assign[(size_t)chain * P.n_frag + f0 + f] = st[f];
+    if (R.final_assign) for (int f = lane; f < F; f += G) R.final_assign[(size_t)chain * P.n_frag + f0 + f] = st[f];
     const double lpf = full_logprob();
     if (lane == 0) {
         if (R.final_logprob) R.final_logprob[sc] = lpf;

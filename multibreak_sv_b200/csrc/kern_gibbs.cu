@@ -1,5 +1,7 @@
-// MBSV_MODE_GIBBS: the heat-bath sampler of the statistical tier (one warp per chain, options across lanes).
+// MBSV_MODE_GIBBS: the heat-bath sampler of the statistical tier (G lanes per chain, options across those lanes).
 #include "gibbs_kernel.cuh"
 namespace mbsv {
-KernelFn get_kernel_gibbs() { return mbsv_gibbs_kernel; }
+KernelFn get_kernel_gibbs(int group) {
+    return group == 4 ? mbsv_gibbs_kernel<4> : group == 8 ? mbsv_gibbs_kernel<8> : mbsv_gibbs_kernel<32>;
+}
 }  // namespace mbsv

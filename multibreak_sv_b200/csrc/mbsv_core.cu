@@ -722,14 +722,19 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         if (lo < k1) launches.push_back({0, 0, 0, false, memo, (int64_t)lo * X, (int64_t)k1 * X, memo ? Lm : L});
     };
     if (gibbs) {
-        // one warp per (subproblem, chain); a class = the ints of shared memory a warp needs: state + one double per option
+        // a group of G lanes per (subproblem, chain): 4 for the smallest states (two or three candidates per fragment),
+        // 8 for small ones, the whole warp otherwise; a class = the ints of shared memory a group needs (state + one
+        // double per option).  `lanes` holds the chains per warp = 32 / G.
         const int extra = 2 * (p->dp.maxn + 2);
         static const int gcls[] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288};
         int lo = 0;
         for (int c : gcls) {
             int a = lo, b = S;
             while (a < b) { const int m = a + (b - a) / 2; if (p->sub_W[p->sub_order[m]] + extra <= c) a = m + 1; else b = m; }
-            if (a > lo) launches.push_back({0, 0, c, true, false, (int64_t)lo * X, (int64_t)a * X, 1});
+            int group = c <= 128 ? 4 : c <= 1024 ? 8 : 32;
+            if (const char* env = std::getenv("MBSV_GIBBS_GROUP")) group = std::atoi(env) == 4 ? 4 : std::atoi(env) == 8 ? 8 : 32;   // (tests)
+            if ((size_t)WARPS_PER_CTA * (32 / group) * c * sizeof(int) > 200 * 1024) group = 32;
+            if (a > lo) launches.push_back({0, 0, c, true, false, (int64_t)lo * X, (int64_t)a * X, 32 / group});
             lo = a;
         }
         if (lo < S) return fail(MBSV_ERR_UNSUPPORTED, "MBSV_MODE_GIBBS keeps a chain's state in shared memory: a subproblem is too large");
@@ -827,12 +832,12 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.n_items = l.i1;                       // the last warp of a class may be partly filled
         r.lanes_per_warp = l.lanes;
         r.memo_mixed = mixed ? 1 : 0;
-        KernelFn fn = gibbs ? mbsv::get_kernel_gibbs()
+        KernelFn fn = gibbs ? mbsv::get_kernel_gibbs(32 / l.lanes)
                      : l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : (!l.smem && l.lanes == 1 && !rp->trace) ? mbsv::get_kernel_packed(rp->mode, p->has_cc)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
                                  : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);
-        const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * l.rows * sizeof(int) : l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
+        const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * l.lanes * l.rows * sizeof(int) : l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
         if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         // MBSV_SERIAL_LAUNCHES=1 (tuning aid): run the size classes back to back on one stream
         static const bool serial = std::getenv("MBSV_SERIAL_LAUNCHES") != nullptr;

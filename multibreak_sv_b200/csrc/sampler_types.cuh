@@ -88,7 +88,7 @@ KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_E
 KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
 KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with connected-component clusters
 KernelFn get_kernel_packed(int mode, bool cc);                   // one chain per warp, contiguous state in the global workspace
-KernelFn get_kernel_gibbs();                                     // heat-bath sampler, one warp per chain (gibbs_kernel.cuh)
+KernelFn get_kernel_gibbs(int group);                            // heat-bath sampler, `group` (4, 8, 32) lanes per chain (gibbs_kernel.cuh)
 KernelFn get_kernel_memo(bool trace, bool mixed);               // memoised subproblems (memo_kernel.cuh)
 // fills the device-memory log-posterior tables of the memoised subproblems listed in tab_sub
 cudaError_t launch_memo_build(const DevProblem& P, const DevRun& R, int n_tab, const long long* state_ptr, const int* tab_sub,

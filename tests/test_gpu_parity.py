@@ -496,6 +496,16 @@ def test_gibbs_mode_limits_and_determinism(mbsv, example_problem):
     for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "counters", "rng_state", "final_logprob"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert (a.counters[:, :, 0] == 500).all() and (a.counters[:, :, 1] <= 500).all()
+    # 4, 8 or 32 lanes per chain (chosen per size class) are the same chains: every lane of a group carries the same RNG
+    for group in ("4", "8", "32"):
+        os.environ["MBSV_GIBBS_GROUP"] = group
+        try:
+            c = dp.run(mbsv.MODE_GIBBS, 500, n_chains=8)
+        finally:
+            del os.environ["MBSV_GIBBS_GROUP"]
+        for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "counters", "rng_state"):
+            assert np.array_equal(getattr(a, k), getattr(c, k)), (group, k)
+        assert np.allclose(a.final_logprob, c.final_logprob, rtol=1e-12, atol=1e-9)
     # the shipped example has a fragment with 32 alignments: 33 options, two lane chunks
     de = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
     g = de.run(mbsv.MODE_GIBBS, 4000, n_chains=64)
