@@ -96,6 +96,11 @@ struct mbsv_problem {
     DevBuf<int> d_tab_sub;
     cudaEvent_t ev_built = nullptr;
     DevBuf<double> d_memo_global;
+    // chain-state workspace of the global class and its per-warp row offsets: kept between runs (grow-only), so that a
+    // repeated mbsv_run pays no multi-gigabyte cudaMalloc / cudaFree; released with the problem
+    DevBuf<int> ws_cache;
+    DevBuf<long long> row_off_cache;
+    std::vector<long long> row_off_host;
     std::vector<int> sub_order;   // memoised-kernel subproblems first, each group by ascending sub_rows (stable)
     int n_tab_subs = 0;
     int64_t csr_bytes = 0;
@@ -599,9 +604,8 @@ struct OutBufs {
     DevBuf<unsigned int> aln_count, frag_err, hist;
     DevBuf<int> final_assign, error, tr_frag, tr_assign, init_assign_out, init_assign_in;
     DevBuf<double> final_logprob, tr_logprob, init_logprob;
-    DevBuf<long long> counters, row_off;
+    DevBuf<long long> counters;
     DevBuf<unsigned long long> rng_state, totals;
-    DevBuf<int> workspace;
 };
 
 int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool results_on_device) {
@@ -797,12 +801,19 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             off[w - l.wb] = acc;
             acc += std::max(1, p->sub_rows[p->sub_order[last / X]]);
         }
-        size_t free_b = 0, total_b = 0;
-        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        if ((size_t)acc * 128 > free_b && !(l.lanes == 1 && !rp->trace && (size_t)acc * 4 <= free_b)) return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory");
         const bool packed = l.lanes == 1 && !rp->trace;     // one chain per warp: contiguous columns (kern_packed.cu)
-        CUDA_TRY(ob.workspace.alloc((size_t)acc * (packed ? 1 : 32)));
-        CUDA_TRY(ob.row_off.upload(off));
+        const size_t need = (size_t)acc * (packed ? 1 : 32);
+        if (need > p->ws_cache.n) {
+            p->ws_cache.release();
+            size_t free_b = 0, total_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            if (need * sizeof(int) > free_b) return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory");
+            if (p->ws_cache.alloc(need) != cudaSuccess) { cudaGetLastError(); p->ws_cache.release(); return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory"); }
+        }
+        if (off != p->row_off_host) {
+            CUDA_TRY(p->row_off_cache.upload(off));
+            p->row_off_host = off;
+        }
     }
     if ((int)launches.size() > NSTREAM - 1) return fail(MBSV_ERR_ARG, "too many size classes");
 
@@ -824,8 +835,8 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         mbsv::DevRun r = dr;
         r.warp_begin = l.wb; r.warp_end = l.we;
         r.rows_per_warp = l.smem ? l.rows : 0;
-        r.warp_row_off = l.smem ? nullptr : ob.row_off.p;
-        r.workspace = l.smem ? nullptr : ob.workspace.p;
+        r.warp_row_off = l.smem ? nullptr : p->row_off_cache.p;
+        r.workspace = l.smem ? nullptr : p->ws_cache.p;
         r.global_warp0 = l.wb;
         r.warp_base = l.wb;
         r.item_base = l.i0;
