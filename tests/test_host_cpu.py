@@ -356,3 +356,30 @@ def test_cli_usage_and_loud_failure_without_gpu(mbsv):
     if not torch.cuda.is_available():
         r = subprocess.run([cli] + files + ["--numiterations", "10", "--perr", "0.001", "--prefix", "/tmp/never"], capture_output=True, text=True)
         assert r.returncode == 2 and "runMCMC:" in r.stderr and not os.path.exists("/tmp/never.finalassignment.longburnin")
+
+
+def test_load_partitioned_reports_the_failing_subset(mbsv, tmp_path):
+    """A rejected subset (an ESP listed twice in one cluster row) fails the whole load and names the subset; an unknown
+    experiment label and a missing file fail as in the single-problem path."""
+    from multibreak_sv_b200 import host
+    from multibreak_sv_b200._abi import MbsvError
+    d = str(tmp_path)
+    open(os.path.join(d, "e.txt"), "w").write("ExperimentLabel\tPseq\tLambdaD\npacbio\t0.15\t3\n")
+    open(os.path.join(d, "a.txt"), "w").write("FragmentID\tDiscordantPairs\tNumErrors\tLen\tExperimentLabel\n"
+                                              "longread_1\tlongread_1_a\t5\t100\tpacbio\nlongread_2\tlongread_2_a\t7\t120\tpacbio\n"
+                                              "longread_2\tlongread_2_b\t9\t130\tpacbio\n")
+    good = "c1\t1\t10.0\tD\tlongread_1_a\t1\t1\t1, 2, 3, 4\nc2\t2\t10.0\tD\tlongread_2_a, longread_2_b\t1\t1\t1, 2, 3, 4\n"
+    open(os.path.join(d, "c.txt"), "w").write(good)
+    p, skipped = host.load_partitioned(os.path.join(d, "c.txt"), os.path.join(d, "a.txt"), os.path.join(d, "e.txt"))
+    assert (p.scalars["n_sub"], p.scalars["n_frag"], p.scalars["n_aln"], skipped) == (2, 2, 3, 0)
+    open(os.path.join(d, "bad.txt"), "w").write(good.replace("longread_2_a, longread_2_b", "longread_2_a, longread_2_a"))
+    with pytest.raises(MbsvError) as e:
+        host.load_partitioned(os.path.join(d, "bad.txt"), os.path.join(d, "a.txt"), os.path.join(d, "e.txt"))
+    assert e.value.status == -6 and "subset 2" in str(e.value) and "listed twice" in str(e.value)
+    open(os.path.join(d, "a2.txt"), "w").write(open(os.path.join(d, "a.txt")).read().replace("130\tpacbio", "130\tillumina"))
+    with pytest.raises(MbsvError) as e:
+        host.load_partitioned(os.path.join(d, "c.txt"), os.path.join(d, "a2.txt"), os.path.join(d, "e.txt"))
+    assert e.value.status == -7 and "illumina" in str(e.value)
+    with pytest.raises(MbsvError) as e:
+        host.load_partitioned(os.path.join(d, "c.txt"), os.path.join(d, "missing.txt"), os.path.join(d, "e.txt"))
+    assert e.value.status == -7
