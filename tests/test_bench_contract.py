@@ -1,4 +1,4 @@
-"""bench.py's reference arm runs on the CPU: its JSON line must carry the contract's keys (the GPU arm prints the same
+"""bench.py: the JSON line of both arms must carry the contract keys (the reference arm runs on the CPU; the GPU arm prints the same
 keys plus roofline/clocks; it is exercised on the GPU box)."""
 import json
 import os
