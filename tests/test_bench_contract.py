@@ -28,3 +28,23 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--n-frag", "20000"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--n-frag", "30000", "--iters", "400", "--steps", "2",
+                        "--warmup", "3", "--cpu-iterations", "2e6"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["scaling"] == "weak"
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["peak"] > 0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
