@@ -307,8 +307,31 @@ class PartitionedBatch:
             pass
 
 
+def main_partition(argv):
+    """`--partition [--chains N] [--listorder] [--fast]`: the manual's multi-subproblem workflow as one GPU batch (the same
+    as `mbsv_cli --partition`): partition + load in memory, one run, concatenated `.final*.longburnin` files."""
+    from ._abi import DeviceProblem, MODE_FAST
+    argv = list(argv)
+    chains, listorder, mode = 1, False, MODE_REPLAY_EXACT
+    argv.remove("--partition")
+    if "--listorder" in argv:
+        argv.remove("--listorder"); listorder = True
+    if "--fast" in argv:
+        argv.remove("--fast"); mode = MODE_FAST
+    if "--chains" in argv:
+        i = argv.index("--chains"); chains = int(argv[i + 1]); del argv[i:i + 2]
+    sv = MultiBreakSV(argv)                                   # option checks and burnin as in the single-problem path
+    b = PartitionedBatch(sv.clusterfile, sv.assignmentfile, sv.experimentfile, tolerate_tree_bins=listorder)
+    dp = DeviceProblem(b.packed, device=sv.device)
+    r = dp.run(mode, sv.numiters, n_chains=chains, perr=sv.perr, java_int_wrap=True, want_state=False, per_chain=False)
+    b.writeFinalFiles(sv.outputname, sv.burnin * chains, r.aln_count, r.frag_err_count, r.cluster_hist)
+    return b, r
+
+
 def main(argv):
     """MultiBreakSV.main (:114-153)."""
+    if "--partition" in argv:
+        return main_partition(argv)
     sv = MultiBreakSV(argv)
     sv.getFragmentAlignments(); sv.constructClusterDiagrams(); sv.precomputePriors(); sv.fillNonSingletonArray()
     sv.runMCMC(None if sv.SAVE_SPACE else sv.outputname + ".mcmc.txt")

@@ -138,3 +138,20 @@ def test_cli_partition_mode(mbsv, oracle, tmp_path):
     for ext in (".finalbreakpoints.longburnin", ".finalassignment.longburnin"):
         assert open(prefix + ext).read() == open(prefix + "_ref" + ext).read()
     assert len(open(prefix + ".finalbreakpoints.longburnin").read().splitlines()) == 11
+
+
+@pytest.mark.gpu
+def test_python_partition_mode_equals_the_cli(mbsv, tmp_path):
+    """python -m multibreak_sv_b200.host --partition and mbsv_cli --partition write the same files."""
+    from multibreak_sv_b200 import host
+    args = ["--clusterfile", FILES[0], "--assignmentfile", FILES[1], "--experimentfile", FILES[2], "--numiterations", "5000",
+            "--perr", "0.001", "--partition", "--chains", "3"]
+    py = os.path.join(str(tmp_path), "py")
+    host.main(args + ["--prefix", py])
+    cli = os.path.join(os.path.dirname(os.path.abspath(host.__file__)), "mbsv_cli")
+    cp = os.path.join(str(tmp_path), "cli")
+    r = subprocess.run([cli] + args + ["--prefix", cp], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for ext in (".finalbreakpoints.longburnin", ".finalassignment.longburnin"):
+        assert open(py + ext).read() == open(cp + ext).read()
+    assert open(py + ".finalbreakpoints.longburnin").read().splitlines()[1].split("\t")[1] == "1500"      # 3 chains x burnin 500
