@@ -1,0 +1,756 @@
+// Speculative-window sampler for chains that are too few to fill the GPU lane-per-chain: one CTA runs ONE
+// (subproblem, chain) — the giant connected component of BASELINE configs[4], or any large subproblem of a small batch.
+//
+// The reference chain (MultiBreakSV.java:1101-1182) is strictly serial: iteration i+1 starts where iteration i stopped
+// drawing from java.util.Random, and how many nextDouble()s an iteration consumes (1 lazy, 4 AlterSV, 5 or 6 Naive)
+// depends on the state of the fragment it picked.  A serial walk therefore pays one dependent memory round trip per
+// iteration (~2 us on a 500k-fragment state).  Here a CTA of NT threads evaluates a WINDOW of NT consecutive RNG
+// offsets at once and stays bit-identical to the serial chain:
+//
+//   P1  thread j assumes "an iteration starts at offset base + j" (LCG jump-ahead), draws its coins, and for a Naive
+//       proposal loads the picked fragment's alignment count and current assignment: that fixes the number of draws
+//       c_j of the iteration, i.e. where the next iteration would start (j + c_j).
+//   P2  the iterations that really happen are the offsets reachable from offset 0 by j -> j + c_j: warp-level
+//       pointer doubling with __shfl, eight-entry transfer tables composed across the warps.  The reachable non-lazy
+//       offsets (the proposals) are compacted onto the first warps.
+//   P3  every proposal gathers what the Delta-log-posterior needs (alignment records, count slots, counts, logprobcov)
+//       with all its loads in flight together, and evaluates its acceptance against the totals at the window start.
+//   P4  the per-experiment error/length totals couple every proposal to every earlier accepted move, so the tentative
+//       accept flags are turned into exact ones by a prefix sum of the accepted (dE, dL) and ONE re-evaluation with
+//       the exact totals each proposal would see; logBinomial(E, L) is a pure function of the totals, so the cached
+//       "old" value of the serial chain is reproduced bit for bit.  A proposal whose exact decision differs from its
+//       tentative one (its ratio and its accept coin agree to ~1e-9) cuts the window there.
+//   P5  a proposal that reads a state row (fragment assignment, cluster count) written by an earlier accepted
+//       proposal of the same window was evaluated on stale data: a shared-memory hash set of the written rows finds
+//       the first such proposal and cuts the window in front of it.
+//   P6  the iterations in front of the cut are committed (state rows, difference tallies, counters), the RNG base moves
+//       to the cut (or to the window's exit offset), and the next window starts from the committed state.
+//
+// Every cut only shortens a window; what is committed is exactly what the serial chain does.  Arithmetic = the FAST
+// arithmetic of sampler_kernel.cuh (same expressions, same order).  Not handled here (the planner keeps those on the
+// lane-per-chain kernels): REPLAY_EXACT / memo-eligible subproblems, traces, connected components, proposals with more
+// than GIANT_MAXENT count entries or GIANT_MAXMV toggled fragments.
+//
+// initializeMatrix (MultiBreakSV.java:999-1015) is the same trick on single LCG steps: a fragment consumes 2 steps
+// (nextDouble() < perr) or 3 (nextDouble, nextInt), so the fragment starts are the offsets reachable by +2 / +3.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "sampler_common.cuh"
+
+namespace mbsv {
+
+constexpr int GIANT_MAXENT = 32;    // count-slot entries of one proposal
+constexpr int GIANT_MAXMV = 32;     // fragments toggled by one AlterSV proposal
+constexpr int GIANT_HASH = 4096;    // written-row hash set (power of two)
+constexpr int GIANT_TMAX = 2048;    // logprobcov doubles staged in shared memory (E * (max_support + 1) <= this)
+constexpr int GIANT_LPCHUNK = 2048; // clusters per chunk of the serial log-posterior sum
+constexpr int GIANT_NOCUT = 0x7fffffff;
+
+// State rows of the chain: a contiguous column in the global workspace, read through L2 (ld.global.cg): rows are written
+// by other threads of the CTA between windows, and nothing is gained from L1 on random rows.
+struct GiantStateGlobal {
+    int* st;
+    int rows;
+#ifdef MBSV_BOUNDS_CHECK
+    __device__ __noinline__ void chk(int i) const {
+        if (i < 0 || i >= rows) { printf("MBSV_ST(giant): row %d outside [0,%d) (block %d thread %d)\n", i, rows, blockIdx.x, threadIdx.x); __trap(); }
+    }
+#else
+    __device__ __forceinline__ void chk(int) const {}
+#endif
+    __device__ __forceinline__ int ld(int i) const { chk(i); return __ldcg(st + i); }
+    __device__ __forceinline__ void stw(int i, int v) const { chk(i); __stcg(st + i, v); }
+    __device__ __forceinline__ void inc(int i) const { chk(i); atomicAdd(st + i, 1); }
+};
+
+// 1-D bulk copy global -> shared through the TMA unit (cp.async.bulk, completion on an mbarrier); bytes % 16 == 0.
+__device__ __forceinline__ void giant_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void giant_bar_init(unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void giant_bar_wait(unsigned long long* bar, unsigned phase) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(b), "r"(phase) : "memory");
+    }
+}
+
+struct GiantReach { bool reach; int rank, drank; };
+
+// Offsets 0..NT-1, one per thread: an item starting at offset j ends at j + c (1 <= c <= 8).  Which offsets are reachable
+// from offset 0?  Per warp, pointer doubling gives for every lane the set of in-warp offsets visited from it and where
+// the walk leaves the warp; the first eight lanes publish that as the warp's transfer table (entry offset -> exit
+// offset, items, dense items), and every warp composes the tables of the warps in front of it.  Contains one
+// __syncthreads.  fin[0..2] = items in the window, dense items, exit offset - NT (valid after the caller's next barrier).
+template <int NT>
+__device__ __forceinline__ GiantReach giant_reach(const int c, const bool dense, unsigned* tab, unsigned* msk, int* fin) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned S = 1u << lane;
+    int J = lane + c;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const int src = J < 32 ? J : lane;
+        const unsigned S2 = __shfl_sync(0xffffffffu, S, src);
+        const int J2 = __shfl_sync(0xffffffffu, J, src);
+        if (J < 32) { S |= S2; J = J2; }
+    }
+    const unsigned dmask = __ballot_sync(0xffffffffu, dense);
+    if (lane < 8) {
+        tab[w * 8 + lane] = (unsigned)(J - 32) | ((unsigned)__popc(S) << 3) | ((unsigned)__popc(S & dmask) << 9);
+        msk[w * 8 + lane] = S;
+    }
+    __syncthreads();
+    int e = 0, rank = 0, drank = 0;
+    for (int k = 0; k < w; ++k) {
+        const unsigned t = tab[k * 8 + e];
+        rank += (t >> 3) & 63;
+        drank += (t >> 9) & 63;
+        e = t & 7;
+    }
+    const unsigned mine = msk[w * 8 + e];
+    if (w == NW - 1 && lane == 0) {
+        const unsigned t = tab[w * 8 + e];
+        fin[0] = rank + ((t >> 3) & 63);
+        fin[1] = drank + ((t >> 9) & 63);
+        fin[2] = t & 7;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    GiantReach r;
+    r.reach = (mine >> lane) & 1u;
+    r.rank = rank + __popc(mine & lt);
+    r.drank = drank + __popc(mine & dmask & lt);
+    return r;
+}
+
+// Shared-memory layout (byte offsets), shared by the kernel and the host's launch code.
+template <int NT, int MAXE>
+struct GiantLayout {
+    static constexpr int NW = NT / 32;
+    static constexpr int MD = NT / 4 + 8;          // proposals per window: every one consumes >= 4 offsets
+    static constexpr int DW = (MD + 31) / 32;      // warps that hold them
+    static constexpr size_t al(size_t b) { return (b + 15) & ~(size_t)15; }
+    static constexpr size_t o_T = 0;
+    static constexpr size_t o_lp = o_T + al(sizeof(double) * GIANT_TMAX);
+    static constexpr size_t o_sj = o_lp + al(sizeof(double) * GIANT_LPCHUNK);
+    static constexpr size_t o_wtot = o_sj + al(sizeof(unsigned long long) * NT);
+    static constexpr size_t o_a0 = o_wtot + al(sizeof(long long) * DW * 2 * MAXE);
+    static constexpr size_t o_n = o_a0 + al(sizeof(int) * NT);
+    static constexpr size_t o_prev = o_n + al(sizeof(int) * NT);
+    static constexpr size_t o_ent = o_prev + al(sizeof(int) * NT);
+    static constexpr size_t o_ecnt = o_ent + al(sizeof(int) * GIANT_MAXENT * MD);
+    static constexpr size_t o_mv = o_ecnt + al(sizeof(int) * GIANT_MAXENT * MD);
+    static constexpr size_t o_hkey = o_mv + al(sizeof(int) * GIANT_MAXMV * MD);
+    static constexpr size_t o_hlane = o_hkey + al(sizeof(int) * GIANT_HASH);
+    static constexpr size_t o_rtab = o_hlane + al(sizeof(int) * GIANT_HASH);
+    static constexpr size_t o_rmsk = o_rtab + al(sizeof(unsigned) * NW * 8);
+    static constexpr size_t o_list = o_rmsk + al(sizeof(unsigned) * NW * 8);
+    static constexpr size_t o_lrank = o_list + al(sizeof(unsigned short) * (NT + 8));
+    static constexpr size_t o_sc = o_lrank + al(sizeof(unsigned short) * (NT + 8));
+    static constexpr size_t bytes = o_sc + 512;    // the Scalars block (static_assert in the kernel)
+};
+
+// MAXE = compile-time bound of the experiments (2 or 4).
+template <int NT, int MAXE>
+__global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ DevRun R) {
+    using LY = GiantLayout<NT, MAXE>;
+    constexpr int MD = LY::MD, DW = LY::DW;
+    extern __shared__ __align__(16) unsigned char giant_smem[];
+    double* sT = (double*)(giant_smem + LY::o_T);
+    double* lpbuf = (double*)(giant_smem + LY::o_lp);
+    unsigned long long* sj = (unsigned long long*)(giant_smem + LY::o_sj);
+    long long* wtot = (long long*)(giant_smem + LY::o_wtot);
+    int* a0_s = (int*)(giant_smem + LY::o_a0);
+    int* n_s = (int*)(giant_smem + LY::o_n);
+    int* prev_s = (int*)(giant_smem + LY::o_prev);
+    int* ent = (int*)(giant_smem + LY::o_ent);        // [e][p]: slot << 1 | (1 = increment)
+    int* ecnt = (int*)(giant_smem + LY::o_ecnt);      // [e][p]: count of the slot before the entry applies
+    int* mv = (int*)(giant_smem + LY::o_mv);          // [q][p]: AlterSV: fragment << 1 | (1 = currently unmapped)
+    int* hkey = (int*)(giant_smem + LY::o_hkey);
+    int* hlane = (int*)(giant_smem + LY::o_hlane);
+    unsigned* rtab = (unsigned*)(giant_smem + LY::o_rtab);
+    unsigned* rmsk = (unsigned*)(giant_smem + LY::o_rmsk);
+    unsigned short* list = (unsigned short*)(giant_smem + LY::o_list);
+    unsigned short* lrank = (unsigned short*)(giant_smem + LY::o_lrank);
+    struct Scalars {
+        unsigned long long s_base, jumpA, jumpC, bar;
+        long long Etot[MAXE], Ltot[MAXE], accE[MAXE], accL[MAXE];
+        double LB[MAXE];
+        unsigned long long cnt[5];
+        int fin[4];
+        int iter_base, cut, errlane, done, err, nerr, frag_base;
+    };
+    static_assert(sizeof(Scalars) <= 512, "Scalars block");
+    Scalars& sc = *(Scalars*)(giant_smem + LY::o_sc);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int witem = R.warp_begin + blockIdx.x;
+    if (witem >= R.warp_end) return;
+    const long long item = R.item_base + (long long)(witem - R.warp_base);
+    const int sub = R.sub_order[item / R.n_chains];
+    const int chain = (int)(item % R.n_chains);
+    GiantStateGlobal st{R.workspace + (size_t)R.warp_row_off[witem - R.global_warp0], R.sub_W[sub]};
+
+    const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
+    const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
+    const int E = P.n_exp;
+    const int sv0 = P.sub_sv_ptr[sub], nsv = P.sub_sv_ptr[sub + 1] - sv0;
+    const int Tstride = P.max_support + 1;
+    const long long scx = (long long)sub * R.n_chains + chain;
+    const int N = R.num_iters;
+    const int W = R.sub_W[sub];
+    const double neglogF = -P.sub_logF[sub];
+    const double logperr = R.logperr;
+    const double dF = (double)F;
+    const unsigned long long perr_thr = prob_threshold53(R.perr);
+    constexpr unsigned long long NAIVE_THR = 0x1CCCCCCCCCCCCDULL;   // 0.9 * 2^53
+    const int win_base = R.win_base;
+    const double neglogNsv = P.sub_neglogNsv[sub];
+    const bool tsm = E * Tstride <= GIANT_TMAX;                    // logprobcov staged in shared memory
+    const double* Tp = tsm ? sT : P.T;
+
+    auto wrapi = [&](long long t) -> long long { return R.java_int_wrap ? (long long)(int)(unsigned int)(unsigned long long)t : t; };
+    auto lb_of = [&](int x, long long e, long long l) -> double {
+        return log_binomial_dev(wrapi(e), wrapi(l), P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi, P.logint, P.maxn);
+    };
+    auto hash_of = [](int key) -> unsigned { return (((unsigned)key * 2654435761u) >> 19) & (GIANT_HASH - 1); };
+
+    // ---- setup: TMA-staged logprobcov, zeroed state, scalars ----
+    if (tid == 0) {
+        giant_bar_init(&sc.bar);
+        JavaRandom r0; r0.seed(R.seed + chain);
+        sc.s_base = r0.s;
+        sc.iter_base = 0; sc.done = 0; sc.err = 0; sc.nerr = 0; sc.frag_base = 0;
+        for (int x = 0; x < MAXE; ++x) { sc.Etot[x] = 0; sc.Ltot[x] = 0; sc.accE[x] = 0; sc.accL[x] = 0; sc.LB[x] = 0.0; }
+        for (int i = 0; i < 5; ++i) sc.cnt[i] = 0;
+    }
+    __syncthreads();
+    if (tid == 0 && tsm) {
+        // (the device copy of logprobcov is padded to a multiple of 16 bytes)
+        const unsigned bytes = (unsigned)(((size_t)E * Tstride * sizeof(double) + 15) & ~(size_t)15);
+        giant_bulk_load(sT, P.T, bytes, &sc.bar);
+    }
+    for (int i = tid; i < W; i += NT) st.stw(i, 0);
+    if (tsm) giant_bar_wait(&sc.bar, 0);
+    __syncthreads();
+
+    // thread j's jump-ahead constants: the state j steps after s is jA * s + jC (one step = step_mul, step_add)
+    unsigned long long jA = 1, jC = 0;
+    auto make_jump = [&](unsigned long long step_mul, unsigned long long step_add) {
+        jA = 1; jC = 0;
+        for (int i = 0; i < tid; ++i) { jA = jA * step_mul; jC = jC * step_mul + step_add; }
+        if (tid == NT - 1) { sc.jumpA = jA * step_mul; sc.jumpC = jC * step_mul + step_add; }     // NT steps
+    };
+
+    // ---------------- initializeMatrix (MultiBreakSV.java:990-1099) ----------------
+    if (R.init_assign) {
+        for (int f = tid; f < F; f += NT) {
+            const int a = R.init_assign[f0 + f];
+            st.stw(f, a);
+            if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
+        }
+    } else {
+        make_jump(JavaRandom::MULT, JavaRandom::ADD);
+        __syncthreads();
+        for (;;) {
+            const int fb = sc.frag_base;
+            if (fb >= F) break;
+            const unsigned long long sb = sc.s_base;
+            // a fragment whose draws start after offset j: nextDouble() = steps j+1, j+2; nextInt = step j+3
+            const unsigned long long s0 = jA * sb + jC;
+            const unsigned long long s1 = s0 * JavaRandom::MULT + JavaRandom::ADD;
+            const unsigned long long s2 = s1 * JavaRandom::MULT + JavaRandom::ADD;
+            const unsigned long long s3 = s2 * JavaRandom::MULT + JavaRandom::ADD;
+            const unsigned long long m53 = (((s1 & JavaRandom::MASK) >> 22) << 27) + ((s2 & JavaRandom::MASK) >> 21);
+            const bool unmapped = m53 < perr_thr;                     // nextDouble() < perr
+            if (tid == 0) sc.cut = GIANT_NOCUT;
+            const GiantReach rr = giant_reach<NT>(unmapped ? 2 : 3, false, rtab, rmsk, sc.fin);
+            const int f = fb + rr.rank;
+            int a = -1;
+            bool reject = false;
+            unsigned long long s_after = s0;
+            if (rr.reach && f < F && !unmapped) {
+                const int bound = P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f];
+                const int r31 = (int)((s3 & JavaRandom::MASK) >> 17);
+                const int m = bound - 1;
+                if ((bound & m) == 0) a = (int)(((long long)bound * (long long)r31) >> 31);
+                else {
+                    a = r31 % bound;
+                    // java.util.Random.nextInt redraws when u - r + m overflows int (about 1e-8 of the draws): serial
+                    if ((int)((unsigned)r31 - (unsigned)a + (unsigned)m) < 0) {
+                        reject = true;
+                        JavaRandom q; q.s = s2;
+                        a = q.nextInt(bound);
+                        s_after = q.s;
+                        atomicMin(&sc.cut, tid);
+                    }
+                }
+            }
+            if (rr.reach && f == F) atomicMin(&sc.cut, tid);            // first offset after the last fragment
+            __syncthreads();
+            const int cut = sc.cut;
+            // fragments in front of the cut are final; a redrawing fragment AT the cut has finished itself serially
+            if (rr.reach && f < F && (tid < cut || (tid == cut && reject))) {
+                st.stw(f, a);
+                if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
+            }
+            if (cut == GIANT_NOCUT) {
+                if (tid == 0) {
+                    unsigned long long s = sc.jumpA * sb + sc.jumpC;
+                    for (int i = 0; i < sc.fin[2]; ++i) s = s * JavaRandom::MULT + JavaRandom::ADD;
+                    sc.s_base = s;
+                    sc.frag_base = fb + sc.fin[0];
+                }
+            } else if (tid == cut) {
+                if (reject) { sc.s_base = s_after; sc.frag_base = f + 1; }
+                else { sc.s_base = s0; sc.frag_base = f; }              // f == F: the state after the last fragment's draws
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // counts, per-experiment totals, unmapped fragments
+    {
+        long long e_loc[MAXE], l_loc[MAXE];
+#pragma unroll
+        for (int x = 0; x < MAXE; ++x) { e_loc[x] = 0; l_loc[x] = 0; }
+        int nerr_loc = 0;
+        constexpr int IB = 4;
+        for (int fb = tid * IB; fb < F; fb += NT * IB) {
+            int a[IB];
+            int4 rec[IB];
+#pragma unroll
+            for (int k = 0; k < IB; ++k) a[k] = (fb + k < F) ? st.ld(fb + k) : -2;
+#pragma unroll
+            for (int k = 0; k < IB; ++k) rec[k] = a[k] >= 0 ? P.aln_rec[P.frag_aln_ptr[f0 + fb + k] + a[k]] : make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < IB; ++k) {
+                if (a[k] == -1) ++nerr_loc;
+                if (a[k] < 0) continue;
+                const int x = rec[k].w & 0xff, ne = rec[k].w >> 8;
+                for (int jj = 0; jj < ne; ++jj) {
+                    const int slot = P.aln_esp_slot[rec[k].z + jj];
+                    if (slot >= 0) st.inc(F + slot);
+                }
+#pragma unroll
+                for (int y = 0; y < MAXE; ++y) if (y == x) { e_loc[y] += rec[k].x; l_loc[y] += rec[k].y; }
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < MAXE; ++x) {
+            if (e_loc[x]) atomicAdd((unsigned long long*)&sc.Etot[x], (unsigned long long)e_loc[x]);
+            if (l_loc[x]) atomicAdd((unsigned long long*)&sc.Ltot[x], (unsigned long long)l_loc[x]);
+        }
+        if (nerr_loc) atomicAdd(&sc.nerr, nerr_loc);
+    }
+    __threadfence();
+    __syncthreads();
+
+    // MultiBreakSVAssignmentMatrix.java:130-246 in the reference's summation order: the per-cluster terms of a chunk are
+    // gathered by the whole CTA, the chunk is added up by one thread (floating-point addition does not reassociate).
+    auto full_logprob = [&]() -> double {
+        double lp = 0;                                                    // (meaningful in thread 0 only)
+        for (int i0 = 0; i0 < C; i0 += GIANT_LPCHUNK) {
+            const int nchunk = min(GIANT_LPCHUNK, C - i0);
+            for (int i = tid; i < nchunk; i += NT) {
+                const int cl = P.supports_order_local[c0 + i0 + i];
+                double lpc = 0.0;
+                for (int x = 0; x < E; ++x) {
+                    const int n = st.ld(F + cl * E + x);
+                    if (n > 0) lpc = lpc + Tp[(size_t)x * Tstride + n];
+                }
+                lpbuf[i] = lpc;
+            }
+            __syncthreads();
+            if (tid == 0) for (int i = 0; i < nchunk; ++i) lp += lpbuf[i];
+            __syncthreads();
+        }
+        if (tid == 0) {
+            lp += 0.0;
+            lp += (double)sc.nerr * logperr;
+            for (int x = 0; x < E; ++x) lp += lb_of(x, sc.Etot[x], sc.Ltot[x]);
+        }
+        return lp;
+    };
+    if (R.initial_logprob) {
+        const double lp = full_logprob();
+        if (tid == 0) R.initial_logprob[scx] = lp;
+    }
+
+    // ---------------- iterations (MultiBreakSV.java:796-837, 1101-1182) ----------------
+    make_jump(JavaRandom::MULT2, JavaRandom::ADD2);                       // one offset = one nextDouble()
+    int n_naive_prop = 0, n_naive_acc = 0, n_sv_prop = 0, n_sv_acc = 0;
+    long long n_reassign = 0;
+    int nerr_delta = 0;                                                   // unmapped fragments: net change committed by this thread
+    if (tid == 0) sc.done = N <= 0;
+    __syncthreads();
+    while (!sc.done) {
+        // ================= P1: one iteration per offset =================
+        const unsigned long long sb = sc.s_base;
+        const int iter_base = sc.iter_base;
+        if (tid == 0) { sc.cut = GIANT_NOCUT; sc.errlane = GIANT_NOCUT; }
+        if (tid < E) sc.LB[tid] = lb_of(tid, sc.Etot[tid], sc.Ltot[tid]);
+        if (tid >= 32 && tid < 32 + MAXE) { sc.accE[tid - 32] = 0; sc.accL[tid - 32] = 0; }
+        for (int i = tid; i < GIANT_HASH; i += NT) { hkey[i] = -1; hlane[i] = GIANT_NOCUT; }
+        JavaRandom rng;
+        rng.s = jA * sb + jC;
+        sj[tid] = rng.s;
+        int c = 1;
+        bool dense = false;
+        {
+            const unsigned long long m0 = rng.bits53();
+            if (m0 >= (1ULL << 52)) {                                     // !(nextDouble() < 0.5)
+                dense = true;
+                bool nv = true;
+                if (nsv == 0) rng.skip<2>(); else nv = rng.bits53() < NAIVE_THR;
+                const double u = rng.nextDouble();
+                if (nv) {
+                    const int ff = (int)(u * dF);
+                    const int fa0 = P.frag_aln_ptr[f0 + ff];
+                    const int n = P.frag_aln_ptr[f0 + ff + 1] - fa0;
+                    const int pv = st.ld(ff);
+                    const unsigned long long m53 = rng.bits53();
+                    const bool from_err = pv == -1;
+                    const bool to_err = !from_err && (m53 < perr_thr || n == 1);
+                    c = 5 + ((!from_err && !to_err) ? 1 : 0);
+                    a0_s[tid] = fa0; n_s[tid] = n; prev_s[tid] = pv;
+                } else c = 4;
+            }
+        }
+        // ================= P2: which offsets are iterations =================
+        const GiantReach rr = giant_reach<NT>(c, dense, rtab, rmsk, sc.fin);
+        if (rr.reach) {
+            if (dense) { list[rr.drank] = (unsigned short)tid; lrank[rr.drank] = (unsigned short)rr.rank; }
+            if (iter_base + rr.rank == N) atomicMin(&sc.cut, tid);       // the run ends in front of this offset
+        }
+        __syncthreads();
+        const int M = sc.fin[1];
+        // ================= P3: gather + tentative evaluation (dense threads) =================
+        const int p = tid;
+        const bool act = p < M;
+        int j = 0, jnext = 0, f = -1, a0 = 0, prev = -1, now = -1, nmoves = 0, nent = 0, t_iter = 0;
+        bool naive = true, bad = false, flagA = false, flagB = false;
+        double dcov = 0.0, derr = 0.0, Alogq = 0.0, Anewlogq = 0.0, r_acc = 0.0;
+        long long dE[MAXE], dL[MAXE];
+#pragma unroll
+        for (int x = 0; x < MAXE; ++x) { dE[x] = 0; dL[x] = 0; }
+        unsigned touched = 0;
+        int dnerr = 0;
+        long long reassign = 0;
+        if (act) {
+            j = list[p];
+            t_iter = iter_base + lrank[p];
+            rng.s = sj[j];
+            rng.skip<2>();                                                // the lazy coin
+            if (nsv == 0) rng.skip<2>(); else naive = rng.bits53() < NAIVE_THR;
+            const double u = rng.nextDouble();
+            if (naive) {
+                f = (int)(u * dF);
+                a0 = a0_s[j];
+                const int n = n_s[j];
+                prev = prev_s[j];
+                const unsigned long long before = rng.s;
+                naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
+                jnext = j + 5 + ((rng.s != before * JavaRandom::MULT2 + JavaRandom::ADD2) ? 1 : 0);
+                reassign = 1;
+                if (now == prev) {                                        // Error at MultiBreakSV.java:1122-1123
+                    bad = true;
+                    atomicMin(&sc.cut, j);
+                    atomicMin(&sc.errlane, j);
+                } else {
+                    int4 recF = make_int4(0, 0, 0, 0), recT = make_int4(0, 0, 0, 0);
+                    if (prev != -1) recF = P.aln_rec[a0 + prev];
+                    if (now != -1) recT = P.aln_rec[a0 + now];
+                    if (prev != -1) {
+                        const int x = recF.w & 0xff, ne = recF.w >> 8;
+                        for (int k = 0; k < ne; ++k) {
+                            const int slot = P.aln_esp_slot[recF.z + k];
+                            if (slot >= 0) { ent[nent * MD + p] = slot << 1; ++nent; }
+                        }
+#pragma unroll
+                        for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] -= recF.x; dL[y] -= recF.y; }
+                        touched |= 1u << x;
+                    } else { derr = derr - logperr; --dnerr; }
+                    if (now != -1) {
+                        const int x = recT.w & 0xff, ne = recT.w >> 8;
+                        for (int k = 0; k < ne; ++k) {
+                            const int slot = P.aln_esp_slot[recT.z + k];
+                            if (slot >= 0) { ent[nent * MD + p] = (slot << 1) | 1; ++nent; }
+                        }
+#pragma unroll
+                        for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] += recT.x; dL[y] += recT.y; }
+                        touched |= 1u << x;
+                    } else { derr = derr + logperr; ++dnerr; }
+                }
+            } else {
+                // ---- svMove (MultiBreakSV.java:1291-1343): toggle the cluster's single-alignment fragments ----
+                const int svk = (int)(u * (double)nsv);
+                jnext = j + 4;
+                reassign = P.sv_numchanged[sv0 + svk];
+                const int q0 = P.sv_frag_ptr[sv0 + svk];
+                nmoves = P.sv_frag_ptr[sv0 + svk + 1] - q0;
+                Alogq = neglogNsv;
+                Anewlogq = neglogNsv;
+                for (int q = 0; q < nmoves; ++q) mv[q * MD + p] = P.sv_frag[q0 + q] - f0;
+                for (int q = 0; q < nmoves; ++q) {                        // independent loads: current assignment of each fragment
+                    const int g = mv[q * MD + p];
+                    mv[q * MD + p] = (g << 1) | (st.ld(g) == -1 ? 1 : 0);
+                }
+                for (int q = 0; q < nmoves; ++q) {
+                    const int g = mv[q * MD + p] >> 1;
+                    const bool from_err = mv[q * MD + p] & 1;
+                    const int4 rec = P.aln_rec[P.frag_aln_ptr[f0 + g]];   // its only alignment
+                    const int x = rec.w & 0xff, ne = rec.w >> 8;
+                    for (int k = 0; k < ne; ++k) {
+                        const int slot = P.aln_esp_slot[rec.z + k];
+                        if (slot >= 0) { ent[nent * MD + p] = (slot << 1) | (from_err ? 1 : 0); ++nent; }
+                    }
+                    if (from_err) {                                       // -1 -> 0
+                        derr = derr - logperr; --dnerr;
+#pragma unroll
+                        for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] += rec.x; dL[y] += rec.y; }
+                    } else {                                              // 0 -> -1
+#pragma unroll
+                        for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] -= rec.x; dL[y] -= rec.y; }
+                        derr = derr + logperr; ++dnerr;
+                    }
+                    touched |= 1u << x;
+                }
+            }
+            r_acc = rng.nextDouble();
+            if (!bad) {
+                // counts the entries see: the stored count plus the earlier entries of this proposal on the same slot
+                for (int k = 0; k < nent; ++k) ecnt[k * MD + p] = st.ld(F + (ent[k * MD + p] >> 1));
+                for (int k = 0; k < nent; ++k) {
+                    const int ek = ent[k * MD + p];
+                    int n = ecnt[k * MD + p];
+                    for (int k2 = 0; k2 < k; ++k2) {
+                        const int e2 = ent[k2 * MD + p];
+                        if ((e2 >> 1) == (ek >> 1)) n += (e2 & 1) ? 1 : -1;
+                    }
+                    ecnt[k * MD + p] = n;
+                    const double* Tx = Tp + (size_t)((ek >> 1) % E) * Tstride;
+                    dcov = dcov + (Tx[n + ((ek & 1) ? 1 : -1)] - Tx[n]);
+                }
+            }
+        }
+        auto evaluate = [&](const long long* Ecur, const long long* Lcur, const bool cached_old) -> bool {
+            double dlb = 0.0;
+            unsigned mask = touched & ((1u << E) - 1u);
+            while (mask) {
+                const int x = __ffs(mask) - 1;
+                mask &= mask - 1;
+                long long ex = 0, lx = 0, de = 0, dl = 0;
+#pragma unroll
+                for (int y = 0; y < MAXE; ++y) if (y == x) { ex = Ecur[y]; lx = Lcur[y]; de = dE[y]; dl = dL[y]; }
+                const double old = cached_old ? sc.LB[x] : lb_of(x, ex, lx);
+                const double nl = lb_of(x, ex + de, lx + dl);
+                dlb = dlb + (nl - old);
+            }
+            const double delta = (dcov + derr) + dlb;
+            const double arg = (delta + Alogq) - Anewlogq;
+            const double e = exp_dev(arg);
+            const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);      // Math.min(1, e)
+            return ratio > r_acc;
+        };
+        long long Ecur[MAXE], Lcur[MAXE];
+#pragma unroll
+        for (int x = 0; x < MAXE; ++x) { Ecur[x] = sc.Etot[x]; Lcur[x] = sc.Ltot[x]; }
+        if (act && !bad) flagA = evaluate(Ecur, Lcur, true);
+        // ================= P4: exact totals per proposal (prefix sum over the tentatively accepted ones) =================
+        long long pre[2 * MAXE];
+#pragma unroll
+        for (int v = 0; v < 2 * MAXE; ++v) pre[v] = 0;
+        if (wid < DW) {
+#pragma unroll
+            for (int x = 0; x < MAXE; ++x) { pre[x] = flagA ? dE[x] : 0; pre[MAXE + x] = flagA ? dL[x] : 0; }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                for (int v = 0; v < 2 * MAXE; ++v) {
+                    const long long y = __shfl_up_sync(0xffffffffu, pre[v], o);
+                    if (lane >= o) pre[v] += y;
+                }
+            }
+            if (lane == 31) {
+#pragma unroll
+                for (int v = 0; v < 2 * MAXE; ++v) wtot[wid * 2 * MAXE + v] = pre[v];
+            }
+        }
+        __syncthreads();
+        if (act && !bad) {
+#pragma unroll
+            for (int x = 0; x < MAXE; ++x) {
+                long long be = pre[x] - (flagA ? dE[x] : 0), bl = pre[MAXE + x] - (flagA ? dL[x] : 0);   // exclusive
+                for (int k = 0; k < wid; ++k) { be += wtot[k * 2 * MAXE + x]; bl += wtot[k * 2 * MAXE + MAXE + x]; }
+                Ecur[x] = sc.Etot[x] + be;
+                Lcur[x] = sc.Ltot[x] + bl;
+            }
+            flagB = evaluate(Ecur, Lcur, false);
+            if (flagB != flagA) atomicMin(&sc.cut, j);                     // the hypothesis fails here: redo from this iteration
+            // ================= P5a: rows an accepted proposal writes =================
+            if (flagB) {
+                bool ok = true;
+                auto insert = [&](int key) {
+                    unsigned h = hash_of(key);
+                    for (int guard = 0; guard < GIANT_HASH; ++guard) {
+                        const int old = atomicCAS(&hkey[h], -1, key);
+                        if (old == -1 || old == key) { atomicMin(&hlane[h], p); return; }
+                        h = (h + 1) & (GIANT_HASH - 1);
+                    }
+                    ok = false;
+                };
+                if (naive) insert(f); else for (int q = 0; q < nmoves; ++q) insert(mv[q * MD + p] >> 1);
+                for (int k = 0; k < nent; ++k) insert(F + (ent[k * MD + p] >> 1));
+                // set full (cannot happen below ~4000 written rows per window): nothing behind this proposal is committed
+                if (!ok && jnext < NT) atomicMin(&sc.cut, jnext);
+            }
+        }
+        __syncthreads();
+        // ================= P5b: first proposal that read a row written in front of it =================
+        if (act && !bad) {
+            auto stale = [&](int key) -> bool {
+                unsigned h = hash_of(key);
+                for (int guard = 0; guard < GIANT_HASH; ++guard) {
+                    const int k = hkey[h];
+                    if (k == -1) return false;
+                    if (k == key) return hlane[h] < p;
+                    h = (h + 1) & (GIANT_HASH - 1);
+                }
+                return false;
+            };
+            bool s = false;
+            if (naive) s = stale(f); else for (int q = 0; q < nmoves; ++q) s = s || stale(mv[q * MD + p] >> 1);
+            for (int k = 0; k < nent; ++k) s = s || stale(F + (ent[k * MD + p] >> 1));
+            if (s) atomicMin(&sc.cut, j);
+        }
+        __syncthreads();
+        // ================= P6: commit the iterations in front of the cut =================
+        const int cut = sc.cut;
+        const int errlane = sc.errlane;
+        if (act && j < cut) {
+            if (naive) ++n_naive_prop; else ++n_sv_prop;
+            n_reassign += reassign;
+            if (flagB) {
+                if (naive) ++n_naive_acc; else ++n_sv_acc;
+                nerr_delta += dnerr;
+                const unsigned d = t_iter > win_base ? (unsigned)(t_iter - win_base) : 0u;
+                for (int k = 0; k < nent; ++k) {
+                    const int ek = ent[k * MD + p];
+                    const int slot = ek >> 1, n = ecnt[k * MD + p], n2 = n + ((ek & 1) ? 1 : -1);
+                    st.stw(F + slot, n2);
+                    if (d) {
+                        unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                        if (n > 0) atomicAdd(&h[n], d);
+                        if (n2 > 0) atomicAdd(&h[n2], 0u - d);
+                    }
+                }
+                if (naive) {
+                    st.stw(f, now);
+                    if (d) {
+                        if (prev == -1) atomicAdd(&R.frag_err_count[f0 + f], d); else atomicAdd(&R.aln_count[a0 + prev], d);
+                        if (now == -1) atomicAdd(&R.frag_err_count[f0 + f], 0u - d); else atomicAdd(&R.aln_count[a0 + now], 0u - d);
+                    }
+                } else {
+                    for (int q = 0; q < nmoves; ++q) {
+                        const int g = mv[q * MD + p] >> 1;
+                        const bool from_err = mv[q * MD + p] & 1;
+                        st.stw(g, from_err ? 0 : -1);
+                        if (d) {
+                            const int ga0 = P.frag_aln_ptr[f0 + g];
+                            if (from_err) { atomicAdd(&R.frag_err_count[f0 + g], d); atomicAdd(&R.aln_count[ga0], 0u - d); }
+                            else { atomicAdd(&R.aln_count[ga0], d); atomicAdd(&R.frag_err_count[f0 + g], 0u - d); }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < MAXE; ++x) {
+                    if (dE[x]) atomicAdd((unsigned long long*)&sc.accE[x], (unsigned long long)dE[x]);
+                    if (dL[x]) atomicAdd((unsigned long long*)&sc.accL[x], (unsigned long long)dL[x]);
+                }
+            }
+        }
+        if (act && bad && j == cut) {
+            // the reference throws here: the chain stops with the proposal counted and its draws consumed
+            ++n_naive_prop; n_reassign += 1;
+            sc.s_base = rng.s;
+            sc.err = -5;                                                  // MBSV_ERR_INVARIANT
+            sc.done = 1;
+        }
+        // base of the next window
+        if (cut == GIANT_NOCUT) {
+            if (tid == 0) {
+                unsigned long long s = sc.jumpA * sb + sc.jumpC;
+                for (int i = 0; i < sc.fin[2]; ++i) s = s * JavaRandom::MULT2 + JavaRandom::ADD2;
+                sc.s_base = s;
+                sc.iter_base = iter_base + sc.fin[0];
+                if (iter_base + sc.fin[0] >= N) sc.done = 1;
+            }
+        } else if (tid == cut && cut != errlane) {
+            sc.s_base = sj[tid];
+            sc.iter_base = iter_base + rr.rank;
+            if (iter_base + rr.rank >= N) sc.done = 1;
+        }
+        __syncthreads();
+        if (tid < MAXE) { sc.Etot[tid] += sc.accE[tid]; sc.Ltot[tid] += sc.accL[tid]; }
+        __syncthreads();
+    }
+
+    // ---------------- epilogue: final tallies, state, counters ----------------
+    {
+        const long long v[5] = {n_naive_prop, n_naive_acc, n_sv_prop, n_sv_acc, n_reassign};
+#pragma unroll
+        for (int i = 0; i < 5; ++i) if (v[i]) atomicAdd(&sc.cnt[i], (unsigned long long)v[i]);
+        if (nerr_delta) atomicAdd(&sc.nerr, nerr_delta);
+    }
+    __syncthreads();
+    const int err = sc.err;
+    if (err == 0) {
+        const long long nwin = (long long)N - win_base;
+        if (nwin > 0) {
+            const unsigned d = (unsigned)nwin;
+            for (int ff = tid; ff < F; ff += NT) {
+                const int a = st.ld(ff);
+                if (a == -1) atomicAdd(&R.frag_err_count[f0 + ff], d);
+                else atomicAdd(&R.aln_count[P.frag_aln_ptr[f0 + ff] + a], d);
+            }
+            const int nslot = C * E;
+            for (int s = tid; s < nslot; s += NT) {
+                const int n = st.ld(F + s);
+                if (n > 0) atomicAdd(&R.cluster_hist[P.cluster_hist_ptr[c0 + s / E] + n], d);
+            }
+        }
+    }
+    if (R.final_assign)
+        for (int ff = tid; ff < F; ff += NT) R.final_assign[(size_t)chain * P.n_frag + f0 + ff] = st.ld(ff);
+    if (R.final_logprob) {
+        const double lp = full_logprob();
+        if (tid == 0) R.final_logprob[scx] = lp;
+    }
+    if (tid == 0) {
+        if (R.counters) {
+            long long* k = R.counters + scx * 5;
+            for (int i = 0; i < 5; ++i) k[i] = (long long)sc.cnt[i];
+        }
+        if (R.rng_state) R.rng_state[scx] = sc.s_base & JavaRandom::MASK;
+        if (R.error) R.error[scx] = err;
+        if (R.totals) {
+            for (int i = 0; i < 5; ++i) atomicAdd(&R.totals[i], sc.cnt[i]);
+            if (err) atomicCAS(&R.totals[5], 0ULL, (unsigned long long)(long long)err);
+        }
+    }
+}
+
+}  // namespace mbsv

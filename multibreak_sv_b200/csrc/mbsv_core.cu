@@ -82,6 +82,7 @@ struct mbsv_problem {
     std::vector<int> sub_F;       // fragments of subproblem s
     std::vector<int> sub_nsv;     // AlterSV candidates of subproblem s
     std::vector<int> sub_nstates; // joint state space prod(n_f + 1), saturated at 2^30; 0 when it has a conn-comp
+    std::vector<int> sub_maxent;  // upper bound of the count entries / toggled fragments of one proposal (giant_kernel.cuh)
     // launch plan, depends on mbsv_run_params.memo_states (cached for the last value used)
     int plan_memo = -1, plan_tab = -1;
     std::vector<int> sub_rows;    // tile rows of a warp of subproblem s (state + memo table)
@@ -281,6 +282,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     std::unique_ptr<int[]> sup_local(new (std::nothrow) int[(size_t)C + 1]);
     if (!rec || !slot || !sup_local) return fail(MBSV_ERR_OOM, "host allocation failed");
     int maxn = 1;
+    std::vector<int> sub_maxent(S, 0);
     {
         const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
         std::vector<int> t_maxn(nthreads, 1);
@@ -303,6 +305,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                         in_aln.resize(Cs); stamp_aln.resize(Cs); per_frag.resize(Cs); stamp_frag.resize(Cs); total.resize(Cs); seen.resize(Cs);
                     }
                     for (int i = 0; i < Cs; ++i) { stamp_aln[i] = -1; stamp_frag[i] = -1; total[i] = 0; seen[i] = 0; }
+                    int max_pos = 0;             // most counted ESP entries of one alignment
                     for (int f = d->sub_frag_ptr[s]; f < d->sub_frag_ptr[s + 1]; ++f) {
                         t_maxn[tid] = std::max(t_maxn[tid], d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]);
                         touched.clear();
@@ -310,9 +313,11 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                             const int x = d->aln_exp[a];
                             const int j0 = d->aln_esp_ptr[a], j1 = d->aln_esp_ptr[a + 1];
                             rec[a] = make_int4(d->aln_numerrors[a], d->aln_len[a], j0, x | ((j1 - j0) << 8));
+                            int pos = 0;
                             for (int j = j0; j < j1; ++j) {
                                 const int c = d->aln_esp_cluster[j];
                                 slot[j] = -1;
+                                if (c != -1) max_pos = std::max(max_pos, ++pos);
                                 if (c == -1) continue;
                                 if (c < c0 || c >= c1) { bad(MBSV_ERR_ARG, "aln_esp_cluster points outside the fragment's subproblem"); continue; }
                                 const int cl = c - c0;
@@ -333,6 +338,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                         }
                         for (int cl : touched) total[cl] += per_frag[cl];
                     }
+                    sub_maxent[s] = 2 * max_pos;   // a Naive proposal leaves one alignment and enters another
                     for (int cl = 0; cl < Cs; ++cl) {
                         if (total[cl] > d->max_support)
                             bad(MBSV_ERR_UNSUPPORTED, "a cluster can collect more selected ESPs than max_support "
@@ -366,13 +372,20 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         sv_frag.assign(d->sv_frag, d->sv_frag + d->n_sv_frag);
         sv_numchanged.assign(d->sv_numchanged, d->sv_numchanged + d->n_sv);
         for (int s = 0; s < S; ++s)
-            for (int k = sub_sv_ptr[s]; k < sub_sv_ptr[s + 1]; ++k)
+            for (int k = sub_sv_ptr[s]; k < sub_sv_ptr[s + 1]; ++k) {
+                int entries = 0;
                 for (int q = sv_frag_ptr[k]; q < sv_frag_ptr[k + 1]; ++q) {
                     const int f = sv_frag[q];
                     if (f < d->sub_frag_ptr[s] || f >= d->sub_frag_ptr[s + 1] ||
                         d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f] != 1)
                         return fail(MBSV_ERR_ARG, "sv_frag must list single-alignment fragments of the same subproblem");
+                    for (int q2 = sv_frag_ptr[k]; q2 < q; ++q2)
+                        if (sv_frag[q2] == f) return fail(MBSV_ERR_ARG, "sv_frag lists a fragment twice for one cluster");
+                    const int a = d->frag_aln_ptr[f];
+                    for (int j = d->aln_esp_ptr[a]; j < d->aln_esp_ptr[a + 1]; ++j) entries += slot[j] >= 0;
                 }
+                sub_maxent[s] = std::max(sub_maxent[s], std::max(entries, sv_frag_ptr[k + 1] - sv_frag_ptr[k]));
+            }
     }
     // the exact-binomial branch (n*p <= 5 or n*(1-p) <= 5, MultiBreakSV.java:1664) only sees n <= 5/min(p, 1-p)
     for (int x = 0; x < E; ++x) {
@@ -422,6 +435,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         p->sub_F.push_back(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]);
         p->sub_nsv.push_back(sub_sv_ptr[s + 1] - sub_sv_ptr[s]);
     }
+    p->sub_maxent = sub_maxent;
 
     auto up = [&](auto& buf, const auto& vec) -> cudaError_t { return buf.upload(vec); };
     cudaError_t e = cudaSuccess;
@@ -439,7 +453,11 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     chk(up(p->d_sv_numchanged, sv_numchanged));
     chk(up(p->d_sub_logF, logF));
     chk(up(p->d_sub_neglogNsv, neglogNsv));
-    chk(up(p->d_T, std::vector<double>(d->logprobcov, d->logprobcov + (size_t)E * (d->max_support + 1))));
+    {   // padded to a multiple of 16 bytes: the speculative-window kernel stages it with one bulk copy (cp.async.bulk)
+        std::vector<double> T(d->logprobcov, d->logprobcov + (size_t)E * (d->max_support + 1));
+        T.resize((T.size() + 1) & ~(size_t)1, 0.0);
+        chk(up(p->d_T, T));
+    }
     chk(up(p->d_logint, logint));
     chk(up(p->d_pseq, std::vector<double>(d->exp_pseq, d->exp_pseq + E)));
     chk(up(p->d_logp, logp));
@@ -712,7 +730,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     // class then picks its own chains-per-warp.  Starting from the batch-wide L, classes are revisited from the largest
     // state down and their L halved while the GPU still has unfilled warp slots: the few chains of the big classes are the
     // critical path of a small batch, and a warp of k diverged chains runs each of them ~k times slower.
-    struct Launch { int wb, we, rows; bool smem, memo; int64_t i0, i1; int lanes; };
+    struct Launch { int wb, we, rows; bool smem, memo; int64_t i0, i1; int lanes; bool giant = false; };
     std::vector<Launch> launches;
     auto add_group = [&](int k0, int k1, bool memo) {
         int lo = k0;
@@ -723,7 +741,20 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             if (a > lo) launches.push_back({0, 0, cls[c], true, memo, (int64_t)lo * X, (int64_t)a * X, memo ? Lm : L});
             lo = a;
         }
-        if (lo < k1) launches.push_back({0, 0, 0, false, memo, (int64_t)lo * X, (int64_t)k1 * X, memo ? Lm : L});
+        if (lo < k1) {
+            launches.push_back({0, 0, 0, false, memo, (int64_t)lo * X, (int64_t)k1 * X, memo ? Lm : L});
+            // Few chains on large states (a giant component): one CTA per chain evaluates windows of consecutive iterations
+            // speculatively (giant_kernel.cuh) instead of one lane walking them one memory round trip at a time.  Up to
+            // 8 CTAs per SM's worth of chains; beyond that the lane-per-chain kernel has the better throughput.
+            const char* gmax_env = std::getenv("MBSV_GIANT_MAX_CHAINS");
+            const int64_t gmax = gmax_env ? std::atoll(gmax_env) : resident_warps / 20 * 8;
+            bool ok = !memo && rp->mode == MBSV_MODE_FAST && !rp->trace && !p->has_cc && (int64_t)(k1 - lo) * X <= gmax;
+            for (int k = lo; ok && k < k1; ++k) {
+                const int s = p->sub_order[k];
+                ok = p->sub_memo[s] == 0 && p->sub_maxent[s] <= mbsv::giant_max_entries();
+            }
+            if (ok) { launches.back().giant = true; launches.back().lanes = 1; }
+        }
     };
     if (gibbs) {
         // a group of G lanes per (subproblem, chain): 4 for the smallest states (two or three candidates per fragment),
@@ -761,7 +792,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         // 8 chains per warp, memoised kernel about half of that).  So: narrow the class with the largest estimate while
         // warp slots are left; when they run out, widen the class that stays cheapest after widening to free some.
         auto est = [&](const Launch& l, int lanes) { return (l.memo ? 0.5 : 1.0) * (1.0 + 0.1 * (lanes - 1)); };
-        auto movable = [&](const Launch& l) { return !(l.memo && !mixed); };     // warps of one subproblem keep their width
+        auto movable = [&](const Launch& l) { return !(l.memo && !mixed) && !l.giant; };     // warps of one subproblem keep their width
         for (int guard = 0; !gibbs && spare >= 0 && guard < 256; ++guard) {
             Launch* worst = nullptr;
             for (Launch& l : launches)
@@ -781,7 +812,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             spare += warps_of(*give, give->lanes) - warps_of(*give, give->lanes * 2);
             give->lanes *= 2;
         }
-        if (!gibbs && std::getenv("MBSV_LANES_PER_WARP")) for (Launch& l : launches) l.lanes = l.memo ? Lm : L;
+        if (!gibbs && std::getenv("MBSV_LANES_PER_WARP")) for (Launch& l : launches) if (!l.giant) l.lanes = l.memo ? Lm : L;
         int64_t w = 0;
         for (Launch& l : launches) {
             if (l.memo && !l.smem) return fail(MBSV_ERR_ARG, "internal: memoised subproblem does not fit the shared-memory classes");
@@ -843,20 +874,24 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.n_items = l.i1;                       // the last warp of a class may be partly filled
         r.lanes_per_warp = l.lanes;
         r.memo_mixed = mixed ? 1 : 0;
+        int giant_threads = 0;
+        size_t giant_smem = 0;
         KernelFn fn = gibbs ? mbsv::get_kernel_gibbs(32 / l.lanes)
+                     : l.giant ? mbsv::get_kernel_giant(p->n_exp, &giant_threads, &giant_smem)
                      : l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : (!l.smem && l.lanes == 1 && !rp->trace) ? mbsv::get_kernel_packed(rp->mode, p->has_cc)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
                                  : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);
-        const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * l.lanes * l.rows * sizeof(int) : l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
+        const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * l.lanes * l.rows * sizeof(int) : l.giant ? giant_smem
+                           : l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
         if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         // MBSV_SERIAL_LAUNCHES=1 (tuning aid): run the size classes back to back on one stream
         static const bool serial = std::getenv("MBSV_SERIAL_LAUNCHES") != nullptr;
         cudaStream_t st = serial ? p->streams[1] : p->streams[1 + nstream];
         CUDA_TRY(cudaStreamWaitEvent(st, (l.memo && have_global_tables) ? p->ev_built : p->ev_start, 0));
-        const int grid = (l.we - l.wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        const int grid = l.giant ? l.we - l.wb : (l.we - l.wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;   // giant: one CTA per chain
         CUDA_TRY(cudaEventRecord(p->ev_cls0[1 + nstream], st));
-        fn<<<grid, WARPS_PER_CTA * 32, shm, st>>>(p->dp, r);
+        fn<<<grid, l.giant ? giant_threads : WARPS_PER_CTA * 32, shm, st>>>(p->dp, r);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(p->ev_cls1[1 + nstream], st));
         g_launch_info.push_back({l.smem ? l.rows : 0, l.we - l.wb, grid, (int)shm, 0.f, l.memo ? 1 : 0});

@@ -90,6 +90,9 @@ KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with 
 KernelFn get_kernel_packed(int mode, bool cc);                   // one chain per warp, contiguous state in the global workspace
 KernelFn get_kernel_gibbs(int group);                            // heat-bath sampler, `group` (4, 8, 32) lanes per chain (gibbs_kernel.cuh)
 KernelFn get_kernel_memo(bool trace, bool mixed);               // memoised subproblems (memo_kernel.cuh)
+// speculative-window kernel, one CTA per (subproblem, chain) (giant_kernel.cuh): FAST, no trace, no connected components
+KernelFn get_kernel_giant(int n_exp, int* threads, size_t* smem_bytes);
+int giant_max_entries();                                         // most count entries / toggled fragments of one proposal it takes
 // fills the device-memory log-posterior tables of the memoised subproblems listed in tab_sub
 cudaError_t launch_memo_build(const DevProblem& P, const DevRun& R, int n_tab, const long long* state_ptr, const int* tab_sub,
                               long long n_states, int scratch_rows, cudaStream_t stream);
