@@ -132,11 +132,83 @@ def slice_subproblems(p, s0: int, s1: int):
     return PackedProblem(sc, arrays)
 
 
-def cpu_sample(p, n_chains: int, iters: int, target_iterations: float):
-    """A prefix of the batch's subproblems holding about target_iterations chain-iterations."""
-    S = p.scalars["n_sub"]
-    n = int(min(S, max(1, round(target_iterations / (n_chains * max(iters, 1))))))
-    return slice_subproblems(p, 0, n), n
+def stratified_sample(p, n_chains: int, iters: int, target_iterations: float, threads: int, seed: int = 20260199):
+    """A bounded sample of the batch's subproblems, stratified by size.
+
+    Every subproblem runs the same number of iterations, but a proposal on a large subproblem costs more (cache misses,
+    O(F) set-up), and a power-law batch holds its large subproblems in a tiny share of the count: a prefix or uniform sample
+    almost surely misses them.  Strata = subproblem sizes by powers of two ([1], [2], [3,4], [5,8], ...); stratum k holds N_k
+    subproblems, of which n_k = min(N_k, max(2 x threads, its proportional share of the budget)) are drawn at random.
+    Returns [(N_k, n_k, lo, hi, sub-batch)], ascending size."""
+    a = p.arrays
+    sizes = np.diff(a["sub_frag_ptr"].astype(np.int64))
+    S = len(sizes)
+    budget = max(1, int(round(target_iterations / (n_chains * max(iters, 1)))))
+    rng = np.random.default_rng(seed)
+    cls = np.ceil(np.log2(np.maximum(sizes, 1))).astype(np.int64)          # 1 -> 0, 2 -> 1, 3..4 -> 2, 5..8 -> 3, ...
+    out = []
+    for k in np.unique(cls):
+        idx = np.nonzero(cls == k)[0]
+        n_k = int(min(len(idx), max(2 * threads, round(budget * len(idx) / S))))
+        pick = np.sort(rng.choice(idx, n_k, replace=False)) if n_k < len(idx) else idx
+        out.append((len(idx), n_k, int(sizes[idx].min()), int(sizes[idx].max()), gather_subproblems(p, pick)))
+    return out
+
+
+def gather_subproblems(p, subs):
+    """The sub-batch holding the subproblems `subs` (ascending indices), re-based; contiguous runs are sliced and joined."""
+    from multibreak_sv_b200 import PackedProblem
+    subs = np.asarray(subs, np.int64)
+    if len(subs) == 0:
+        raise ValueError("empty sample")
+    # runs of consecutive subproblems
+    cut = np.nonzero(np.diff(subs) != 1)[0] + 1
+    runs = [(int(r[0]), int(r[-1]) + 1) for r in np.split(subs, cut)]
+    parts = [slice_subproblems(p, s0, s1) for s0, s1 in runs]
+    if len(parts) == 1:
+        return parts[0]
+    return concat_problems(parts)
+
+
+# (name, the *_ptr array that indexes it or None, what its values index: scalar holding that base's size or None)
+_PTRS = ("sub_frag_ptr", "sub_cluster_ptr", "sub_sv_ptr", "frag_aln_ptr", "aln_esp_ptr", "cluster_hist_ptr",
+         "cluster_leaf_ptr", "cluster_root_ptr", "root_leaf_ptr", "sv_frag_ptr")
+_VALUE_BASE = {"sub_frag_ptr": "n_frag", "sub_cluster_ptr": "n_cluster", "sub_sv_ptr": "n_sv", "frag_aln_ptr": "n_aln",
+               "aln_esp_ptr": "n_aln_esp", "cluster_hist_ptr": "n_hist", "cluster_leaf_ptr": "n_leaf",
+               "cluster_root_ptr": "n_root", "root_leaf_ptr": "n_root_leaf", "sv_frag_ptr": "n_sv_frag",
+               "aln_esp_cluster": "n_cluster", "supports_order": "n_cluster", "leaf_owner": "n_frag",
+               "sv_cluster": "n_cluster", "sv_frag": "n_frag"}
+
+
+def concat_problems(parts):
+    """Join independent sub-batches into one PackedProblem (indices shifted by the sizes of the parts in front)."""
+    from multibreak_sv_b200 import PackedProblem
+    keys = list(parts[0].arrays.keys())
+    base = {k: 0 for k in set(_VALUE_BASE.values())}
+    cols = {k: [] for k in keys}
+    for q in parts:
+        for k in keys:
+            v = np.asarray(q.arrays[k])
+            if k in ("exp_pseq", "exp_lambda", "logprobcov"):
+                continue
+            if k in _VALUE_BASE:
+                off = base[_VALUE_BASE[k]]
+                if k in _PTRS:
+                    v = v + off
+                    if cols[k]:
+                        v = v[1:]                      # the first offset repeats the previous part's last one
+                else:
+                    v = np.where(v >= 0, v + off, v)
+            cols[k].append(v)
+        for name in base:
+            base[name] += int(q.scalars[name])
+    arrays = {k: (np.concatenate(cols[k]).astype(np.asarray(parts[0].arrays[k]).dtype) if cols[k] else parts[0].arrays[k])
+              for k in keys}
+    sc = dict(parts[0].scalars)
+    for name in ("n_sub", "n_frag", "n_aln", "n_aln_esp", "n_cluster", "n_sv", "n_sv_frag", "n_leaf", "n_root",
+                 "n_root_leaf", "n_hist"):
+        sc[name] = int(sum(q.scalars[name] for q in parts))
+    return PackedProblem(sc, arrays)
 
 
 def run_cpu(sample, n_chains, iters, mode, threads):
@@ -148,6 +220,21 @@ def run_cpu(sample, n_chains, iters, mode, threads):
     return int(r.totals[4]), dt
 
 
+def cpu_estimate(strata, n_chains, iters, mode, threads):
+    """Whole-batch CPU throughput from the stratified sample: every stratum is timed on all host threads and scaled by
+    N_k / n_k.  Returns (reassignments/s, sampled reassignments, sampled seconds, description)."""
+    r_hat = t_hat = r_s = t_s = 0.0
+    desc = []
+    for N_k, n_k, lo, hi, sub in strata:
+        r, dt = run_cpu(sub, n_chains, iters, mode, threads)
+        r_hat += r * N_k / n_k
+        t_hat += dt * N_k / n_k
+        r_s += r
+        t_s += dt
+        desc.append(f"{n_k}/{N_k} of size {lo}" + (f"-{hi}" if hi != lo else ""))
+    return r_hat / t_hat, r_s, t_s, "; ".join(desc)
+
+
 def algorithmic_bytes(p, proposals: float, accepted: float) -> float:
     """(52 + 6k) B per proposal + (28 + 26k) B per accepted move, k = ESPs in old + new alignment."""
     k = 2.0 * p.scalars["n_aln_esp"] / p.scalars["n_aln"]
@@ -157,12 +244,14 @@ def algorithmic_bytes(p, proposals: float, accepted: float) -> float:
 def build_workload(args, rank, world):
     from multibreak_sv_b200 import sharding, synth
     cfg = synth.CONFIGS[args.config]
-    per_gpu = args.n_frag if args.n_frag else cfg.n_frag
+    base = args.n_frag if args.n_frag else cfg.n_frag
     if cfg.sub_sizes == "single":
         # giant component (BASELINE configs[4]): cannot be split spatially; every rank holds the same subproblem and
-        # runs its share of the chains (sharding.split_chains), tallies are summed with one reduce
-        return cfg, synth.generate(cfg, n_frag=per_gpu)
-    sk = synth.draw_skeleton(cfg, n_frag=per_gpu * world)
+        # runs its share of the chains (mbsv_split_chains), tallies are summed with one ncclReduce
+        return cfg, synth.generate(cfg, n_frag=base)
+    # weak: `base` fragments PER GPU (the global skeleton has world x base); strong: `base` fragments in total
+    total = base * world if args.scaling == "weak" else base
+    sk = synth.draw_skeleton(cfg, n_frag=total)
     if world > 1:
         part = sharding.lpt_shard(sk.weights * args.chains, world)
         mine = np.nonzero(part == rank)[0]
@@ -171,39 +260,56 @@ def build_workload(args, rank, world):
     return cfg, p
 
 
+def config_of(cfg, args):
+    """The workload description: identical in both arms (`--impl ours` and `--impl reference`)."""
+    return {"workload": cfg.name, "fragments": args.n_frag or cfg.n_frag,
+            "fragments_are": "per GPU" if (args.scaling == "weak" and cfg.sub_sizes != "single") else "total",
+            "chains": args.chains, "iters_per_step": args.iters, "mode": args.mode,
+            "l2": "inputs larger than L2 (CSR + chain state >> 126 MB); no flush"}
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU path on the host cores: the oracle port (Java cannot be built or run in this image),
-    all host threads, on a bounded sample of the same workload."""
+    all host threads, on a bounded stratified sample of the same workload."""
     if rank != 0:
         return
     from oracle import oracle as orc
-    orc.build()
+    orc.use_native_build()
     cfg, p = build_workload(args, 0, 1)
     threads = os.cpu_count() or 1
     iters = args.iters
-    sample, nsub = cpu_sample(p, args.chains, iters, args.cpu_iterations)
+    strata = stratified_sample(p, args.chains, iters, args.cpu_iterations, threads)
     mode = args.ref_variant
     for _ in range(args.warmup):
-        run_cpu(sample, args.chains, max(1, iters // 10), mode, threads)
-    tot, tsum = 0, 0.0
+        run_cpu(strata[0][4], args.chains, max(1, iters // 10), mode, threads)
+    vals, tsum, rsum = [], 0.0, 0.0
     for _ in range(args.steps):
-        n, dt = run_cpu(sample, args.chains, iters, mode, threads)
-        tot += n
-        tsum += dt
-    val = tot / tsum
-    desc = (f"first {nsub} of {p.scalars['n_sub']} subproblems of {cfg.name} x {args.chains} chains x {iters} "
-            f"iterations per step")
+        v, r_s, t_s, desc = cpu_estimate(strata, args.chains, iters, mode, threads)
+        vals.append(v)
+        tsum += t_s
+        rsum += r_s
+    val = float(np.mean(vals))
+    sample = (f"stratified by subproblem size, {sum(n for _, n, *_ in strata)} of {p.scalars['n_sub']} subproblems x "
+              f"{args.chains} chains x {iters} iterations per step ({desc}); every stratum timed on all threads and scaled "
+              f"by its share of the batch; oracle {mode} variant, -O3 -march=native")
     print(json.dumps({
         "impl": "reference", "metric": "MCMC fragment-reassignments/sec", "value": val,
         "unit": "fragment-reassignments/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tsum / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg.name, "chains": args.chains, "iters_per_step": iters,
-                   "reference_impl": f"C++ restatement of the Java sampler ({mode}), not Java: no JDK in this image"},
+        "ms_per_step": 1e3 * tsum / max(args.steps, 1), "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(cfg, args),
+        "reference_impl": f"C++ restatement of the Java sampler ({mode}), not Java: no JDK in this image",
         "cpu_baseline": {"value": val, "unit": "fragment-reassignments/s", "cores": threads, "kind": "port",
-                         "sample": desc},
+                         "sample": sample},
         "e2e": {"value": val, "unit": "fragment-reassignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def load_json(path):
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
 
 
 def main():
@@ -212,11 +318,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg4")
-    ap.add_argument("--n-frag", type=int, default=0, help="fragments per GPU (default: the config's)")
+    ap.add_argument("--config", default="cfg4", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's fragment count PER GPU; strong: in total, sharded over the GPUs")
+    ap.add_argument("--n-frag", type=int, default=0, help="fragments (default: the config's)")
     ap.add_argument("--chains", type=int, default=0)
-    ap.add_argument("--iters", type=int, default=10000,
-                    help="MH iterations per chain per step (a full reference run is 1e5; setup costs amortise with it)")
+    ap.add_argument("--iters", type=int, default=0,
+                    help="MH iterations per chain per step (default 10000; 1000000 for the giant component, SURVEY 8d; a full "
+                         "reference run of the batch configs is 1e5: setup costs amortise with it)")
     ap.add_argument("--mode", default="fast", choices=["fast", "replay"])
     ap.add_argument("--cpu-iterations", type=float, default=2.0e9,
                     help="chain-iterations in the bounded CPU sample (about 10-30 s on the host cores)")
@@ -227,8 +336,14 @@ def main():
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     from multibreak_sv_b200 import synth
+    cfg0 = synth.CONFIGS[args.config]
     if not args.chains:
-        args.chains = synth.CONFIGS[args.config].n_chains
+        args.chains = cfg0.n_chains
+    if not args.iters:
+        args.iters = 1_000_000 if cfg0.sub_sizes == "single" else 10_000
+    giant = cfg0.sub_sizes == "single"
+    if giant:
+        args.scaling = "strong"          # the chains of ONE component are split over the GPUs: total work is fixed
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
@@ -253,27 +368,38 @@ def main():
     sc = p.scalars
     mode = mbsv.MODE_FAST if args.mode == "fast" else mbsv.MODE_REPLAY_EXACT
     dp = mbsv.DeviceProblem(p, device=local_rank)
-    t_u32 = lambda n: torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
-    bufs = {"aln_count": t_u32(sc["n_aln"]), "frag_err_count": t_u32(sc["n_frag"]), "cluster_hist": t_u32(sc["n_hist"]),
-            "totals": torch.zeros(6, dtype=torch.int64, device=dev)}
-    ptrs = {k: v.data_ptr() for k, v in bufs.items()}
+    # ONE contiguous tally buffer [aln_count | frag_err_count | cluster_hist]: what mbsv_reduce_tallies sums with one ncclReduce
+    n_words = sc["n_aln"] + sc["n_frag"] + sc["n_hist"]
+    tallies = torch.zeros(max(n_words, 1), dtype=torch.int32, device=dev)
+    totals_t = torch.zeros(6, dtype=torch.int64, device=dev)
+    base = tallies.data_ptr()
+    ptrs = {"aln_count": base, "frag_err_count": base + 4 * sc["n_aln"],
+            "cluster_hist": base + 4 * (sc["n_aln"] + sc["n_frag"]), "totals": totals_t.data_ptr()}
 
-    giant = cfg.sub_sizes == "single"
     my_first, my_chains = 0, args.chains
+    comm = None
     if giant:
         from multibreak_sv_b200 import sharding
         my_first, my_chains = sharding.split_chains(args.chains, world, rank)
+        if world > 1:
+            def exchange(ident):          # rank 0's NCCL id to every rank (host-side plumbing)
+                t = torch.from_numpy(ident.copy()).to(dev)
+                dist.broadcast(t, src=0)
+                return t.cpu().numpy()
+            comm = mbsv.Comm(world, rank, local_rank, exchange)
+
+    reduce_ms = []
 
     def step():
         st, ms = dp.run_device(ptrs, mode=mode, num_iters=args.iters, n_chains=my_chains, seed=123456 + my_first)
-        if giant and world > 1:
-            # one reduce of the integer tallies onto rank 0 (NCCL over NVLink)
-            for k in ("aln_count", "frag_err_count", "cluster_hist"):
-                dist.reduce(bufs[k], dst=0, op=dist.ReduceOp.SUM)
+        if comm is not None:
+            # the library's one ncclReduce of the integer tallies onto rank 0 (NVLink)
+            reduce_ms.append(comm.reduce_tallies(base, n_words, 0))
         return ms
 
     for _ in range(args.warmup):
         step()
+    reduce_ms.clear()
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -282,12 +408,12 @@ def main():
     launches = 0
     for _ in range(args.steps):
         kernel_ms += step()
-        launches += int(dp.lib.mbsv_last_launch_count())
+        launches += int(dp.lib.mbsv_last_launch_count()) + (1 if comm is not None else 0)
     barrier()
     dt = time.perf_counter() - t0
     clk = clocks.stop()
     launch_info = dp.launch_info()
-    totals = bufs["totals"].cpu().numpy().astype(np.int64)      # of the last step (every step is identical)
+    totals = totals_t.cpu().numpy().astype(np.int64)      # of the last step (every step is identical)
     if int(totals[5]) != 0:
         raise SystemExit(f"a chain reported status {int(totals[5])}")
     proposals, accepted, reassign = int(totals[0] + totals[2]), int(totals[1] + totals[3]), int(totals[4])
@@ -305,7 +431,7 @@ def main():
         dt_max, kern_max, reassign_all, prop_all, acc_all = dt, kernel_ms / 1e3, reassign, proposals, accepted
     value = reassign_all * args.steps / dt_max
 
-    # ---- end to end through the C ABI with host buffers ----
+    # ---- end to end through the C ABI with host buffers: create (validation, packing, H2D) + run (D2H) + destroy ----
     e2e = None
     if not args.no_e2e:
         h2d = p.host_bytes
@@ -313,16 +439,20 @@ def main():
         barrier()
         t0 = time.perf_counter()
         e2e_launches = 0
-        e2e_steps = max(1, min(args.steps, 3))      # every step repeats the same create + run + destroy; 3 bound the run time
-        for _ in range(e2e_steps):
+        for _ in range(args.steps):
             d2 = mbsv.DeviceProblem(p, device=local_rank)
             out = d2.run(mode, args.iters, n_chains=my_chains, seed=123456 + my_first, want_state=False, per_chain=False)
             e2e_launches += out.launches
             d2h = out.result_bytes
-            if int(out.totals[5]) != 0:
-                raise SystemExit("e2e: chain status != 0")
             re2e = int(out.totals[4])
             d2.close()
+            if comm is not None:
+                # host tallies of every rank pooled on rank 0: H2D of the tallies + the library's reduce + D2H on rank 0
+                t = torch.from_numpy(np.concatenate([out.aln_count, out.frag_err_count, out.cluster_hist]).view(np.int32)).to(dev)
+                comm.reduce_tallies(t.data_ptr(), n_words, 0)
+                if rank == 0:
+                    t.cpu()
+                e2e_launches += 1
         barrier()
         et = time.perf_counter() - t0
         es = torch.tensor([et, float(re2e)], dtype=torch.float64, device=dev)
@@ -330,73 +460,75 @@ def main():
             emx = es.clone(); dist.all_reduce(emx, op=dist.ReduceOp.MAX)
             esm = es.clone(); dist.all_reduce(esm, op=dist.ReduceOp.SUM)
             et, re2e = float(emx[0]), float(esm[1])
-        e2e = {"value": re2e * e2e_steps / et, "unit": "fragment-reassignments/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * et / e2e_steps, "steps": e2e_steps}
+        e2e = {"value": re2e * args.steps / et, "unit": "fragment-reassignments/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * et / args.steps, "steps": args.steps}
         launches += e2e_launches
 
-    # ---- roofline of the sampler launches (one kernel template, one launch per state-size class) ----
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    # ---- roofline.  The chain state of this path is SM-resident (shared memory / L1 / L2), so HBM does not bind; what binds
+    # is the SM's issue slots times the share of lanes doing useful work.  The issue-slot figures come from the ncu capture of
+    # THIS workload (profiles/r02_issue_<config>.json, written by profiles/summarize_ncu.py from the .ncu-rep); the HBM
+    # figure from SURVEY 8d's algorithmic bytes is kept beside it as `hbm_notional`. ----
+    peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
+    if peaks:
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg = algorithmic_bytes(p, proposals, accepted)                      # this rank, per step
     achieved = alg / (kernel_ms / 1e3 / args.steps) / 1e9
-    # DRAM traffic comes from an `ncu --set full` capture (profiles/traffic.json); it only fills `traffic` when the
-    # capture was taken on this same workload, otherwise it is reported beside it with its own configuration.
-    traffic, traffic_other = None, None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            if tj.get("n_frag") == sc["n_frag"] and tj.get("iters") == args.iters and tj.get("chains") == args.chains:
-                traffic = tj.get("dram_bytes_per_launch")
-            else:
-                traffic_other = tj
-        except Exception:
-            pass
-    issue = None
-    ipath = os.path.join(ROOT, "profiles", "issue.json")
-    if os.path.exists(ipath):
-        try:
-            issue = json.load(open(ipath))
-        except Exception:
-            issue = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_reduced_config": traffic_other, "peak_source": peak_src,
-                "kernel": "mbsv_memo_kernel + mbsv_chain_kernel<FAST> (one launch per state-size class, concurrent streams)",
-                "kernel_ms_per_step": kernel_ms / args.steps, "algorithmic_bytes_per_step": alg,
-                "binding": issue,
-                "note": "algorithmic bytes are served from shared memory / L1 / L2 (chain state is SM-resident), so "
-                        "HBM is not the binding roofline; `binding` holds the ncu issue-slot figures of the dominant "
-                        "launch (profiles/), see DESIGN.md section 4"}
+    issue = load_json(os.path.join(ROOT, "profiles", f"r02_issue_{args.config}.json"))
+    per_class = []
+    tot_ms = sum(li["ms"] for li in launch_info) or 1.0
+    for li in launch_info:
+        kind = ("memo" if li["rows"] < 0 else "window" if (li["rows"] == 0 and li["smem_bytes"] > 0)
+                else "global" if li["rows"] == 0 else "smem")
+        per_class.append({"kernel": kind, "rows": abs(li["rows"]), "warps": li["warps"], "ms": li["ms"],
+                          "reassignments": li["reassignments"], "accepted": li["accepted"],
+                          "reassignments_per_s_alone": li["reassignments"] / (li["ms"] / 1e3) if li["ms"] > 0 else None})
+    if issue and issue.get("dominant"):
+        d = issue["dominant"]
+        roofline = {"bound": "sm-issue", "achieved": d["issue_active_pct"] * d["active_lanes"] / 32.0, "peak": 100.0,
+                    "unit": "% of issue slots x active lanes / 32", "frac": d["issue_active_pct"] * d["active_lanes"] / 3200.0,
+                    "traffic": d.get("dram_bytes_per_launch"), "kernel": d["kernel"], "kernels": issue.get("kernels"),
+                    "source": issue.get("source")}
+    else:
+        roofline = {"bound": "sm-issue", "achieved": None, "peak": 100.0, "unit": "% of issue slots x active lanes / 32",
+                    "frac": None, "traffic": None, "source": "no ncu capture of this config committed"}
+    roofline["hbm_notional"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                                "kernel_ms_per_step": kernel_ms / args.steps,
+                                "note": "SURVEY 8d algorithmic bytes / the library's CUDA-event time of the sampler launches; the "
+                                        "bytes are served from shared memory / L1 / L2, measured DRAM traffic is `traffic`"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
-        orc.build()
+        orc.use_native_build()
         threads = os.cpu_count() or 1
-        sample, nsub = cpu_sample(p, args.chains, args.iters, args.cpu_iterations)
-        n, cdt = run_cpu(sample, args.chains, args.iters, "incremental", threads)
-        cpu_baseline = {"value": n / cdt, "unit": "fragment-reassignments/s", "cores": threads, "kind": "port",
-                        "sample": f"first {nsub} of {sc['n_sub']} subproblems x {args.chains} chains x {args.iters} "
-                                  f"iterations ({n} reassignments in {cdt:.1f} s), oracle incremental variant"}
+        strata = stratified_sample(p, args.chains, args.iters, args.cpu_iterations, threads)
+        v, r_s, t_s, desc = cpu_estimate(strata, args.chains, args.iters, "incremental", threads)
+        cpu_baseline = {"value": v, "unit": "fragment-reassignments/s", "cores": threads, "kind": "port",
+                        "sample": f"stratified by subproblem size, {sum(n for _, n, *_ in strata)} of {sc['n_sub']} subproblems "
+                                  f"x {args.chains} chains x {args.iters} iterations ({int(r_s)} reassignments in {t_s:.1f} s: "
+                                  f"{desc}); strata scaled by their share of the batch; oracle incremental variant, "
+                                  f"-O3 -march=native"}
 
     if rank == 0:
         line = {
             "metric": "MCMC fragment-reassignments/sec", "value": value, "unit": "fragment-reassignments/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg.name, "fragments_per_gpu": sc["n_frag"] if world == 1 else args.n_frag or cfg.n_frag,
-                       "subproblems_rank0": sc["n_sub"], "alignments_rank0": sc["n_aln"], "chains": args.chains,
-                       "iters_per_step": args.iters, "mode": args.mode,
-                       "sharding": ("chains split + reduce" if giant else "lpt") if world > 1 else "none",
-                       "l2": "inputs larger than L2 (CSR + chain state >> 126 MB); no flush"},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(cfg, args),
+            "sharding": ("chains split over the GPUs + one ncclReduce of the tallies (mbsv_reduce_tallies)" if giant else "lpt") if world > 1 else "none",
+            "rank0": {"subproblems": sc["n_sub"], "fragments": sc["n_frag"], "alignments": sc["n_aln"], "chains": my_chains},
+            "reduce_ms_per_step": (sum(reduce_ms) / len(reduce_ms)) if reduce_ms else None,
+            "reduce_bytes": 4 * n_words if comm is not None else None,
             "iterations_per_s": (sc["n_sub"] * args.chains * args.iters) * args.steps / dt_max if world == 1 else None,
             "accepted_per_s": acc_all * args.steps / dt_max, "proposals_per_s": prop_all * args.steps / dt_max,
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "launch_info": launch_info}
+            "per_class": per_class}
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

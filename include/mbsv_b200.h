@@ -20,6 +20,14 @@
  *   - one caller thread per handle (the reference is single-threaded with static state,
  *     MultiBreakSV.java:50-63,78); distinct handles are independent.  mbsv_run is synchronous.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with MBSV_ERR_CUDA.
+ *
+ * Host setup
+ *   - a mbsv_problem handle is NOT thread-safe: it owns its launch plan, chain-state workspace, streams and events;
+ *     one mbsv_run / mbsv_run_device at a time per handle (distinct handles may run concurrently from distinct threads).
+ *   - a run overlaps one kernel per state-size class on up to 19 streams.  CUDA's default of 8 hardware queues makes the
+ *     9th stream wait for the 1st; export CUDA_DEVICE_MAX_CONNECTIONS=32 in the host's environment before its first CUDA
+ *     call (the variable is read when the context is created).  The library never modifies the environment.  Results do
+ *     not depend on it.
  */
 #ifndef MBSV_B200_H
 #define MBSV_B200_H
@@ -36,7 +44,7 @@ typedef enum mbsv_status {
     MBSV_OK = 0,
     MBSV_ERR_ARG = -1,         /* bad argument / malformed descriptor */
     MBSV_ERR_CUDA = -2,        /* CUDA runtime error or no device */
-    MBSV_ERR_NCCL = -3,        /* reserved for the multi-GPU reduce */
+    MBSV_ERR_NCCL = -3,        /* NCCL missing or failing (mbsv_comm_*, mbsv_reduce_tallies, mbsv_run_multi) */
     MBSV_ERR_OOM = -4,         /* host or device allocation failed */
     MBSV_ERR_INVARIANT = -5,   /* the reference would have thrown Error (MultiBreakSV.java:1122-1130,1142-1144;
                                   MultiBreakSVAssignmentMatrix.java:375-376) */
@@ -195,17 +203,52 @@ int mbsv_run(mbsv_problem* p, const mbsv_run_params* params, mbsv_results* resul
 int mbsv_run_device(mbsv_problem* p, const mbsv_run_params* params, mbsv_results* results);
 
 /* Introspection for benchmarks / tests. */
-int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n);   /* see DESIGN.md */
+int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n);   /* {n_sub, n_frag, n_aln, n_cluster, CSR bytes on the
+                                                                             device, largest chain state in rows, memoised
+                                                                             subproblems of the last plan, n_hist, device} */
 int64_t mbsv_last_launch_count(void);             /* kernels launched by the last mbsv_run on this thread */
 /* out[i*5..] = {tile rows per warp of the size class (0 = global-workspace class, negative = memoised kernel), warps, grid, dynamic shared
    memory bytes, device milliseconds} for each of those launches; returns their number. */
 int mbsv_last_launch_info(double* out, int32_t max_launches);
+/* out[i*6..] = {Naive proposals, Naive moves, AlterSV proposals, AlterSV moves, fragment-reassignments, first non-zero chain
+   status} summed over the chains of launch i (same order as mbsv_last_launch_info); returns their number. */
+int mbsv_last_launch_totals(int64_t* out, int32_t max_launches);
 
 /* Multi-GPU sharding of independent subproblems (the reference's only scale-out is one JVM
    per subset-N.clusters file, doc/MultiBreakSV-Manual.txt:411-473): longest-processing-time-first greedy —
    subproblems by descending weight (ties: lower index first), each to the currently least loaded of n_parts
    (ties: lowest part).  out_part[i] in [0, n_parts). */
 int mbsv_lpt_shard(const int64_t* weights, int64_t n, int32_t n_parts, int32_t* out_part);
+
+/*
+ * Giant component over several GPUs.  One connected component cannot be split spatially — every
+ * fragment is coupled through the per-experiment totals (MultiBreakSVAssignmentMatrix.java:203-230) — so its CHAINS are
+ * split over the GPUs (mbsv_split_chains; chain c keeps the seed `seed + c` wherever it runs, so chain 0 stays the
+ * reference's chain) and the integer tallies are summed with ONE ncclReduce over NVLink.  The reference has no
+ * counterpart: its manual only says that a few subproblems are "quite large" (doc/MultiBreakSV-Manual.txt:420-423).
+ * NCCL is loaded on first use (dlopen libnccl.so.2); without it these entry points fail with MBSV_ERR_NCCL.
+ */
+#define MBSV_COMM_ID_BYTES 128
+typedef struct mbsv_comm mbsv_comm;
+
+/* (first chain, number of chains) of part `part` when n_chains chains are split over n_parts GPUs */
+int mbsv_split_chains(int32_t n_chains, int32_t n_parts, int32_t part, int32_t* first, int32_t* count);
+
+/* One host process per GPU: rank 0 draws an id (ncclGetUniqueId), the host passes it to every rank by its own means,
+   every rank creates its communicator, runs its chains with mbsv_run_device into ONE contiguous device buffer
+   [aln_count | frag_err_count | cluster_hist] (mbsv_problem_stats: n_aln + n_frag + n_hist words) and calls
+   mbsv_reduce_tallies: one ncclReduce(sum, u32) onto `root`, in place.  reduce_ms = device time of the reduce. */
+int mbsv_comm_unique_id(uint8_t* out /* [MBSV_COMM_ID_BYTES] */);
+int mbsv_comm_create(const uint8_t* id, int32_t n_ranks, int32_t rank, int32_t device, mbsv_comm** out);
+int mbsv_comm_destroy(mbsv_comm* c);
+int mbsv_reduce_tallies(mbsv_comm* c, uint32_t* tallies_dev, int64_t n_words, int32_t root, double* reduce_ms);
+
+/* One host process, n_dev GPUs (a JVM calling through Panama FFM): problems[d] is the SAME problem created on device d.
+   Splits params->n_chains over the devices, runs them concurrently, pools the tallies on problems[0]'s device with one
+   ncclReduce per device inside one group call, and fills results->aln_count / frag_err_count / cluster_hist / totals
+   (host buffers; every per-chain array must be NULL).  params->device is ignored. */
+int mbsv_run_multi(mbsv_problem* const* problems, int32_t n_dev, const mbsv_run_params* params, mbsv_results* results,
+                   double* reduce_ms);
 
 /* Host-side math the Java host would otherwise do itself (fdlibm-equivalent, no FMA contraction). */
 double mbsv_log(double x);

@@ -67,7 +67,10 @@ class Results(C.Structure):
 
 EXPORTS = ["mbsv_abi_version", "mbsv_device_count", "mbsv_last_error", "mbsv_status_string", "mbsv_problem_create",
            "mbsv_problem_destroy", "mbsv_run", "mbsv_run_device", "mbsv_problem_stats", "mbsv_last_launch_count",
-           "mbsv_log", "mbsv_exp", "mbsv_fill_logprobcov", "mbsv_lpt_shard", "mbsv_last_launch_info"]
+           "mbsv_log", "mbsv_exp", "mbsv_fill_logprobcov", "mbsv_lpt_shard", "mbsv_last_launch_info",
+           "mbsv_last_launch_totals", "mbsv_split_chains", "mbsv_comm_unique_id", "mbsv_comm_create", "mbsv_comm_destroy", "mbsv_reduce_tallies",
+           "mbsv_run_multi"]
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -104,6 +107,16 @@ def load_library():
     L.mbsv_fill_logprobcov.argtypes = [C.c_double, C.c_int32, F64P]; L.mbsv_fill_logprobcov.restype = C.c_int
     L.mbsv_last_launch_info.argtypes = [F64P, C.c_int32]; L.mbsv_last_launch_info.restype = C.c_int
     L.mbsv_lpt_shard.argtypes = [I64P, C.c_int64, C.c_int32, I32P]; L.mbsv_lpt_shard.restype = C.c_int
+    L.mbsv_last_launch_totals.argtypes = [I64P, C.c_int32]; L.mbsv_last_launch_totals.restype = C.c_int
+    L.mbsv_split_chains.argtypes = [C.c_int32, C.c_int32, C.c_int32, I32P, I32P]; L.mbsv_split_chains.restype = C.c_int
+    L.mbsv_comm_unique_id.argtypes = [U8P]; L.mbsv_comm_unique_id.restype = C.c_int
+    L.mbsv_comm_create.argtypes = [U8P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.mbsv_comm_create.restype = C.c_int
+    L.mbsv_comm_destroy.argtypes = [C.c_void_p]; L.mbsv_comm_destroy.restype = C.c_int
+    L.mbsv_reduce_tallies.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, F64P]
+    L.mbsv_reduce_tallies.restype = C.c_int
+    L.mbsv_run_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(RunParams), C.POINTER(Results), F64P]
+    L.mbsv_run_multi.restype = C.c_int
     if L.mbsv_abi_version() != MBSV_ABI_VERSION:
         raise ImportError("libmbsv_b200.so ABI version mismatch")
     _lib = L
@@ -194,8 +207,13 @@ class DeviceProblem:
 
     def run(self, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 1, perr: float = 0.001,
             seed: int = 123456, burnin: int | None = None, java_int_wrap: bool | None = None, init_assign=None,
-            trace: bool = False, want_state: bool = True, per_chain: bool = True, memo_states: int = 65536) -> RunOutput:
-        """MultiBreakSV.runMCMC (MultiBreakSV.java:773-877) for every (subproblem, chain), on the GPU."""
+            trace: bool = False, want_state: bool = True, per_chain: bool = True, memo_states: int = 65536,
+            allow_invariant: bool = False) -> RunOutput:
+        """MultiBreakSV.runMCMC (MultiBreakSV.java:773-877) for every (subproblem, chain), on the GPU.
+
+        A chain that hits an invariant the reference turns into an Error (MBSV_ERR_INVARIANT: its tallies are not
+        balanced and must not be used) raises, like every other failure; allow_invariant=True returns the outputs with
+        the per-chain `error` array instead (tests of that path)."""
         s = self.packed.scalars
         S, F = s["n_sub"], s["n_frag"]
         rp = RunParams()
@@ -239,19 +257,22 @@ class DeviceProblem:
         out.kernel_ms = r.kernel_ms
         out.launches = int(self.lib.mbsv_last_launch_count())
         self.last_status = st
-        if st != 0 and st != -5:
+        if st != 0 and not (st == -5 and allow_invariant):
             check(st)
         return out
 
     def launch_info(self) -> list[dict]:
         buf = np.zeros(20 * 5, np.float64)
         n = self.lib.mbsv_last_launch_info(buf.ctypes.data_as(F64P), 20)
+        tot = np.zeros(20 * 6, np.int64)
+        self.lib.mbsv_last_launch_totals(tot.ctypes.data_as(I64P), 20)
         return [dict(rows=int(buf[i * 5]), warps=int(buf[i * 5 + 1]), grid=int(buf[i * 5 + 2]),
-                     smem_bytes=int(buf[i * 5 + 3]), ms=float(buf[i * 5 + 4])) for i in range(n)]
+                     smem_bytes=int(buf[i * 5 + 3]), ms=float(buf[i * 5 + 4]), proposals=int(tot[i * 6] + tot[i * 6 + 2]),
+                     accepted=int(tot[i * 6 + 1] + tot[i * 6 + 3]), reassignments=int(tot[i * 6 + 4])) for i in range(n)]
 
     def run_device(self, tensors: dict, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 1,
                    perr: float = 0.001, seed: int = 123456, burnin: int | None = None, java_int_wrap: bool = False,
-                   memo_states: int = 65536):
+                   memo_states: int = 65536, allow_invariant: bool = False):
         """mbsv_run_device: `tensors` maps result-field names to DEVICE pointers (e.g. torch tensor.data_ptr()) on
         this problem's GPU; aln_count, frag_err_count, cluster_hist and totals are required.  Returns
         (status, kernel_ms)."""
@@ -270,6 +291,71 @@ class DeviceProblem:
         for k, ptr in tensors.items():
             setattr(r, k, C.cast(C.c_void_p(int(ptr)), ft[k]))
         st = self.lib.mbsv_run_device(self.handle, C.byref(rp), C.byref(r))
-        if st != 0 and st != -5:
+        if st != 0 and not (st == -5 and allow_invariant):
             check(st)
         return st, r.kernel_ms
+
+
+def _host_nccl_first():
+    """The library takes the NCCL the process already has (same SONAME); a Python host that also uses PyTorch must have
+    torch's bundled NCCL loaded BEFORE the library opens the system one, or `import torch` fails later on missing symbols."""
+    import importlib.util
+    if importlib.util.find_spec("torch") is not None:
+        import torch  # noqa: F401
+
+
+class Comm:
+    """mbsv_comm: the NCCL communicator of the giant-component path, one process per GPU.  `exchange` hands rank 0's
+    128-byte id to every rank (e.g. a torch.distributed broadcast of a uint8 tensor, or a file)."""
+
+    def __init__(self, n_ranks: int, rank: int, device: int, exchange):
+        _host_nccl_first()
+        self.lib = load_library()
+        ident = np.zeros(COMM_ID_BYTES, np.uint8)
+        if rank == 0:
+            check(self.lib.mbsv_comm_unique_id(ident.ctypes.data_as(U8P)))
+        ident = np.ascontiguousarray(exchange(ident), np.uint8)
+        self.handle = C.c_void_p()
+        check(self.lib.mbsv_comm_create(ident.ctypes.data_as(U8P), n_ranks, rank, device, C.byref(self.handle)))
+
+    def reduce_tallies(self, dev_ptr: int, n_words: int, root: int = 0) -> float:
+        """One ncclReduce(sum, u32) of the contiguous device tallies onto `root`, in place; returns its device time (ms)."""
+        ms = C.c_double(0.0)
+        check(self.lib.mbsv_reduce_tallies(self.handle, C.c_void_p(int(dev_ptr)), int(n_words), root, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mbsv_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def run_multi(problems, mode: int = MODE_FAST, num_iters: int = 10000, n_chains: int = 8, perr: float = 0.001,
+              seed: int = 123456, burnin: int | None = None, java_int_wrap: bool = False, memo_states: int = 65536):
+    """mbsv_run_multi: `problems` = the same PackedProblem created on several GPUs of this process (DeviceProblem
+    objects); chains split over them, tallies pooled with one ncclReduce.  Returns (RunOutput with the pooled tallies and
+    totals, reduce_ms)."""
+    _host_nccl_first()
+    L = load_library()
+    s = problems[0].packed.scalars
+    rp = RunParams()
+    rp.mode, rp.n_chains, rp.num_iters = mode, n_chains, num_iters
+    rp.burnin = reference_burnin(num_iters) if burnin is None else burnin
+    rp.perr, rp.seed, rp.device = perr, seed, problems[0].device
+    rp.java_int_wrap, rp.memo_states = int(java_int_wrap), memo_states
+    out = RunOutput(aln_count=np.zeros(s["n_aln"], np.uint32), frag_err_count=np.zeros(s["n_frag"], np.uint32),
+                    cluster_hist=np.zeros(s["n_hist"], np.uint32), final_assign=np.zeros((0, 0), np.int32),
+                    final_logprob=np.zeros((0, 0)), counters=np.zeros((0, 0, 0), np.int64),
+                    rng_state=np.zeros((0, 0), np.uint64), error=np.zeros((0, 0), np.int32),
+                    initial_assign=np.zeros((0, 0), np.int32), initial_logprob=np.zeros((0, 0)), trace_logprob=None,
+                    trace_move_frag=None, trace_move_assign=None, kernel_ms=0.0, launches=0, totals=np.zeros(6, np.int64))
+    r = Results()
+    ft = dict(Results._fields_)
+    for k in ("aln_count", "frag_err_count", "cluster_hist", "totals"):
+        a = getattr(out, k)
+        setattr(r, k, a.ctypes.data_as(ft[k]) if a.size else ft[k]())
+    handles = (C.c_void_p * len(problems))(*[p.handle for p in problems])
+    ms = C.c_double(0.0)
+    check(L.mbsv_run_multi(handles, len(problems), C.byref(rp), C.byref(r), C.byref(ms)))
+    out.kernel_ms = r.kernel_ms
+    return out, ms.value

@@ -43,6 +43,7 @@ namespace mbsv {
 
 constexpr int GIANT_MAXENT = 32;    // count-slot entries of one proposal
 constexpr int GIANT_MAXMV = 32;     // fragments toggled by one AlterSV proposal
+constexpr int GIANT_ALN_SLOTS = 4;  // counted slots of one alignment (aln_ent4)
 constexpr int GIANT_HASH = 4096;    // written-row hash set (power of two)
 constexpr int GIANT_TMAX = 2048;    // logprobcov doubles staged in shared memory (E * (max_support + 1) <= this)
 constexpr int GIANT_LPCHUNK = 2048; // clusters per chunk of the serial log-posterior sum
@@ -140,41 +141,45 @@ template <int NT, int MAXE>
 struct GiantLayout {
     static constexpr int NW = NT / 32;
     static constexpr int MD = NT / 4 + 8;          // proposals per window: every one consumes >= 4 offsets
-    static constexpr int DW = (MD + 31) / 32;      // warps that hold them
     static constexpr size_t al(size_t b) { return (b + 15) & ~(size_t)15; }
     static constexpr size_t o_T = 0;
     static constexpr size_t o_lp = o_T + al(sizeof(double) * GIANT_TMAX);
-    static constexpr size_t o_sj = o_lp + al(sizeof(double) * GIANT_LPCHUNK);
-    static constexpr size_t o_wtot = o_sj + al(sizeof(unsigned long long) * NT);
-    static constexpr size_t o_a0 = o_wtot + al(sizeof(long long) * DW * 2 * MAXE);
-    static constexpr size_t o_n = o_a0 + al(sizeof(int) * NT);
-    static constexpr size_t o_prev = o_n + al(sizeof(int) * NT);
-    static constexpr size_t o_ent = o_prev + al(sizeof(int) * NT);
+    static constexpr size_t o_wtot = o_lp + al(sizeof(double) * GIANT_LPCHUNK);
+    static constexpr size_t o_wlast = o_wtot + al(sizeof(long long) * NW * 2 * MAXE);
+    static constexpr size_t o_nls = o_wlast + al(sizeof(int) * NW * MAXE);
+    static constexpr size_t o_ent = o_nls + al(sizeof(double) * MAXE * MD);
     static constexpr size_t o_ecnt = o_ent + al(sizeof(int) * GIANT_MAXENT * MD);
     static constexpr size_t o_mv = o_ecnt + al(sizeof(int) * GIANT_MAXENT * MD);
     static constexpr size_t o_hkey = o_mv + al(sizeof(int) * GIANT_MAXMV * MD);
     static constexpr size_t o_hlane = o_hkey + al(sizeof(int) * GIANT_HASH);
     static constexpr size_t o_rtab = o_hlane + al(sizeof(int) * GIANT_HASH);
     static constexpr size_t o_rmsk = o_rtab + al(sizeof(unsigned) * NW * 8);
-    static constexpr size_t o_list = o_rmsk + al(sizeof(unsigned) * NW * 8);
-    static constexpr size_t o_lrank = o_list + al(sizeof(unsigned short) * (NT + 8));
-    static constexpr size_t o_sc = o_lrank + al(sizeof(unsigned short) * (NT + 8));
+    static constexpr size_t o_sc = o_rmsk + al(sizeof(unsigned) * NW * 8);
     static constexpr size_t bytes = o_sc + 512;    // the Scalars block (static_assert in the kernel)
 };
+
+// logBinomial for the tentative decisions only: same formula as log_binomial_dev's normal branch with a hardware
+// reciprocal and a single-precision logarithm (absolute error ~1e-6).  Whatever it decides is verified with the exact
+// arithmetic; a wrong guess only shortens a window.
+static __device__ __forceinline__ double giant_lb_approx(long long k, long long n, double p, double logp, double log1mp,
+                                                         double log2pi, const double* __restrict__ logtab, int ntab) {
+    const double dn = (double)n;
+    if (dn * p <= 5 || dn * (1 - p) <= 5) return log_binomial_dev(k, n, p, logp, log1mp, log2pi, logtab, ntab);
+    const double mu = dn * p, sig = mu * (1 - p), d = (double)k - mu;
+    return -(d * d) * __drcp_rn(2 * sig) - 0.5 * (log2pi + (double)__logf((float)sig));
+}
 
 // MAXE = compile-time bound of the experiments (2 or 4).
 template <int NT, int MAXE>
 __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ DevRun R) {
     using LY = GiantLayout<NT, MAXE>;
-    constexpr int MD = LY::MD, DW = LY::DW;
+    constexpr int MD = LY::MD, NW = LY::NW;
     extern __shared__ __align__(16) unsigned char giant_smem[];
     double* sT = (double*)(giant_smem + LY::o_T);
     double* lpbuf = (double*)(giant_smem + LY::o_lp);
-    unsigned long long* sj = (unsigned long long*)(giant_smem + LY::o_sj);
-    long long* wtot = (long long*)(giant_smem + LY::o_wtot);
-    int* a0_s = (int*)(giant_smem + LY::o_a0);
-    int* n_s = (int*)(giant_smem + LY::o_n);
-    int* prev_s = (int*)(giant_smem + LY::o_prev);
+    long long* wtot = (long long*)(giant_smem + LY::o_wtot);   // [warp][2 * MAXE]: accepted (dE, dL) of the warp
+    int* wlast = (int*)(giant_smem + LY::o_wlast);             // [warp][MAXE]: last accepted proposal of the warp touching x
+    double* nls = (double*)(giant_smem + LY::o_nls);           // [x][p]: logBinomial of experiment x after accepted proposal p
     int* ent = (int*)(giant_smem + LY::o_ent);        // [e][p]: slot << 1 | (1 = increment)
     int* ecnt = (int*)(giant_smem + LY::o_ecnt);      // [e][p]: count of the slot before the entry applies
     int* mv = (int*)(giant_smem + LY::o_mv);          // [q][p]: AlterSV: fragment << 1 | (1 = currently unmapped)
@@ -182,11 +187,9 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
     int* hlane = (int*)(giant_smem + LY::o_hlane);
     unsigned* rtab = (unsigned*)(giant_smem + LY::o_rtab);
     unsigned* rmsk = (unsigned*)(giant_smem + LY::o_rmsk);
-    unsigned short* list = (unsigned short*)(giant_smem + LY::o_list);
-    unsigned short* lrank = (unsigned short*)(giant_smem + LY::o_lrank);
     struct Scalars {
         unsigned long long s_base, jumpA, jumpC, bar;
-        long long Etot[MAXE], Ltot[MAXE], accE[MAXE], accL[MAXE];
+        long long Etot[MAXE], Ltot[MAXE];
         double LB[MAXE];
         unsigned long long cnt[5];
         int fin[4];
@@ -225,6 +228,9 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
     auto lb_of = [&](int x, long long e, long long l) -> double {
         return log_binomial_dev(wrapi(e), wrapi(l), P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi, P.logint, P.maxn);
     };
+    // slot = cluster * E + experiment (one and two experiments without an integer division)
+    auto slot_exp = [&](int slot) -> int { return E == 1 ? 0 : E == 2 ? (slot & 1) : slot % E; };
+    auto slot_cluster = [&](int slot) -> int { return E == 1 ? slot : E == 2 ? (slot >> 1) : slot / E; };
     auto hash_of = [](int key) -> unsigned { return (((unsigned)key * 2654435761u) >> 19) & (GIANT_HASH - 1); };
 
     // ---- setup: TMA-staged logprobcov, zeroed state, scalars ----
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         JavaRandom r0; r0.seed(R.seed + chain);
         sc.s_base = r0.s;
         sc.iter_base = 0; sc.done = 0; sc.err = 0; sc.nerr = 0; sc.frag_base = 0;
-        for (int x = 0; x < MAXE; ++x) { sc.Etot[x] = 0; sc.Ltot[x] = 0; sc.accE[x] = 0; sc.accL[x] = 0; sc.LB[x] = 0.0; }
+        for (int x = 0; x < MAXE; ++x) { sc.Etot[x] = 0; sc.Ltot[x] = 0; sc.LB[x] = 0.0; }
         for (int i = 0; i < 5; ++i) sc.cnt[i] = 0;
     }
     __syncthreads();
@@ -395,53 +401,65 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
     long long n_reassign = 0;
     int nerr_delta = 0;                                                   // unmapped fragments: net change committed by this thread
     if (tid == 0) sc.done = N <= 0;
+    // logBinomial of the current totals (the chain's cached "old" value): computed once, then handed from window to window
+    if (tid < E) sc.LB[tid] = lb_of(tid, sc.Etot[tid], sc.Ltot[tid]);
     __syncthreads();
+#ifdef MBSV_GIANT_PROF
+    long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
+    long long nwindows = 0, ncuts = 0;
+#define GPROF(i) do { if (tid == 0) { const long long c_ = clock64(); prof[i] += c_ - pc; pc = c_; } } while (0)
+    if (tid == 0) pc = clock64();
+    // per-thread step times inside the gather: maximum over the threads of a window, summed over the windows
+    __shared__ int pmax[12];
+    long long ptot[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp0 = 0;
+    if (tid < 12) pmax[tid] = 0;
+#define TPROF(i) do { const long long c_ = clock64(); atomicMax(&pmax[i], (int)(c_ - tp0)); tp0 = c_; } while (0)
+#else
+#define GPROF(i) do {} while (0)
+#define TPROF(i) do {} while (0)
+#endif
     while (!sc.done) {
         // ================= P1: one iteration per offset =================
         const unsigned long long sb = sc.s_base;
         const int iter_base = sc.iter_base;
         if (tid == 0) { sc.cut = GIANT_NOCUT; sc.errlane = GIANT_NOCUT; }
-        if (tid < E) sc.LB[tid] = lb_of(tid, sc.Etot[tid], sc.Ltot[tid]);
-        if (tid >= 32 && tid < 32 + MAXE) { sc.accE[tid - 32] = 0; sc.accL[tid - 32] = 0; }
-        for (int i = tid; i < GIANT_HASH; i += NT) { hkey[i] = -1; hlane[i] = GIANT_NOCUT; }
         JavaRandom rng;
         rng.s = jA * sb + jC;
-        sj[tid] = rng.s;
         int c = 1;
-        bool dense = false;
+        bool dense = false, naive = false;
+        int f = 0;                                                        // Naive: the fragment; AlterSV: the candidate
+        unsigned long long m53 = 0, s_mid = 0;                            // s_mid: state after the fragment / candidate pick
         {
             const unsigned long long m0 = rng.bits53();
             if (m0 >= (1ULL << 52)) {                                     // !(nextDouble() < 0.5)
                 dense = true;
-                bool nv = true;
-                if (nsv == 0) rng.skip<2>(); else nv = rng.bits53() < NAIVE_THR;
+                naive = true;
+                if (nsv == 0) rng.skip<2>(); else naive = rng.bits53() < NAIVE_THR;
                 const double u = rng.nextDouble();
-                if (nv) {
-                    const int ff = (int)(u * dF);
-                    const int fa0 = P.frag_aln_ptr[f0 + ff];
-                    const int n = P.frag_aln_ptr[f0 + ff + 1] - fa0;
-                    const int pv = st.ld(ff);
-                    const unsigned long long m53 = rng.bits53();
-                    const bool from_err = pv == -1;
-                    const bool to_err = !from_err && (m53 < perr_thr || n == 1);
-                    c = 5 + ((!from_err && !to_err) ? 1 : 0);
-                    a0_s[tid] = fa0; n_s[tid] = n; prev_s[tid] = pv;
-                } else c = 4;
+                s_mid = rng.s;
+                if (naive) { f = (int)(u * dF); m53 = rng.bits53(); } else { f = sv0 + (int)(u * (double)nsv); c = 4; }
             }
         }
+        int a0 = 0, fa1 = 0, prev = -1;
+        if (naive) { a0 = __ldg(P.frag_aln_ptr + f0 + f); fa1 = __ldg(P.frag_aln_ptr + f0 + f + 1); prev = st.ld(f); }
+        for (int i = tid; i < GIANT_HASH; i += NT) { hkey[i] = -1; hlane[i] = GIANT_NOCUT; }
+        const int n = fa1 - a0;
+        if (naive) {
+            const bool from_err = prev == -1;
+            const bool to_err = !from_err && (m53 < perr_thr || n == 1);
+            c = 5 + ((!from_err && !to_err) ? 1 : 0);
+        }
+        GPROF(0);
         // ================= P2: which offsets are iterations =================
         const GiantReach rr = giant_reach<NT>(c, dense, rtab, rmsk, sc.fin);
-        if (rr.reach) {
-            if (dense) { list[rr.drank] = (unsigned short)tid; lrank[rr.drank] = (unsigned short)rr.rank; }
-            if (iter_base + rr.rank == N) atomicMin(&sc.cut, tid);       // the run ends in front of this offset
-        }
-        __syncthreads();
-        const int M = sc.fin[1];
-        // ================= P3: gather + tentative evaluation (dense threads) =================
-        const int p = tid;
-        const bool act = p < M;
-        int j = 0, jnext = 0, f = -1, a0 = 0, prev = -1, now = -1, nmoves = 0, nent = 0, t_iter = 0;
-        bool naive = true, bad = false, flagA = false, flagB = false;
+        const bool act = rr.reach && dense;                               // this thread's offset is a proposal of the chain
+        const int p = rr.drank;                                           // its slot in the per-proposal arrays
+        const int t_iter = iter_base + rr.rank;
+        if (rr.reach && t_iter == N) atomicMin(&sc.cut, tid);             // the run ends in front of this offset
+        GPROF(1);
+        // ================= P3: gather + tentative decision =================
+        int now = -1, nmoves = 0, nent = 0, q0 = 0;
+        bool bad = false, flagA = false, flagB = false;
         double dcov = 0.0, derr = 0.0, Alogq = 0.0, Anewlogq = 0.0, r_acc = 0.0;
         long long dE[MAXE], dL[MAXE];
 #pragma unroll
@@ -449,198 +467,293 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         unsigned touched = 0;
         int dnerr = 0;
         long long reassign = 0;
+#ifdef MBSV_GIANT_PROF
+        tp0 = clock64();
+#endif
         if (act) {
-            j = list[p];
-            t_iter = iter_base + lrank[p];
-            rng.s = sj[j];
-            rng.skip<2>();                                                // the lazy coin
-            if (nsv == 0) rng.skip<2>(); else naive = rng.bits53() < NAIVE_THR;
-            const double u = rng.nextDouble();
+            rng.s = s_mid;
             if (naive) {
-                f = (int)(u * dF);
-                a0 = a0_s[j];
-                const int n = n_s[j];
-                prev = prev_s[j];
-                const unsigned long long before = rng.s;
-                naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
-                jnext = j + 5 + ((rng.s != before * JavaRandom::MULT2 + JavaRandom::ADD2) ? 1 : 0);
+                naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, P.invint, now, Alogq, Anewlogq);
+                TPROF(0);
                 reassign = 1;
                 if (now == prev) {                                        // Error at MultiBreakSV.java:1122-1123
                     bad = true;
-                    atomicMin(&sc.cut, j);
-                    atomicMin(&sc.errlane, j);
+                    atomicMin(&sc.cut, tid);
+                    atomicMin(&sc.errlane, tid);
                 } else {
+                    // one round trip: both alignment records and their counted slots
                     int4 recF = make_int4(0, 0, 0, 0), recT = make_int4(0, 0, 0, 0);
-                    if (prev != -1) recF = P.aln_rec[a0 + prev];
-                    if (now != -1) recT = P.aln_rec[a0 + now];
+                    int4 slF = make_int4(-1, -1, -1, -1), slT = make_int4(-1, -1, -1, -1);
+                    if (prev != -1) { recF = __ldg(P.aln_rec + a0 + prev); slF = __ldg(P.aln_ent4 + a0 + prev); }
+                    if (now != -1) { recT = __ldg(P.aln_rec + a0 + now); slT = __ldg(P.aln_ent4 + a0 + now); }
+#ifdef MBSV_GIANT_PROF
+                    if (recF.x + recT.x + slF.x + slT.x == 0x7ffffff0) printf("x");     // (profile build: wait for the loads here)
+#endif
+                    TPROF(1);
                     if (prev != -1) {
-                        const int x = recF.w & 0xff, ne = recF.w >> 8;
-                        for (int k = 0; k < ne; ++k) {
-                            const int slot = P.aln_esp_slot[recF.z + k];
-                            if (slot >= 0) { ent[nent * MD + p] = slot << 1; ++nent; }
-                        }
+                        const int x = recF.w & 0xff;
+                        const int sl[4] = {slF.x, slF.y, slF.z, slF.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (sl[k] >= 0) { ent[nent * MD + p] = sl[k] << 1; ++nent; }
 #pragma unroll
                         for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] -= recF.x; dL[y] -= recF.y; }
                         touched |= 1u << x;
                     } else { derr = derr - logperr; --dnerr; }
                     if (now != -1) {
-                        const int x = recT.w & 0xff, ne = recT.w >> 8;
-                        for (int k = 0; k < ne; ++k) {
-                            const int slot = P.aln_esp_slot[recT.z + k];
-                            if (slot >= 0) { ent[nent * MD + p] = (slot << 1) | 1; ++nent; }
-                        }
+                        const int x = recT.w & 0xff;
+                        const int sl[4] = {slT.x, slT.y, slT.z, slT.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (sl[k] >= 0) { ent[nent * MD + p] = (sl[k] << 1) | 1; ++nent; }
 #pragma unroll
                         for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] += recT.x; dL[y] += recT.y; }
                         touched |= 1u << x;
                     } else { derr = derr + logperr; ++dnerr; }
+                    TPROF(2);
                 }
             } else {
                 // ---- svMove (MultiBreakSV.java:1291-1343): toggle the cluster's single-alignment fragments ----
-                const int svk = (int)(u * (double)nsv);
-                jnext = j + 4;
-                reassign = P.sv_numchanged[sv0 + svk];
-                const int q0 = P.sv_frag_ptr[sv0 + svk];
-                nmoves = P.sv_frag_ptr[sv0 + svk + 1] - q0;
+                // round trip 1: the candidate's fragment list and entry list
+                q0 = __ldg(P.sv_frag_ptr + f);
+                const int q1 = __ldg(P.sv_frag_ptr + f + 1);
+                const int e0 = __ldg(P.sv_ent_ptr + f), e1 = __ldg(P.sv_ent_ptr + f + 1);
+                reassign = __ldg(P.sv_numchanged + f);
+                nmoves = q1 - q0;
+                nent = e1 - e0;
                 Alogq = neglogNsv;
                 Anewlogq = neglogNsv;
-                for (int q = 0; q < nmoves; ++q) mv[q * MD + p] = P.sv_frag[q0 + q] - f0;
-                for (int q = 0; q < nmoves; ++q) {                        // independent loads: current assignment of each fragment
-                    const int g = mv[q * MD + p];
-                    mv[q * MD + p] = (g << 1) | (st.ld(g) == -1 ? 1 : 0);
+                TPROF(3);
+                // round trip 2: fragments and slots (four loads in flight at a time)
+                for (int qb = 0; qb < nmoves; qb += 4) {
+                    int g[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) g[i] = qb + i < nmoves ? __ldg(&P.sv_mv[q0 + qb + i].x) : 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (qb + i < nmoves) mv[(qb + i) * MD + p] = g[i];
                 }
-                for (int q = 0; q < nmoves; ++q) {
-                    const int g = mv[q * MD + p] >> 1;
-                    const bool from_err = mv[q * MD + p] & 1;
-                    const int4 rec = P.aln_rec[P.frag_aln_ptr[f0 + g]];   // its only alignment
-                    const int x = rec.w & 0xff, ne = rec.w >> 8;
-                    for (int k = 0; k < ne; ++k) {
-                        const int slot = P.aln_esp_slot[rec.z + k];
-                        if (slot >= 0) { ent[nent * MD + p] = (slot << 1) | (from_err ? 1 : 0); ++nent; }
-                    }
-                    if (from_err) {                                       // -1 -> 0
+                for (int kb = 0; kb < nent; kb += 4) {
+                    int2 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = kb + i < nent ? __ldg(P.sv_ent + e0 + kb + i) : make_int2(0, 0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (kb + i < nent) ent[(kb + i) * MD + p] = (v[i].x << 5) | v[i].y;
+                }
+                TPROF(4);
+                // round trip 3 (first half; the counts follow below): current assignment of every fragment
+                for (int qb = 0; qb < nmoves; qb += 4) {
+                    int a[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = qb + i < nmoves ? st.ld(mv[(qb + i) * MD + p]) : 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (qb + i < nmoves) mv[(qb + i) * MD + p] = (mv[(qb + i) * MD + p] << 1) | (a[i] == -1 ? 1 : 0);
+                }
+                TPROF(5);
+                for (int k = 0; k < nent; ++k) {                          // direction of every entry = direction of its fragment
+                    const int v = ent[k * MD + p];
+                    ent[k * MD + p] = ((v >> 5) << 1) | (mv[(v & 31) * MD + p] & 1);
+                }
+                for (int q = 0; q < nmoves; ++q) {                        // (records again: cached)
+                    const int4 m = __ldg(P.sv_mv + q0 + q);
+                    const int x = m.w;
+                    if (mv[q * MD + p] & 1) {                             // -1 -> 0
                         derr = derr - logperr; --dnerr;
 #pragma unroll
-                        for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] += rec.x; dL[y] += rec.y; }
+                        for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] += m.y; dL[y] += m.z; }
                     } else {                                              // 0 -> -1
 #pragma unroll
-                        for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] -= rec.x; dL[y] -= rec.y; }
+                        for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] -= m.y; dL[y] -= m.z; }
                         derr = derr + logperr; ++dnerr;
                     }
                     touched |= 1u << x;
                 }
             }
+            if (!naive) TPROF(6);
             r_acc = rng.nextDouble();
             if (!bad) {
                 // counts the entries see: the stored count plus the earlier entries of this proposal on the same slot
-                for (int k = 0; k < nent; ++k) ecnt[k * MD + p] = st.ld(F + (ent[k * MD + p] >> 1));
+                for (int kb = 0; kb < nent; kb += 4) {
+                    int v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = kb + i < nent ? st.ld(F + (ent[(kb + i) * MD + p] >> 1)) : 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (kb + i < nent) ecnt[(kb + i) * MD + p] = v[i];
+                }
+                TPROF(7);
                 for (int k = 0; k < nent; ++k) {
                     const int ek = ent[k * MD + p];
-                    int n = ecnt[k * MD + p];
+                    int cn = ecnt[k * MD + p];
                     for (int k2 = 0; k2 < k; ++k2) {
                         const int e2 = ent[k2 * MD + p];
-                        if ((e2 >> 1) == (ek >> 1)) n += (e2 & 1) ? 1 : -1;
+                        if ((e2 >> 1) == (ek >> 1)) cn += (e2 & 1) ? 1 : -1;
                     }
-                    ecnt[k * MD + p] = n;
-                    const double* Tx = Tp + (size_t)((ek >> 1) % E) * Tstride;
-                    dcov = dcov + (Tx[n + ((ek & 1) ? 1 : -1)] - Tx[n]);
+                    ecnt[k * MD + p] = cn;
+                    const double* Tx = Tp + (size_t)slot_exp(ek >> 1) * Tstride;
+                    dcov = dcov + (Tx[cn + ((ek & 1) ? 1 : -1)] - Tx[cn]);
                 }
+                TPROF(8);
+                // tentative decision against the totals at the window start (approximate arithmetic, see giant_lb_approx)
+                double dlb = 0.0;
+                unsigned mask = touched & ((1u << E) - 1u);
+                while (mask) {
+                    const int x = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    long long de = 0, dl = 0;
+#pragma unroll
+                    for (int y = 0; y < MAXE; ++y) if (y == x) { de = dE[y]; dl = dL[y]; }
+                    dlb += giant_lb_approx(wrapi(sc.Etot[x] + de), wrapi(sc.Ltot[x] + dl), P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x],
+                                           P.log2pi, P.logint, P.maxn) -
+                           giant_lb_approx(wrapi(sc.Etot[x]), wrapi(sc.Ltot[x]), P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x],
+                                           P.log2pi, P.logint, P.maxn);
+                }
+                const double arg = ((dcov + derr) + dlb + Alogq) - Anewlogq;
+                const double e = (double)__expf((float)arg);
+                flagA = fmin(1.0, e) > r_acc;                             // (NaN: not accepted, like the exact test)
+                TPROF(9);
             }
         }
-        auto evaluate = [&](const long long* Ecur, const long long* Lcur, const bool cached_old) -> bool {
+        GPROF(2);
+        // ================= P4: exact totals per proposal: prefix sums over the tentatively accepted ones =================
+        long long pre[2 * MAXE];                                         // inclusive prefix of (dE, dL)
+        int last[MAXE];                                                   // last accepted proposal touching x, this one included
+#pragma unroll
+        for (int x = 0; x < MAXE; ++x) {
+            pre[x] = flagA ? dE[x] : 0; pre[MAXE + x] = flagA ? dL[x] : 0;
+            last[x] = (flagA && ((touched >> x) & 1u)) ? p : -1;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int v = 0; v < 2 * MAXE; ++v) {
+                const long long y = __shfl_up_sync(0xffffffffu, pre[v], o);
+                if (lane >= o) pre[v] += y;
+            }
+#pragma unroll
+            for (int x = 0; x < MAXE; ++x) {
+                const int y = __shfl_up_sync(0xffffffffu, last[x], o);
+                if (lane >= o) last[x] = max(last[x], y);
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int v = 0; v < 2 * MAXE; ++v) wtot[wid * 2 * MAXE + v] = pre[v];
+#pragma unroll
+            for (int x = 0; x < MAXE; ++x) wlast[wid * MAXE + x] = last[x];
+        }
+        // exclusive within the warp
+        long long Ecur[MAXE], Lcur[MAXE];
+        int lastx[MAXE];
+#pragma unroll
+        for (int x = 0; x < MAXE; ++x) {
+            Ecur[x] = pre[x] - (flagA ? dE[x] : 0);
+            Lcur[x] = pre[MAXE + x] - (flagA ? dL[x] : 0);
+            const int y = __shfl_up_sync(0xffffffffu, last[x], 1);
+            lastx[x] = lane > 0 ? y : -1;
+        }
+        __syncthreads();
+        for (int k = 0; k < wid; ++k) {
+#pragma unroll
+            for (int x = 0; x < MAXE; ++x) {
+                Ecur[x] += wtot[k * 2 * MAXE + x];
+                Lcur[x] += wtot[k * 2 * MAXE + MAXE + x];
+                lastx[x] = max(lastx[x], wlast[k * MAXE + x]);
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < MAXE; ++x) { Ecur[x] += sc.Etot[x]; Lcur[x] += sc.Ltot[x]; }   // the totals this offset would see
+        GPROF(3);
+        // logBinomial of the totals AFTER this proposal; the accepted ones publish it: it is the "old" value of whoever follows
+        double nl[MAXE];
+#pragma unroll
+        for (int x = 0; x < MAXE; ++x) nl[x] = 0.0;
+        if (act && !bad) {
+            unsigned mask = touched & ((1u << E) - 1u);
+            while (mask) {
+                const int x = __ffs(mask) - 1;
+                mask &= mask - 1;
+                long long ex = 0, lx = 0;
+#pragma unroll
+                for (int y = 0; y < MAXE; ++y) if (y == x) { ex = Ecur[y] + dE[y]; lx = Lcur[y] + dL[y]; }
+                const double v = lb_of(x, ex, lx);
+#pragma unroll
+                for (int y = 0; y < MAXE; ++y) if (y == x) nl[y] = v;
+                if (flagA) nls[x * MD + p] = v;
+            }
+        }
+        __syncthreads();
+        GPROF(4);
+        if (act && !bad) {
+            // ---- the exact decision (MultiBreakSV.java:1146), FAST arithmetic ----
             double dlb = 0.0;
             unsigned mask = touched & ((1u << E) - 1u);
             while (mask) {
                 const int x = __ffs(mask) - 1;
                 mask &= mask - 1;
-                long long ex = 0, lx = 0, de = 0, dl = 0;
+                double nlx = 0.0;
+                int lx = -1;
 #pragma unroll
-                for (int y = 0; y < MAXE; ++y) if (y == x) { ex = Ecur[y]; lx = Lcur[y]; de = dE[y]; dl = dL[y]; }
-                const double old = cached_old ? sc.LB[x] : lb_of(x, ex, lx);
-                const double nl = lb_of(x, ex + de, lx + dl);
-                dlb = dlb + (nl - old);
+                for (int y = 0; y < MAXE; ++y) if (y == x) { nlx = nl[y]; lx = lastx[y]; }
+                const double old = lx >= 0 ? nls[x * MD + lx] : sc.LB[x];
+                dlb = dlb + (nlx - old);
             }
             const double delta = (dcov + derr) + dlb;
             const double arg = (delta + Alogq) - Anewlogq;
             const double e = exp_dev(arg);
             const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);      // Math.min(1, e)
-            return ratio > r_acc;
-        };
-        long long Ecur[MAXE], Lcur[MAXE];
-#pragma unroll
-        for (int x = 0; x < MAXE; ++x) { Ecur[x] = sc.Etot[x]; Lcur[x] = sc.Ltot[x]; }
-        if (act && !bad) flagA = evaluate(Ecur, Lcur, true);
-        // ================= P4: exact totals per proposal (prefix sum over the tentatively accepted ones) =================
-        long long pre[2 * MAXE];
-#pragma unroll
-        for (int v = 0; v < 2 * MAXE; ++v) pre[v] = 0;
-        if (wid < DW) {
-#pragma unroll
-            for (int x = 0; x < MAXE; ++x) { pre[x] = flagA ? dE[x] : 0; pre[MAXE + x] = flagA ? dL[x] : 0; }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-                for (int v = 0; v < 2 * MAXE; ++v) {
-                    const long long y = __shfl_up_sync(0xffffffffu, pre[v], o);
-                    if (lane >= o) pre[v] += y;
-                }
-            }
-            if (lane == 31) {
-#pragma unroll
-                for (int v = 0; v < 2 * MAXE; ++v) wtot[wid * 2 * MAXE + v] = pre[v];
-            }
+            flagB = ratio > r_acc;
+            if (flagB != flagA) atomicMin(&sc.cut, tid);                  // the hypothesis fails here: redo from this iteration
         }
-        __syncthreads();
-        if (act && !bad) {
+        // ================= P5: stale reads.  Accepted proposals publish the rows they write ... =================
+        const int nfr = naive ? 1 : nmoves;
+        const int nkeys = (act && !bad) ? nfr + nent : 0;
+        auto key_at = [&](int i) -> int { return i < nfr ? (naive ? f : (mv[i * MD + p] >> 1)) : F + (ent[(i - nfr) * MD + p] >> 1); };
+        if (flagB) {
+            bool ok = true;
+            for (int kb = 0; kb < nkeys; kb += 4) {
+                int key[4], old[4];
+                unsigned h[4];
 #pragma unroll
-            for (int x = 0; x < MAXE; ++x) {
-                long long be = pre[x] - (flagA ? dE[x] : 0), bl = pre[MAXE + x] - (flagA ? dL[x] : 0);   // exclusive
-                for (int k = 0; k < wid; ++k) { be += wtot[k * 2 * MAXE + x]; bl += wtot[k * 2 * MAXE + MAXE + x]; }
-                Ecur[x] = sc.Etot[x] + be;
-                Lcur[x] = sc.Ltot[x] + bl;
-            }
-            flagB = evaluate(Ecur, Lcur, false);
-            if (flagB != flagA) atomicMin(&sc.cut, j);                     // the hypothesis fails here: redo from this iteration
-            // ================= P5a: rows an accepted proposal writes =================
-            if (flagB) {
-                bool ok = true;
-                auto insert = [&](int key) {
-                    unsigned h = hash_of(key);
-                    for (int guard = 0; guard < GIANT_HASH; ++guard) {
-                        const int old = atomicCAS(&hkey[h], -1, key);
-                        if (old == -1 || old == key) { atomicMin(&hlane[h], p); return; }
-                        h = (h + 1) & (GIANT_HASH - 1);
+                for (int i = 0; i < 4; ++i) if (kb + i < nkeys) { key[i] = key_at(kb + i); h[i] = hash_of(key[i]); old[i] = atomicCAS(&hkey[h[i]], -1, key[i]); }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (kb + i < nkeys) {
+                    bool placed = old[i] == -1 || old[i] == key[i];
+                    for (int guard = 0; !placed && guard < GIANT_HASH; ++guard) {
+                        h[i] = (h[i] + 1) & (GIANT_HASH - 1);
+                        const int o = atomicCAS(&hkey[h[i]], -1, key[i]);
+                        placed = o == -1 || o == key[i];
                     }
-                    ok = false;
-                };
-                if (naive) insert(f); else for (int q = 0; q < nmoves; ++q) insert(mv[q * MD + p] >> 1);
-                for (int k = 0; k < nent; ++k) insert(F + (ent[k * MD + p] >> 1));
-                // set full (cannot happen below ~4000 written rows per window): nothing behind this proposal is committed
-                if (!ok && jnext < NT) atomicMin(&sc.cut, jnext);
-            }
-        }
-        __syncthreads();
-        // ================= P5b: first proposal that read a row written in front of it =================
-        if (act && !bad) {
-            auto stale = [&](int key) -> bool {
-                unsigned h = hash_of(key);
-                for (int guard = 0; guard < GIANT_HASH; ++guard) {
-                    const int k = hkey[h];
-                    if (k == -1) return false;
-                    if (k == key) return hlane[h] < p;
-                    h = (h + 1) & (GIANT_HASH - 1);
+                    if (placed) atomicMin(&hlane[h[i]], tid); else ok = false;
                 }
-                return false;
-            };
-            bool s = false;
-            if (naive) s = stale(f); else for (int q = 0; q < nmoves; ++q) s = s || stale(mv[q * MD + p] >> 1);
-            for (int k = 0; k < nent; ++k) s = s || stale(F + (ent[k * MD + p] >> 1));
-            if (s) atomicMin(&sc.cut, j);
+            }
+            // set full (cannot happen below ~4000 written rows per window): nothing behind this proposal is committed
+            if (!ok && tid + c < NT) atomicMin(&sc.cut, tid + c);
         }
         __syncthreads();
+        GPROF(5);
+        // ... and the first proposal that read a row written in front of it cuts the window
+        if (nkeys) {
+            bool stale = false;
+            for (int kb = 0; kb < nkeys; kb += 4) {
+                int key[4], k0[4], l0[4];
+                unsigned h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (kb + i < nkeys) { key[i] = key_at(kb + i); h[i] = hash_of(key[i]); k0[i] = hkey[h[i]]; l0[i] = hlane[h[i]]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (kb + i < nkeys) {
+                    int k = k0[i], l = l0[i];
+                    for (int guard = 0; k != -1 && k != key[i] && guard < GIANT_HASH; ++guard) {
+                        h[i] = (h[i] + 1) & (GIANT_HASH - 1);
+                        k = hkey[h[i]]; l = hlane[h[i]];
+                    }
+                    if (k == key[i] && l < tid) stale = true;
+                }
+            }
+            if (stale) atomicMin(&sc.cut, tid);
+        }
+        __syncthreads();
+        GPROF(6);
         // ================= P6: commit the iterations in front of the cut =================
         const int cut = sc.cut;
         const int errlane = sc.errlane;
-        if (act && j < cut) {
+        if (act && tid < cut) {
             if (naive) ++n_naive_prop; else ++n_sv_prop;
             n_reassign += reassign;
             if (flagB) {
@@ -649,12 +762,12 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 const unsigned d = t_iter > win_base ? (unsigned)(t_iter - win_base) : 0u;
                 for (int k = 0; k < nent; ++k) {
                     const int ek = ent[k * MD + p];
-                    const int slot = ek >> 1, n = ecnt[k * MD + p], n2 = n + ((ek & 1) ? 1 : -1);
-                    st.stw(F + slot, n2);
+                    const int slot = ek >> 1, cn = ecnt[k * MD + p], cn2 = cn + ((ek & 1) ? 1 : -1);
+                    st.stw(F + slot, cn2);
                     if (d) {
-                        unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
-                        if (n > 0) atomicAdd(&h[n], d);
-                        if (n2 > 0) atomicAdd(&h[n2], 0u - d);
+                        unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot_cluster(slot)];
+                        if (cn > 0) atomicAdd(&h[cn], d);
+                        if (cn2 > 0) atomicAdd(&h[cn2], 0u - d);
                     }
                 }
                 if (naive) {
@@ -675,38 +788,56 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                         }
                     }
                 }
-#pragma unroll
-                for (int x = 0; x < MAXE; ++x) {
-                    if (dE[x]) atomicAdd((unsigned long long*)&sc.accE[x], (unsigned long long)dE[x]);
-                    if (dL[x]) atomicAdd((unsigned long long*)&sc.accL[x], (unsigned long long)dL[x]);
-                }
             }
         }
-        if (act && bad && j == cut) {
+        if (act && bad && tid == cut) {
             // the reference throws here: the chain stops with the proposal counted and its draws consumed
             ++n_naive_prop; n_reassign += 1;
             sc.s_base = rng.s;
             sc.err = -5;                                                  // MBSV_ERR_INVARIANT
             sc.done = 1;
         }
-        // base of the next window
+        // base of the next window: RNG position, iteration count, totals (= what the first uncommitted offset would see)
         if (cut == GIANT_NOCUT) {
-            if (tid == 0) {
+            if (tid == NT - 1) {
                 unsigned long long s = sc.jumpA * sb + sc.jumpC;
                 for (int i = 0; i < sc.fin[2]; ++i) s = s * JavaRandom::MULT2 + JavaRandom::ADD2;
                 sc.s_base = s;
                 sc.iter_base = iter_base + sc.fin[0];
                 if (iter_base + sc.fin[0] >= N) sc.done = 1;
+#pragma unroll
+                for (int x = 0; x < MAXE; ++x) {
+                    sc.Etot[x] = Ecur[x] + (flagA ? dE[x] : 0); sc.Ltot[x] = Lcur[x] + (flagA ? dL[x] : 0);
+                    if (flagA && ((touched >> x) & 1u)) sc.LB[x] = nl[x]; else if (lastx[x] >= 0) sc.LB[x] = nls[x * MD + lastx[x]];
+                }
             }
         } else if (tid == cut && cut != errlane) {
-            sc.s_base = sj[tid];
-            sc.iter_base = iter_base + rr.rank;
-            if (iter_base + rr.rank >= N) sc.done = 1;
+            sc.s_base = jA * sb + jC;
+            sc.iter_base = t_iter;
+            if (t_iter >= N) sc.done = 1;
+#pragma unroll
+            for (int x = 0; x < MAXE; ++x) {
+                sc.Etot[x] = Ecur[x]; sc.Ltot[x] = Lcur[x];
+                if (lastx[x] >= 0) sc.LB[x] = nls[x * MD + lastx[x]];      // logBinomial after the last committed accepted move
+            }
         }
         __syncthreads();
-        if (tid < MAXE) { sc.Etot[tid] += sc.accE[tid]; sc.Ltot[tid] += sc.accL[tid]; }
-        __syncthreads();
+        GPROF(7);
+#ifdef MBSV_GIANT_PROF
+        ++nwindows; if (cut != GIANT_NOCUT) ++ncuts;
+        if (tid == 0) for (int i = 0; i < 12; ++i) { ptot[i] += pmax[i]; pmax[i] = 0; }
+#endif
     }
+#ifdef MBSV_GIANT_PROF
+    if (tid == 0 && blockIdx.x == 0)
+        printf("giant prof: windows %lld cuts %lld iters %d | cycles/window: P1 %lld reach %lld gather+A %lld scan %lld nl %lld evalB+ins %lld stale %lld commit %lld\n",
+               nwindows, ncuts, N, prof[0] / max(nwindows, 1LL), prof[1] / max(nwindows, 1LL), prof[2] / max(nwindows, 1LL), prof[3] / max(nwindows, 1LL),
+               prof[4] / max(nwindows, 1LL), prof[5] / max(nwindows, 1LL), prof[6] / max(nwindows, 1LL), prof[7] / max(nwindows, 1LL));
+    if (tid == 0 && blockIdx.x == 0)
+        printf("giant prof (max over threads): naive: pick %lld rt1 %lld entries %lld | sv: rt1 %lld rt2 %lld rt3 %lld dir+rec %lld | counts %lld dcov %lld approxA %lld\n",
+               ptot[0] / max(nwindows, 1LL), ptot[1] / max(nwindows, 1LL), ptot[2] / max(nwindows, 1LL), ptot[3] / max(nwindows, 1LL), ptot[4] / max(nwindows, 1LL),
+               ptot[5] / max(nwindows, 1LL), ptot[6] / max(nwindows, 1LL), ptot[7] / max(nwindows, 1LL), ptot[8] / max(nwindows, 1LL), ptot[9] / max(nwindows, 1LL));
+#endif
 
     // ---------------- epilogue: final tallies, state, counters ----------------
     {
@@ -729,7 +860,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
             const int nslot = C * E;
             for (int s = tid; s < nslot; s += NT) {
                 const int n = st.ld(F + s);
-                if (n > 0) atomicAdd(&R.cluster_hist[P.cluster_hist_ptr[c0 + s / E] + n], d);
+                if (n > 0) atomicAdd(&R.cluster_hist[P.cluster_hist_ptr[c0 + slot_cluster(s)] + n], d);
             }
         }
     }

@@ -1,6 +1,30 @@
 // Speculative-window kernel: one CTA per (subproblem, chain) (giant_kernel.cuh).
+// logBinomial / exp are inlined here: a proposal evaluates two or three of them back to back, independent of each other,
+// and only a handful of warps are active, so instruction-level overlap is worth more than code size.
+#define MBSV_INLINE_MATH 1
 #include "giant_kernel.cuh"
 namespace mbsv {
+
+// aln_ent4[a] = the counted slots (aln_esp_slot >= 0) of alignment a in ESP order, -1 padded
+__global__ void mbsv_giant_prep_kernel(const __grid_constant__ DevProblem P, int4* __restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P.n_aln) return;
+    const int4 rec = P.aln_rec[a];
+    const int ne = rec.w >> 8;
+    int s[GIANT_ALN_SLOTS] = {-1, -1, -1, -1};
+    int n = 0;
+    for (int j = 0; j < ne; ++j) {
+        const int slot = P.aln_esp_slot[rec.z + j];
+        if (slot >= 0 && n < GIANT_ALN_SLOTS) s[n++] = slot;
+    }
+    out[a] = make_int4(s[0], s[1], s[2], s[3]);
+}
+
+cudaError_t launch_giant_prep(const DevProblem& P, int4* aln_ent4, cudaStream_t stream) {
+    mbsv_giant_prep_kernel<<<(P.n_aln + 255) / 256, 256, 0, stream>>>(P, aln_ent4);
+    return cudaGetLastError();
+}
+
 KernelFn get_kernel_giant(int n_exp, int* threads, size_t* smem_bytes) {
     constexpr int NT = 512;
     *threads = NT;
@@ -9,4 +33,5 @@ KernelFn get_kernel_giant(int n_exp, int* threads, size_t* smem_bytes) {
     return mbsv_giant_kernel<NT, 4>;
 }
 int giant_max_entries() { return GIANT_MAXENT < GIANT_MAXMV ? GIANT_MAXENT : GIANT_MAXMV; }
+int giant_max_aln_entries() { return GIANT_ALN_SLOTS; }
 }  // namespace mbsv

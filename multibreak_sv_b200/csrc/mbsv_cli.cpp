@@ -45,6 +45,7 @@ std::string jd(double v) {
 }  // namespace
 
 int main(int argc, char** argv) {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);   // host setup (include/mbsv_b200.h): before the first CUDA call
     const auto t0 = std::chrono::steady_clock::now();
     std::string clusterfile, assignmentfile, experimentfile, matchfile, prefix = "out";
     long numiters = -1;

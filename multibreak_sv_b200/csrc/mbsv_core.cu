@@ -24,12 +24,13 @@ thread_local std::string g_err;
 thread_local int64_t g_launches = 0;
 // One run launches up to NSTREAM - 1 kernels (one per state-size class) that must overlap.  With the default of 8
 // hardware work queues, the 9th stream shares a queue with the 1st and its kernel silently waits for that one to finish
-// (measured: a 200 ms tail on a latency-bound batch).  The variable is read when the CUDA context is created, so it is set
-// when the library is loaded; a host that initialises CUDA earlier sets it itself (bench.py, the Python package do).
-__attribute__((constructor)) static void mbsv_more_hardware_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+// (measured: a 200 ms tail on a latency-bound batch).  CUDA reads CUDA_DEVICE_MAX_CONNECTIONS when the context is created:
+// the HOST sets it to 32 before its first CUDA call (include/mbsv_b200.h "Host setup"; bench.py and the Python package do).
+// The library never touches the process environment: setenv in a library constructor races with getenv in a JVM host.
 
 struct LaunchInfo { int rows; int warps; int grid; int smem_bytes; float ms; int memo; };
 thread_local std::vector<LaunchInfo> g_launch_info;
+thread_local std::vector<long long> g_launch_totals;    // [launch][6]: the counters of results.totals per launch
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -82,7 +83,11 @@ struct mbsv_problem {
     std::vector<int> sub_F;       // fragments of subproblem s
     std::vector<int> sub_nsv;     // AlterSV candidates of subproblem s
     std::vector<int> sub_nstates; // joint state space prod(n_f + 1), saturated at 2^30; 0 when it has a conn-comp
-    std::vector<int> sub_maxent;  // upper bound of the count entries / toggled fragments of one proposal (giant_kernel.cuh)
+    std::vector<int> sub_maxent;  // most count entries / toggled fragments of one AlterSV proposal (giant_kernel.cuh)
+    std::vector<int> sub_maxpos;  // most counted slots of one alignment
+    DevBuf<int4> d_aln_ent4, d_sv_mv;      // flattened views for the speculative-window kernel
+    DevBuf<int> d_sv_ent_ptr;
+    DevBuf<int2> d_sv_ent;
     // launch plan, depends on mbsv_run_params.memo_states (cached for the last value used)
     int plan_memo = -1, plan_tab = -1;
     std::vector<int> sub_rows;    // tile rows of a warp of subproblem s (state + memo table)
@@ -109,7 +114,8 @@ struct mbsv_problem {
     DevBuf<int> d_sub_frag_ptr, d_sub_cluster_ptr, d_sub_sv_ptr, d_frag_aln_ptr, d_aln_esp_slot, d_supports_local,
         d_cluster_hist_ptr, d_sv_frag_ptr, d_sv_frag, d_sv_numchanged, d_sub_order, d_sub_W, d_sub_memo;
     DevBuf<int4> d_aln_rec;
-    DevBuf<double> d_sub_logF, d_sub_neglogNsv, d_T, d_logint, d_pseq, d_logp, d_log1mp;
+    DevBuf<double> d_sub_logF, d_sub_neglogNsv, d_T, d_logint, d_invint, d_pseq, d_logp, d_log1mp;
+    DevBuf<unsigned long long> d_launch_totals;     // [NSTREAM][6]: every launch pools its chains' counters in its own row
     cudaStream_t streams[NSTREAM] = {};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done[NSTREAM] = {}, ev_cls0[NSTREAM] = {}, ev_cls1[NSTREAM] = {};
     bool streams_ok = false;
@@ -175,6 +181,15 @@ int mbsv_last_launch_info(double* out, int32_t max_launches) {
         ++n;
     }
     return n;
+}
+
+// out[i*6..] = {Naive proposals, Naive moves, AlterSV proposals, AlterSV moves, fragment-reassignments, first non-zero chain
+// status} of the chains of launch i of the last mbsv_run on this thread (same order as mbsv_last_launch_info).
+int mbsv_last_launch_totals(int64_t* out, int32_t max_launches) {
+    const int n = (int)(g_launch_totals.size() / 6);
+    for (int i = 0; i < n && i < max_launches && out; ++i)
+        for (int k = 0; k < 6; ++k) out[i * 6 + k] = g_launch_totals[6 * (size_t)i + k];
+    return n < max_launches ? n : max_launches;
 }
 
 int mbsv_lpt_shard(const int64_t* weights, int64_t n, int32_t n_parts, int32_t* out_part) {
@@ -282,7 +297,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     std::unique_ptr<int[]> sup_local(new (std::nothrow) int[(size_t)C + 1]);
     if (!rec || !slot || !sup_local) return fail(MBSV_ERR_OOM, "host allocation failed");
     int maxn = 1;
-    std::vector<int> sub_maxent(S, 0);
+    std::vector<int> sub_maxent(S, 0), sub_maxpos(S, 0);
     {
         const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
         std::vector<int> t_maxn(nthreads, 1);
@@ -338,7 +353,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                         }
                         for (int cl : touched) total[cl] += per_frag[cl];
                     }
-                    sub_maxent[s] = 2 * max_pos;   // a Naive proposal leaves one alignment and enters another
+                    sub_maxpos[s] = max_pos;
                     for (int cl = 0; cl < Cs; ++cl) {
                         if (total[cl] > d->max_support)
                             bad(MBSV_ERR_UNSUPPORTED, "a cluster can collect more selected ESPs than max_support "
@@ -365,7 +380,9 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         }
     }
     lap("pack");
-    std::vector<int> sub_sv_ptr(S + 1, 0), sv_frag_ptr(1, 0), sv_frag, sv_numchanged;
+    std::vector<int> sub_sv_ptr(S + 1, 0), sv_frag_ptr(1, 0), sv_frag, sv_numchanged, sv_ent_ptr(1, 0);
+    std::vector<int4> sv_mv;
+    std::vector<int2> sv_ent;
     if (d->n_sv > 0) {
         sub_sv_ptr.assign(d->sub_sv_ptr, d->sub_sv_ptr + S + 1);
         sv_frag_ptr.assign(d->sv_frag_ptr, d->sv_frag_ptr + d->n_sv + 1);
@@ -382,10 +399,14 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                     for (int q2 = sv_frag_ptr[k]; q2 < q; ++q2)
                         if (sv_frag[q2] == f) return fail(MBSV_ERR_ARG, "sv_frag lists a fragment twice for one cluster");
                     const int a = d->frag_aln_ptr[f];
-                    for (int j = d->aln_esp_ptr[a]; j < d->aln_esp_ptr[a + 1]; ++j) entries += slot[j] >= 0;
+                    sv_mv.push_back(make_int4(f - d->sub_frag_ptr[s], d->aln_numerrors[a], d->aln_len[a], d->aln_exp[a]));
+                    for (int j = d->aln_esp_ptr[a]; j < d->aln_esp_ptr[a + 1]; ++j)
+                        if (slot[j] >= 0) { sv_ent.push_back(make_int2(slot[j], q - sv_frag_ptr[k])); ++entries; }
                 }
+                sv_ent_ptr.push_back((int)sv_ent.size());
                 sub_maxent[s] = std::max(sub_maxent[s], std::max(entries, sv_frag_ptr[k + 1] - sv_frag_ptr[k]));
             }
+        if ((int)sv_ent_ptr.size() != d->n_sv + 1) return fail(MBSV_ERR_ARG, "sub_sv_ptr does not cover every AlterSV candidate");
     }
     // the exact-binomial branch (n*p <= 5 or n*(1-p) <= 5, MultiBreakSV.java:1664) only sees n <= 5/min(p, 1-p)
     for (int x = 0; x < E; ++x) {
@@ -399,6 +420,8 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         if (nsv > 0) neglogNsv[s] = -mbsv::jm_log((double)nsv);
     }
     for (int n = 1; n <= maxn; ++n) logint[n] = mbsv::jm_log((double)n);
+    std::vector<double> invint(maxn + 1);
+    for (int n = 0; n <= maxn; ++n) invint[n] = (double)1 / n;
     for (int x = 0; x < E; ++x) { logp[x] = mbsv::jm_log(d->exp_pseq[x]); log1mp[x] = mbsv::jm_log(1 - d->exp_pseq[x]); }
 
     lap("sv+logs");
@@ -436,6 +459,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         p->sub_nsv.push_back(sub_sv_ptr[s + 1] - sub_sv_ptr[s]);
     }
     p->sub_maxent = sub_maxent;
+    p->sub_maxpos = sub_maxpos;
 
     auto up = [&](auto& buf, const auto& vec) -> cudaError_t { return buf.upload(vec); };
     cudaError_t e = cudaSuccess;
@@ -451,6 +475,9 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     chk(up(p->d_sv_frag_ptr, sv_frag_ptr));
     chk(up(p->d_sv_frag, sv_frag));
     chk(up(p->d_sv_numchanged, sv_numchanged));
+    chk(up(p->d_sv_mv, sv_mv));
+    chk(up(p->d_sv_ent_ptr, sv_ent_ptr));
+    chk(up(p->d_sv_ent, sv_ent));
     chk(up(p->d_sub_logF, logF));
     chk(up(p->d_sub_neglogNsv, neglogNsv));
     {   // padded to a multiple of 16 bytes: the speculative-window kernel stages it with one bulk copy (cp.async.bulk)
@@ -459,6 +486,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         chk(up(p->d_T, T));
     }
     chk(up(p->d_logint, logint));
+    chk(up(p->d_invint, invint));
     chk(up(p->d_pseq, std::vector<double>(d->exp_pseq, d->exp_pseq + E)));
     chk(up(p->d_logp, logp));
     chk(up(p->d_log1mp, log1mp));
@@ -488,7 +516,8 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     dp.cluster_leaf_ptr = p->d_cluster_leaf_ptr.p; dp.leaf_owner = p->d_leaf_owner.p; dp.aln_esp_leaf = p->d_aln_esp_leaf.p;
     dp.cluster_root_ptr = p->d_cluster_root_ptr.p; dp.root_leaf_ptr = p->d_root_leaf_ptr.p; dp.root_leaf = p->d_root_leaf.p;
     dp.cluster_hist_ptr = p->d_cluster_hist_ptr.p; dp.sv_frag_ptr = p->d_sv_frag_ptr.p; dp.sv_frag = p->d_sv_frag.p;
-    dp.sv_numchanged = p->d_sv_numchanged.p; dp.T = p->d_T.p; dp.logint = p->d_logint.p; dp.exp_pseq = p->d_pseq.p;
+    dp.sv_mv = p->d_sv_mv.p; dp.sv_ent_ptr = p->d_sv_ent_ptr.p; dp.sv_ent = p->d_sv_ent.p; dp.aln_ent4 = nullptr;
+    dp.sv_numchanged = p->d_sv_numchanged.p; dp.T = p->d_T.p; dp.logint = p->d_logint.p; dp.invint = p->d_invint.p; dp.exp_pseq = p->d_pseq.p;
     dp.exp_logp = p->d_logp.p; dp.exp_log1mp = p->d_log1mp.p;
     dp.log2pi = mbsv::jm_log(2.0) + mbsv::jm_log(3.141592653589793);
     int prio_lo = 0, prio_hi = 0;
@@ -529,9 +558,9 @@ int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n) {
     if (!p || !out) return fail(MBSV_ERR_ARG, "mbsv_problem_stats: NULL");
     int64_t memo = 0;
     for (int v2 : p->sub_memo) memo += v2 > 0;
-    int64_t v[7] = {p->n_sub, p->n_frag, p->n_aln, p->n_cluster, p->csr_bytes,
-                    p->sub_W.empty() ? 0 : *std::max_element(p->sub_W.begin(), p->sub_W.end()), memo};
-    for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
+    int64_t v[9] = {p->n_sub, p->n_frag, p->n_aln, p->n_cluster, p->csr_bytes,
+                    p->sub_W.empty() ? 0 : *std::max_element(p->sub_W.begin(), p->sub_W.end()), memo, p->n_hist, p->device};
+    for (int i = 0; i < n && i < 9; ++i) out[i] = v[i];
     return MBSV_OK;
 }
 
@@ -718,7 +747,8 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     CUDA_TRY(cudaMemsetAsync(dr.frag_err_count, 0, sizeof(unsigned) * p->n_frag, s0));
     if (p->n_hist > 0) CUDA_TRY(cudaMemsetAsync(dr.cluster_hist, 0, sizeof(unsigned) * p->n_hist, s0));
     if (dr.error) CUDA_TRY(cudaMemsetAsync(dr.error, 0, sizeof(int) * sc_total, s0));
-    CUDA_TRY(cudaMemsetAsync(dr.totals, 0, sizeof(unsigned long long) * 6, s0));
+    if (!p->d_launch_totals.p) CUDA_TRY(p->d_launch_totals.alloc(6 * NSTREAM));
+    CUDA_TRY(cudaMemsetAsync(p->d_launch_totals.p, 0, sizeof(unsigned long long) * 6 * NSTREAM, s0));
 
     // ---- plan: warps of 32 consecutive (sorted subproblem, chain) items; size classes by state rows ----
     std::vector<int> cls = {16, 24, 32, 48, 64, 96, 128};
@@ -751,8 +781,10 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             bool ok = !memo && rp->mode == MBSV_MODE_FAST && !rp->trace && !p->has_cc && (int64_t)(k1 - lo) * X <= gmax;
             for (int k = lo; ok && k < k1; ++k) {
                 const int s = p->sub_order[k];
-                ok = p->sub_memo[s] == 0 && p->sub_maxent[s] <= mbsv::giant_max_entries();
+                ok = p->sub_memo[s] == 0 && p->sub_maxent[s] <= mbsv::giant_max_entries() &&
+                     p->sub_maxpos[s] <= mbsv::giant_max_aln_entries();
             }
+            ok = ok && (int64_t)p->n_cluster * p->n_exp < (1 << 25);          // slot and fragment index share a word
             if (ok) { launches.back().giant = true; launches.back().lanes = 1; }
         }
     };
@@ -848,6 +880,13 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     }
     if ((int)launches.size() > NSTREAM - 1) return fail(MBSV_ERR_ARG, "too many size classes");
 
+    for (const Launch& l : launches)
+        if (l.giant && !p->d_aln_ent4.p) {       // first speculative-window launch of this problem: flatten the alignments' slots
+            CUDA_TRY(p->d_aln_ent4.alloc(p->n_aln));
+            CUDA_TRY(mbsv::launch_giant_prep(p->dp, p->d_aln_ent4.p, s0));
+            p->dp.aln_ent4 = p->d_aln_ent4.p;
+            ++g_launches;
+        }
     CUDA_TRY(cudaEventRecord(p->ev_start, s0));
     // device-memory memo tables are filled once per run by a fully parallel kernel; only the launches that read them
     // wait for it
@@ -874,6 +913,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.n_items = l.i1;                       // the last warp of a class may be partly filled
         r.lanes_per_warp = l.lanes;
         r.memo_mixed = mixed ? 1 : 0;
+        r.totals = p->d_launch_totals.p + 6 * (size_t)nstream;
         int giant_threads = 0;
         size_t giant_smem = 0;
         KernelFn fn = gibbs ? mbsv::get_kernel_gibbs(32 / l.lanes)
@@ -922,9 +962,15 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
                      p->tab_sub.size(), p->memo_global_doubles, bms, L, Lm, mixed ? ", mixed" : "");
     }
 
-    // chain status
+    // counters per launch -> totals; chain status
     long long htot[6] = {0, 0, 0, 0, 0, 0};
-    CUDA_TRY(cudaMemcpy(htot, dr.totals, sizeof(htot), cudaMemcpyDeviceToHost));
+    g_launch_totals.assign(6 * (size_t)nstream, 0);
+    if (nstream > 0) CUDA_TRY(cudaMemcpy(g_launch_totals.data(), p->d_launch_totals.p, sizeof(long long) * 6 * nstream, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nstream; ++i) {
+        for (int k = 0; k < 5; ++k) htot[k] += g_launch_totals[6 * i + k];
+        if (!htot[5]) htot[5] = g_launch_totals[6 * i + 5];
+    }
+    if (results_on_device) CUDA_TRY(cudaMemcpy(dr.totals, htot, sizeof(htot), cudaMemcpyHostToDevice));
     const int worst = (int)htot[5];
     if (!results_on_device) {
         auto down = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {

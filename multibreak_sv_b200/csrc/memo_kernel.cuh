@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
             ++n_naive_prop;
             a0 = P.frag_aln_ptr[f0];
             prev = sidx - 1;
-            now = naive_draw(rng, nst - 1, prev, perr_thr);
+            now = naive_draw(rng, nst - 1, prev, perr_thr, P.invint);
             if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
             newidx = now + 1;
             newlogprob = tab[newidx];
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
                 a0 = P.frag_aln_ptr[f0 + f];
                 const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
                 prev = MBSV_ST(f);
-                naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
+                naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, P.invint, now, Alogq, Anewlogq);
                 if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
                 newidx += (now - prev) * strides[f * sstr];
             } else {

@@ -112,7 +112,8 @@ __device__ __forceinline__ unsigned long long prob_threshold53(double p) {
 
 // which alignment naiveMove draws (MultiBreakSV.java:1198-1256); -1 = "unmapped".  Consumes one or two nextDouble()s
 // exactly as the reference does.
-__device__ __forceinline__ int naive_draw(JavaRandom& rng, const int n, const int prev, const unsigned long long perr_thr) {
+__device__ __forceinline__ int naive_draw(JavaRandom& rng, const int n, const int prev, const unsigned long long perr_thr,
+                                          const double* __restrict__ invint) {
     // The reference has two scans (:1205-1209 from "unmapped": thresholds k/n, no index skipped; :1251-1256 to another
     // alignment: thresholds k/(n-1), index `prev` skipped).  With prev == -1 the second loop never skips, so ONE loop with
     // m = n or n-1 reproduces both, and lanes taking different branches stay converged.
@@ -121,7 +122,7 @@ __device__ __forceinline__ int naive_draw(JavaRandom& rng, const int n, const in
     const bool to_err = !from_err && (m53 < perr_thr || n == 1);
     double r = JavaRandom::to_double(m53);
     if (!from_err && !to_err) r = rng.nextDouble();          // the second draw of :1248
-    const double inc = (double)1 / (from_err ? n : n - 1);
+    const double inc = invint[from_err ? n : n - 1];       // (double)1 / m, tabulated with the same IEEE division
     double sum = inc;
     int thisassign = 0;
     while (!to_err && thisassign < n - 1 && (thisassign == prev || r > sum)) {
@@ -143,8 +144,9 @@ __device__ __forceinline__ void naive_logq(const int n, const int prev, const in
 
 __device__ __forceinline__ void naive_pick(JavaRandom& rng, const int n, const int prev, const double neglogF,
                                            const unsigned long long perr_thr, const double logperr, const double log1mperr,
-                                           const double* __restrict__ logint, int& now, double& Alogq, double& Anewlogq) {
-    now = naive_draw(rng, n, prev, perr_thr);
+                                           const double* __restrict__ logint, const double* __restrict__ invint, int& now,
+                                           double& Alogq, double& Anewlogq) {
+    now = naive_draw(rng, n, prev, perr_thr, invint);
     naive_logq(n, prev, now, neglogF, logperr, log1mperr, logint, Alogq, Anewlogq);
 }
 

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
             a0 = P.frag_aln_ptr[f0 + f];
             const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
             prev = MBSV_ST(f);
-            naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, now, Alogq, Anewlogq);
+            naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, P.invint, now, Alogq, Anewlogq);
             if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
         } else {
             // ---- svMove (:1291-1343) ----

@@ -30,9 +30,16 @@ struct DevProblem {
     const int* sv_frag_ptr;
     const int* sv_frag;
     const int* sv_numchanged;
+    // flattened views for the speculative-window kernel (giant_kernel.cuh): every load address of a proposal's gather is
+    // known one round trip after the proposal is drawn
+    const int4* aln_ent4;            // per alignment: its counted slots in ESP order, -1 padded (built on first use)
+    const int4* sv_mv;               // per sv_frag entry: {fragment (local), numerrors, len, exp} of its only alignment
+    const int* sv_ent_ptr;           // per AlterSV candidate: its counted slot entries ...
+    const int2* sv_ent;              // ... {slot, index of the fragment in the candidate's list}, in application order
     const double* T;                 // logprobcov [E][max_support+1]
     const double* logint;            // log(n), n = 1..maxn (maxn >= max alignments per fragment and the
                                      // largest n the exact-binomial branch can see, capped at 65536)
+    const double* invint;            // (double)1 / n, n = 0..maxn (the cumulative thresholds of naiveMove, MultiBreakSV.java:1205,1251)
     const double* exp_pseq;
     const double* exp_logp;
     const double* exp_log1mp;
@@ -93,6 +100,8 @@ KernelFn get_kernel_memo(bool trace, bool mixed);               // memoised subp
 // speculative-window kernel, one CTA per (subproblem, chain) (giant_kernel.cuh): FAST, no trace, no connected components
 KernelFn get_kernel_giant(int n_exp, int* threads, size_t* smem_bytes);
 int giant_max_entries();                                         // most count entries / toggled fragments of one proposal it takes
+int giant_max_aln_entries();                                     // most counted slots of one alignment it takes
+cudaError_t launch_giant_prep(const DevProblem& P, int4* aln_ent4, cudaStream_t stream);   // fills aln_ent4
 // fills the device-memory log-posterior tables of the memoised subproblems listed in tab_sub
 cudaError_t launch_memo_build(const DevProblem& P, const DevRun& R, int n_tab, const long long* state_ptr, const int* tab_sub,
                               long long n_states, int scratch_rows, cudaStream_t stream);

@@ -27,9 +27,9 @@ def lpt_shard(weights: np.ndarray, n_parts: int) -> np.ndarray:
 def split_chains(n_chains: int, n_parts: int, rank: int) -> tuple[int, int]:
     """(first chain, number of chains) of `rank` when one subproblem's chains are split over n_parts GPUs.
     Chain c keeps the seed 123456 + c wherever it runs, so chain 0 stays the reference's chain."""
-    base, extra = divmod(n_chains, n_parts)
-    first = rank * base + min(rank, extra)
-    return first, base + (1 if rank < extra else 0)
+    first, count = C.c_int32(0), C.c_int32(0)
+    check(load_library().mbsv_split_chains(n_chains, n_parts, rank, C.byref(first), C.byref(count)))
+    return first.value, count.value
 
 
 def reduce_tallies(out, dst: int = 0, device=None):

@@ -16,11 +16,12 @@ for decoys; one "true SV" cluster per ~lambda_D fragments plus small decoy clust
 from __future__ import annotations
 
 import os
+import struct
 from dataclasses import dataclass
 
 import numpy as np
 
-from ._abi import PackedProblem, load_library
+from ._abi import PackedProblem
 
 EXPERIMENTS = {"illumina": (0.01, 10.0), "pacbio": (0.15, 3.0)}
 
@@ -43,6 +44,77 @@ CONFIGS = {
     "cfg4": SynthConfig("cfg4-mixed-5M", 5_000_000, 0.7, "zipf2", seed=20260104, n_chains=64),
     "cfg5": SynthConfig("cfg5-giant-500k", 500_000, 0.7, "single", seed=20260105, n_chains=64),
 }
+
+
+def _hi_lo(x: float) -> tuple[int, int]:
+    u = struct.unpack("<Q", struct.pack("<d", x))[0]
+    hi = u >> 32
+    return (hi - (1 << 32) if hi & 0x80000000 else hi), u & 0xFFFFFFFF
+
+
+def _from_hi_lo(hi: int, lo: int) -> float:
+    return struct.unpack("<d", struct.pack("<Q", ((hi & 0xFFFFFFFF) << 32) | (lo & 0xFFFFFFFF)))[0]
+
+
+def jlog(x: float) -> float:
+    """fdlibm 5.3 __ieee754_log (what java.lang.StrictMath.log specifies) in plain Python doubles: the generator fills
+    Experiment.logprobcov (MultiBreakSV.java:612-614,1644-1649) itself, bit for bit like mbsv_fill_logprobcov, without
+    calling into the library it generates inputs for (tests/test_abi_cpu.py compares the two)."""
+    ln2_hi, ln2_lo = _from_hi_lo(0x3fe62e42, 0xfee00000), _from_hi_lo(0x3dea39ef, 0x35793c76)
+    two54 = _from_hi_lo(0x43500000, 0)
+    Lg = [_from_hi_lo(h, l) for h, l in ((0x3FE55555, 0x55555593), (0x3FD99999, 0x9997FA04), (0x3FD24924, 0x94229359),
+                                          (0x3FCC71C5, 0x1D8E78AF), (0x3FC74664, 0x96CB03DE), (0x3FC39A09, 0xD078C69F),
+                                          (0x3FC2F112, 0xDF3E5244))]
+    hx, lx = _hi_lo(x)
+    k = 0
+    if hx < 0x00100000:
+        if ((hx & 0x7fffffff) | lx) == 0:
+            return float("-inf")
+        if hx < 0:
+            return float("nan")
+        k -= 54
+        x *= two54
+        hx, lx = _hi_lo(x)
+    if hx >= 0x7ff00000:
+        return x + x
+    k += (hx >> 20) - 1023
+    hx &= 0x000fffff
+    i = (hx + 0x95f64) & 0x100000
+    x = _from_hi_lo(hx | (i ^ 0x3ff00000), lx)
+    k += i >> 20
+    f = x - 1.0
+    dk = float(k)
+    if (0x000fffff & (2 + hx)) < 3:
+        if f == 0.0:
+            return 0.0 if k == 0 else dk * ln2_hi + dk * ln2_lo
+        R = f * f * (0.5 - 0.33333333333333333 * f)
+        return f - R if k == 0 else dk * ln2_hi - ((R - dk * ln2_lo) - f)
+    s_ = f / (2.0 + f)
+    z = s_ * s_
+    i = hx - 0x6147a
+    w = z * z
+    j = 0x6b851 - hx
+    t1 = w * (Lg[1] + w * (Lg[3] + w * Lg[5]))
+    t2 = z * (Lg[0] + w * (Lg[2] + w * (Lg[4] + w * Lg[6])))
+    i |= j
+    R = t2 + t1
+    if i > 0:
+        hfsq = 0.5 * f * f
+        return f - (hfsq - s_ * (hfsq + R)) if k == 0 else dk * ln2_hi - ((hfsq - (s_ * (hfsq + R) + dk * ln2_lo)) - f)
+    return f - s_ * (f - R) if k == 0 else dk * ln2_hi - ((s_ * (f - R) - dk * ln2_lo) - f)
+
+
+def logprobcov_table(lam: float, max_support: int) -> np.ndarray:
+    """logprobcov[k] = logPoisson(k; lambda), k = 1..max_support, [0] = 0 (MultiBreakSV.java:612-614,1644-1649)."""
+    out = np.zeros(max_support + 1, np.float64)
+    ll = jlog(lam)
+    logs = [0.0] + [jlog(float(i)) for i in range(1, max_support + 1)]
+    for k in range(1, max_support + 1):
+        val = -lam + k * ll
+        for i in range(1, k + 1):
+            val -= logs[i]
+        out[k] = val
+    return out
 
 
 def _sub_sizes(rng: np.random.Generator, cfg: SynthConfig, n_frag: int) -> np.ndarray:
@@ -234,11 +306,9 @@ def generate(cfg: SynthConfig | str, n_frag: int | None = None, seed: int | None
         root_leaf_ptr = np.array(rlp, np.int32)
         root_leaf = np.array(rl, np.int32)
 
-    L = load_library()
     T = np.zeros((E, max_support + 1), np.float64)
-    import ctypes as C_
     for x in range(E):
-        L.mbsv_fill_logprobcov(float(lam[x]), max_support, T[x].ctypes.data_as(C_.POINTER(C_.c_double)))
+        T[x] = logprobcov_table(float(lam[x]), max_support)
 
     arrays = dict(
         sub_frag_ptr=sub_frag_ptr.astype(np.int32), sub_cluster_ptr=sub_cluster_ptr.astype(np.int32),

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -108,7 +109,9 @@ static View make_view(const orc_desc* d, int s) {
     return v;
 }
 
-// Runs every (subproblem, chain); subproblems are spread over nthreads host threads.
+// Runs every (subproblem, chain).  Subproblems are spread over nthreads host threads; a batch with fewer subproblems than
+// twice the threads (a giant component) spreads its (subproblem, chain) pairs instead, every thread pooling its tallies in
+// private arrays that are added up at the end (the chains of one subproblem share their tally bins).
 int orc_run(const orc_desc* d, const orc_params* p, orc_results* r, int nthreads) {
     if (!d || !p || !r || p->n_chains < 1 || p->num_iters < 0) return -1;
     std::memset(r->aln_count, 0, sizeof(uint32_t) * (size_t)d->n_aln);
@@ -118,7 +121,54 @@ int orc_run(const orc_desc* d, const orc_params* p, orc_results* r, int nthreads
     std::atomic<int> worst{0};
     std::atomic<long long> tot[5];
     for (auto& t : tot) t.store(0);
+    const bool by_chain = nthreads > 1 && d->n_sub < 2 * nthreads && p->n_chains > 1;
+    std::mutex merge;
+    auto chain_worker = [&]() {
+        std::vector<uint32_t> ac((size_t)d->n_aln, 0), fe((size_t)d->n_frag, 0), ch((size_t)d->n_hist, 0);
+        const long long n_items = (long long)d->n_sub * p->n_chains;
+        for (;;) {
+            const long long it = next.fetch_add(1);
+            if (it >= n_items) break;
+            const int s = (int)(it / p->n_chains), c = (int)(it % p->n_chains);
+            View v = make_view(d, s);
+            RunParams rp;
+            rp.mode = p->mode; rp.num_iters = p->num_iters; rp.burnin = p->burnin; rp.perr = p->perr;
+            rp.java_int_wrap = p->java_int_wrap;
+            rp.memo_states = p->memo_states;
+            rp.init_assign = p->init_assign ? p->init_assign + v.f0 : nullptr;
+            std::vector<double> lpcache;     // (a pure cache: not sharing it between the chains only costs time)
+            size_t sc = (size_t)s * p->n_chains + c;
+            Trace tr, *trp = nullptr;
+            if (p->trace && r->trace_logprob) {
+                tr.logprob = r->trace_logprob + sc * p->num_iters;
+                tr.move_frag = r->trace_move_frag + sc * p->num_iters;
+                tr.move_assign = r->trace_move_assign + sc * p->num_iters;
+                trp = &tr;
+            }
+            int32_t* fa = r->final_assign ? r->final_assign + (size_t)c * d->n_frag + v.f0 : nullptr;
+            int32_t* ia = r->initial_assign ? r->initial_assign + (size_t)c * d->n_frag + v.f0 : nullptr;
+            double* il = r->initial_logprob ? r->initial_logprob + sc : nullptr;
+            ChainResult cr = run_chain(v, rp, p->seed + c, ac.data(), fe.data(), ch.data(), fa, trp, ia, il, &lpcache);
+            if (trp) for (int i = 0; i < p->num_iters; ++i) if (tr.move_frag[i] >= 0) tr.move_frag[i] += v.f0;
+            if (r->final_logprob) r->final_logprob[sc] = cr.final_logprob;
+            if (r->counters) {
+                int64_t* k = r->counters + sc * 5;
+                k[0] = cr.naive_proposed; k[1] = cr.naive_accepted; k[2] = cr.sv_proposed; k[3] = cr.sv_accepted;
+                k[4] = cr.reassignments;
+            }
+            tot[0] += cr.naive_proposed; tot[1] += cr.naive_accepted; tot[2] += cr.sv_proposed; tot[3] += cr.sv_accepted;
+            tot[4] += cr.reassignments;
+            if (r->rng_state) r->rng_state[sc] = cr.rng_state;
+            if (r->error) r->error[sc] = cr.error;
+            if (cr.error) worst.store(cr.error);
+        }
+        std::lock_guard<std::mutex> lk(merge);
+        for (size_t i = 0; i < ac.size(); ++i) r->aln_count[i] += ac[i];
+        for (size_t i = 0; i < fe.size(); ++i) r->frag_err_count[i] += fe[i];
+        for (size_t i = 0; i < ch.size(); ++i) r->cluster_hist[i] += ch[i];
+    };
     auto worker = [&]() {
+        if (by_chain) { chain_worker(); return; }
         for (;;) {
             int s = next.fetch_add(1);
             if (s >= d->n_sub) break;

@@ -63,7 +63,30 @@ def build(force: bool = False) -> str:
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
-    subprocess.check_call(["make", "-C", _HERE, "-s"])
+    if "_native" not in _LIB_PATH:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+def use_native_build() -> str:
+    """Switch this process to the -O3 -march=native build of the same sources (bench.py's CPU baseline).  It is compiled
+    on the machine that runs it, into a directory named after that machine's CPU flags, and never shipped (.gpurunignore):
+    results are bit-identical to the portable build (floating-point contraction stays off)."""
+    global _LIB_PATH, _lib
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    rel = os.path.join("_native", hashlib.sha1(flags.encode()).hexdigest()[:12], "libmbsv_oracle_native.so")
+    subprocess.check_call(["make", "-C", _HERE, "-s", "native", f"NATIVE={rel}"])
+    _LIB_PATH = os.path.join(_HERE, rel)
+    _lib = None
     return _LIB_PATH
 
 

@@ -45,6 +45,48 @@ def test_gpu_arm_json_line():
     assert d["value"] > 0 and d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["scaling"] == "weak"
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     rf = d["roofline"]
-    assert rf["bound"] == "hbm" and rf["peak"] > 0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["bound"] == "sm-issue" and rf["peak"] == 100.0 and "traffic" in rf
+    hb = rf["hbm_notional"]
+    assert hb["bound"] == "hbm" and hb["peak"] > 0 and abs(hb["frac"] - hb["achieved"] / hb["peak"]) < 1e-9
+    assert sum(c["reassignments"] for c in d["per_class"]) * d["steps"] > 0
+    assert d["e2e"]["steps"] == d["steps"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_stratified_sample_is_a_valid_sub_batch(oracle):
+    """bench.py's CPU sample: the gathered sub-batch of arbitrary subproblems runs exactly like those subproblems inside
+    the full batch (tallies of the picked subproblems, counters, RNG states)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg4", n_frag=4000, seed=5, conncomp_frac=0.3)
+    a = p.arrays
+    full = oracle.run(oracle.Problem(p.scalars, a), "incremental", 400, n_chains=2, nthreads=4, java_int_wrap=False)
+    pick = np.array([0, 1, 2, 7, 8, 30, 31, 32, 33, p.scalars["n_sub"] - 1])
+    q = bench.gather_subproblems(p, pick)
+    sub = oracle.run(oracle.Problem(q.scalars, q.arrays), "incremental", 400, n_chains=2, nthreads=4, java_int_wrap=False)
+    assert np.array_equal(sub.counters, full.counters[pick]) and np.array_equal(sub.rng_state, full.rng_state[pick])
+    fptr, aptr, hptr = a["sub_frag_ptr"], a["frag_aln_ptr"], a["cluster_hist_ptr"]
+    cptr = a["sub_cluster_ptr"]
+    al = np.concatenate([full.aln_count[aptr[fptr[s]]:aptr[fptr[s + 1]]] for s in pick])
+    fe = np.concatenate([full.frag_err_count[fptr[s]:fptr[s + 1]] for s in pick])
+    hi = np.concatenate([full.cluster_hist[hptr[cptr[s]]:hptr[cptr[s + 1]]] for s in pick])
+    assert np.array_equal(sub.aln_count, al) and np.array_equal(sub.frag_err_count, fe) and np.array_equal(sub.cluster_hist, hi)
+    strata = bench.stratified_sample(p, 2, 400, 2 * 400 * 60, 4)
+    assert sum(N for N, *_ in strata) == p.scalars["n_sub"] and all(n >= min(N, 8) for N, n, *_ in strata)
+
+
+def test_generator_does_not_need_the_product_library(mbsv):
+    """synth fills logprobcov with its own fdlibm log; it must agree bit for bit with mbsv_fill_logprobcov."""
+    import ctypes as C
+    import numpy as np
+    from multibreak_sv_b200 import synth
+    L = mbsv.load_library()
+    for lam, ms in ((10.0, 60), (3.0, 17), (0.7, 5)):
+        T = np.zeros(ms + 1)
+        L.mbsv_fill_logprobcov(lam, ms, T.ctypes.data_as(C.POINTER(C.c_double)))
+        assert np.array_equal(T, synth.logprobcov_table(lam, ms))
+    src = open(os.path.join(ROOT, "multibreak_sv_b200", "synth.py")).read()
+    assert "load_library" not in src
