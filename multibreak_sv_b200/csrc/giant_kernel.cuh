@@ -34,6 +34,7 @@
 // initializeMatrix (MultiBreakSV.java:999-1015) is the same trick on single LCG steps: a fragment consumes 2 steps
 // (nextDouble() < perr) or 3 (nextDouble, nextInt), so the fragment starts are the offsets reachable by +2 / +3.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -90,14 +91,14 @@ __device__ __forceinline__ void giant_bar_wait(unsigned long long* bar, unsigned
 
 struct GiantReach { bool reach; int rank, drank; };
 
-// Offsets 0..NT-1, one per thread: an item starting at offset j ends at j + c (1 <= c <= 8).  Which offsets are reachable
-// from offset 0?  Per warp, pointer doubling gives for every lane the set of in-warp offsets visited from it and where
-// the walk leaves the warp; the first eight lanes publish that as the warp's transfer table (entry offset -> exit
-// offset, items, dense items), and every warp composes the tables of the warps in front of it.  Contains one
-// __syncthreads.  fin[0..2] = items in the window, dense items, exit offset - NT (valid after the caller's next barrier).
+// Offsets 0..NT-1 of this CTA, one per thread: an item starting at offset j ends at j + c (1 <= c <= 8).  Which offsets are
+// reachable?  Per warp, pointer doubling gives for every lane the set of in-warp offsets visited from it and where the walk
+// leaves the warp; the first eight lanes publish that as the warp's transfer table (entry offset -> exit offset, items,
+// dense items).  giant_reach_tables ends with a __syncthreads; giant_reach_walk composes the tables of the warps in front
+// of a thread's warp, starting from the offset `entry` at which the walk enters this CTA (0 for the first CTA of a window)
+// with `rank0` items / `drank0` dense items in front of it.
 template <int NT>
-__device__ __forceinline__ GiantReach giant_reach(const int c, const bool dense, unsigned* tab, unsigned* msk, int* fin) {
-    constexpr int NW = NT / 32;
+__device__ __forceinline__ unsigned giant_reach_tables(const int c, const bool dense, unsigned* tab, unsigned* msk) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned S = 1u << lane;
     int J = lane + c;
@@ -114,7 +115,25 @@ __device__ __forceinline__ GiantReach giant_reach(const int c, const bool dense,
         msk[w * 8 + lane] = S;
     }
     __syncthreads();
-    int e = 0, rank = 0, drank = 0;
+    return dmask;
+}
+// the whole CTA as one transfer table entry: entered at offset e, where does the walk leave, how many items / dense items
+template <int NT>
+__device__ __forceinline__ unsigned giant_reach_cta_entry(int e, const unsigned* tab) {
+    int rank = 0, drank = 0;
+    for (int k = 0; k < NT / 32; ++k) {
+        const unsigned t = tab[k * 8 + e];
+        rank += (t >> 3) & 63;
+        drank += (t >> 9) & 63;
+        e = t & 7;
+    }
+    return (unsigned)e | ((unsigned)rank << 3) | ((unsigned)drank << 16);      // rank <= NT (13 bits), drank <= NT / 4
+}
+template <int NT>
+__device__ __forceinline__ GiantReach giant_reach_walk(int e, int rank, int drank, const unsigned dmask, const unsigned* tab,
+                                                       const unsigned* msk, int* fin) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int k = 0; k < w; ++k) {
         const unsigned t = tab[k * 8 + e];
         rank += (t >> 3) & 63;
@@ -122,7 +141,7 @@ __device__ __forceinline__ GiantReach giant_reach(const int c, const bool dense,
         e = t & 7;
     }
     const unsigned mine = msk[w * 8 + e];
-    if (w == NW - 1 && lane == 0) {
+    if (fin && w == NW - 1 && lane == 0) {
         const unsigned t = tab[w * 8 + e];
         fin[0] = rank + ((t >> 3) & 63);
         fin[1] = drank + ((t >> 9) & 63);
@@ -135,12 +154,19 @@ __device__ __forceinline__ GiantReach giant_reach(const int c, const bool dense,
     r.drank = drank + __popc(mine & dmask & lt);
     return r;
 }
+template <int NT>
+__device__ __forceinline__ GiantReach giant_reach(const int c, const bool dense, unsigned* tab, unsigned* msk, int* fin) {
+    const unsigned dmask = giant_reach_tables<NT>(c, dense, tab, msk);
+    return giant_reach_walk<NT>(0, 0, 0, dmask, tab, msk, fin);
+}
+
+constexpr int GIANT_MAXCS = 8;      // CTAs of a cluster that share one chain's windows
 
 // Shared-memory layout (byte offsets), shared by the kernel and the host's launch code.
 template <int NT, int MAXE>
 struct GiantLayout {
     static constexpr int NW = NT / 32;
-    static constexpr int MD = NT / 4 + 8;          // proposals per window: every one consumes >= 4 offsets
+    static constexpr int MD = NT / 4 + 8;          // proposals per CTA per window: every one consumes >= 4 offsets
     static constexpr size_t al(size_t b) { return (b + 15) & ~(size_t)15; }
     static constexpr size_t o_T = 0;
     static constexpr size_t o_lp = o_T + al(sizeof(double) * GIANT_TMAX);
@@ -154,7 +180,10 @@ struct GiantLayout {
     static constexpr size_t o_hlane = o_hkey + al(sizeof(int) * GIANT_HASH);
     static constexpr size_t o_rtab = o_hlane + al(sizeof(int) * GIANT_HASH);
     static constexpr size_t o_rmsk = o_rtab + al(sizeof(unsigned) * NW * 8);
-    static constexpr size_t o_sc = o_rmsk + al(sizeof(unsigned) * NW * 8);
+    static constexpr size_t o_ctab = o_rmsk + al(sizeof(unsigned) * NW * 8);
+    static constexpr size_t o_ctot = o_ctab + al(sizeof(unsigned) * GIANT_MAXCS * 8);
+    static constexpr size_t o_clast = o_ctot + al(sizeof(long long) * GIANT_MAXCS * 2 * MAXE);
+    static constexpr size_t o_sc = o_clast + al(sizeof(int) * GIANT_MAXCS * MAXE);
     static constexpr size_t bytes = o_sc + 512;    // the Scalars block (static_assert in the kernel)
 };
 
@@ -169,11 +198,15 @@ static __device__ __forceinline__ double giant_lb_approx(long long k, long long 
     return -(d * d) * __drcp_rn(2 * sig) - 0.5 * (log2pi + (double)__logf((float)sig));
 }
 
-// MAXE = compile-time bound of the experiments (2 or 4).
-template <int NT, int MAXE>
+// MAXE = compile-time bound of the experiments (2 or 4).  CS = CTAs per chain: a thread-block cluster of CS CTAs evaluates
+// windows of CS * NT offsets, CTA r the offsets [r * NT, (r + 1) * NT); what the CTAs of a window owe each other — transfer
+// tables of the reachability walk, prefix sums of the accepted totals, the logBinomial values accepted proposals publish,
+// the rows they write, the cut — goes through distributed shared memory, one cluster barrier per exchange.
+template <int NT, int MAXE, int CS>
 __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ DevRun R) {
     using LY = GiantLayout<NT, MAXE>;
     constexpr int MD = LY::MD, NW = LY::NW;
+    static_assert(CS >= 1 && CS <= GIANT_MAXCS, "cluster size");
     extern __shared__ __align__(16) unsigned char giant_smem[];
     double* sT = (double*)(giant_smem + LY::o_T);
     double* lpbuf = (double*)(giant_smem + LY::o_lp);
@@ -187,6 +220,9 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
     int* hlane = (int*)(giant_smem + LY::o_hlane);
     unsigned* rtab = (unsigned*)(giant_smem + LY::o_rtab);
     unsigned* rmsk = (unsigned*)(giant_smem + LY::o_rmsk);
+    unsigned* ctab = (unsigned*)(giant_smem + LY::o_ctab);     // [cta][8]: the CTAs' transfer tables (every CTA holds all)
+    long long* ctot = (long long*)(giant_smem + LY::o_ctot);   // [cta][2 * MAXE]: accepted (dE, dL) of the CTA
+    int* clast = (int*)(giant_smem + LY::o_clast);             // [cta][MAXE]: last accepted proposal of the CTA touching x
     struct Scalars {
         unsigned long long s_base, jumpA, jumpC, bar;
         long long Etot[MAXE], Ltot[MAXE];
@@ -198,9 +234,17 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
     static_assert(sizeof(Scalars) <= 512, "Scalars block");
     Scalars& sc = *(Scalars*)(giant_smem + LY::o_sc);
 
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = CS > 1 ? (int)cluster.block_rank() : 0;
+    auto csync = [&]() { if (CS > 1) cluster.sync(); else __syncthreads(); };
+    // the same shared-memory object in CTA k of the cluster (distributed shared memory)
+    auto remote = [&](auto* ptr, int k) { return CS > 1 ? cluster.map_shared_rank(ptr, k) : ptr; };
+
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int witem = R.warp_begin + blockIdx.x;
-    if (witem >= R.warp_end) return;
+    const int goff = crank * NT + tid;                             // this thread's offset inside a window
+    const int witem = R.warp_begin + blockIdx.x / CS;
+    if (witem >= R.warp_end) return;                               // (whole clusters leave together)
     const long long item = R.item_base + (long long)(witem - R.warp_base);
     const int sub = R.sub_order[item / R.n_chains];
     const int chain = (int)(item % R.n_chains);
@@ -231,7 +275,10 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
     // slot = cluster * E + experiment (one and two experiments without an integer division)
     auto slot_exp = [&](int slot) -> int { return E == 1 ? 0 : E == 2 ? (slot & 1) : slot % E; };
     auto slot_cluster = [&](int slot) -> int { return E == 1 ? slot : E == 2 ? (slot >> 1) : slot / E; };
+    // the set of rows written in a window is ONE hash set spread over the CTAs of the cluster: a key lives in the table of
+    // CTA owner_of(key), at slot hash_of(key) (linear probing inside that table)
     auto hash_of = [](int key) -> unsigned { return (((unsigned)key * 2654435761u) >> 19) & (GIANT_HASH - 1); };
+    auto owner_of = [](int key) -> int { return CS > 1 ? (int)((((unsigned)key * 2654435761u) >> 16) & (CS - 1)) : 0; };
 
     // ---- setup: TMA-staged logprobcov, zeroed state, scalars ----
     if (tid == 0) {
@@ -248,99 +295,156 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         const unsigned bytes = (unsigned)(((size_t)E * Tstride * sizeof(double) + 15) & ~(size_t)15);
         giant_bulk_load(sT, P.T, bytes, &sc.bar);
     }
-    for (int i = tid; i < W; i += NT) st.stw(i, 0);
+    for (int i = goff; i < W; i += CS * NT) st.stw(i, 0);
     if (tsm) giant_bar_wait(&sc.bar, 0);
-    __syncthreads();
+    csync();
 
     // thread j's jump-ahead constants: the state j steps after s is jA * s + jC (one step = step_mul, step_add)
     unsigned long long jA = 1, jC = 0;
-    auto make_jump = [&](unsigned long long step_mul, unsigned long long step_add) {
+    auto make_jump = [&](unsigned long long step_mul, unsigned long long step_add, int steps, int total) {
         jA = 1; jC = 0;
-        for (int i = 0; i < tid; ++i) { jA = jA * step_mul; jC = jC * step_mul + step_add; }
-        if (tid == NT - 1) { sc.jumpA = jA * step_mul; sc.jumpC = jC * step_mul + step_add; }     // NT steps
+        for (int i = 0; i < steps; ++i) { jA = jA * step_mul; jC = jC * step_mul + step_add; }
+        if (tid == NT - 1) {                                             // `total` steps: the whole window
+            unsigned long long a = jA, c = jC;
+            for (int i = steps; i < total; ++i) { a = a * step_mul; c = c * step_mul + step_add; }
+            sc.jumpA = a; sc.jumpC = c;
+        }
     };
 
-    // ---------------- initializeMatrix (MultiBreakSV.java:990-1099) ----------------
-    if (R.init_assign) {
-        for (int f = tid; f < F; f += NT) {
-            const int a = R.init_assign[f0 + f];
-            st.stw(f, a);
-            if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
-        }
-    } else {
-        make_jump(JavaRandom::MULT, JavaRandom::ADD);
-        __syncthreads();
-        for (;;) {
-            const int fb = sc.frag_base;
-            if (fb >= F) break;
-            const unsigned long long sb = sc.s_base;
-            // a fragment whose draws start after offset j: nextDouble() = steps j+1, j+2; nextInt = step j+3
-            const unsigned long long s0 = jA * sb + jC;
-            const unsigned long long s1 = s0 * JavaRandom::MULT + JavaRandom::ADD;
-            const unsigned long long s2 = s1 * JavaRandom::MULT + JavaRandom::ADD;
-            const unsigned long long s3 = s2 * JavaRandom::MULT + JavaRandom::ADD;
-            const unsigned long long m53 = (((s1 & JavaRandom::MASK) >> 22) << 27) + ((s2 & JavaRandom::MASK) >> 21);
-            const bool unmapped = m53 < perr_thr;                     // nextDouble() < perr
-            if (tid == 0) sc.cut = GIANT_NOCUT;
-            const GiantReach rr = giant_reach<NT>(unmapped ? 2 : 3, false, rtab, rmsk, sc.fin);
-            const int f = fb + rr.rank;
-            int a = -1;
-            bool reject = false;
-            unsigned long long s_after = s0;
-            if (rr.reach && f < F && !unmapped) {
-                const int bound = P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f];
-                const int r31 = (int)((s3 & JavaRandom::MASK) >> 17);
-                const int m = bound - 1;
-                if ((bound & m) == 0) a = (int)(((long long)bound * (long long)r31) >> 31);
-                else {
-                    a = r31 % bound;
-                    // java.util.Random.nextInt redraws when u - r + m overflows int (about 1e-8 of the draws): serial
-                    if ((int)((unsigned)r31 - (unsigned)a + (unsigned)m) < 0) {
-                        reject = true;
-                        JavaRandom q; q.s = s2;
-                        a = q.nextInt(bound);
-                        s_after = q.s;
-                        atomicMin(&sc.cut, tid);
-                    }
-                }
-            }
-            if (rr.reach && f == F) atomicMin(&sc.cut, tid);            // first offset after the last fragment
-            __syncthreads();
-            const int cut = sc.cut;
-            // fragments in front of the cut are final; a redrawing fragment AT the cut has finished itself serially
-            if (rr.reach && f < F && (tid < cut || (tid == cut && reject))) {
+    // ---------------- initializeMatrix (MultiBreakSV.java:990-1099): the first CTA of the cluster ----------------
+    if (crank == 0) {
+        if (R.init_assign) {
+            for (int f = tid; f < F; f += NT) {
+                const int a = R.init_assign[f0 + f];
                 st.stw(f, a);
                 if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
             }
-            if (cut == GIANT_NOCUT) {
-                if (tid == 0) {
-                    unsigned long long s = sc.jumpA * sb + sc.jumpC;
-                    for (int i = 0; i < sc.fin[2]; ++i) s = s * JavaRandom::MULT + JavaRandom::ADD;
-                    sc.s_base = s;
-                    sc.frag_base = fb + sc.fin[0];
-                }
-            } else if (tid == cut) {
-                if (reject) { sc.s_base = s_after; sc.frag_base = f + 1; }
-                else { sc.s_base = s0; sc.frag_base = f; }              // f == F: the state after the last fragment's draws
-            }
+        } else if (R.perr * NT < 0.5) {
+            // Almost every fragment consumes three LCG steps (nextDouble() >= perr, then nextInt): thread t takes fragment
+            // base + t at offset 3 t.  That is right for every fragment up to and including the first one of the window that
+            // draws "unmapped" (two steps) or has to redraw its nextInt; the window is cut behind that fragment.
+            make_jump(JavaRandom::jump_mul(3), JavaRandom::jump_add(3), tid, NT);
             __syncthreads();
+            for (;;) {
+                const int fb = sc.frag_base;
+                if (fb >= F) break;
+                const unsigned long long sb = sc.s_base;
+                const int f = fb + tid;
+                const unsigned long long s0 = jA * sb + jC;
+                const unsigned long long s1 = s0 * JavaRandom::MULT + JavaRandom::ADD;
+                const unsigned long long s2 = s1 * JavaRandom::MULT + JavaRandom::ADD;
+                const unsigned long long s3 = s2 * JavaRandom::MULT + JavaRandom::ADD;
+                const unsigned long long m53 = (((s1 & JavaRandom::MASK) >> 22) << 27) + ((s2 & JavaRandom::MASK) >> 21);
+                if (tid == 0) sc.cut = GIANT_NOCUT;
+                __syncthreads();
+                int a = -1;
+                unsigned long long s_after = s2;                          // unmapped: two steps
+                if (f < F) {
+                    if (m53 < perr_thr) atomicMin(&sc.cut, tid);
+                    else {
+                        const int bound = P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f];
+                        const int r31 = (int)((s3 & JavaRandom::MASK) >> 17);
+                        const int m = bound - 1;
+                        s_after = s3;
+                        if ((bound & m) == 0) a = (int)(((long long)bound * (long long)r31) >> 31);
+                        else {
+                            a = r31 % bound;
+                            if ((int)((unsigned)r31 - (unsigned)a + (unsigned)m) < 0) {      // java.util.Random.nextInt redraws
+                                JavaRandom q; q.s = s2;
+                                a = q.nextInt(bound);
+                                s_after = q.s;
+                                atomicMin(&sc.cut, tid);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                const int cut = sc.cut;
+                if (f < F && tid <= cut) {
+                    st.stw(f, a);
+                    if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
+                }
+                const int last = min(min(cut, NT - 1), F - 1 - fb);      // last fragment of this window that is final
+                if (tid == last) { sc.s_base = s_after; sc.frag_base = fb + last + 1; }
+                __syncthreads();
+            }
+        } else {
+            make_jump(JavaRandom::MULT, JavaRandom::ADD, tid, NT);
+            __syncthreads();
+            for (;;) {
+                const int fb = sc.frag_base;
+                if (fb >= F) break;
+                const unsigned long long sb = sc.s_base;
+                // a fragment whose draws start after offset j: nextDouble() = steps j+1, j+2; nextInt = step j+3
+                const unsigned long long s0 = jA * sb + jC;
+                const unsigned long long s1 = s0 * JavaRandom::MULT + JavaRandom::ADD;
+                const unsigned long long s2 = s1 * JavaRandom::MULT + JavaRandom::ADD;
+                const unsigned long long s3 = s2 * JavaRandom::MULT + JavaRandom::ADD;
+                const unsigned long long m53 = (((s1 & JavaRandom::MASK) >> 22) << 27) + ((s2 & JavaRandom::MASK) >> 21);
+                const bool unmapped = m53 < perr_thr;                     // nextDouble() < perr
+                if (tid == 0) sc.cut = GIANT_NOCUT;
+                const GiantReach rr = giant_reach<NT>(unmapped ? 2 : 3, false, rtab, rmsk, sc.fin);
+                const int f = fb + rr.rank;
+                int a = -1;
+                bool reject = false;
+                unsigned long long s_after = s0;
+                if (rr.reach && f < F && !unmapped) {
+                    const int bound = P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f];
+                    const int r31 = (int)((s3 & JavaRandom::MASK) >> 17);
+                    const int m = bound - 1;
+                    if ((bound & m) == 0) a = (int)(((long long)bound * (long long)r31) >> 31);
+                    else {
+                        a = r31 % bound;
+                        // java.util.Random.nextInt redraws when u - r + m overflows int (about 1e-8 of the draws): serial
+                        if ((int)((unsigned)r31 - (unsigned)a + (unsigned)m) < 0) {
+                            reject = true;
+                            JavaRandom q; q.s = s2;
+                            a = q.nextInt(bound);
+                            s_after = q.s;
+                            atomicMin(&sc.cut, tid);
+                        }
+                    }
+                }
+                if (rr.reach && f == F) atomicMin(&sc.cut, tid);            // first offset after the last fragment
+                __syncthreads();
+                const int cut = sc.cut;
+                // fragments in front of the cut are final; a redrawing fragment AT the cut has finished itself serially
+                if (rr.reach && f < F && (tid < cut || (tid == cut && reject))) {
+                    st.stw(f, a);
+                    if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
+                }
+                if (cut == GIANT_NOCUT) {
+                    if (tid == 0) {
+                        unsigned long long s = sc.jumpA * sb + sc.jumpC;
+                        for (int i = 0; i < sc.fin[2]; ++i) s = s * JavaRandom::MULT + JavaRandom::ADD;
+                        sc.s_base = s;
+                        sc.frag_base = fb + sc.fin[0];
+                    }
+                } else if (tid == cut) {
+                    if (reject) { sc.s_base = s_after; sc.frag_base = f + 1; }
+                    else { sc.s_base = s0; sc.frag_base = f; }              // f == F: the state after the last fragment's draws
+                }
+                __syncthreads();
+            }
         }
     }
-    __syncthreads();
-    // counts, per-experiment totals, unmapped fragments
+    csync();
+    // counts, per-experiment totals, unmapped fragments (all CTAs; pooled in the first CTA's scalars)
     {
         long long e_loc[MAXE], l_loc[MAXE];
 #pragma unroll
         for (int x = 0; x < MAXE; ++x) { e_loc[x] = 0; l_loc[x] = 0; }
         int nerr_loc = 0;
-        constexpr int IB = 4;
-        for (int fb = tid * IB; fb < F; fb += NT * IB) {
-            int a[IB];
+        constexpr int IB = 8;
+        for (int fb = goff * IB; fb < F; fb += CS * NT * IB) {
+            int a[IB], ap[IB];
             int4 rec[IB];
 #pragma unroll
             for (int k = 0; k < IB; ++k) a[k] = (fb + k < F) ? st.ld(fb + k) : -2;
 #pragma unroll
-            for (int k = 0; k < IB; ++k) rec[k] = a[k] >= 0 ? P.aln_rec[P.frag_aln_ptr[f0 + fb + k] + a[k]] : make_int4(0, 0, 0, 0);
+            for (int k = 0; k < IB; ++k) ap[k] = a[k] >= 0 ? __ldg(P.frag_aln_ptr + f0 + fb + k) : 0;
+#pragma unroll
+            for (int k = 0; k < IB; ++k) rec[k] = a[k] >= 0 ? __ldg(P.aln_rec + ap[k] + a[k]) : make_int4(0, 0, 0, 0);
 #pragma unroll
             for (int k = 0; k < IB; ++k) {
                 if (a[k] == -1) ++nerr_loc;
@@ -354,18 +458,20 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 for (int y = 0; y < MAXE; ++y) if (y == x) { e_loc[y] += rec[k].x; l_loc[y] += rec[k].y; }
             }
         }
+        Scalars* s0p = remote(&sc, 0);
 #pragma unroll
         for (int x = 0; x < MAXE; ++x) {
-            if (e_loc[x]) atomicAdd((unsigned long long*)&sc.Etot[x], (unsigned long long)e_loc[x]);
-            if (l_loc[x]) atomicAdd((unsigned long long*)&sc.Ltot[x], (unsigned long long)l_loc[x]);
+            if (e_loc[x]) atomicAdd((unsigned long long*)&s0p->Etot[x], (unsigned long long)e_loc[x]);
+            if (l_loc[x]) atomicAdd((unsigned long long*)&s0p->Ltot[x], (unsigned long long)l_loc[x]);
         }
-        if (nerr_loc) atomicAdd(&sc.nerr, nerr_loc);
+        if (nerr_loc) atomicAdd(&s0p->nerr, nerr_loc);
     }
     __threadfence();
-    __syncthreads();
+    csync();
 
     // MultiBreakSVAssignmentMatrix.java:130-246 in the reference's summation order: the per-cluster terms of a chunk are
     // gathered by the whole CTA, the chunk is added up by one thread (floating-point addition does not reassociate).
+    // (first CTA of the cluster only)
     auto full_logprob = [&]() -> double {
         double lp = 0;                                                    // (meaningful in thread 0 only)
         for (int i0 = 0; i0 < C; i0 += GIANT_LPCHUNK) {
@@ -390,34 +496,41 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         }
         return lp;
     };
-    if (R.initial_logprob) {
+    if (R.initial_logprob && crank == 0) {
         const double lp = full_logprob();
         if (tid == 0) R.initial_logprob[scx] = lp;
     }
 
     // ---------------- iterations (MultiBreakSV.java:796-837, 1101-1182) ----------------
-    make_jump(JavaRandom::MULT2, JavaRandom::ADD2);                       // one offset = one nextDouble()
+    make_jump(JavaRandom::MULT2, JavaRandom::ADD2, goff, CS * NT);        // one offset = one nextDouble()
     int n_naive_prop = 0, n_naive_acc = 0, n_sv_prop = 0, n_sv_acc = 0;
     long long n_reassign = 0;
     int nerr_delta = 0;                                                   // unmapped fragments: net change committed by this thread
-    if (tid == 0) sc.done = N <= 0;
-    // logBinomial of the current totals (the chain's cached "old" value): computed once, then handed from window to window
-    if (tid < E) sc.LB[tid] = lb_of(tid, sc.Etot[tid], sc.Ltot[tid]);
-    __syncthreads();
+    // the chain's scalars live in every CTA of the cluster; the first CTA holds them now
+    if (crank == 0 && tid == 0) {
+        // logBinomial of the current totals (the chain's cached "old" value): computed once, then handed from window to window
+        for (int x = 0; x < E; ++x) sc.LB[x] = lb_of(x, sc.Etot[x], sc.Ltot[x]);
+        sc.done = N <= 0;
+        for (int k = 1; k < CS; ++k) {
+            Scalars* o = remote(&sc, k);
+            o->s_base = sc.s_base; o->iter_base = 0; o->done = sc.done; o->err = 0;
+            for (int x = 0; x < MAXE; ++x) { o->Etot[x] = sc.Etot[x]; o->Ltot[x] = sc.Ltot[x]; o->LB[x] = sc.LB[x]; }
+        }
+    }
+    csync();
 #ifdef MBSV_GIANT_PROF
     long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
     long long nwindows = 0, ncuts = 0;
 #define GPROF(i) do { if (tid == 0) { const long long c_ = clock64(); prof[i] += c_ - pc; pc = c_; } } while (0)
     if (tid == 0) pc = clock64();
-    // per-thread step times inside the gather: maximum over the threads of a window, summed over the windows
-    __shared__ int pmax[12];
-    long long ptot[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp0 = 0;
-    if (tid < 12) pmax[tid] = 0;
-#define TPROF(i) do { const long long c_ = clock64(); atomicMax(&pmax[i], (int)(c_ - tp0)); tp0 = c_; } while (0)
 #else
 #define GPROF(i) do {} while (0)
-#define TPROF(i) do {} while (0)
 #endif
+    // a cut found by any CTA is posted in every CTA's scalars (cuts are rare: a handful of remote atomics per window)
+    auto post_cut = [&](int off) {
+#pragma unroll
+        for (int k = 0; k < CS; ++k) atomicMin(&remote(&sc, k)->cut, off);
+    };
     while (!sc.done) {
         // ================= P1: one iteration per offset =================
         const unsigned long long sb = sc.s_base;
@@ -442,6 +555,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         }
         int a0 = 0, fa1 = 0, prev = -1;
         if (naive) { a0 = __ldg(P.frag_aln_ptr + f0 + f); fa1 = __ldg(P.frag_aln_ptr + f0 + f + 1); prev = st.ld(f); }
+        // (while those loads are in flight)
         for (int i = tid; i < GIANT_HASH; i += NT) { hkey[i] = -1; hlane[i] = GIANT_NOCUT; }
         const int n = fa1 - a0;
         if (naive) {
@@ -451,11 +565,32 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         }
         GPROF(0);
         // ================= P2: which offsets are iterations =================
-        const GiantReach rr = giant_reach<NT>(c, dense, rtab, rmsk, sc.fin);
+        const unsigned dmask = giant_reach_tables<NT>(c, dense, rtab, rmsk);
+        int entry = 0, rank0 = 0, drank0 = 0;
+        int cbase[CS + 1];                                                // proposals in front of every CTA of the window
+        cbase[0] = 0;
+        if (CS > 1) {
+            // every CTA publishes its transfer table (entered at offset e -> exit, items, proposals) in every CTA
+            if (tid < 8 * CS) remote(ctab, tid >> 3)[crank * 8 + (tid & 7)] = giant_reach_cta_entry<NT>(tid & 7, rtab);
+            cluster.sync();
+            int e = 0, rk = 0, dr = 0;
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+                if (k == crank) { entry = e; rank0 = rk; drank0 = dr; }
+                const unsigned t = ctab[k * 8 + e];
+                rk += (t >> 3) & 8191;
+                dr += t >> 16;
+                e = t & 7;
+                cbase[k + 1] = dr;
+            }
+            if (tid == 0) { sc.fin[0] = rk; sc.fin[1] = dr; sc.fin[2] = e; }     // the whole window: iterations, proposals, exit
+        }
+        const GiantReach rr = giant_reach_walk<NT>(entry, rank0, drank0, dmask, rtab, rmsk, CS > 1 ? nullptr : sc.fin);
         const bool act = rr.reach && dense;                               // this thread's offset is a proposal of the chain
-        const int p = rr.drank;                                           // its slot in the per-proposal arrays
+        const int pg = rr.drank;                                          // its index among the window's proposals
+        const int p = pg - drank0;                                        // its slot in this CTA's per-proposal arrays
         const int t_iter = iter_base + rr.rank;
-        if (rr.reach && t_iter == N) atomicMin(&sc.cut, tid);             // the run ends in front of this offset
+        if (rr.reach && t_iter == N) post_cut(goff);                      // the run ends in front of this offset
         GPROF(1);
         // ================= P3: gather + tentative decision =================
         int now = -1, nmoves = 0, nent = 0, q0 = 0;
@@ -467,29 +602,22 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         unsigned touched = 0;
         int dnerr = 0;
         long long reassign = 0;
-#ifdef MBSV_GIANT_PROF
-        tp0 = clock64();
-#endif
         if (act) {
             rng.s = s_mid;
             if (naive) {
                 naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, P.invint, now, Alogq, Anewlogq);
-                TPROF(0);
                 reassign = 1;
                 if (now == prev) {                                        // Error at MultiBreakSV.java:1122-1123
                     bad = true;
-                    atomicMin(&sc.cut, tid);
-                    atomicMin(&sc.errlane, tid);
+                    post_cut(goff);
+#pragma unroll
+                    for (int k = 0; k < CS; ++k) atomicMin(&remote(&sc, k)->errlane, goff);
                 } else {
                     // one round trip: both alignment records and their counted slots
                     int4 recF = make_int4(0, 0, 0, 0), recT = make_int4(0, 0, 0, 0);
                     int4 slF = make_int4(-1, -1, -1, -1), slT = make_int4(-1, -1, -1, -1);
                     if (prev != -1) { recF = __ldg(P.aln_rec + a0 + prev); slF = __ldg(P.aln_ent4 + a0 + prev); }
                     if (now != -1) { recT = __ldg(P.aln_rec + a0 + now); slT = __ldg(P.aln_ent4 + a0 + now); }
-#ifdef MBSV_GIANT_PROF
-                    if (recF.x + recT.x + slF.x + slT.x == 0x7ffffff0) printf("x");     // (profile build: wait for the loads here)
-#endif
-                    TPROF(1);
                     if (prev != -1) {
                         const int x = recF.w & 0xff;
                         const int sl[4] = {slF.x, slF.y, slF.z, slF.w};
@@ -508,7 +636,6 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                         for (int y = 0; y < MAXE; ++y) if (y == x) { dE[y] += recT.x; dL[y] += recT.y; }
                         touched |= 1u << x;
                     } else { derr = derr + logperr; ++dnerr; }
-                    TPROF(2);
                 }
             } else {
                 // ---- svMove (MultiBreakSV.java:1291-1343): toggle the cluster's single-alignment fragments ----
@@ -521,7 +648,6 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 nent = e1 - e0;
                 Alogq = neglogNsv;
                 Anewlogq = neglogNsv;
-                TPROF(3);
                 // round trip 2: fragments and slots (four loads in flight at a time)
                 for (int qb = 0; qb < nmoves; qb += 4) {
                     int g[4];
@@ -537,7 +663,6 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 4; ++i) if (kb + i < nent) ent[(kb + i) * MD + p] = (v[i].x << 5) | v[i].y;
                 }
-                TPROF(4);
                 // round trip 3 (first half; the counts follow below): current assignment of every fragment
                 for (int qb = 0; qb < nmoves; qb += 4) {
                     int a[4];
@@ -546,7 +671,6 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 4; ++i) if (qb + i < nmoves) mv[(qb + i) * MD + p] = (mv[(qb + i) * MD + p] << 1) | (a[i] == -1 ? 1 : 0);
                 }
-                TPROF(5);
                 for (int k = 0; k < nent; ++k) {                          // direction of every entry = direction of its fragment
                     const int v = ent[k * MD + p];
                     ent[k * MD + p] = ((v >> 5) << 1) | (mv[(v & 31) * MD + p] & 1);
@@ -566,7 +690,6 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                     touched |= 1u << x;
                 }
             }
-            if (!naive) TPROF(6);
             r_acc = rng.nextDouble();
             if (!bad) {
                 // counts the entries see: the stored count plus the earlier entries of this proposal on the same slot
@@ -577,7 +700,6 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 4; ++i) if (kb + i < nent) ecnt[(kb + i) * MD + p] = v[i];
                 }
-                TPROF(7);
                 for (int k = 0; k < nent; ++k) {
                     const int ek = ent[k * MD + p];
                     int cn = ecnt[k * MD + p];
@@ -589,7 +711,6 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                     const double* Tx = Tp + (size_t)slot_exp(ek >> 1) * Tstride;
                     dcov = dcov + (Tx[cn + ((ek & 1) ? 1 : -1)] - Tx[cn]);
                 }
-                TPROF(8);
                 // tentative decision against the totals at the window start (approximate arithmetic, see giant_lb_approx)
                 double dlb = 0.0;
                 unsigned mask = touched & ((1u << E) - 1u);
@@ -607,7 +728,6 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 const double arg = ((dcov + derr) + dlb + Alogq) - Anewlogq;
                 const double e = (double)__expf((float)arg);
                 flagA = fmin(1.0, e) > r_acc;                             // (NaN: not accepted, like the exact test)
-                TPROF(9);
             }
         }
         GPROF(2);
@@ -617,7 +737,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
 #pragma unroll
         for (int x = 0; x < MAXE; ++x) {
             pre[x] = flagA ? dE[x] : 0; pre[MAXE + x] = flagA ? dL[x] : 0;
-            last[x] = (flagA && ((touched >> x) & 1u)) ? p : -1;
+            last[x] = (flagA && ((touched >> x) & 1u)) ? pg : -1;
         }
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -657,6 +777,31 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 lastx[x] = max(lastx[x], wlast[k * MAXE + x]);
             }
         }
+        if (CS > 1) {
+            // the CTA's own totals go to every CTA; the ones of the CTAs in front are added
+            if (tid == NT - 1) {
+#pragma unroll
+                for (int k = 0; k < CS; ++k) {
+                    long long* ct = remote(ctot, k) + crank * 2 * MAXE;
+                    int* cl = remote(clast, k) + crank * MAXE;
+#pragma unroll
+                    for (int x = 0; x < MAXE; ++x) {
+                        ct[x] = Ecur[x] + (flagA ? dE[x] : 0);
+                        ct[MAXE + x] = Lcur[x] + (flagA ? dL[x] : 0);
+                        cl[x] = max(lastx[x], (flagA && ((touched >> x) & 1u)) ? pg : -1);
+                    }
+                }
+            }
+            cluster.sync();
+            for (int k = 0; k < crank; ++k) {
+#pragma unroll
+                for (int x = 0; x < MAXE; ++x) {
+                    Ecur[x] += ctot[k * 2 * MAXE + x];
+                    Lcur[x] += ctot[k * 2 * MAXE + MAXE + x];
+                    lastx[x] = max(lastx[x], clast[k * MAXE + x]);
+                }
+            }
+        }
 #pragma unroll
         for (int x = 0; x < MAXE; ++x) { Ecur[x] += sc.Etot[x]; Lcur[x] += sc.Ltot[x]; }   // the totals this offset would see
         GPROF(3);
@@ -678,8 +823,15 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 if (flagA) nls[x * MD + p] = v;
             }
         }
-        __syncthreads();
+        csync();
         GPROF(4);
+        // the value proposal `q` (window index) published for experiment x: in the shared memory of the CTA that owns q
+        auto published = [&](int x, int q) -> double {
+            int k = 0;
+#pragma unroll
+            for (int kk = 1; kk < CS; ++kk) if (q >= cbase[kk]) k = kk;
+            return remote(nls, k)[x * MD + (q - cbase[k])];
+        };
         if (act && !bad) {
             // ---- the exact decision (MultiBreakSV.java:1146), FAST arithmetic ----
             double dlb = 0.0;
@@ -691,7 +843,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 int lx = -1;
 #pragma unroll
                 for (int y = 0; y < MAXE; ++y) if (y == x) { nlx = nl[y]; lx = lastx[y]; }
-                const double old = lx >= 0 ? nls[x * MD + lx] : sc.LB[x];
+                const double old = lx >= 0 ? published(x, lx) : sc.LB[x];
                 dlb = dlb + (nlx - old);
             }
             const double delta = (dcov + derr) + dlb;
@@ -699,7 +851,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
             const double e = exp_dev(arg);
             const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);      // Math.min(1, e)
             flagB = ratio > r_acc;
-            if (flagB != flagA) atomicMin(&sc.cut, tid);                  // the hypothesis fails here: redo from this iteration
+            if (flagB != flagA) post_cut(goff);                           // the hypothesis fails here: redo from this iteration
         }
         // ================= P5: stale reads.  Accepted proposals publish the rows they write ... =================
         const int nfr = naive ? 1 : nmoves;
@@ -710,23 +862,30 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
             for (int kb = 0; kb < nkeys; kb += 4) {
                 int key[4], old[4];
                 unsigned h[4];
+                int* hk[4];
+                int* hl[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) if (kb + i < nkeys) { key[i] = key_at(kb + i); h[i] = hash_of(key[i]); old[i] = atomicCAS(&hkey[h[i]], -1, key[i]); }
+                for (int i = 0; i < 4; ++i) if (kb + i < nkeys) {
+                    key[i] = key_at(kb + i); h[i] = hash_of(key[i]);
+                    const int ow = owner_of(key[i]);
+                    hk[i] = remote(hkey, ow); hl[i] = remote(hlane, ow);
+                    old[i] = atomicCAS(&hk[i][h[i]], -1, key[i]);
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) if (kb + i < nkeys) {
                     bool placed = old[i] == -1 || old[i] == key[i];
                     for (int guard = 0; !placed && guard < GIANT_HASH; ++guard) {
                         h[i] = (h[i] + 1) & (GIANT_HASH - 1);
-                        const int o = atomicCAS(&hkey[h[i]], -1, key[i]);
+                        const int o = atomicCAS(&hk[i][h[i]], -1, key[i]);
                         placed = o == -1 || o == key[i];
                     }
-                    if (placed) atomicMin(&hlane[h[i]], tid); else ok = false;
+                    if (placed) atomicMin(&hl[i][h[i]], goff); else ok = false;
                 }
             }
             // set full (cannot happen below ~4000 written rows per window): nothing behind this proposal is committed
-            if (!ok && tid + c < NT) atomicMin(&sc.cut, tid + c);
+            if (!ok && goff + c < CS * NT) post_cut(goff + c);
         }
-        __syncthreads();
+        csync();
         GPROF(5);
         // ... and the first proposal that read a row written in front of it cuts the window
         if (nkeys) {
@@ -734,26 +893,33 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
             for (int kb = 0; kb < nkeys; kb += 4) {
                 int key[4], k0[4], l0[4];
                 unsigned h[4];
+                const int* hk[4];
+                const int* hl[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) if (kb + i < nkeys) { key[i] = key_at(kb + i); h[i] = hash_of(key[i]); k0[i] = hkey[h[i]]; l0[i] = hlane[h[i]]; }
+                for (int i = 0; i < 4; ++i) if (kb + i < nkeys) {
+                    key[i] = key_at(kb + i); h[i] = hash_of(key[i]);
+                    const int ow = owner_of(key[i]);
+                    hk[i] = remote(hkey, ow); hl[i] = remote(hlane, ow);
+                    k0[i] = hk[i][h[i]]; l0[i] = hl[i][h[i]];
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) if (kb + i < nkeys) {
                     int k = k0[i], l = l0[i];
                     for (int guard = 0; k != -1 && k != key[i] && guard < GIANT_HASH; ++guard) {
                         h[i] = (h[i] + 1) & (GIANT_HASH - 1);
-                        k = hkey[h[i]]; l = hlane[h[i]];
+                        k = hk[i][h[i]]; l = hl[i][h[i]];
                     }
-                    if (k == key[i] && l < tid) stale = true;
+                    if (k == key[i] && l < goff) stale = true;
                 }
             }
-            if (stale) atomicMin(&sc.cut, tid);
+            if (stale) post_cut(goff);
         }
-        __syncthreads();
+        csync();
         GPROF(6);
         // ================= P6: commit the iterations in front of the cut =================
         const int cut = sc.cut;
         const int errlane = sc.errlane;
-        if (act && tid < cut) {
+        if (act && goff < cut) {
             if (naive) ++n_naive_prop; else ++n_sv_prop;
             n_reassign += reassign;
             if (flagB) {
@@ -790,98 +956,122 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 }
             }
         }
-        if (act && bad && tid == cut) {
+        // base of the next window: RNG position, iteration count, totals and cached logBinomial (= what the first uncommitted
+        // offset would see), written into every CTA of the cluster by the one thread that knows them
+        bool writer = false;
+        unsigned long long nb_s = 0;
+        int nb_iter = 0, nb_err = 0;
+        if (act && bad && goff == cut) {
             // the reference throws here: the chain stops with the proposal counted and its draws consumed
             ++n_naive_prop; n_reassign += 1;
-            sc.s_base = rng.s;
-            sc.err = -5;                                                  // MBSV_ERR_INVARIANT
-            sc.done = 1;
-        }
-        // base of the next window: RNG position, iteration count, totals (= what the first uncommitted offset would see)
-        if (cut == GIANT_NOCUT) {
-            if (tid == NT - 1) {
-                unsigned long long s = sc.jumpA * sb + sc.jumpC;
-                for (int i = 0; i < sc.fin[2]; ++i) s = s * JavaRandom::MULT2 + JavaRandom::ADD2;
-                sc.s_base = s;
-                sc.iter_base = iter_base + sc.fin[0];
-                if (iter_base + sc.fin[0] >= N) sc.done = 1;
+            writer = true; nb_s = rng.s; nb_iter = t_iter; nb_err = -5;   // MBSV_ERR_INVARIANT
+        } else if (cut == GIANT_NOCUT) {
+            if (crank == CS - 1 && tid == NT - 1) {
+                writer = true;
+                nb_s = sc.jumpA * sb + sc.jumpC;
+                for (int i = 0; i < sc.fin[2]; ++i) nb_s = nb_s * JavaRandom::MULT2 + JavaRandom::ADD2;
+                nb_iter = iter_base + sc.fin[0];
 #pragma unroll
-                for (int x = 0; x < MAXE; ++x) {
-                    sc.Etot[x] = Ecur[x] + (flagA ? dE[x] : 0); sc.Ltot[x] = Lcur[x] + (flagA ? dL[x] : 0);
-                    if (flagA && ((touched >> x) & 1u)) sc.LB[x] = nl[x]; else if (lastx[x] >= 0) sc.LB[x] = nls[x * MD + lastx[x]];
+                for (int x = 0; x < MAXE; ++x) {                          // inclusive: this thread's own proposal counts
+                    if (flagA && ((touched >> x) & 1u)) lastx[x] = -2;    // (its logBinomial is in nl[x])
+                    Ecur[x] += flagA ? dE[x] : 0; Lcur[x] += flagA ? dL[x] : 0;
                 }
             }
-        } else if (tid == cut && cut != errlane) {
-            sc.s_base = jA * sb + jC;
-            sc.iter_base = t_iter;
-            if (t_iter >= N) sc.done = 1;
+        } else if (goff == cut && cut != errlane) {
+            writer = true; nb_s = jA * sb + jC; nb_iter = t_iter;
+        }
+        if (writer) {
+            double lbn[MAXE];
 #pragma unroll
-            for (int x = 0; x < MAXE; ++x) {
-                sc.Etot[x] = Ecur[x]; sc.Ltot[x] = Lcur[x];
-                if (lastx[x] >= 0) sc.LB[x] = nls[x * MD + lastx[x]];      // logBinomial after the last committed accepted move
+            for (int x = 0; x < MAXE; ++x) lbn[x] = lastx[x] == -2 ? nl[x] : lastx[x] >= 0 ? published(x, lastx[x]) : sc.LB[x];
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+                Scalars* o = remote(&sc, k);
+                o->s_base = nb_s;
+                if (nb_err) { o->err = nb_err; o->done = 1; }
+                else {
+                    o->iter_base = nb_iter;
+                    if (nb_iter >= N) o->done = 1;
+#pragma unroll
+                    for (int x = 0; x < MAXE; ++x) { o->Etot[x] = Ecur[x]; o->Ltot[x] = Lcur[x]; o->LB[x] = lbn[x]; }
+                }
             }
         }
-        __syncthreads();
+        csync();
         GPROF(7);
 #ifdef MBSV_GIANT_PROF
         ++nwindows; if (cut != GIANT_NOCUT) ++ncuts;
-        if (tid == 0) for (int i = 0; i < 12; ++i) { ptot[i] += pmax[i]; pmax[i] = 0; }
 #endif
     }
 #ifdef MBSV_GIANT_PROF
     if (tid == 0 && blockIdx.x == 0)
-        printf("giant prof: windows %lld cuts %lld iters %d | cycles/window: P1 %lld reach %lld gather+A %lld scan %lld nl %lld evalB+ins %lld stale %lld commit %lld\n",
-               nwindows, ncuts, N, prof[0] / max(nwindows, 1LL), prof[1] / max(nwindows, 1LL), prof[2] / max(nwindows, 1LL), prof[3] / max(nwindows, 1LL),
+        printf("giant prof (CS %d): windows %lld cuts %lld iters %d | cycles/window: P1 %lld reach %lld gather+A %lld scan %lld nl %lld evalB+ins %lld stale %lld commit %lld\n",
+               CS, nwindows, ncuts, N, prof[0] / max(nwindows, 1LL), prof[1] / max(nwindows, 1LL), prof[2] / max(nwindows, 1LL), prof[3] / max(nwindows, 1LL),
                prof[4] / max(nwindows, 1LL), prof[5] / max(nwindows, 1LL), prof[6] / max(nwindows, 1LL), prof[7] / max(nwindows, 1LL));
-    if (tid == 0 && blockIdx.x == 0)
-        printf("giant prof (max over threads): naive: pick %lld rt1 %lld entries %lld | sv: rt1 %lld rt2 %lld rt3 %lld dir+rec %lld | counts %lld dcov %lld approxA %lld\n",
-               ptot[0] / max(nwindows, 1LL), ptot[1] / max(nwindows, 1LL), ptot[2] / max(nwindows, 1LL), ptot[3] / max(nwindows, 1LL), ptot[4] / max(nwindows, 1LL),
-               ptot[5] / max(nwindows, 1LL), ptot[6] / max(nwindows, 1LL), ptot[7] / max(nwindows, 1LL), ptot[8] / max(nwindows, 1LL), ptot[9] / max(nwindows, 1LL));
 #endif
 
-    // ---------------- epilogue: final tallies, state, counters ----------------
+    // ---------------- epilogue: final tallies, state, counters (pooled in the first CTA of the cluster) ----------------
     {
+        Scalars* s0p = remote(&sc, 0);
         const long long v[5] = {n_naive_prop, n_naive_acc, n_sv_prop, n_sv_acc, n_reassign};
 #pragma unroll
-        for (int i = 0; i < 5; ++i) if (v[i]) atomicAdd(&sc.cnt[i], (unsigned long long)v[i]);
-        if (nerr_delta) atomicAdd(&sc.nerr, nerr_delta);
+        for (int i = 0; i < 5; ++i) if (v[i]) atomicAdd(&s0p->cnt[i], (unsigned long long)v[i]);
+        if (nerr_delta) atomicAdd(&s0p->nerr, nerr_delta);
     }
-    __syncthreads();
+    csync();
     const int err = sc.err;
     if (err == 0) {
         const long long nwin = (long long)N - win_base;
         if (nwin > 0) {
             const unsigned d = (unsigned)nwin;
-            for (int ff = tid; ff < F; ff += NT) {
-                const int a = st.ld(ff);
-                if (a == -1) atomicAdd(&R.frag_err_count[f0 + ff], d);
-                else atomicAdd(&R.aln_count[P.frag_aln_ptr[f0 + ff] + a], d);
+            // eight loads in flight per thread: these passes over the whole state are latency bound
+            constexpr int EB = 8;
+            for (int fb = goff; fb < F; fb += CS * NT * EB) {
+                int a[EB], ap[EB];
+#pragma unroll
+                for (int k = 0; k < EB; ++k) { const int ff = fb + k * CS * NT; a[k] = ff < F ? st.ld(ff) : -2; }
+#pragma unroll
+                for (int k = 0; k < EB; ++k) { const int ff = fb + k * CS * NT; ap[k] = a[k] >= 0 ? __ldg(P.frag_aln_ptr + f0 + ff) : 0; }
+#pragma unroll
+                for (int k = 0; k < EB; ++k) {
+                    const int ff = fb + k * CS * NT;
+                    if (a[k] == -1) atomicAdd(&R.frag_err_count[f0 + ff], d);
+                    else if (a[k] >= 0) atomicAdd(&R.aln_count[ap[k] + a[k]], d);
+                }
             }
             const int nslot = C * E;
-            for (int s = tid; s < nslot; s += NT) {
-                const int n = st.ld(F + s);
-                if (n > 0) atomicAdd(&R.cluster_hist[P.cluster_hist_ptr[c0 + slot_cluster(s)] + n], d);
+            for (int sb = goff; sb < nslot; sb += CS * NT * EB) {
+                int n[EB], hp[EB];
+#pragma unroll
+                for (int k = 0; k < EB; ++k) { const int s = sb + k * CS * NT; n[k] = s < nslot ? st.ld(F + s) : 0; }
+#pragma unroll
+                for (int k = 0; k < EB; ++k) { const int s = sb + k * CS * NT; hp[k] = n[k] > 0 ? __ldg(P.cluster_hist_ptr + c0 + slot_cluster(s)) : 0; }
+#pragma unroll
+                for (int k = 0; k < EB; ++k) if (n[k] > 0) atomicAdd(&R.cluster_hist[hp[k] + n[k]], d);
             }
         }
     }
     if (R.final_assign)
-        for (int ff = tid; ff < F; ff += NT) R.final_assign[(size_t)chain * P.n_frag + f0 + ff] = st.ld(ff);
-    if (R.final_logprob) {
-        const double lp = full_logprob();
-        if (tid == 0) R.final_logprob[scx] = lp;
-    }
-    if (tid == 0) {
-        if (R.counters) {
-            long long* k = R.counters + scx * 5;
-            for (int i = 0; i < 5; ++i) k[i] = (long long)sc.cnt[i];
+        for (int ff = goff; ff < F; ff += CS * NT) R.final_assign[(size_t)chain * P.n_frag + f0 + ff] = st.ld(ff);
+    if (crank == 0) {
+        if (R.final_logprob) {
+            const double lp = full_logprob();
+            if (tid == 0) R.final_logprob[scx] = lp;
         }
-        if (R.rng_state) R.rng_state[scx] = sc.s_base & JavaRandom::MASK;
-        if (R.error) R.error[scx] = err;
-        if (R.totals) {
-            for (int i = 0; i < 5; ++i) atomicAdd(&R.totals[i], sc.cnt[i]);
-            if (err) atomicCAS(&R.totals[5], 0ULL, (unsigned long long)(long long)err);
+        if (tid == 0) {
+            if (R.counters) {
+                long long* k = R.counters + scx * 5;
+                for (int i = 0; i < 5; ++i) k[i] = (long long)sc.cnt[i];
+            }
+            if (R.rng_state) R.rng_state[scx] = sc.s_base & JavaRandom::MASK;
+            if (R.error) R.error[scx] = err;
+            if (R.totals) {
+                for (int i = 0; i < 5; ++i) atomicAdd(&R.totals[i], sc.cnt[i]);
+                if (err) atomicCAS(&R.totals[5], 0ULL, (unsigned long long)(long long)err);
+            }
         }
     }
+    csync();       // no CTA of the cluster leaves while another may still address its shared memory
 }
 
 }  // namespace mbsv

@@ -25,13 +25,29 @@ cudaError_t launch_giant_prep(const DevProblem& P, int4* aln_ent4, cudaStream_t 
     return cudaGetLastError();
 }
 
-KernelFn get_kernel_giant(int n_exp, int* threads, size_t* smem_bytes) {
+// cluster = CTAs per chain (1, 2, 4 or 8): launched as a thread-block cluster of that size (cudaLaunchKernelEx)
+KernelFn get_kernel_giant(int n_exp, int cluster, int* threads, size_t* smem_bytes) {
     constexpr int NT = 512;
     *threads = NT;
-    if (n_exp <= 2) { *smem_bytes = GiantLayout<NT, 2>::bytes; return mbsv_giant_kernel<NT, 2>; }
-    *smem_bytes = GiantLayout<NT, 4>::bytes;
-    return mbsv_giant_kernel<NT, 4>;
+    *smem_bytes = n_exp <= 2 ? GiantLayout<NT, 2>::bytes : GiantLayout<NT, 4>::bytes;
+    if (n_exp <= 2) {
+        switch (cluster) {
+            case 1: return mbsv_giant_kernel<NT, 2, 1>;
+            case 2: return mbsv_giant_kernel<NT, 2, 2>;
+            case 4: return mbsv_giant_kernel<NT, 2, 4>;
+            case 8: return mbsv_giant_kernel<NT, 2, 8>;
+        }
+    } else {
+        switch (cluster) {
+            case 1: return mbsv_giant_kernel<NT, 4, 1>;
+            case 2: return mbsv_giant_kernel<NT, 4, 2>;
+            case 4: return mbsv_giant_kernel<NT, 4, 4>;
+            case 8: return mbsv_giant_kernel<NT, 4, 8>;
+        }
+    }
+    return nullptr;
 }
+int giant_window_offsets() { return 512; }
 int giant_max_entries() { return GIANT_MAXENT < GIANT_MAXMV ? GIANT_MAXENT : GIANT_MAXMV; }
 int giant_max_aln_entries() { return GIANT_ALN_SLOTS; }
 }  // namespace mbsv

@@ -10,6 +10,7 @@
 #include <numeric>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <string>
 #include <thread>
 #include <vector>
@@ -83,6 +84,7 @@ struct mbsv_problem {
     std::vector<int> sub_F;       // fragments of subproblem s
     std::vector<int> sub_nsv;     // AlterSV candidates of subproblem s
     std::vector<int> sub_nstates; // joint state space prod(n_f + 1), saturated at 2^30; 0 when it has a conn-comp
+    std::vector<int> frag_nal;    // alignments per fragment (validation of a host-supplied initial state)
     std::vector<int> sub_maxent;  // most count entries / toggled fragments of one AlterSV proposal (giant_kernel.cuh)
     std::vector<int> sub_maxpos;  // most counted slots of one alignment
     DevBuf<int4> d_aln_ent4, d_sv_mv;      // flattened views for the speculative-window kernel
@@ -268,6 +270,11 @@ static int validate(const mbsv_problem_desc* d) {
                     if (d->root_leaf[j] < 0 || d->root_leaf[j] >= nl) return fail(MBSV_ERR_ARG, "root_leaf out of range");
         }
     }
+    // Experiment.logprobcov[0] is never written by the reference (Java zero-initialises it, MultiBreakSV.java:612-614) and
+    // the Delta arithmetic of MBSV_MODE_FAST relies on it
+    for (int x = 0; x < d->n_exp; ++x)
+        if (d->logprobcov[(size_t)x * (d->max_support + 1)] != 0.0)
+            return fail(MBSV_ERR_ARG, "logprobcov[x][0] must be 0 (MultiBreakSV.java:612-614 fills k = 1..maxSupport)");
     for (int a = 0; a < d->n_aln; ++a) {
         if (d->aln_exp[a] < 0 || d->aln_exp[a] >= d->n_exp) return fail(MBSV_ERR_ARG, "aln_exp out of range");
         if (d->aln_esp_ptr[a + 1] - d->aln_esp_ptr[a] >= (1 << 23)) return fail(MBSV_ERR_ARG, "alignment with too many ESPs");
@@ -459,6 +466,8 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         p->sub_nsv.push_back(sub_sv_ptr[s + 1] - sub_sv_ptr[s]);
     }
     p->sub_maxent = sub_maxent;
+    p->frag_nal.resize(F);
+    for (int f = 0; f < F; ++f) p->frag_nal[f] = d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f];
     p->sub_maxpos = sub_maxpos;
 
     auto up = [&](auto& buf, const auto& vec) -> cudaError_t { return buf.upload(vec); };
@@ -607,11 +616,12 @@ int ensure_plan(mbsv_problem* p, int memo_states, int tab_mode) {
             // whole tile still fits the small size classes, else it lives in the global table buffer
             const int fr = (p->sub_F[s] + 1) & ~1;
             // one-fragment subproblems without AlterSV candidates also tabulate the acceptance ratios (nst^2)
-            const int ratio_words = (p->sub_F[s] == 1 && p->sub_nsv[s] == 0) ? 2 * nst * nst : 0;
-            const int with_table = rows + (fr + 2 * nst + ratio_words + 31) / 32;
+            // (64-bit: nst may be 65536; a ratio table that cannot fit simply makes with_table exceed SMEM_TABLE_ROWS)
+            const long long ratio_words = (p->sub_F[s] == 1 && p->sub_nsv[s] == 0) ? 2LL * nst * nst : 0;
+            const long long with_table = rows + (fr + 2LL * nst + ratio_words + 31) / 32;
             int trows = 0;
             bool global_table = true;
-            if (tab_mode == 1 && with_table <= SMEM_TABLE_ROWS) { trows = with_table; global_table = false; }
+            if (tab_mode == 1 && with_table <= SMEM_TABLE_ROWS) { trows = (int)with_table; global_table = false; }
             else if (tab_mode == 1) trows = rows + (fr + 31) / 32;
             else if (tab_mode == 2) trows = rows + p->sub_F[s];
             // the memoised kernel keeps its state in shared memory: larger tiles (many clusters) stay in the general kernel
@@ -710,6 +720,10 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     if (rp->init_assign) {
         if (results_on_device) dr.init_assign = rp->init_assign;
         else {
+            // the kernels index the alignment records with it: every entry must be -1 or an alignment of its fragment
+            for (int f = 0; f < p->n_frag; ++f)
+                if (rp->init_assign[f] < -1 || rp->init_assign[f] >= p->frag_nal[f])
+                    return fail(MBSV_ERR_ARG, "init_assign: entry outside [-1, alignments of the fragment)");
             CUDA_TRY(ob.init_assign_in.alloc(p->n_frag));
             CUDA_TRY(cudaMemcpy(ob.init_assign_in.p, rp->init_assign, sizeof(int) * p->n_frag, cudaMemcpyHostToDevice));
             dr.init_assign = ob.init_assign_in.p;
@@ -914,10 +928,26 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         r.lanes_per_warp = l.lanes;
         r.memo_mixed = mixed ? 1 : 0;
         r.totals = p->d_launch_totals.p + 6 * (size_t)nstream;
-        int giant_threads = 0;
+        int giant_threads = 0, giant_cs = 1;
         size_t giant_smem = 0;
+        if (l.giant) {
+            // CTAs per chain: a cluster of CS CTAs evaluates windows CS times as long.  As many as the GPU has SMs for
+            // (every CTA takes a whole SM), capped where stale reads would cut most windows short: the expected number of
+            // proposals reading a row written earlier in the same window grows like (window length)^2 / fragments.
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+            const int64_t chains = l.i1 - l.i0;
+            int minF = 1 << 30;
+            for (int64_t it = l.i0; it < l.i1; it += X) minF = std::min(minF, p->sub_F[p->sub_order[it / X]]);
+            const double by_conflicts = std::sqrt(32.0 * minF) / mbsv::giant_window_offsets();
+            while (giant_cs < 8 && (int64_t)giant_cs * 2 * chains <= sms && giant_cs * 2 <= by_conflicts) giant_cs *= 2;
+            if (const char* env = std::getenv("MBSV_GIANT_CLUSTER")) {
+                const int v = std::atoi(env);
+                if (v == 1 || v == 2 || v == 4 || v == 8) giant_cs = v;
+            }
+        }
         KernelFn fn = gibbs ? mbsv::get_kernel_gibbs(32 / l.lanes)
-                     : l.giant ? mbsv::get_kernel_giant(p->n_exp, &giant_threads, &giant_smem)
+                     : l.giant ? mbsv::get_kernel_giant(p->n_exp, giant_cs, &giant_threads, &giant_smem)
                      : l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : (!l.smem && l.lanes == 1 && !rp->trace) ? mbsv::get_kernel_packed(rp->mode, p->has_cc)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
@@ -929,9 +959,20 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         static const bool serial = std::getenv("MBSV_SERIAL_LAUNCHES") != nullptr;
         cudaStream_t st = serial ? p->streams[1] : p->streams[1 + nstream];
         CUDA_TRY(cudaStreamWaitEvent(st, (l.memo && have_global_tables) ? p->ev_built : p->ev_start, 0));
-        const int grid = l.giant ? l.we - l.wb : (l.we - l.wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;   // giant: one CTA per chain
+        // giant: one CTA (or one cluster of giant_cs CTAs) per chain
+        const int grid = l.giant ? (l.we - l.wb) * giant_cs : (l.we - l.wb + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         CUDA_TRY(cudaEventRecord(p->ev_cls0[1 + nstream], st));
-        fn<<<grid, l.giant ? giant_threads : WARPS_PER_CTA * 32, shm, st>>>(p->dp, r);
+        if (l.giant) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(giant_threads); cfg.dynamicSmemBytes = shm; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = giant_cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, p->dp, r));
+        } else {
+            fn<<<grid, WARPS_PER_CTA * 32, shm, st>>>(p->dp, r);
+        }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(p->ev_cls1[1 + nstream], st));
         g_launch_info.push_back({l.smem ? l.rows : 0, l.we - l.wb, grid, (int)shm, 0.f, l.memo ? 1 : 0});

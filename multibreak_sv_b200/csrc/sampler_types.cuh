@@ -98,7 +98,8 @@ KernelFn get_kernel_packed(int mode, bool cc);                   // one chain pe
 KernelFn get_kernel_gibbs(int group);                            // heat-bath sampler, `group` (4, 8, 32) lanes per chain (gibbs_kernel.cuh)
 KernelFn get_kernel_memo(bool trace, bool mixed);               // memoised subproblems (memo_kernel.cuh)
 // speculative-window kernel, one CTA per (subproblem, chain) (giant_kernel.cuh): FAST, no trace, no connected components
-KernelFn get_kernel_giant(int n_exp, int* threads, size_t* smem_bytes);
+KernelFn get_kernel_giant(int n_exp, int cluster, int* threads, size_t* smem_bytes);   // cluster = CTAs per chain: 1, 2, 4, 8
+int giant_window_offsets();                                      // RNG offsets one CTA evaluates per window
 int giant_max_entries();                                         // most count entries / toggled fragments of one proposal it takes
 int giant_max_aln_entries();                                     // most counted slots of one alignment it takes
 cudaError_t launch_giant_prep(const DevProblem& P, int4* aln_ent4, cudaStream_t stream);   // fills aln_ent4

@@ -111,6 +111,12 @@ def test_descriptor_validation(mbsv, example_problem):
         bad = to_packed(mbsv, example_problem)
         bad.scalars[key] = 0
         assert create(bad) == -1 and b"out of range" in L.mbsv_last_error()
+    # Experiment.logprobcov[0] is always 0 in the reference; the Delta arithmetic relies on it
+    bad = to_packed(mbsv, example_problem)
+    lp = p.arrays["logprobcov"].copy()
+    lp[0] = -1.5
+    bad.arrays["logprobcov"] = lp
+    assert create(bad) == -1 and b"logprobcov" in L.mbsv_last_error()
     # a fragment without any alignment is ragged input the packer rejects too
     bad = to_packed(mbsv, example_problem)
     fp = p.arrays["frag_aln_ptr"].copy()

@@ -22,11 +22,15 @@ def all_global(monkeypatch):
     monkeypatch.setenv("MBSV_SMEM_CLASSES", "0")
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 @pytest.mark.parametrize("nfrag,chains,iters,perr,seed", [(3000, 3, 6000, 0.001, 1), (20000, 2, 30000, 0.001, 2),
                                                           (60, 4, 3000, 0.001, 3), (700, 5, 4000, 0.3, 4),
                                                           (2500, 1, 700, 0.6, 5)])
-def test_giant_component_matches_oracle(oracle, mbsv, all_global, nfrag, chains, iters, perr, seed):
+def test_giant_component_matches_oracle(oracle, mbsv, all_global, monkeypatch, nfrag, chains, iters, perr, seed, cluster):
+    """cluster = CTAs per chain (a thread-block cluster shares one chain's windows through distributed shared memory);
+    forced here also where the planner would not pick it: on small states most windows are cut by stale reads."""
     from multibreak_sv_b200 import synth
+    monkeypatch.setenv("MBSV_GIANT_CLUSTER", str(cluster))
     p = synth.generate("cfg5", n_frag=nfrag, seed=seed, shuffle_orders=True)
     op = oracle.Problem(p.scalars, p.arrays)
     dp = mbsv.DeviceProblem(p)
@@ -37,10 +41,12 @@ def test_giant_component_matches_oracle(oracle, mbsv, all_global, nfrag, chains,
     assert int(g.counters[..., 2].sum()) > 0 or nfrag < 100          # AlterSV proposals went through the windows too
 
 
+@pytest.mark.parametrize("cluster", [1, 4])
 @pytest.mark.parametrize("iters", [0, 1, 2, 3, 5, 8, 13, 40, 157, 158, 159, 1000])
-def test_giant_run_lengths(oracle, mbsv, all_global, iters):
+def test_giant_run_lengths(oracle, mbsv, all_global, monkeypatch, iters, cluster):
     """Runs that end inside the first window, exactly at a window's last iteration, and after several windows."""
     from multibreak_sv_b200 import synth
+    monkeypatch.setenv("MBSV_GIANT_CLUSTER", str(cluster))
     p = synth.generate("cfg5", n_frag=1500, seed=11)
     op = oracle.Problem(p.scalars, p.arrays)
     dp = mbsv.DeviceProblem(p)
@@ -65,9 +71,10 @@ def test_giant_host_supplied_initial_state_and_int_wrap(oracle, mbsv, all_global
     assert np.array_equal(g.initial_assign[0], init)
 
 
-@pytest.mark.parametrize("n_exp", [1, 3, 4])
-def test_giant_experiment_counts(oracle, mbsv, all_global, n_exp):
+@pytest.mark.parametrize("n_exp,cluster", [(1, 1), (3, 1), (4, 1), (3, 2), (4, 8)])
+def test_giant_experiment_counts(oracle, mbsv, all_global, monkeypatch, n_exp, cluster):
     from multibreak_sv_b200 import synth
+    monkeypatch.setenv("MBSV_GIANT_CLUSTER", str(cluster))
     p = _with_experiments(mbsv, synth.generate("cfg5", n_frag=2500, seed=13), n_exp, 5)
     op = oracle.Problem(p.scalars, p.arrays)
     dp = mbsv.DeviceProblem(p)

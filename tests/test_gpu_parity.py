@@ -49,6 +49,61 @@ def test_example_replay_exact(oracle, mbsv, example_problem):
     assert h.hexdigest() == KAT6_SHA
 
 
+def used_kernels(dp):
+    """'memo' / 'smem' / 'global' per launch of the last run (mbsv_last_launch_info: negative rows = memoised kernel)."""
+    return ["memo" if li["rows"] < 0 else "global" if li["rows"] == 0 else "smem" for li in dp.launch_info()]
+
+
+def test_example_replay_exact_general_kernel(oracle, mbsv, example_problem):
+    """BASELINE config 1 again with the memo disabled (memo_states = 0): the shipped example has 32,670 joint states, so
+    with the default memo_states it runs in mbsv_memo_kernel; here mbsv_chain_kernel<REPLAY_EXACT, TRACE> and
+    mbsv_chain_kernel<FAST> replay the same chain (MultiBreakSV.java:78,773-877): KAT-6 trajectory SHA, counters, LCG state."""
+    dp = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
+    o = oracle.run(example_problem, "faithful", 10000, trace=True)
+    for trace in (True, False):
+        g = dp.run(mbsv.MODE_REPLAY_EXACT, 10000, trace=trace, memo_states=0)
+        assert used_kernels(dp) == ["smem"]
+        assert_same(o, g, trace=trace)
+        assert g.counters[0, 0].tolist() == [5006, 1174, 0, 0, 5006]
+        assert int(g.rng_state[0, 0]) == 0x226A00D3B97D
+    g = dp.run(mbsv.MODE_REPLAY_EXACT, 10000, trace=True, memo_states=0)
+    st = oracle.replay_states(example_problem, g.initial_assign[0], g.trace_move_frag[0, 0], g.trace_move_assign[0, 0])
+    order = example_problem.names["sorted_frag"]
+    h = hashlib.sha256()
+    for row in st:
+        h.update((",".join(str(row[i]) for i in order) + "\n").encode())
+    assert h.hexdigest() == KAT6_SHA
+    # FAST (Delta arithmetic, general kernel), with and without trace, one and many chains
+    oi = oracle.run(example_problem, "incremental", 10000, trace=True, memo_states=0)
+    for trace in (True, False):
+        f = dp.run(mbsv.MODE_FAST, 10000, trace=trace, java_int_wrap=True, memo_states=0)
+        assert used_kernels(dp) == ["smem"]
+        assert_same(oi, f, trace=trace)
+        assert f.counters[0, 0].tolist() == [5006, 1174, 0, 0, 5006] and int(f.rng_state[0, 0]) == 0x226A00D3B97D
+    assert np.array_equal(oi.trace_move_frag, o.trace_move_frag)          # the Delta arithmetic takes the same decisions
+    o64 = oracle.run(example_problem, "incremental", 3000, n_chains=64, memo_states=0)
+    f64 = dp.run(mbsv.MODE_FAST, 3000, n_chains=64, java_int_wrap=True, memo_states=0)
+    assert_same(o64, f64)
+
+
+def test_second_shipped_data_set_general_kernel(oracle, mbsv):
+    """Preprocessor-example (16 long reads, 10 clusters, AlterSV candidates) with the memo disabled: Naive and AlterSV
+    proposals of real data through mbsv_chain_kernel in both modes."""
+    from conftest import GOLDEN
+    pre = os.path.join(GOLDEN, "preproc_infiles")
+    prob = oracle.load_files(os.path.join(pre, "gasv.in.clusters"), os.path.join(pre, "assignments.txt"),
+                             os.path.join(pre, "experiments.txt"))
+    dp = mbsv.DeviceProblem(to_packed(mbsv, prob))
+    for mode, om in ((mbsv.MODE_REPLAY_EXACT, "faithful"), (mbsv.MODE_FAST, "incremental")):
+        o = oracle.run(prob, om, 10000, trace=True, memo_states=0)
+        g = dp.run(mode, 10000, trace=True, java_int_wrap=True, memo_states=0)
+        assert "memo" not in used_kernels(dp)
+        assert_same(o, g, trace=True)
+        assert int(g.counters[0, 0, 2]) > 100                             # AlterSV proposals
+        g = dp.run(mode, 10000, java_int_wrap=True, memo_states=0)
+        assert_same(o, g)
+
+
 def test_example_fast_matches_incremental_and_replay(oracle, mbsv, example_problem):
     dp = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
     g = dp.run(mbsv.MODE_FAST, 10000, trace=True, java_int_wrap=True)

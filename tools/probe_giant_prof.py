@@ -5,6 +5,8 @@ import multibreak_sv_b200 as m
 from multibreak_sv_b200 import synth
 p = synth.generate("cfg5")
 dp = m.DeviceProblem(p)
-for X in (8, 64):
+import os
+for X, cs in ((64, 1), (64, 2), (8, 1), (8, 4), (8, 8)):
+    os.environ["MBSV_GIANT_CLUSTER"] = str(cs)
     o = dp.run(m.MODE_FAST, 100000, n_chains=X, want_state=False, per_chain=False)
-    print('X', X, 'kernel %.1f ms' % o.kernel_ms, 'reassign', int(o.totals[4]), 'accepted', int(o.totals[1] + o.totals[3]), flush=True)
+    print('X', X, 'cluster', cs, 'kernel %.1f ms' % o.kernel_ms, 'reassign', int(o.totals[4]), 'accepted', int(o.totals[1] + o.totals[3]), flush=True)
