@@ -26,6 +26,14 @@ namespace mbsv {
 #endif
 // Launch bounds of the global-workspace class (large subproblems).  Measured on B200: 8 blocks/SM (64 registers, spills)
 // is slower than 5 (96 registers) both alone (289 vs 267 ms) and next to the other classes.
+// Read-only evaluation of Naive proposals in FAST mode (1) instead of tentative application + undo (0).  Measured on B200
+// (5M-fragment mixed batch, 64 chains, 2000 iterations, classes run back to back; profiles/r02_readonly_eval_ab.json):
+// SLOWER in every class of this kernel — shared-memory classes 28.8 -> 55.7 ms (128 rows), 60.4 -> 92.1 ms (48 rows), global
+// workspace 198.8 -> 235.7 ms: the eight-entry register lists push the 96-register kernel to ~1 KB of spills per thread,
+// which costs more than the undo pass saves.  Kept as a build option; the default stays do/undo.
+#ifndef MBSV_READONLY_EVAL
+#define MBSV_READONLY_EVAL 0
+#endif
 #ifndef MBSV_MIN_BLOCKS_GLOBAL
 #define MBSV_MIN_BLOCKS_GLOBAL 5
 #endif
@@ -438,7 +446,74 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
         bool written = false;
         double newLB[MAXE];
         double newlogprob, arg;
-        {
+        // Read-only evaluation (FAST, Naive, at most four ESPs per alignment, no connected component): the Delta is computed
+        // from the counts as they are; nothing is written unless the move is accepted, so a rejected proposal (four in five)
+        // costs no state writes and no undo pass.  ro_sl = counted slots of the alignment left (0..3) and entered (4..7),
+        // ro_cn = the count each entry sees: the stored count plus the earlier entries of this proposal on the same slot.
+        bool ro = false;
+        int ro_sl[8], ro_cn[8];
+        long long roE[MAXE], roL[MAXE];
+        if (MBSV_READONLY_EVAL && MODE == 1 && !TRACE && naive && !use_full && !has_cc) {
+            int4 recF = make_int4(0, 0, 0, 0), recT = make_int4(0, 0, 0, 0);
+            if (prev != -1) recF = P.aln_rec[a0 + prev];
+            if (now != -1) recT = P.aln_rec[a0 + now];
+            const int neF = recF.w >> 8, neT = recT.w >> 8;
+            if (neF <= 4 && neT <= 4) {
+                ro = true;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ro_sl[j] = j < neF ? P.aln_esp_slot[recF.z + j] : -1;
+                    ro_sl[4 + j] = j < neT ? P.aln_esp_slot[recT.z + j] : -1;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ro_cn[i] = ro_sl[i] >= 0 ? MBSV_ST(F + ro_sl[i]) : 0;
+#pragma unroll
+                for (int i = 1; i < 8; ++i)
+#pragma unroll
+                    for (int i2 = 0; i2 < i; ++i2)
+                        if (ro_sl[i] >= 0 && ro_sl[i2] == ro_sl[i]) ro_cn[i] += i2 < 4 ? -1 : 1;
+#pragma unroll
+                for (int x = 0; x < MAXE; ++x) { roE[x] = Etot[x]; roL[x] = Ltot[x]; }
+                if (prev != -1) {
+                    const int x = recF.w & 0xff;
+                    const double* Tx = P.T + (size_t)x * Tstride;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (ro_sl[j] >= 0) dcov = dcov + (Tx[ro_cn[j] - 1] - Tx[ro_cn[j]]);
+#pragma unroll
+                    for (int y = 0; y < MAXE; ++y) if (y == x) { roE[y] -= recF.x; roL[y] -= recF.y; }
+                    touched |= 1u << x;
+                } else derr = derr - logperr;
+                if (now != -1) {
+                    const int x = recT.w & 0xff;
+                    const double* Tx = P.T + (size_t)x * Tstride;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (ro_sl[4 + j] >= 0) dcov = dcov + (Tx[ro_cn[4 + j] + 1] - Tx[ro_cn[4 + j]]);
+#pragma unroll
+                    for (int y = 0; y < MAXE; ++y) if (y == x) { roE[y] += recT.x; roL[y] += recT.y; }
+                    touched |= 1u << x;
+                } else derr = derr + logperr;
+                double dlb = 0.0;
+#pragma unroll
+                for (int x = 0; x < MAXE; ++x) newLB[x] = LB[x];
+                unsigned mask = touched & ((1u << E) - 1u);
+                while (mask) {
+                    const int x = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    long long ex = 0, lx = 0;
+                    double old = 0.0;
+#pragma unroll
+                    for (int y = 0; y < MAXE; ++y) if (y == x) { ex = roE[y]; lx = roL[y]; old = LB[y]; }
+                    const double nl = lb_of(x, ex, lx);
+#pragma unroll
+                    for (int y = 0; y < MAXE; ++y) if (y == x) newLB[y] = nl;
+                    dlb = dlb + (nl - old);
+                }
+                const double delta = (dcov + derr) + dlb;
+                newlogprob = logprob + delta;
+                arg = (delta + Alogq) - Anewlogq;
+            }
+        }
+        if (!ro) {
         // ---- tentative application ----
         for (int q = 0; q < nmoves; ++q) {
             int ga0 = a0, from = prev, to = now;
@@ -516,7 +591,31 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
         const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);   // Math.min(1, e)
         r = rng.nextDouble();
         const bool accept = ratio > r;
-        if (accept) {
+        if (accept && ro) {
+            // apply the accepted move: counts (in entry order, so a slot hit twice ends at its final value), totals,
+            // difference tallies (value cn leaves: +d, value cn +- 1 enters: -d), assignment
+            logprob = newlogprob;
+            ++n_naive_acc;
+#pragma unroll
+            for (int x = 0; x < MAXE; ++x) { LB[x] = newLB[x]; Etot[x] = roE[x]; Ltot[x] = roL[x]; }
+            nerr += (now == -1 ? 1 : 0) - (prev == -1 ? 1 : 0);
+            const unsigned d = t > win_base ? (unsigned)(t - win_base) : 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (ro_sl[i] < 0) continue;
+                const int cn2 = ro_cn[i] + (i < 4 ? -1 : 1);
+                MBSV_ST(F + ro_sl[i]) = cn2;
+                if (d) {
+                    unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + ro_sl[i] / E];
+                    if (ro_cn[i] > 0) atomicAdd(&h[ro_cn[i]], d);
+                    if (cn2 > 0) atomicAdd(&h[cn2], 0u - d);
+                }
+            }
+            tally_frag(f, a0, prev, now, t);
+            MBSV_ST(f) = now;
+        } else if (ro) {
+            // rejected: nothing was written
+        } else if (accept) {
             logprob = newlogprob;
 #pragma unroll
             for (int x = 0; x < MAXE; ++x) LB[x] = newLB[x];

@@ -44,6 +44,48 @@ def main():
         w.writerow([units[idx[c]] for c in cols])
         for r in data:
             w.writerow([r[idx[c]] for c in cols])
+    # ---- per-kernel table of the binding bound (SM issue slots x lane utilisation), consumed by bench.py as roofline ----
+    # python profiles/summarize_ncu.py <rep> <out> --issue profiles/r02_issue_<config>.json "<what was captured>"
+    if "--issue" in sys.argv:
+        ia = sys.argv.index("--issue")
+        issue_path, what = sys.argv[ia + 1], (sys.argv[ia + 2] if len(sys.argv) > ia + 2 else "")
+        del sys.argv[ia:ia + 3]
+
+        def num(r, m):
+            try:
+                return float(r[idx[m]])
+            except (KeyError, ValueError):
+                return None
+
+        def to_b(r, m):
+            return float(r[idx[m]]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[idx[m]]]
+        dur_unit = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3}
+        du = dur_unit.get(units[idx["gpu__time_duration.sum"]], 1.0)
+        ks = []
+        for r in data:
+            name = r[idx["Kernel Name"]]
+            if "mbsv_" not in name:
+                continue
+            shm = num(r, "launch__shared_mem_per_block_dynamic") or 0.0
+            shm *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6}.get(units[idx["launch__shared_mem_per_block_dynamic"]], 1)
+            issue, lanes = num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"), num(r, "smsp__thread_inst_executed_per_inst_executed.ratio")
+            ks.append({"kernel": name.replace("void ", "").split("(")[0], "grid": int(num(r, "launch__grid_size")),
+                       "block": int(num(r, "launch__block_size")), "smem_bytes": int(shm),
+                       "state_rows": int(shm // 512) if "giant" not in name and shm else 0,
+                       "ms": num(r, "gpu__time_duration.sum") * du, "issue_active_pct": issue, "active_lanes": lanes,
+                       "frac": issue * lanes / 3200.0, "warps_active_per_smsp": num(r, "smsp__warps_active.avg.per_cycle_active"),
+                       "long_scoreboard_per_issue": num(r, "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+                       "barrier_per_issue": num(r, "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
+                       "registers": int(num(r, "launch__registers_per_thread")),
+                       "dram_bytes_per_launch": to_b(r, "dram__bytes_read.sum") + to_b(r, "dram__bytes_write.sum")})
+        tot = sum(k["ms"] for k in ks) or 1.0
+        for k in ks:
+            k["share_of_kernel_time"] = k["ms"] / tot
+        dom = max(ks, key=lambda k: k["ms"])
+        with open(issue_path, "w") as fh:
+            json.dump({"source": f"ncu --set full --clock-control none ({what}); serialised cold-cache launches, shares by gpu__time_duration; "
+                                 f"written by profiles/summarize_ncu.py", "bound": "SM issue slots x active lanes / 32",
+                       "dominant": dom, "kernels": ks}, fh, indent=1)
     # dominant launch = the one that executed the most warp-instructions (the bulk of the chains)
     inst = [float(r[idx["smsp__inst_executed.sum"]]) for r in data]
     k = max(range(len(data)), key=lambda i: inst[i])
