@@ -112,6 +112,13 @@ int mbsv_host_partition(const char* clusterfile, const char* outdir, int32_t* ro
 int mbsv_java_double_to_string(double v, char* buf, int32_t buflen);
 /* keySet() order of a java.util.HashMap<String,?> after inserting the n NUL-separated keys (test hook). */
 int mbsv_java_hashmap_order(const char* keys, int32_t n, int32_t* out_order, int32_t* out_capacity);
+/* keySet() order of a java.util.HashMap<String,?> after a sequence of puts and removes, tree bins included (JDK 8+:
+   treeifyBin / TreeNode.putTreeVal / removeTreeNode / split / moveRootToFront, csrc/java_hashmap.hpp).  keys = n
+   NUL-terminated strings; ops[k] = id + 1 puts key id (at most once), -(id + 1) removes it.  flags bit 0: always the
+   literal emulation instead of the closed form.  out_info[0] = 1 if some bin is treeified at the end (literal) or ever
+   was (closed form), out_info[1] = final capacity.  Returns the number of ids written to out_order. */
+int mbsv_java_hashmap_replay(const char* keys, int32_t n, const int32_t* ops, int32_t n_ops, int32_t flags,
+                             int32_t* out_order, int32_t* out_info);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,11 @@ public class MultiBreakSVGpu extends MultiBreakSV {
     static final MethodHandle RUN = h("mbsv_run", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle DESTROY = h("mbsv_problem_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle LAST_ERROR = h("mbsv_last_error", FunctionDescriptor.of(ADDRESS));
+    // giant component on every GPU of the box: chains split over the devices, tallies pooled with one ncclReduce
+    // (include/mbsv_b200.h: mbsv_run_multi; problems = one handle per device, created from the same descriptor)
+    static final MethodHandle RUN_MULTI = h("mbsv_run_multi",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle DEVICE_COUNT = h("mbsv_device_count", FunctionDescriptor.of(JAVA_INT));
 
     public int device = 0;
     public int mode = 0;   // MBSV_MODE_REPLAY_EXACT

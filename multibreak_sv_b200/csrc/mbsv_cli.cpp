@@ -7,8 +7,7 @@
 //
 // --partition [--chains N]: the whole multi-subproblem workflow of the manual (IV: generateIndependentSubproblems.pl, then
 // one run per subset-k.clusters with --readclustersfirst) in one process: partition + load in memory, one GPU batch, and
-// the concatenated .final*.longburnin files.  Implies --savespace.  --listorder lets subsets whose java.util.HashMap
-// would treeify a bin (iteration order not reproducible here) run with the plain-list order instead of failing the load.
+// the concatenated .final*.longburnin files.  Implies --savespace.
 //
 // Exit codes: 0 ok; 1 bad usage (the reference prints its usage and exits); 2 the library reported an error.
 #include <chrono>
@@ -27,7 +26,7 @@ void usage(const char* why) {
                  "ERROR: %s\n\n"
                  "Usage: mbsv_cli --clusterfile F --assignmentfile F --experimentfile F --numiterations N --perr P\n"
                  "                [--prefix OUT] [--matchfile F] [--savespace] [--readclustersfirst]\n"
-                 "                [--device N] [--mode replay|fast] [--partition [--chains N] [--listorder]]\n",
+                 "                [--device N] [--mode replay|fast] [--partition [--chains N]]\n",
                  why);
 }
 
@@ -50,7 +49,7 @@ int main(int argc, char** argv) {
     std::string clusterfile, assignmentfile, experimentfile, matchfile, prefix = "out";
     long numiters = -1;
     double perr = -1;
-    bool save_space = false, clusters_first = false, partition = false, listorder = false;
+    bool save_space = false, clusters_first = false, partition = false;
     int device = 0, mode = MBSV_MODE_REPLAY_EXACT, chains = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -59,7 +58,6 @@ int main(int argc, char** argv) {
         if (a == "--savespace") { save_space = true; continue; }
         if (a == "--readclustersfirst") { clusters_first = true; continue; }
         if (a == "--partition") { partition = true; continue; }
-        if (a == "--listorder") { listorder = true; continue; }
         if (a == "--enumerate") { usage("--enumerate is outside the sampler path"); return 1; }
         if (a != "--clusterfile" && a != "--assignmentfile" && a != "--experimentfile" && a != "--matchfile" && a != "--prefix" &&
             a != "--numiterations" && a != "--perr" && a != "--device" && a != "--mode" && a != "--chains") {
@@ -94,13 +92,13 @@ int main(int argc, char** argv) {
         if (!matchfile.empty()) { usage("--matchfile cannot be combined with --partition"); return 1; }
         mbsv_host_batch* b = nullptr;
         int32_t info[2] = {0, 0};
-        const int S = mbsv_host_load_partitioned(clusterfile.c_str(), assignmentfile.c_str(), experimentfile.c_str(), 2 | (listorder ? 1 : 0), &b, info);
+        const int S = mbsv_host_load_partitioned(clusterfile.c_str(), assignmentfile.c_str(), experimentfile.c_str(), 2, &b, info);
         if (S < 0) return fail_lib("partition + load");
         mbsv_problem_desc d;
         if (mbsv_host_batch_desc(b, &d)) return fail_lib("batch");
         std::printf("%d independent subproblems (%d empty skipped): %d fragments, %d alignments, %d clusters\n", S, info[0], d.n_frag,
                     d.n_aln, d.n_cluster);
-        if (info[1]) std::printf("%d subproblems run with the plain-list HashMap order (--listorder)\n", info[1]);
+        if (info[1]) std::printf("%d subproblems have a treeified java.util.HashMap bin (red-black order emulated)\n", info[1]);
         mbsv_problem* prob = nullptr;
         if (mbsv_problem_create(&d, device, &prob)) return fail_lib("create");
         mbsv_run_params rp;

@@ -312,6 +312,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         std::vector<std::string> t_msg(nthreads);
         std::atomic<int> next{0};
         const int CHUNK = 1024;
+        const int BIG_SUB = 32768;       // fragments: a larger subproblem (a giant component) is packed by all threads together
         auto worker = [&](int tid) {
             std::vector<int> in_aln, stamp_aln, per_frag, stamp_frag, total;   // indexed by local cluster
             std::vector<char> seen;
@@ -323,6 +324,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
                 const int s_end = std::min(S, s_begin + CHUNK);
                 for (int s = s_begin; s < s_end; ++s) {
                     const int c0 = d->sub_cluster_ptr[s], c1 = d->sub_cluster_ptr[s + 1], Cs = c1 - c0;
+                    if (d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s] > BIG_SUB) continue;      // packed by all threads below
                     if ((int)in_aln.size() < Cs) {
                         in_aln.resize(Cs); stamp_aln.resize(Cs); per_frag.resize(Cs); stamp_frag.resize(Cs); total.resize(Cs); seen.resize(Cs);
                     }
@@ -381,6 +383,84 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
         worker(0);
         for (auto& t : th) t.join();
+        // Subproblems too large for one thread: the same packing and checks, the fragments spread over the threads; a
+        // fragment's per-cluster maxima come from its (few) entries sorted by cluster instead of per-cluster stamp arrays.
+        for (int s = 0; s < S; ++s) {
+            const int fs0 = d->sub_frag_ptr[s], fs1 = d->sub_frag_ptr[s + 1];
+            if (fs1 - fs0 <= BIG_SUB) continue;
+            const int c0 = d->sub_cluster_ptr[s], c1 = d->sub_cluster_ptr[s + 1], Cs = c1 - c0;
+            std::unique_ptr<std::atomic<int>[]> total(new (std::nothrow) std::atomic<int>[(size_t)Cs + 1]);
+            if (!total) return fail(MBSV_ERR_OOM, "host allocation failed");
+            for (int i = 0; i < Cs; ++i) total[i].store(0, std::memory_order_relaxed);
+            std::vector<int> t_pos(nthreads, 0);
+            std::atomic<int> nextf{fs0};
+            auto big_worker = [&](int tid) {
+                auto bad = [&](int code, const char* msg) { if (!t_err[tid]) { t_err[tid] = code; t_msg[tid] = msg; } };
+                std::vector<std::pair<int, int>> ent;        // (cluster, alignment) of the fragment's counted entries
+                for (;;) {
+                    const int fb = nextf.fetch_add(4096);
+                    if (fb >= fs1) break;
+                    for (int f = fb; f < std::min(fs1, fb + 4096); ++f) {
+                        t_maxn[tid] = std::max(t_maxn[tid], d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]);
+                        ent.clear();
+                        for (int a = d->frag_aln_ptr[f]; a < d->frag_aln_ptr[f + 1]; ++a) {
+                            const int x = d->aln_exp[a];
+                            const int j0 = d->aln_esp_ptr[a], j1 = d->aln_esp_ptr[a + 1];
+                            rec[a] = make_int4(d->aln_numerrors[a], d->aln_len[a], j0, x | ((j1 - j0) << 8));
+                            int pos = 0;
+                            for (int j = j0; j < j1; ++j) {
+                                const int c = d->aln_esp_cluster[j];
+                                slot[j] = -1;
+                                if (c != -1) t_pos[tid] = std::max(t_pos[tid], ++pos);
+                                if (c == -1) continue;
+                                if (c < c0 || c >= c1) { bad(MBSV_ERR_ARG, "aln_esp_cluster points outside the fragment's subproblem"); continue; }
+                                const int cl = c - c0;
+                                if (d->cluster_kind[c] == 1) {
+                                    const int nl = d->cluster_leaf_ptr[c + 1] - d->cluster_leaf_ptr[c];
+                                    if (d->aln_esp_leaf[j] < 0 || d->aln_esp_leaf[j] >= nl) bad(MBSV_ERR_ARG, "aln_esp_leaf out of range");
+                                    slot[j] = -(2 + cl);
+                                    continue;
+                                }
+                                slot[j] = cl * E + x;
+                                ent.emplace_back(cl, a);
+                            }
+                        }
+                        std::sort(ent.begin(), ent.end());
+                        for (size_t i = 0; i < ent.size();) {                 // per cluster: the most entries of one alignment
+                            const int cl = ent[i].first;
+                            int best = 0;
+                            while (i < ent.size() && ent[i].first == cl) {
+                                const int a = ent[i].second;
+                                int n = 0;
+                                while (i < ent.size() && ent[i].first == cl && ent[i].second == a) { ++n; ++i; }
+                                best = std::max(best, n);
+                            }
+                            total[cl].fetch_add(best, std::memory_order_relaxed);
+                        }
+                    }
+                }
+            };
+            std::vector<std::thread> tb;
+            for (int t = 1; t < nthreads; ++t) tb.emplace_back(big_worker, t);
+            big_worker(0);
+            for (auto& t : tb) t.join();
+            sub_maxpos[s] = *std::max_element(t_pos.begin(), t_pos.end());
+            std::vector<char> seen(Cs, 0);
+            for (int cl = 0; cl < Cs; ++cl) {
+                const int tot = total[cl].load(std::memory_order_relaxed);
+                if (tot > d->max_support)
+                    return fail(MBSV_ERR_UNSUPPORTED, "a cluster can collect more selected ESPs than max_support "
+                                                      "(the reference would index logprobcov out of bounds)");
+                if (tot + 1 > d->cluster_hist_ptr[c0 + cl + 1] - d->cluster_hist_ptr[c0 + cl])
+                    return fail(MBSV_ERR_ARG, "cluster_hist_ptr leaves too few bins for a cluster");
+            }
+            for (int i = c0; i < c1; ++i) {
+                const int c = d->supports_order[i];
+                if (c < c0 || c >= c1 || seen[c - c0]) return fail(MBSV_ERR_ARG, "supports_order is not a permutation of the subproblem's clusters");
+                seen[c - c0] = 1;
+                sup_local[i] = c - c0;
+            }
+        }
         for (int t = 0; t < nthreads; ++t) {
             if (t_err[t]) return fail(t_err[t], t_msg[t]);
             maxn = std::max(maxn, t_maxn[t]);

@@ -2,6 +2,7 @@
 // reference's semantics, packs them into mbsv_problem_desc, runs the sampler through the C ABI and writes the
 // reference's output files.  No sampling happens here: mbsv_host_run_mcmc calls mbsv_problem_create / mbsv_run.
 #include "../../include/mbsv_host.h"
+#include "java_hashmap.hpp"
 
 #include <algorithm>
 #include <charconv>
@@ -38,12 +39,15 @@ uint32_t java_hash(std::string_view s) {               // String.hashCode then H
 // entries stay in insertion order (tail insertion; resize splits preserve order; removal unlinks), so the
 // keySet() order is "by bucket index at the final capacity, then by insertion".  The capacity is tracked through
 // every put: doubling when size exceeds 0.75 capacity, and treeifyBin()'s extra doubling when a bin receives its
-// 9th entry while the table is smaller than 64.  A bin that would be treeified at capacity >= 64 changes the
-// order in ways we do not model: `tree_bin` is raised and the input is rejected.
+// 9th entry while the table is smaller than 64.  A bin that is treeified at capacity >= 64 reorders its `next` links
+// (red-black tree, root moved to the front): `tree_bin` is raised and order() replays the map's puts and removes through
+// the literal emulation of java_hashmap.hpp instead of the closed form.
 struct JavaMapOrder {
     std::vector<uint32_t> hash;
     std::vector<char> alive;
     std::vector<int> bin;     // live entries per bucket
+    std::vector<std::string> keys;   // (replay of a treeified map)
+    std::vector<int> ops;            // id + 1 = put, -(id + 1) = remove
     int cap = 0, thr = 0, size = 0;
     bool tree_bin = false;
     void resize() {
@@ -57,6 +61,8 @@ struct JavaMapOrder {
         const uint32_t h = java_hash(key);
         hash.push_back(h);
         alive.push_back(1);
+        keys.emplace_back(key);
+        ops.push_back((int)hash.size());
         const int before = bin[h & (cap - 1)]++;
         if (before >= 8) { if (cap < 64) resize(); else tree_bin = true; }
         if (++size > thr) resize();
@@ -67,8 +73,14 @@ struct JavaMapOrder {
         alive[id] = 0;
         --bin[hash[id] & (cap - 1)];
         --size;
+        ops.push_back(-(id + 1));
     }
     std::vector<int> order() const {
+        if (tree_bin) {
+            mbsv_java::HashMapLiteral m;
+            for (int op : ops) { if (op > 0) m.put(keys[op - 1]); else m.remove(-op - 1); }
+            return m.order();
+        }
         std::vector<int> o;
         for (size_t i = 0; i < hash.size(); ++i) if (alive[i]) o.push_back((int)i);
         const uint32_t m = cap ? (uint32_t)cap - 1 : 0;
@@ -431,12 +443,19 @@ int read_clusters_file(mbsv_host* h) {
         h->bp_of_cl[cid] = h->breakpoints.put(h->cl_name[cid]);
         h->cl_of_bp.push_back(cid);
     }
-    if (h->clust.tree_bin) h->breakpoints.tree_bin = true;
     return 0;
 }
 
 // MultiBreakSV.java:475-550
 void intersect_clusters_and_fragments(mbsv_host* h) {
+    // the reference collects the names in a HashSet (`toRemove`) and removes them in THAT set's iteration order
+    // (:481-516, :525-547); the order of the removals only matters for a map with a treeified bin
+    auto remove_in_hashset_order = [](JavaMapOrder& map, const std::vector<int>& ids) {
+        JavaMapOrder to_remove;
+        for (int id : ids) to_remove.put(map.keys[id]);
+        for (int k : to_remove.order()) map.remove(ids[k]);
+    };
+    std::vector<int> drop;
     for (int fe : h->fragments.order()) {
         Fragment& fr = h->frags[fe];
         std::vector<Alignment> keep;
@@ -445,14 +464,17 @@ void intersect_clusters_and_fragments(mbsv_host* h) {
             for (int e : al.esps) if (h->esp2cid[e] < 0) { all = false; break; }
             if (all) keep.push_back(al);
         }
-        if (keep.empty()) h->fragments.remove(fe); else fr.alns.swap(keep);
+        if (keep.empty()) drop.push_back(fe); else fr.alns.swap(keep);
     }
+    remove_in_hashset_order(h->fragments, drop);
     std::vector<char> used(h->cl_name.size(), 0);
     for (int fe : h->fragments.order())
         for (const Alignment& al : h->frags[fe].alns)
             for (int e : al.esps) used[h->esp2cid[e]] = 1;
+    drop.clear();
     for (int be : h->breakpoints.order())
-        if (!used[h->cl_of_bp[be]]) { h->breakpoints.remove(be); h->bp_of_cl[h->cl_of_bp[be]] = -1; }
+        if (!used[h->cl_of_bp[be]]) { drop.push_back(be); h->bp_of_cl[h->cl_of_bp[be]] = -1; }
+    remove_in_hashset_order(h->breakpoints, drop);
 }
 
 // MultiBreakSV.java:658-746 + MultiBreakSVDiagram.java:56-139
@@ -527,7 +549,6 @@ int pack(mbsv_host* h) {
         for (int i = 0; i < C; ++i) sup.put(h->cl_name[h->cl_order[i]]);
         h->supports_order.clear();
         for (int id : sup.order()) h->supports_order.push_back(id);
-        if (sup.tree_bin) h->breakpoints.tree_bin = true;
     }
     // fragments in fragments.keySet() order
     h->frag_order = h->fragments.order();
@@ -718,8 +739,6 @@ int mbsv_host_load(mbsv_host* h) {
     int rc;
     if ((rc = mbsv_host_get_fragment_alignments(h)) || (rc = mbsv_host_construct_cluster_diagrams(h)) ||
         (rc = mbsv_host_precompute_priors(h)) || (rc = mbsv_host_fill_non_singleton_array(h))) return rc;
-    if (h->experiments.tree_bin || h->fragments.tree_bin || h->breakpoints.tree_bin)
-        h->unsupported = "a java.util.HashMap bin would be treeified: iteration order not reproducible";
     return MBSV_OK;
 }
 
@@ -1167,13 +1186,7 @@ int mbsv_host_load_partitioned(const char* clusterfile, const char* assignmentfi
             h->clusters_first = true;
             h->text_clusters = &ctext[k]; h->text_assignments = &atext[k]; h->text_experiments = &ebuf;
             int rc = mbsv_host_load(h);
-            if (rc == MBSV_OK && (flags & 1) && (h->experiments.tree_bin || h->fragments.tree_bin || h->breakpoints.tree_bin) &&
-                h->unsupported.rfind("a java.util.HashMap bin", 0) == 0) {
-                // a bin Java would treeify: keep the plain-list iteration order (a valid chain, but not the trajectory a
-                // JVM would produce for this subset) and count it
-                h->unsupported.clear();
-                ++t_approx[t];
-            }
+            if (rc == MBSV_OK && (h->experiments.tree_bin || h->fragments.tree_bin || h->breakpoints.tree_bin)) ++t_approx[t];   // (counted: treeified maps)
             if (rc == MBSV_OK && h->frag_order.empty()) { ++t_skipped[t]; continue; }
             if (rc == MBSV_OK) rc = batch_append(&part[t], h, (flags & 2) != 0, k);
             if (rc != MBSV_OK) { t_rc[t] = rc; t_msg[t] = "subset " + std::to_string(k) + ": " + mbsv_last_error(); }
@@ -1396,7 +1409,49 @@ int mbsv_java_hashmap_order(const char* keys, int32_t n, int32_t* out_order, int
     int i = 0;
     for (int id : m.order()) out_order[i++] = id;
     if (out_capacity) *out_capacity = m.cap;
-    return m.tree_bin ? -1 : i;
+    return i;
+}
+// keySet() order after a sequence of puts and removes: keys = n NUL-terminated strings; ops[k] = id + 1 puts key id (every
+// key at most once), -(id + 1) removes it.  out_order receives the ids in iteration order; returns their number.
+// flags bit 0: always use the literal emulation (java_hashmap.hpp) instead of the closed form; out_info[0] = 1 if a bin was
+// treeified, out_info[1] = final capacity.
+int mbsv_java_hashmap_replay(const char* keys, int32_t n, const int32_t* ops, int32_t n_ops, int32_t flags, int32_t* out_order,
+                             int32_t* out_info) {
+    std::vector<std::string> ks;
+    const char* p = keys;
+    for (int i = 0; i < n; ++i) { ks.emplace_back(p); p += ks.back().size() + 1; }
+    std::vector<int> order;
+    int treeified = 0, cap = 0;
+    if (flags & 1) {
+        mbsv_java::HashMapLiteral m;
+        std::vector<int> id_of(n, -1);                        // key id -> node id (insertion index)
+        for (int k = 0; k < n_ops; ++k) {
+            const int id = ops[k] > 0 ? ops[k] - 1 : -ops[k] - 1;
+            if (id < 0 || id >= n) return -1;
+            if (ops[k] > 0) id_of[id] = m.put(ks[id]); else m.remove(id_of[id]);
+        }
+        std::vector<int> key_of(m.nd.size(), -1);
+        for (int i = 0; i < n; ++i) if (id_of[i] >= 0) key_of[id_of[i]] = i;
+        for (int e : m.order()) order.push_back(key_of[e]);
+        for (const auto& nd : m.nd) if (nd.alive && nd.tree) treeified = 1;
+        cap = m.capacity();
+    } else {
+        JavaMapOrder m;
+        std::vector<int> id_of(n, -1);
+        for (int k = 0; k < n_ops; ++k) {
+            const int id = ops[k] > 0 ? ops[k] - 1 : -ops[k] - 1;
+            if (id < 0 || id >= n) return -1;
+            if (ops[k] > 0) id_of[id] = m.put(ks[id]); else m.remove(id_of[id]);
+        }
+        std::vector<int> key_of(m.hash.size(), -1);
+        for (int i = 0; i < n; ++i) if (id_of[i] >= 0) key_of[id_of[i]] = i;
+        for (int e : m.order()) order.push_back(key_of[e]);
+        treeified = m.tree_bin;
+        cap = m.cap;
+    }
+    for (size_t i = 0; i < order.size(); ++i) out_order[i] = order[i];
+    if (out_info) { out_info[0] = treeified; out_info[1] = cap; }
+    return (int)order.size();
 }
 
 }  // extern "C"

@@ -61,8 +61,6 @@ def java_hashmap_order(keys):
     out = np.zeros(max(1, len(keys)), np.int32)
     cap = C.c_int32(0)
     n = L.mbsv_java_hashmap_order(blob, len(keys), out.ctypes.data_as(I32P), C.byref(cap))
-    if n < 0:
-        raise ValueError("a HashMap bin would be treeified")
     return [keys[i] for i in out[:n]], cap.value
 
 
@@ -249,18 +247,19 @@ def batch(hosts) -> PackedProblem:
         L.mbsv_host_batch_destroy(b)
 
 
-def load_partitioned(clusterfile: str, assignmentfile: str, experimentfile: str, tolerate_tree_bins: bool = False, info=None):
+def load_partitioned(clusterfile: str, assignmentfile: str, experimentfile: str, info=None):
     """Partition + load in memory (mbsv_host_load_partitioned): one subproblem per subset of
     generateIndependentSubproblems.pl, each packed as a run on `subset-k.clusters --readclustersfirst` would see it; the
     assignments file is read once.  Returns (PackedProblem, number of skipped empty subsets); `info` (a dict) also receives
-    the number of subsets whose HashMap order could not be reproduced (only with tolerate_tree_bins)."""
+    the number of subsets one of whose java.util.HashMaps has a treeified bin (their order comes from the literal
+    red-black emulation, csrc/java_hashmap.hpp)."""
     L = _bind(load_library())
     b = C.c_void_p()
     skipped = np.zeros(2, np.int32)
     n = L.mbsv_host_load_partitioned(clusterfile.encode(), assignmentfile.encode(), experimentfile.encode(),
-                                     int(tolerate_tree_bins), C.byref(b), skipped.ctypes.data_as(I32P))
+                                     0, C.byref(b), skipped.ctypes.data_as(I32P))
     if info is not None:
-        info.update(skipped=int(skipped[0]), unreproducible_order=int(skipped[1]))
+        info.update(skipped=int(skipped[0]), treeified=int(skipped[1]))
     if n < 0:
         check(n)
     try:
@@ -275,15 +274,15 @@ class PartitionedBatch:
     """Files -> partition -> one batched problem that remembers its names, so that the reference's output files can be
     written for the whole batch (mbsv_host_load_partitioned with names + mbsv_host_batch_write_final_files)."""
 
-    def __init__(self, clusterfile: str, assignmentfile: str, experimentfile: str, tolerate_tree_bins: bool = False):
+    def __init__(self, clusterfile: str, assignmentfile: str, experimentfile: str):
         self.lib = _bind(load_library())
         self.h = C.c_void_p()
         info = np.zeros(2, np.int32)
         n = self.lib.mbsv_host_load_partitioned(clusterfile.encode(), assignmentfile.encode(), experimentfile.encode(),
-                                                2 | int(tolerate_tree_bins), C.byref(self.h), info.ctypes.data_as(I32P))
+                                                2, C.byref(self.h), info.ctypes.data_as(I32P))
         if n < 0:
             check(n)
-        self.skipped, self.unreproducible_order = int(info[0]), int(info[1])
+        self.skipped, self.treeified = int(info[0]), int(info[1])
         d = ProblemDesc()
         check(self.lib.mbsv_host_batch_desc(self.h, C.byref(d)))
         self.packed = _desc_to_packed(d)
@@ -308,20 +307,18 @@ class PartitionedBatch:
 
 
 def main_partition(argv):
-    """`--partition [--chains N] [--listorder] [--fast]`: the manual's multi-subproblem workflow as one GPU batch (the same
+    """`--partition [--chains N] [--fast]`: the manual's multi-subproblem workflow as one GPU batch (the same
     as `mbsv_cli --partition`): partition + load in memory, one run, concatenated `.final*.longburnin` files."""
     from ._abi import DeviceProblem, MODE_FAST
     argv = list(argv)
-    chains, listorder, mode = 1, False, MODE_REPLAY_EXACT
+    chains, mode = 1, MODE_REPLAY_EXACT
     argv.remove("--partition")
-    if "--listorder" in argv:
-        argv.remove("--listorder"); listorder = True
     if "--fast" in argv:
         argv.remove("--fast"); mode = MODE_FAST
     if "--chains" in argv:
         i = argv.index("--chains"); chains = int(argv[i + 1]); del argv[i:i + 2]
     sv = MultiBreakSV(argv)                                   # option checks and burnin as in the single-problem path
-    b = PartitionedBatch(sv.clusterfile, sv.assignmentfile, sv.experimentfile, tolerate_tree_bins=listorder)
+    b = PartitionedBatch(sv.clusterfile, sv.assignmentfile, sv.experimentfile)
     dp = DeviceProblem(b.packed, device=sv.device)
     r = dp.run(mode, sv.numiters, n_chains=chains, perr=sv.perr, java_int_wrap=True, want_state=False, per_chain=False)
     b.writeFinalFiles(sv.outputname, sv.burnin * chains, r.aln_count, r.frag_err_count, r.cluster_hist)

@@ -67,7 +67,7 @@ def main():
             if "mbsv_" not in name:
                 continue
             shm = num(r, "launch__shared_mem_per_block_dynamic") or 0.0
-            shm *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6}.get(units[idx["launch__shared_mem_per_block_dynamic"]], 1)
+            shm *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6}.get(units[idx["launch__shared_mem_per_block_dynamic"]].split("/")[0], 1)
             issue, lanes = num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"), num(r, "smsp__thread_inst_executed_per_inst_executed.ratio")
             ks.append({"kernel": name.replace("void ", "").split("(")[0], "grid": int(num(r, "launch__grid_size")),
                        "block": int(num(r, "launch__block_size")), "smem_bytes": int(shm),

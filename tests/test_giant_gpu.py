@@ -25,7 +25,7 @@ def all_global(monkeypatch):
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 @pytest.mark.parametrize("nfrag,chains,iters,perr,seed", [(3000, 3, 6000, 0.001, 1), (20000, 2, 30000, 0.001, 2),
                                                           (60, 4, 3000, 0.001, 3), (700, 5, 4000, 0.3, 4),
-                                                          (2500, 1, 700, 0.6, 5)])
+                                                          (2500, 1, 700, 0.6, 5), (40000, 2, 20000, 0.001, 6)])
 def test_giant_component_matches_oracle(oracle, mbsv, all_global, monkeypatch, nfrag, chains, iters, perr, seed, cluster):
     """cluster = CTAs per chain (a thread-block cluster shares one chain's windows through distributed shared memory);
     forced here also where the planner would not pick it: on small states most windows are cut by stale reads."""

@@ -132,8 +132,14 @@ def test_hashmap_order_matches_oracle_including_collisions(mbsv, oracle):
         assert h_order == o_order and h_cap == o_cap
     assert oracle.hashmap_order(coll[:10])[1] == 64                      # 9th and 10th entries doubled 16 -> 32 -> 64
     assert oracle.hashmap_order(coll[:11])[2] is True                    # next one lands in a 10-entry bin at capacity 64
-    with pytest.raises(ValueError):
-        host.java_hashmap_order(coll[:11])
+    # ... which the host mirror no longer refuses: it replays the map through the literal red-black emulation
+    # (csrc/java_hashmap.hpp; tests/test_hashmap_tree_bins.py); the order is NOT the plain-list order any more
+    import java_hashmap_ref
+    m = java_hashmap_ref.JavaHashMap()
+    for k in coll[:11]:
+        m.put(k)
+    h_order, h_cap = host.java_hashmap_order(coll[:11])
+    assert h_order == m.keys() and h_cap == 64 and h_order != coll[:11]
 
 
 def test_double_to_string(mbsv):

@@ -16,8 +16,8 @@ t0 = time.time()
 paths = synth.write_reference_files(g, out)
 print("wrote files %.1f s: %s MB" % (time.time() - t0, {k: os.path.getsize(v) >> 20 for k, v in paths.items()}), flush=True)
 t0 = time.time()
-b = host.PartitionedBatch(paths["clusters"], paths["assignments"], paths["experiments"], tolerate_tree_bins=True)
-p, info = b.packed, {"skipped": b.skipped, "unreproducible_order": b.unreproducible_order}
+b = host.PartitionedBatch(paths["clusters"], paths["assignments"], paths["experiments"])
+p, info = b.packed, {"skipped": b.skipped, "treeified": b.treeified}
 t_load = time.time() - t0
 print("partition + load: %.2f s -> %d subproblems, %d fragments, %d alignments %s" % (t_load, p.scalars["n_sub"], p.scalars["n_frag"], p.scalars["n_aln"], info), flush=True)
 t0 = time.time()

@@ -22,6 +22,6 @@ n, rows = host.generateIndependentSubproblems(paths["clusters"], None)
 print("partition %.2f s -> %d subsets" % (time.time() - t0, n))
 t0 = time.time()
 info = {}
-p, skipped = host.load_partitioned(paths["clusters"], paths["assignments"], paths["experiments"], tolerate_tree_bins=True, info=info)
+p, skipped = host.load_partitioned(paths["clusters"], paths["assignments"], paths["experiments"], info=info)
 print(info)
 print("load_partitioned %.2f s -> %d subproblems (%d skipped), %d fragments" % (time.time() - t0, p.scalars["n_sub"], skipped, p.scalars["n_frag"]))
