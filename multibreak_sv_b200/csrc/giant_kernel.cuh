@@ -280,6 +280,14 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
     auto hash_of = [](int key) -> unsigned { return (((unsigned)key * 2654435761u) >> 19) & (GIANT_HASH - 1); };
     auto owner_of = [](int key) -> int { return CS > 1 ? (int)((((unsigned)key * 2654435761u) >> 16) & (CS - 1)) : 0; };
 
+#ifdef MBSV_GIANT_PROF
+    long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int spn = 0;
+#define SPROF() do { if (tid == 0 && spn < 8) sp[spn++] = clock64(); } while (0)
+#else
+#define SPROF() do {} while (0)
+#endif
+    SPROF();
     // ---- setup: TMA-staged logprobcov, zeroed state, scalars ----
     if (tid == 0) {
         giant_bar_init(&sc.bar);
@@ -311,6 +319,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         }
     };
 
+    SPROF();
     // ---------------- initializeMatrix (MultiBreakSV.java:990-1099): the first CTA of the cluster ----------------
     if (crank == 0) {
         if (R.init_assign) {
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 st.stw(f, a);
                 if (R.initial_assign) R.initial_assign[(size_t)chain * P.n_frag + f0 + f] = a;
             }
-        } else if (R.perr * NT < 0.5) {
+        } else if (R.perr < 0.004) {                 // (windows of ~min(NT, 1/perr) fragments; the general scheme below manages ~NT/3)
             // Almost every fragment consumes three LCG steps (nextDouble() >= perr, then nextInt): thread t takes fragment
             // base + t at offset 3 t.  That is right for every fragment up to and including the first one of the window that
             // draws "unmapped" (two steps) or has to redraw its nextInt; the window is cut behind that fragment.
@@ -429,6 +438,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         }
     }
     csync();
+    SPROF();
     // counts, per-experiment totals, unmapped fragments (all CTAs; pooled in the first CTA's scalars)
     {
         long long e_loc[MAXE], l_loc[MAXE];
@@ -501,6 +511,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         if (tid == 0) R.initial_logprob[scx] = lp;
     }
 
+    SPROF();
     // ---------------- iterations (MultiBreakSV.java:796-837, 1101-1182) ----------------
     make_jump(JavaRandom::MULT2, JavaRandom::ADD2, goff, CS * NT);        // one offset = one nextDouble()
     int n_naive_prop = 0, n_naive_acc = 0, n_sv_prop = 0, n_sv_acc = 0;
@@ -554,7 +565,13 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
             }
         }
         int a0 = 0, fa1 = 0, prev = -1;
+        int sv_q0 = 0, sv_q1 = 0, sv_e0 = 0, sv_e1 = 0, sv_nch = 0;       // AlterSV: the candidate's fragment list and entry list
         if (naive) { a0 = __ldg(P.frag_aln_ptr + f0 + f); fa1 = __ldg(P.frag_aln_ptr + f0 + f + 1); prev = st.ld(f); }
+        else if (dense) {
+            sv_q0 = __ldg(P.sv_frag_ptr + f); sv_q1 = __ldg(P.sv_frag_ptr + f + 1);
+            sv_e0 = __ldg(P.sv_ent_ptr + f); sv_e1 = __ldg(P.sv_ent_ptr + f + 1);
+            sv_nch = __ldg(P.sv_numchanged + f);
+        }
         // (while those loads are in flight)
         for (int i = tid; i < GIANT_HASH; i += NT) { hkey[i] = -1; hlane[i] = GIANT_NOCUT; }
         const int n = fa1 - a0;
@@ -639,16 +656,15 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                 }
             } else {
                 // ---- svMove (MultiBreakSV.java:1291-1343): toggle the cluster's single-alignment fragments ----
-                // round trip 1: the candidate's fragment list and entry list
-                q0 = __ldg(P.sv_frag_ptr + f);
-                const int q1 = __ldg(P.sv_frag_ptr + f + 1);
-                const int e0 = __ldg(P.sv_ent_ptr + f), e1 = __ldg(P.sv_ent_ptr + f + 1);
-                reassign = __ldg(P.sv_numchanged + f);
-                nmoves = q1 - q0;
-                nent = e1 - e0;
+                // (the candidate's fragment list and entry list were loaded with the window's first round trip)
+                q0 = sv_q0;
+                const int e0 = sv_e0;
+                reassign = sv_nch;
+                nmoves = sv_q1 - sv_q0;
+                nent = sv_e1 - sv_e0;
                 Alogq = neglogNsv;
                 Anewlogq = neglogNsv;
-                // round trip 2: fragments and slots (four loads in flight at a time)
+                // round trip 1: fragments and slots (four loads in flight at a time)
                 for (int qb = 0; qb < nmoves; qb += 4) {
                     int g[4];
 #pragma unroll
@@ -663,11 +679,20 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 4; ++i) if (kb + i < nent) ent[(kb + i) * MD + p] = (v[i].x << 5) | v[i].y;
                 }
-                // round trip 3 (first half; the counts follow below): current assignment of every fragment
+                // round trip 2: current assignment of every fragment and current count of every slot, together
                 for (int qb = 0; qb < nmoves; qb += 4) {
                     int a[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) a[i] = qb + i < nmoves ? st.ld(mv[(qb + i) * MD + p]) : 0;
+                    if (qb == 0) {
+                        for (int kb = 0; kb < nent; kb += 4) {
+                            int v[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[i] = kb + i < nent ? st.ld(F + (ent[(kb + i) * MD + p] >> 5)) : 0;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) if (kb + i < nent) ecnt[(kb + i) * MD + p] = v[i];
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) if (qb + i < nmoves) mv[(qb + i) * MD + p] = (mv[(qb + i) * MD + p] << 1) | (a[i] == -1 ? 1 : 0);
                 }
@@ -693,7 +718,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
             r_acc = rng.nextDouble();
             if (!bad) {
                 // counts the entries see: the stored count plus the earlier entries of this proposal on the same slot
-                for (int kb = 0; kb < nent; kb += 4) {
+                for (int kb = 0; naive && kb < nent; kb += 4) {            // (AlterSV: loaded above with the assignments)
                     int v[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) v[i] = kb + i < nent ? st.ld(F + (ent[(kb + i) * MD + p] >> 1)) : 0;
@@ -1010,6 +1035,7 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
                prof[4] / max(nwindows, 1LL), prof[5] / max(nwindows, 1LL), prof[6] / max(nwindows, 1LL), prof[7] / max(nwindows, 1LL));
 #endif
 
+    SPROF();
     // ---------------- epilogue: final tallies, state, counters (pooled in the first CTA of the cluster) ----------------
     {
         Scalars* s0p = remote(&sc, 0);
@@ -1072,6 +1098,12 @@ __global__ void __launch_bounds__(NT, 1) mbsv_giant_kernel(const __grid_constant
         }
     }
     csync();       // no CTA of the cluster leaves while another may still address its shared memory
+#ifdef MBSV_GIANT_PROF
+    SPROF();
+    if (tid == 0 && blockIdx.x == 0)
+        printf("giant prof setup (cycles): zero+stage %lld init %lld counts %lld iterations %lld epilogue %lld\n", sp[1] - sp[0], sp[2] - sp[1],
+               sp[3] - sp[2], sp[4] - sp[3], sp[5] - sp[4]);
+#endif
 }
 
 }  // namespace mbsv

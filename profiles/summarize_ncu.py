@@ -53,7 +53,8 @@ def main():
 
         def num(r, m):
             try:
-                return float(r[idx[m]])
+                v = float(r[idx[m]])
+                return None if v != v else v          # ncu prints n/a -> nan for counters it could not collect
             except (KeyError, ValueError):
                 return None
 
@@ -73,7 +74,7 @@ def main():
                        "block": int(num(r, "launch__block_size")), "smem_bytes": int(shm),
                        "state_rows": int(shm // 512) if "giant" not in name and shm else 0,
                        "ms": num(r, "gpu__time_duration.sum") * du, "issue_active_pct": issue, "active_lanes": lanes,
-                       "frac": issue * lanes / 3200.0, "warps_active_per_smsp": num(r, "smsp__warps_active.avg.per_cycle_active"),
+                       "frac": issue * lanes / 3200.0 if issue is not None and lanes is not None else None, "warps_active_per_smsp": num(r, "smsp__warps_active.avg.per_cycle_active"),
                        "long_scoreboard_per_issue": num(r, "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
                        "barrier_per_issue": num(r, "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
                        "registers": int(num(r, "launch__registers_per_thread")),
@@ -81,7 +82,7 @@ def main():
         tot = sum(k["ms"] for k in ks) or 1.0
         for k in ks:
             k["share_of_kernel_time"] = k["ms"] / tot
-        dom = max(ks, key=lambda k: k["ms"])
+        dom = max((k for k in ks if k["frac"] is not None), key=lambda k: k["ms"])
         with open(issue_path, "w") as fh:
             json.dump({"source": f"ncu --set full --clock-control none ({what}); serialised cold-cache launches, shares by gpu__time_duration; "
                                  f"written by profiles/summarize_ncu.py", "bound": "SM issue slots x active lanes / 32",
