@@ -5,7 +5,7 @@
 #include "giant_kernel.cuh"
 namespace mbsv {
 
-// aln_ent4[a] = the counted slots (aln_esp_slot >= 0) of alignment a in ESP order, -1 padded
+// aln_ent4[a] = the counted slots (aln_esp_slot >= 0) of alignment a in ESP order, -1 padded; {-3,-1,-1,-1} if more than four
 __global__ void mbsv_giant_prep_kernel(const __grid_constant__ DevProblem P, int4* __restrict__ out) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= P.n_aln) return;
@@ -15,9 +15,11 @@ __global__ void mbsv_giant_prep_kernel(const __grid_constant__ DevProblem P, int
     int n = 0;
     for (int j = 0; j < ne; ++j) {
         const int slot = P.aln_esp_slot[rec.z + j];
-        if (slot >= 0 && n < GIANT_ALN_SLOTS) s[n++] = slot;
+        if (slot >= 0) { if (n < GIANT_ALN_SLOTS) s[n] = slot; ++n; }
     }
-    out[a] = make_int4(s[0], s[1], s[2], s[3]);
+    // more counted slots than the record holds: marked, the general kernel then walks aln_esp_slot (the speculative-window
+    // kernel never sees such an alignment: sub_maxpos <= giant_max_aln_entries() is a condition of its launch)
+    out[a] = n > GIANT_ALN_SLOTS ? make_int4(-3, -1, -1, -1) : make_int4(s[0], s[1], s[2], s[3]);
 }
 
 cudaError_t launch_giant_prep(const DevProblem& P, int4* aln_ent4, cudaStream_t stream) {

@@ -621,6 +621,9 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     chk(cudaEventCreateWithFlags(&p->ev_built, cudaEventDisableTiming));
     chk(cudaEventCreate(&p->ev_start));
     chk(cudaEventCreate(&p->ev_stop));
+    // The uploads above are cudaMemcpy calls from pageable host memory on the legacy stream: they return when the data is
+    // staged, not when the last DMA has landed, and the kernels run on non-blocking streams that do not wait for it.
+    chk(cudaStreamSynchronize(0));
     if (e != cudaSuccess) { delete p; return fail(MBSV_ERR_CUDA, std::string("stream setup: ") + cudaGetErrorString(e)); }
     p->streams_ok = true;
     *out = p;
@@ -661,9 +664,10 @@ int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n) {
 namespace {
 
 using mbsv::KernelFn;
-KernelFn pick(int mode, bool trace, bool smem, int E) {
+KernelFn pick(int mode, bool trace, bool smem, int E, int rows, size_t* extra_smem) {
+    *extra_smem = 0;
     if (trace) return mbsv::get_kernel_trace(mode, smem, E);
-    return mode == 0 ? mbsv::get_kernel_replay(smem, E) : mbsv::get_kernel_fast(smem, E);
+    return mode == 0 ? mbsv::get_kernel_replay(smem, E) : mbsv::get_kernel_fast(smem, E, rows, extra_smem);
 }
 
 // (Re)build the launch plan: which subproblems use the memoised arithmetic (memo_states), which of those run in the
@@ -749,6 +753,14 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     g_launches = 0;
     g_launch_info.clear();
     if (!p || !rp || !res) return fail(MBSV_ERR_ARG, "mbsv_run: NULL argument");
+    static const bool dbg_timing = std::getenv("MBSV_DEBUG_TIMING") != nullptr;
+    auto lap_t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg_timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mbsv run] %-12s %.3f s\n", what, std::chrono::duration<double>(t1 - lap_t0).count());
+        lap_t0 = t1;
+    };
     if (rp->mode != MBSV_MODE_REPLAY_EXACT && rp->mode != MBSV_MODE_FAST && rp->mode != MBSV_MODE_GIBBS) return fail(MBSV_ERR_ARG, "unknown mode");
     const bool gibbs = rp->mode == MBSV_MODE_GIBBS;
     if (gibbs && rp->trace) return fail(MBSV_ERR_ARG, "MBSV_MODE_GIBBS has no per-iteration trace");
@@ -788,11 +800,16 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     const int64_t tab_items = (int64_t)p->n_tab_subs * X;
     const int64_t sc_total = n_items;
 
+    lap("plan");
     OutBufs ob;
     mbsv::DevRun dr{};
     dr.n_chains = X; dr.num_iters = rp->num_iters; dr.burnin = rp->burnin; dr.win_base = (int)win_base;
     dr.java_int_wrap = rp->java_int_wrap; dr.perr = rp->perr; dr.logperr = mbsv::jm_log(rp->perr);
     dr.log1mperr = mbsv::jm_log(1 - rp->perr); dr.seed = rp->seed;
+    {   // ceil(perr * 2^53); the product is exact
+        const double x = rp->perr * 9007199254740992.0;
+        dr.perr_thr53 = !(x > 0.0) ? 0ULL : x >= 9007199254740992.0 ? (1ULL << 53) : (unsigned long long)std::ceil(x);
+    }
     dr.sub_order = p->d_sub_order.p; dr.sub_W = p->d_sub_W.p; dr.sub_memo = p->d_sub_memo.p; dr.n_items = n_items;
     dr.sub_tab_off = p->d_sub_tab_off.p; dr.memo_global = p->d_memo_global.p;
     dr.lanes_per_warp = L;
@@ -836,6 +853,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         if (res->initial_assign) { CUDA_TRY(ob.init_assign_out.alloc((size_t)X * p->n_frag)); dr.initial_assign = ob.init_assign_out.p; }
         if (res->initial_logprob) { CUDA_TRY(ob.init_logprob.alloc(sc_total)); dr.initial_logprob = ob.init_logprob.p; }
     }
+    lap("out alloc");
     cudaStream_t s0 = p->streams[0];
     CUDA_TRY(cudaMemsetAsync(dr.aln_count, 0, sizeof(unsigned) * p->n_aln, s0));
     CUDA_TRY(cudaMemsetAsync(dr.frag_err_count, 0, sizeof(unsigned) * p->n_frag, s0));
@@ -973,9 +991,10 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         }
     }
     if ((int)launches.size() > NSTREAM - 1) return fail(MBSV_ERR_ARG, "too many size classes");
+    lap("classes+ws");
 
     for (const Launch& l : launches)
-        if (l.giant && !p->d_aln_ent4.p) {       // first speculative-window launch of this problem: flatten the alignments' slots
+        if (!l.memo && !gibbs && !p->d_aln_ent4.p) {   // first launch of the general / speculative-window kernel: flatten the alignments' slots
             CUDA_TRY(p->d_aln_ent4.alloc(p->n_aln));
             CUDA_TRY(mbsv::launch_giant_prep(p->dp, p->d_aln_ent4.p, s0));
             p->dp.aln_ent4 = p->d_aln_ent4.p;
@@ -1026,14 +1045,15 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
                 if (v == 1 || v == 2 || v == 4 || v == 8) giant_cs = v;
             }
         }
+        size_t extra_smem = 0;
         KernelFn fn = gibbs ? mbsv::get_kernel_gibbs(32 / l.lanes)
                      : l.giant ? mbsv::get_kernel_giant(p->n_exp, giant_cs, &giant_threads, &giant_smem)
                      : l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : (!l.smem && l.lanes == 1 && !rp->trace) ? mbsv::get_kernel_packed(rp->mode, p->has_cc)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
-                                 : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp);
+                                 : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp, l.rows, &extra_smem);
         const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * l.lanes * l.rows * sizeof(int) : l.giant ? giant_smem
-                           : l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0;
+                           : (l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0) + extra_smem;
         if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         // MBSV_SERIAL_LAUNCHES=1 (tuning aid): run the size classes back to back on one stream
         static const bool serial = std::getenv("MBSV_SERIAL_LAUNCHES") != nullptr;
@@ -1062,7 +1082,9 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         ++nstream;
     }
     CUDA_TRY(cudaEventRecord(p->ev_stop, s0));
+    lap("launch");
     CUDA_TRY(cudaStreamSynchronize(s0));
+    lap("kernels");
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, p->ev_start, p->ev_stop));
     res->kernel_ms = ms;
@@ -1113,6 +1135,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         CUDA_TRY(down(res->initial_assign, dr.initial_assign, sizeof(int) * (size_t)X * p->n_frag));
         CUDA_TRY(down(res->initial_logprob, dr.initial_logprob, sizeof(double) * sc_total));
     }
+    lap("d2h");
     if (worst) return fail(worst, "a chain hit an invariant the reference turns into an Error (see results.error)");
     return MBSV_OK;
 }

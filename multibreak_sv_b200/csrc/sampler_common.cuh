@@ -18,7 +18,7 @@ namespace mbsv {
 #else
 #define MBSV_MATH_INLINE __noinline__
 #endif
-static __device__ MBSV_MATH_INLINE double log_binomial_dev(long long k, long long n, double p, double logp, double log1mp,
+static __device__ __forceinline__ double log_binomial_impl(long long k, long long n, double p, double logp, double log1mp,
                                                 double log2pi, const double* __restrict__ logtab, int ntab) {
     double dn = (double)n;
     if (dn * p <= 5 || dn * (1 - p) <= 5) {
@@ -37,6 +37,11 @@ static __device__ MBSV_MATH_INLINE double log_binomial_dev(long long k, long lon
     double sig = dn * p * (1 - p);
     double d = (double)k - mu;
     return -(d * d) / (2 * sig) - (log2pi + jm_log(sig)) / 2;
+}
+
+static __device__ MBSV_MATH_INLINE double log_binomial_dev(long long k, long long n, double p, double logp, double log1mp,
+                                                double log2pi, const double* __restrict__ logtab, int ntab) {
+    return log_binomial_impl(k, n, p, logp, log1mp, log2pi, logtab, ntab);
 }
 
 static __device__ MBSV_MATH_INLINE double exp_dev(double x) { return jm_exp(x); }

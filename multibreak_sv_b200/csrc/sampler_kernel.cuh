@@ -26,13 +26,20 @@ namespace mbsv {
 #endif
 // Launch bounds of the global-workspace class (large subproblems).  Measured on B200: 8 blocks/SM (64 registers, spills)
 // is slower than 5 (96 registers) both alone (289 vs 267 ms) and next to the other classes.
-// Read-only evaluation of Naive proposals in FAST mode (1) instead of tentative application + undo (0).  Measured on B200
-// (5M-fragment mixed batch, 64 chains, 2000 iterations, classes run back to back; profiles/r02_readonly_eval_ab.json):
-// SLOWER in every class of this kernel — shared-memory classes 28.8 -> 55.7 ms (128 rows), 60.4 -> 92.1 ms (48 rows), global
-// workspace 198.8 -> 235.7 ms: the eight-entry register lists push the 96-register kernel to ~1 KB of spills per thread,
-// which costs more than the undo pass saves.  Kept as a build option; the default stays do/undo.
-#ifndef MBSV_READONLY_EVAL
-#define MBSV_READONLY_EVAL 0
+// Read-only evaluation of Naive proposals (no tentative write, no undo pass) was built and measured in round 2: slower in
+// every class (register lists -> ~1 KB of spills per thread; profiles/r02_readonly_eval_ab.json), so do/undo stays.
+//
+// Drawing the NEXT proposal's header right after the current proposal's acceptance coin (no draw lies between them), so that
+// its fragment -> alignment-range / assignment loads overlap the current evaluation, plus L1 prefetches of its alignment
+// records, was built and measured in round 2 as well: 15-40 % slower in every class (the carried header costs registers the
+// kernel does not have).  What stayed from that work: the counted slots of an alignment come from one 16-byte record
+// (aln_ent4) instead of a walk over aln_esp_slot.
+// AlterSV proposals are held until this many lanes of the warp have one pending (1 = run them as they come)
+#ifndef MBSV_INLINE_MATH_GLOBAL
+#define MBSV_INLINE_MATH_GLOBAL 1
+#endif
+#ifndef MBSV_SV_BATCH
+#define MBSV_SV_BATCH 8
 #endif
 #ifndef MBSV_MIN_BLOCKS_GLOBAL
 #define MBSV_MIN_BLOCKS_GLOBAL 5
@@ -40,10 +47,48 @@ namespace mbsv {
 
 // CC = the batch contains connected-component clusters (GASV localization -1): their support is the sorted
 // multiset of a greedy set cover (MultiBreakSVAssignmentMatrix.java:337-409) kept per chain next to the counts.
-template <int MODE, bool TRACE, bool SMEM, int MAXE, bool CC = false, bool PACKED = false>
-__global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_GLOBAL) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
+// A per-thread array of N values indexed at run time: in registers (selected by compare chains) or, INSMEM, in the thread's
+// column of a [N][128] block of shared memory (plain address arithmetic, and no registers held across the proposal).
+template <typename T, int N, bool INSMEM> struct LaneArr;
+template <typename T, int N> struct LaneArr<T, N, false> {
+    T v[N];
+    __device__ __forceinline__ explicit LaneArr(void*) {}
+    __device__ __forceinline__ T get(int x) const {
+        T r = v[0];
+#pragma unroll
+        for (int y = 1; y < N; ++y) if (y == x) r = v[y];
+        return r;
+    }
+    __device__ __forceinline__ void set(int x, T val) {
+#pragma unroll
+        for (int y = 0; y < N; ++y) if (y == x) v[y] = val;
+    }
+    __device__ __forceinline__ void add(int x, T d) {
+#pragma unroll
+        for (int y = 0; y < N; ++y) if (y == x) v[y] += d;
+    }
+};
+template <typename T, int N> struct LaneArr<T, N, true> {
+    T* p;
+    __device__ __forceinline__ explicit LaneArr(void* base) : p((T*)base + threadIdx.x) {}
+    __device__ __forceinline__ T get(int x) const { return p[x * 128]; }
+    __device__ __forceinline__ void set(int x, T val) { p[x * 128] = val; }
+    __device__ __forceinline__ void add(int x, T d) { p[x * 128] += d; }
+};
+
+// MINB = CTAs per SM the register allocation is bounded for (0 = the build default).  The kernel wants ~190 registers; at 5
+// CTAs/SM it gets 96 and spills, and the spills cost more than the occupancy buys once the state tile limits a class to 3 or
+// 4 CTAs/SM anyway (measured per class on B200, 6000 iterations: 128 rows 87 -> 68 ms at MINB 3, 96 rows 129 -> 98 ms and
+// 64 rows 118 -> 102 ms at MINB 4; 48 rows and below are fastest at 5; 6 and 8 CTAs/SM are 1.6x and 2.1x slower).
+// SMTOT = the per-experiment totals and logBinomial terms of the chain live in shared memory (4 * MAXE * 8 bytes per thread
+// behind the counters) instead of registers.
+template <int MODE, bool TRACE, bool SMEM, int MAXE, bool CC = false, bool PACKED = false, int MINB = 0, bool SMTOT = false>
+__global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_GLOBAL) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
                                                          const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
+    // logBinomial / exp inlined into the proposal code: measured faster for the global-workspace class only (fewer values
+    // saved around the calls; its warps wait on memory, not on instruction fetch), slower for the shared-memory classes
+    constexpr bool INLINE_MATH = !SMEM && !PACKED && MODE == 1 && !TRACE && !CC && (MBSV_INLINE_MATH_GLOBAL != 0);
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const int warp = R.warp_begin + blockIdx.x * 4 + wic;
     if (warp >= R.warp_end) return;
@@ -74,8 +119,7 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
     const double logF = P.sub_logF[sub];
     const double neglogF = -logF;
     const double perr = R.perr, logperr = R.logperr;
-    const double dF = (double)F;
-    const unsigned long long perr_thr = prob_threshold53(perr);
+    const unsigned long long perr_thr = R.perr_thr53;
     constexpr unsigned long long NAIVE_THR = 0x1CCCCCCCCCCCCDULL;   // 0.9 * 2^53 exactly: nextDouble() < 0.9
 
     JavaRandom rng;
@@ -86,17 +130,27 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
     const int nst = (alive && R.sub_memo) ? R.sub_memo[sub] : 0;
     const bool use_full = (MODE == 0) || (nst > 0);
 
-    long long Etot[MAXE], Ltot[MAXE];
-    double LB[MAXE];
+    char* const tot_base = (char*)(smem_tile + (SMEM ? 4 * R.rows_per_warp * 32 : 0) + 5 * 128);
+    LaneArr<long long, MAXE, SMTOT> Etot(tot_base), Ltot(tot_base + MAXE * 1024);
+    LaneArr<double, MAXE, SMTOT> LB(tot_base + 2 * MAXE * 1024), newLB(tot_base + 3 * MAXE * 1024);
 #pragma unroll
-    for (int x = 0; x < MAXE; ++x) { Etot[x] = 0; Ltot[x] = 0; LB[x] = 0.0; }
+    for (int x = 0; x < MAXE; ++x) { Etot.set(x, 0); Ltot.set(x, 0); LB.set(x, 0.0); }
     int nerr = 0;
     int err = 0;
-    int n_naive_prop = 0, n_naive_acc = 0, n_sv_prop = 0, n_sv_acc = 0;   // <= num_iters each
-    long long n_reassign = 0;
+    // Proposal counters.  With SMTOT only the Naive proposals are counted in a register; the others change on a minority of
+    // the rounds and live in shared memory behind the state tiles ([5][128] words, one column per thread): at 96 registers
+    // the kernel spills (see MINB), and every value kept out of the registers is a spill less in the proposal loop.  The
+    // classes with large tiles have registers to spare and need their shared memory: more of it per CTA pushes the SM to the
+    // next carve-out step and halves the L1 that serves the CSR reads (measured: 128-row class 68 -> 88 ms).
+    int n_naive_prop = 0;                        // <= num_iters
+    LaneArr<int, 5, SMTOT> cnt(smem_tile + (SMEM ? 4 * R.rows_per_warp * 32 : 0));
+    constexpr int C_NACC = 0, C_SVPROP = 1, C_SVACC = 2, C_RLO = 3, C_RHI = 4;   // Naive accepted, AlterSV proposed / accepted,
+#pragma unroll
+    for (int i = 0; i < 5; ++i) cnt.set(i, 0);                                    // fragments toggled by AlterSV proposals (64 bit)
 
     auto wrapi = [&](long long t) -> long long { return R.java_int_wrap ? (long long)(int)(unsigned int)(unsigned long long)t : t; };
     auto lb_of = [&](int x, long long e, long long l) -> double {
+        if (INLINE_MATH) return log_binomial_impl(wrapi(e), wrapi(l), P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi, P.logint, P.maxn);
         return log_binomial_dev(wrapi(e), wrapi(l), P.exp_pseq[x], P.exp_logp[x], P.exp_log1mp[x], P.log2pi, P.logint,
                                 P.maxn);
     };
@@ -107,6 +161,17 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
             const int4 rec = P.aln_rec[a0 + from];
             const int x = rec.w & 0xff, ne = rec.w >> 8;
             const double* Tx = P.T + (size_t)x * Tstride;
+            const int4 e4 = P.aln_ent4[a0 + from];
+            if (e4.x != -3) {
+                const int sl[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (sl[j] < 0) continue;
+                    const int n = MBSV_ST(F + sl[j]);
+                    dcov = dcov + (Tx[n - 1] - Tx[n]);
+                    MBSV_ST(F + sl[j]) = n - 1;
+                }
+            } else
             for (int j = 0; j < ne; ++j) {
                 const int slot = P.aln_esp_slot[rec.z + j];
                 if (slot < 0) continue;
@@ -114,8 +179,7 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
                 dcov = dcov + (Tx[n - 1] - Tx[n]);
                 MBSV_ST(F + slot) = n - 1;
             }
-#pragma unroll
-            for (int y = 0; y < MAXE; ++y) if (y == x) { Etot[y] -= rec.x; Ltot[y] -= rec.y; }
+            Etot.add(x, -(long long)rec.x); Ltot.add(x, -(long long)rec.y);
             touched |= 1u << x;
         } else {
             derr = derr - logperr;
@@ -125,6 +189,17 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
             const int4 rec = P.aln_rec[a0 + to];
             const int x = rec.w & 0xff, ne = rec.w >> 8;
             const double* Tx = P.T + (size_t)x * Tstride;
+            const int4 e4 = P.aln_ent4[a0 + to];
+            if (e4.x != -3) {
+                const int sl[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (sl[j] < 0) continue;
+                    const int n = MBSV_ST(F + sl[j]);
+                    dcov = dcov + (Tx[n + 1] - Tx[n]);
+                    MBSV_ST(F + sl[j]) = n + 1;
+                }
+            } else
             for (int j = 0; j < ne; ++j) {
                 const int slot = P.aln_esp_slot[rec.z + j];
                 if (slot < 0) continue;
@@ -132,8 +207,7 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
                 dcov = dcov + (Tx[n + 1] - Tx[n]);
                 MBSV_ST(F + slot) = n + 1;
             }
-#pragma unroll
-            for (int y = 0; y < MAXE; ++y) if (y == x) { Etot[y] += rec.x; Ltot[y] += rec.y; }
+            Etot.add(x, rec.x); Ltot.add(x, rec.y);
             touched |= 1u << x;
         } else {
             derr = derr + logperr;
@@ -276,7 +350,7 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
         lp += 0.0;
         lp += (double)nerr * logperr;
 #pragma unroll
-        for (int x = 0; x < MAXE; ++x) if (x < E) lp += lb_of(x, Etot[x], Ltot[x]);
+        for (int x = 0; x < MAXE; ++x) if (x < E) lp += lb_of(x, Etot.get(x), Ltot.get(x));
         return lp;
     };
     // difference tallies
@@ -370,12 +444,11 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
                     if (slot < 0) continue;
                     if (SMEM) MBSV_ST(F + slot) += 1; else atomicAdd(&MBSV_ST(F + slot), 1);
                 }
-#pragma unroll
-                for (int y = 0; y < MAXE; ++y) if (y == x) { Etot[y] += rec[k].x; Ltot[y] += rec[k].y; }
+                Etot.add(x, rec[k].x); Ltot.add(x, rec[k].y);
             }
         }
 #pragma unroll
-        for (int x = 0; x < MAXE; ++x) if (x < E) LB[x] = lb_of(x, Etot[x], Ltot[x]);
+        for (int x = 0; x < MAXE; ++x) if (x < E) LB.set(x, lb_of(x, Etot.get(x), Ltot.get(x)));
         if (has_cc)
             for (int cl = 0; cl < C; ++cl) if (P.cluster_cc_off[c0 + cl] >= 0) cc_recompute(cl);
     }
@@ -384,136 +457,98 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
 
     // ---------------- iterations (MultiBreakSV.java:796-837, 1101-1182) ----------------
     const int q_base = P.sv_frag_ptr[sv0];   // only dereferenced when nsv > 0
-    const double neglogNsv = P.sub_neglogNsv[sub];
     int iter = 0;
-    bool done = false;
+    bool done = false, live = false;
+    // header of the pending proposal: the draws that do not depend on the state (move type; fragment or AlterSV candidate)
+    // and the loads that depend only on them (alignment range and current assignment of the fragment)
+    bool h_naive = true;
+    int h_idx = 0, h_a0 = 0, h_n = 0, h_prev = -1;
+    // Move-type coin (:1115-1118): its value cannot matter when there is no AlterSV candidate; the fragment pick
+    // (:1400) cannot matter for a one-fragment problem.  The draws are still consumed.
+    auto draw_header = [&]() {
+        h_naive = true;
+        if (nsv == 0) rng.skip<2>(); else h_naive = rng.bits53() < NAIVE_THR;
+        double u = 0.0;
+        if (h_naive && F == 1) rng.skip<2>(); else u = rng.nextDouble();
+        if (h_naive) {
+            h_idx = (int)(u * (double)F);
+            h_a0 = P.frag_aln_ptr[f0 + h_idx];
+            h_n = P.frag_aln_ptr[f0 + h_idx + 1] - h_a0;
+            h_prev = MBSV_ST(h_idx);
+        } else {
+            h_idx = (int)(u * (double)nsv);
+        }
+    };
     for (;;) {
         // Lazy chain: with probability 1/2 stay (:1106-1113).  Lazy iterations only advance the RNG (tallies
         // are difference tallies), so each lane skips them in a tight loop; the warp-wide vote below is the
         // convergence point that brings all 32 lanes back together for the proposal code.
-        double r = 0.0;
-        bool live = false;
-        if (TRACE) {
-            if (!done) {
-                while (iter < N) {
-                    r = rng.nextDouble();
-                    if (!(r < 0.5)) { live = true; break; }
-                    R.trace_logprob[sc * N + iter] = logprob;
-                    R.trace_move_frag[sc * N + iter] = -1;
-                    R.trace_move_assign[sc * N + iter] = -1;
-                    ++iter;
+        if (!live) {
+            if (TRACE) {
+                if (!done) {
+                    while (iter < N) {
+                        const double r = rng.nextDouble();
+                        if (!(r < 0.5)) { live = true; break; }
+                        R.trace_logprob[sc * N + iter] = logprob;
+                        R.trace_move_frag[sc * N + iter] = -1;
+                        R.trace_move_assign[sc * N + iter] = -1;
+                        ++iter;
+                    }
+                    done = !live;
                 }
-                done = !live;
+            } else if (!done) {
+                lazy_skip(rng, iter, N, live, done);
             }
-        } else if (!done) {
-            lazy_skip(rng, iter, N, live, done);
+            if (live) draw_header();
         }
-        if (__all_sync(0xffffffffu, done)) break;
-        if (!live) continue;
+        if (__all_sync(0xffffffffu, done && !live)) break;
+        // AlterSV proposals (one in ten where a subproblem has candidates) walk a list of fragments while the Naive lanes of
+        // the warp wait, and with 32 chains nearly every round has one.  Chains are independent, so a lane that drew an
+        // AlterSV proposal HOLDS it until MBSV_SV_BATCH lanes of the warp hold one (or no other lane can advance); the list
+        // walk then runs once for all of them.  Only the interleaving of the chains changes, not any chain.
+        bool hold = false;
+        if (MBSV_SV_BATCH > 1) {
+            const unsigned svm = __ballot_sync(0xffffffffu, live && !h_naive);
+            if (svm) {
+                const unsigned prog = __ballot_sync(0xffffffffu, (live && h_naive) || (!live && !done));
+                if (__popc(svm) < MBSV_SV_BATCH && prog != 0) hold = live && !h_naive;
+            }
+        }
+        if (hold || !live) continue;
+        live = false;
         const int t = iter;
-        // Move-type coin (:1115-1118): its value cannot matter when there is no AlterSV candidate; the fragment pick
-        // (:1400) cannot matter for a one-fragment problem.  The draws are still consumed.
-        bool naive = true;
-        if (nsv == 0) rng.skip<2>(); else naive = rng.bits53() < NAIVE_THR;
+        const bool naive = h_naive;
         // A proposal is a list of single-fragment moves: one for Naive, the cluster's single-alignment
         // fragments for AlterSV.  Both kinds run through the same code below.
         int f = -1, a0 = 0, prev = -1, now = -1, svk = -1, q0 = 0, nmoves = 1;
-        double Alogq, Anewlogq;
-        double u = 0.0;
-        if (naive && F == 1) rng.skip<2>(); else u = rng.nextDouble();
+        double Alogq = 0.0, Anewlogq = 0.0;
         if (naive) {
             // ---- naiveMove (:1184-1273) ----
-            ++n_naive_prop; ++n_reassign;
-            f = (int)(u * dF);
-            a0 = P.frag_aln_ptr[f0 + f];
-            const int n = P.frag_aln_ptr[f0 + f + 1] - a0;
-            prev = MBSV_ST(f);
-            naive_pick(rng, n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, P.invint, now, Alogq, Anewlogq);
+            ++n_naive_prop;
+            f = h_idx;
+            a0 = h_a0;
+            prev = h_prev;
+            naive_pick(rng, h_n, prev, neglogF, perr_thr, logperr, R.log1mperr, P.logint, P.invint, now, Alogq, Anewlogq);
             if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
         } else {
             // ---- svMove (:1291-1343) ----
-            ++n_sv_prop;
-            svk = (int)(u * (double)nsv);
-            n_reassign += P.sv_numchanged[sv0 + svk];
+            cnt.add(C_SVPROP, 1);
+            svk = h_idx;
+            {
+                const unsigned lo = (unsigned)cnt.get(C_RLO), nlo = lo + (unsigned)P.sv_numchanged[sv0 + svk];
+                cnt.set(C_RLO, (int)nlo);
+                if (nlo < lo) cnt.add(C_RHI, 1);
+            }
             q0 = P.sv_frag_ptr[sv0 + svk];
             nmoves = P.sv_frag_ptr[sv0 + svk + 1] - q0;
-            Alogq = neglogNsv;
-            Anewlogq = neglogNsv;
+            Alogq = P.sub_neglogNsv[sub];
+            Anewlogq = Alogq;
         }
         // ---- evaluate the proposal ----
         double dcov = 0.0, derr = 0.0;
         unsigned touched = 0;
         bool written = false;
-        double newLB[MAXE];
         double newlogprob, arg;
-        // Read-only evaluation (FAST, Naive, at most four ESPs per alignment, no connected component): the Delta is computed
-        // from the counts as they are; nothing is written unless the move is accepted, so a rejected proposal (four in five)
-        // costs no state writes and no undo pass.  ro_sl = counted slots of the alignment left (0..3) and entered (4..7),
-        // ro_cn = the count each entry sees: the stored count plus the earlier entries of this proposal on the same slot.
-        bool ro = false;
-        int ro_sl[8], ro_cn[8];
-        long long roE[MAXE], roL[MAXE];
-        if (MBSV_READONLY_EVAL && MODE == 1 && !TRACE && naive && !use_full && !has_cc) {
-            int4 recF = make_int4(0, 0, 0, 0), recT = make_int4(0, 0, 0, 0);
-            if (prev != -1) recF = P.aln_rec[a0 + prev];
-            if (now != -1) recT = P.aln_rec[a0 + now];
-            const int neF = recF.w >> 8, neT = recT.w >> 8;
-            if (neF <= 4 && neT <= 4) {
-                ro = true;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ro_sl[j] = j < neF ? P.aln_esp_slot[recF.z + j] : -1;
-                    ro_sl[4 + j] = j < neT ? P.aln_esp_slot[recT.z + j] : -1;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ro_cn[i] = ro_sl[i] >= 0 ? MBSV_ST(F + ro_sl[i]) : 0;
-#pragma unroll
-                for (int i = 1; i < 8; ++i)
-#pragma unroll
-                    for (int i2 = 0; i2 < i; ++i2)
-                        if (ro_sl[i] >= 0 && ro_sl[i2] == ro_sl[i]) ro_cn[i] += i2 < 4 ? -1 : 1;
-#pragma unroll
-                for (int x = 0; x < MAXE; ++x) { roE[x] = Etot[x]; roL[x] = Ltot[x]; }
-                if (prev != -1) {
-                    const int x = recF.w & 0xff;
-                    const double* Tx = P.T + (size_t)x * Tstride;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (ro_sl[j] >= 0) dcov = dcov + (Tx[ro_cn[j] - 1] - Tx[ro_cn[j]]);
-#pragma unroll
-                    for (int y = 0; y < MAXE; ++y) if (y == x) { roE[y] -= recF.x; roL[y] -= recF.y; }
-                    touched |= 1u << x;
-                } else derr = derr - logperr;
-                if (now != -1) {
-                    const int x = recT.w & 0xff;
-                    const double* Tx = P.T + (size_t)x * Tstride;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (ro_sl[4 + j] >= 0) dcov = dcov + (Tx[ro_cn[4 + j] + 1] - Tx[ro_cn[4 + j]]);
-#pragma unroll
-                    for (int y = 0; y < MAXE; ++y) if (y == x) { roE[y] += recT.x; roL[y] += recT.y; }
-                    touched |= 1u << x;
-                } else derr = derr + logperr;
-                double dlb = 0.0;
-#pragma unroll
-                for (int x = 0; x < MAXE; ++x) newLB[x] = LB[x];
-                unsigned mask = touched & ((1u << E) - 1u);
-                while (mask) {
-                    const int x = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    long long ex = 0, lx = 0;
-                    double old = 0.0;
-#pragma unroll
-                    for (int y = 0; y < MAXE; ++y) if (y == x) { ex = roE[y]; lx = roL[y]; old = LB[y]; }
-                    const double nl = lb_of(x, ex, lx);
-#pragma unroll
-                    for (int y = 0; y < MAXE; ++y) if (y == x) newLB[y] = nl;
-                    dlb = dlb + (nl - old);
-                }
-                const double delta = (dcov + derr) + dlb;
-                newlogprob = logprob + delta;
-                arg = (delta + Alogq) - Anewlogq;
-            }
-        }
-        if (!ro) {
         // ---- tentative application ----
         for (int q = 0; q < nmoves; ++q) {
             int ga0 = a0, from = prev, to = now;
@@ -554,72 +589,42 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
                 if (from != -1) cc_visit(ga0 + from, touch);
                 if (to != -1) cc_visit(ga0 + to, touch);
             }
-            if (err) { done = true; continue; }   // set cover failed to cover: the reference throws Error
+            if (err) { done = true; live = false; continue; }   // set cover failed to cover: the reference throws Error
         }
         // ---- acceptance ratio (:1146) ----
         if (use_full) {
             // full re-sum in the reference's order; the assignment change only enters through nerr, counts, totals
 #pragma unroll
-            for (int x = 0; x < MAXE; ++x) newLB[x] = LB[x];
+            for (int x = 0; x < MAXE; ++x) newLB.set(x, LB.get(x));
             newlogprob = full_logprob();
             arg = (newlogprob + Alogq) - (logprob + Anewlogq);
         } else {
             double dlb = 0.0;
 #pragma unroll
-            for (int x = 0; x < MAXE; ++x) newLB[x] = LB[x];
+            for (int x = 0; x < MAXE; ++x) newLB.set(x, LB.get(x));
             // Each lane walks ITS touched experiments in ascending order (same summation order as before), so lanes
             // whose proposals touch different platforms evaluate logBinomial together instead of one platform at a time.
             unsigned mask = touched & ((1u << E) - 1u);
             while (mask) {
                 const int x = __ffs(mask) - 1;
                 mask &= mask - 1;
-                long long ex = 0, lx = 0;
-                double old = 0.0;
-#pragma unroll
-                for (int y = 0; y < MAXE; ++y) if (y == x) { ex = Etot[y]; lx = Ltot[y]; old = LB[y]; }
-                const double nl = lb_of(x, ex, lx);
-#pragma unroll
-                for (int y = 0; y < MAXE; ++y) if (y == x) newLB[y] = nl;
-                dlb = dlb + (nl - old);
+                const double nl = lb_of(x, Etot.get(x), Ltot.get(x));
+                newLB.set(x, nl);
+                dlb = dlb + (nl - LB.get(x));
             }
             const double delta = (dcov + derr) + dlb;
             newlogprob = logprob + delta;
             arg = (delta + Alogq) - Anewlogq;
         }
-        }
-        const double e = exp_dev(arg);
+        const double e = INLINE_MATH ? jm_exp(arg) : exp_dev(arg);
         const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);   // Math.min(1, e)
-        r = rng.nextDouble();
-        const bool accept = ratio > r;
-        if (accept && ro) {
-            // apply the accepted move: counts (in entry order, so a slot hit twice ends at its final value), totals,
-            // difference tallies (value cn leaves: +d, value cn +- 1 enters: -d), assignment
-            logprob = newlogprob;
-            ++n_naive_acc;
-#pragma unroll
-            for (int x = 0; x < MAXE; ++x) { LB[x] = newLB[x]; Etot[x] = roE[x]; Ltot[x] = roL[x]; }
-            nerr += (now == -1 ? 1 : 0) - (prev == -1 ? 1 : 0);
-            const unsigned d = t > win_base ? (unsigned)(t - win_base) : 0u;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (ro_sl[i] < 0) continue;
-                const int cn2 = ro_cn[i] + (i < 4 ? -1 : 1);
-                MBSV_ST(F + ro_sl[i]) = cn2;
-                if (d) {
-                    unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + ro_sl[i] / E];
-                    if (ro_cn[i] > 0) atomicAdd(&h[ro_cn[i]], d);
-                    if (cn2 > 0) atomicAdd(&h[cn2], 0u - d);
-                }
-            }
-            tally_frag(f, a0, prev, now, t);
-            MBSV_ST(f) = now;
-        } else if (ro) {
-            // rejected: nothing was written
-        } else if (accept) {
+        const double r_acc = rng.nextDouble();
+        const bool accept = ratio > r_acc;
+        if (accept) {
             logprob = newlogprob;
 #pragma unroll
-            for (int x = 0; x < MAXE; ++x) LB[x] = newLB[x];
-            if (naive) ++n_naive_acc; else ++n_sv_acc;
+            for (int x = 0; x < MAXE; ++x) LB.set(x, newLB.get(x));
+            cnt.add(naive ? C_NACC : C_SVACC, 1);
             if (t > win_base) {
                 // support-histogram difference tallies: walk the move backwards, then re-apply it
                 for (int q = nmoves - 1; q >= 0; --q) {
@@ -715,9 +720,9 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
             }
         }
         if (TRACE) {
-            R.trace_logprob[sc * N + iter] = logprob;
-            R.trace_move_frag[sc * N + iter] = accept ? (naive ? f0 + f : -(2 + svk)) : -1;
-            R.trace_move_assign[sc * N + iter] = (accept && naive) ? now : -1;
+            R.trace_logprob[sc * N + t] = logprob;
+            R.trace_move_frag[sc * N + t] = accept ? (naive ? f0 + f : -(2 + svk)) : -1;
+            R.trace_move_assign[sc * N + t] = (accept && naive) ? now : -1;
         }
         ++iter;
     }
@@ -762,6 +767,8 @@ __global__ void __launch_bounds__(128, SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_
     if (R.final_assign)
         for (int f = 0; f < F; ++f) R.final_assign[(size_t)chain * P.n_frag + f0 + f] = MBSV_ST(f);
     if (R.final_logprob) R.final_logprob[sc] = (MODE == 0) ? logprob : full_logprob();
+    const int n_naive_acc = cnt.get(C_NACC), n_sv_prop = cnt.get(C_SVPROP), n_sv_acc = cnt.get(C_SVACC);
+    const long long n_reassign = (long long)n_naive_prop + (long long)(((unsigned long long)(unsigned)cnt.get(C_RHI) << 32) | (unsigned)cnt.get(C_RLO));
     if (R.counters) {
         long long* k = R.counters + sc * 5;
         k[0] = n_naive_prop; k[1] = n_naive_acc; k[2] = n_sv_prop; k[3] = n_sv_acc; k[4] = n_reassign;

@@ -49,6 +49,7 @@ struct DevProblem {
 struct DevRun {
     int n_chains, num_iters, burnin, win_base, java_int_wrap;
     double perr, logperr, log1mperr;
+    unsigned long long perr_thr53;   // ceil(perr * 2^53): nextDouble() < perr  <=>  bits53() < perr_thr53
     long long seed;
     const int* init_assign;
     // plan: item g = item_base + (warp - warp_base)*lanes_per_warp + lane is chain (g % n_chains) of subproblem
@@ -90,7 +91,7 @@ struct DevRun {
 
 using KernelFn = void (*)(const DevProblem, const DevRun);
 // kernel selectors, one per translation unit (kern_fast.cu / kern_replay.cu / kern_trace.cu)
-KernelFn get_kernel_fast(bool smem, int n_exp);                 // MODE_FAST, no trace: the throughput path
+KernelFn get_kernel_fast(bool smem, int n_exp, int rows, size_t* extra_smem);   // MODE_FAST, no trace: the throughput path (rows = shared-memory class)
 KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_EXACT, no trace
 KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
 KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with connected-component clusters
