@@ -413,6 +413,20 @@ def main():
     dt = time.perf_counter() - t0
     clk = clocks.stop()
     launch_info = dp.launch_info()
+    if not clk.get("samples"):
+        # the timed region was shorter than nvidia-smi's sampling period (giant component: tens of ms per step): sample
+        # the clocks while the same step repeats, untimed, for about a second
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        n_rep = torch.tensor([int(1.2 / max(dt / args.steps, 1e-3)) + 1], device=dev)
+        if world > 1:
+            dist.all_reduce(n_rep, op=dist.ReduceOp.MAX)      # the step holds a collective: every rank repeats it equally often
+        for _ in range(int(n_rep.item())):
+            step()
+        barrier()
+        clk = clocks.stop()
+        clk["sampled"] = "untimed repeats of the step right after the timed region (the region is shorter than the sampling period)"
+        reduce_ms[:] = reduce_ms[:args.steps]
     totals = totals_t.cpu().numpy().astype(np.int64)      # of the last step (every step is identical)
     if int(totals[5]) != 0:
         raise SystemExit(f"a chain reported status {int(totals[5])}")
@@ -479,7 +493,7 @@ def main():
     per_class = []
     tot_ms = sum(li["ms"] for li in launch_info) or 1.0
     for li in launch_info:
-        kind = ("memo" if li["rows"] < 0 else "window" if (li["rows"] == 0 and li["smem_bytes"] > 0)
+        kind = ("memo" if li["rows"] < 0 else "window" if (li["rows"] == 0 and li["smem_bytes"] > 32768)
                 else "global" if li["rows"] == 0 else "smem")
         per_class.append({"kernel": kind, "rows": abs(li["rows"]), "warps": li["warps"], "ms": li["ms"],
                           "reassignments": li["reassignments"], "accepted": li["accepted"],

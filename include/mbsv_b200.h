@@ -194,6 +194,10 @@ const char* mbsv_status_string(int status);
 /* Validates and copies the descriptor, uploads the packed CSR to `device`. */
 int mbsv_problem_create(const mbsv_problem_desc* desc, int32_t device, mbsv_problem** out);
 int mbsv_problem_destroy(mbsv_problem* p);
+/* The library keeps large device blocks of destroyed problems for the next problem on the same device (a caching
+   allocator: one run after another does not pay a multi-gigabyte cudaMalloc / cudaFree each).  mbsv_trim returns them to
+   the driver; device < 0 = every device.  An allocation that fails trims and retries by itself. */
+int mbsv_trim(int32_t device);
 
 /* Runs n_chains chains of num_iters iterations on every subproblem (blocking). */
 int mbsv_run(mbsv_problem* p, const mbsv_run_params* params, mbsv_results* results);

@@ -11,7 +11,7 @@ import os as _os
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from ._abi import (MODE_FAST, MODE_GIBBS, MODE_REPLAY_EXACT, Comm, DeviceProblem, MbsvError, PackedProblem, RunOutput,
-                   load_library, reference_burnin, run_multi)
+                   load_library, reference_burnin, run_multi, trim)
 
 __all__ = ["MODE_FAST", "MODE_GIBBS", "MODE_REPLAY_EXACT", "Comm", "DeviceProblem", "MbsvError", "PackedProblem", "RunOutput",
-           "load_library", "reference_burnin", "run_multi"]
+           "load_library", "reference_burnin", "run_multi", "trim"]

@@ -69,7 +69,7 @@ EXPORTS = ["mbsv_abi_version", "mbsv_device_count", "mbsv_last_error", "mbsv_sta
            "mbsv_problem_destroy", "mbsv_run", "mbsv_run_device", "mbsv_problem_stats", "mbsv_last_launch_count",
            "mbsv_log", "mbsv_exp", "mbsv_fill_logprobcov", "mbsv_lpt_shard", "mbsv_last_launch_info",
            "mbsv_last_launch_totals", "mbsv_split_chains", "mbsv_comm_unique_id", "mbsv_comm_create", "mbsv_comm_destroy", "mbsv_reduce_tallies",
-           "mbsv_run_multi"]
+           "mbsv_run_multi", "mbsv_trim"]
 COMM_ID_BYTES = 128
 
 _lib = None
@@ -97,6 +97,7 @@ def load_library():
     L.mbsv_problem_create.argtypes = [C.POINTER(ProblemDesc), C.c_int32, C.POINTER(C.c_void_p)]
     L.mbsv_problem_create.restype = C.c_int
     L.mbsv_problem_destroy.argtypes = [C.c_void_p]; L.mbsv_problem_destroy.restype = C.c_int
+    L.mbsv_trim.argtypes = [C.c_int32]; L.mbsv_trim.restype = C.c_int
     L.mbsv_run.argtypes = [C.c_void_p, C.POINTER(RunParams), C.POINTER(Results)]; L.mbsv_run.restype = C.c_int
     L.mbsv_run_device.argtypes = [C.c_void_p, C.POINTER(RunParams), C.POINTER(Results)]
     L.mbsv_run_device.restype = C.c_int
@@ -175,6 +176,11 @@ class RunOutput:
         return int(sum(a.nbytes for a in (self.aln_count, self.frag_err_count, self.cluster_hist, self.final_assign,
                                           self.final_logprob, self.counters, self.rng_state, self.error, self.totals)
                        if a is not None))
+
+
+def trim(device: int = -1) -> None:
+    """mbsv_trim: return the device memory the library keeps for reuse by the next problem (device < 0: every device)."""
+    check(load_library().mbsv_trim(device))
 
 
 def reference_burnin(num_iters: int) -> int:

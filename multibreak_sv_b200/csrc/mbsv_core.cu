@@ -11,8 +11,10 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mbsv_b200.h"
@@ -45,17 +47,93 @@ int fail(int code, const std::string& msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(_e));                         \
     } while (0)
 
+// Device allocations of at least POOL_MIN bytes are kept when a problem releases them and handed to the next problem that
+// asks for a block of about that size on the same device: a host that runs one problem after another (the reference's
+// workflow is one run per subset of clusters) pays the multi-gigabyte cudaMalloc / cudaFree of the chain-state workspace
+// and the memo tables once.  Measured on the 5M-fragment batch: create + run + destroy 5.16 -> see profiles/ (fresh blocks
+// also made the first kernel touching them ~250 ms slower than reused ones).  mbsv_trim() returns the kept blocks.
+struct DevPool {
+    static constexpr size_t POOL_MIN = 1 << 20;
+    struct Block { void* p; size_t bytes; int device; };
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    cudaError_t get(void** out, size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (bytes >= POOL_MIN) {
+            std::lock_guard<std::mutex> lk(mu);
+            int best = -1;
+            for (int i = 0; i < (int)free_blocks.size(); ++i) {
+                const Block& b = free_blocks[i];
+                if (b.device != dev || b.bytes < bytes || b.bytes > bytes + bytes / 4 + POOL_MIN) continue;
+                if (best < 0 || b.bytes < free_blocks[best].bytes) best = i;
+            }
+            if (best >= 0) {
+                *out = free_blocks[best].p;
+                live[*out] = free_blocks[best].bytes;
+                free_blocks.erase(free_blocks.begin() + best);
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaErrorMemoryAllocation) {          // give the kept blocks back and try once more
+            cudaGetLastError();
+            trim(dev);
+            e = cudaMalloc(out, bytes);
+        }
+        if (e == cudaSuccess && bytes >= POOL_MIN) { std::lock_guard<std::mutex> lk(mu); live[*out] = bytes; }
+        return e;
+    }
+    void put(void* ptr) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = live.find(ptr);
+            if (it != live.end()) {
+                cudaPointerAttributes a{};
+                if (cudaPointerGetAttributes(&a, ptr) == cudaSuccess) dev = a.device;
+                free_blocks.push_back({ptr, it->second, dev});
+                live.erase(it);
+                return;
+            }
+        }
+        cudaFree(ptr);
+    }
+    void trim(int device) {                             // device < 0: every device
+        std::vector<Block> drop;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t i = 0; i < free_blocks.size();)
+                if (device < 0 || free_blocks[i].device == device) { drop.push_back(free_blocks[i]); free_blocks.erase(free_blocks.begin() + i); }
+                else ++i;
+        }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (const Block& b : drop) { cudaSetDevice(b.device); cudaFree(b.p); }
+        cudaSetDevice(cur);
+    }
+    size_t kept(int device) {                           // bytes waiting for reuse on `device`
+        std::lock_guard<std::mutex> lk(mu);
+        size_t b = 0;
+        for (const Block& k : free_blocks) if (k.device == device) b += k.bytes;
+        return b;
+    }
+    std::unordered_map<void*, size_t> live;             // pooled-size blocks currently handed out
+};
+DevPool g_pool;
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) g_pool.put(p); p = nullptr; n = 0; }
     cudaError_t alloc(size_t count) {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc((void**)&p, count * sizeof(T));
+        return g_pool.get((void**)&p, count * sizeof(T));
     }
     cudaError_t upload_raw(const T* src, size_t count) {
         cudaError_t e = alloc(count);
@@ -147,6 +225,12 @@ const char* mbsv_status_string(int s) {
         case MBSV_ERR_IO: return "I/O error";
         default: return "unknown";
     }
+}
+
+// Returns the device memory kept for reuse (see DevPool) to the driver; device < 0 = every device.
+int mbsv_trim(int32_t device) {
+    g_pool.trim(device);
+    return MBSV_OK;
 }
 
 int mbsv_device_count(void) {
@@ -690,6 +774,7 @@ int ensure_plan(mbsv_problem* p, int memo_states, int tab_mode) {
     // device-memory tables may take a quarter of what is free now (the chain-state workspace needs the rest)
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    free_b += g_pool.kept(p->device);                  // blocks kept for reuse are available to this problem
     const long long table_budget = (long long)(free_b / 4 / sizeof(double));
     for (int s = 0; s < S; ++s) {
         int rows = p->sub_W[s];
@@ -982,7 +1067,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             p->ws_cache.release();
             size_t free_b = 0, total_b = 0;
             CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-            if (need * sizeof(int) > free_b) return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory");
+            if (need * sizeof(int) > free_b + g_pool.kept(p->device)) return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory");
             if (p->ws_cache.alloc(need) != cudaSuccess) { cudaGetLastError(); p->ws_cache.release(); return fail(MBSV_ERR_OOM, "chain state workspace does not fit in device memory"); }
         }
         if (off != p->row_off_host) {
