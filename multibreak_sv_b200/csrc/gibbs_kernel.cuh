@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
             if (slot < 0) continue;
             const int n = st[F + slot];
             if (d) {
-                unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                unsigned int* h = R.cluster_hist + P.slot_hist_ptr[c0 * E + slot];
                 if (n > 0) atomicAdd(&h[n], d);
                 if (n + sgn > 0) atomicAdd(&h[n + sgn], 0u - d);
             }
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
         }
         for (int i = lane; i < C * E; i += G) {
             const int nn = st[F + i];
-            if (nn > 0) atomicAdd(&(R.cluster_hist + P.cluster_hist_ptr[c0 + i / E])[nn], d);
+            if (nn > 0) atomicAdd(&(R.cluster_hist + P.slot_hist_ptr[c0 * E + i])[nn], d);
         }
     }
     if (R.final_assign) for (int f = lane; f < F; f += G) R.final_assign[(size_t)chain * P.n_frag + f0 + f] = st[f];

@@ -192,7 +192,7 @@ struct mbsv_problem {
     int64_t csr_bytes = 0;
     // device CSR
     DevBuf<int> d_sub_frag_ptr, d_sub_cluster_ptr, d_sub_sv_ptr, d_frag_aln_ptr, d_aln_esp_slot, d_supports_local,
-        d_cluster_hist_ptr, d_sv_frag_ptr, d_sv_frag, d_sv_numchanged, d_sub_order, d_sub_W, d_sub_memo;
+        d_cluster_hist_ptr, d_slot_hist_ptr, d_sv_frag_ptr, d_sv_frag, d_sv_numchanged, d_sub_order, d_sub_W, d_sub_memo;
     DevBuf<int4> d_aln_rec;
     DevBuf<double> d_sub_logF, d_sub_neglogNsv, d_T, d_logint, d_invint, d_pseq, d_logp, d_log1mp;
     DevBuf<unsigned long long> d_launch_totals;     // [NSTREAM][6]: every launch pools its chains' counters in its own row
@@ -645,6 +645,11 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     chk(p->d_aln_esp_slot.upload_raw(slot.get(), K));
     chk(p->d_supports_local.upload_raw(sup_local.get(), C));
     if (C > 0) chk(p->d_cluster_hist_ptr.upload_raw(d->cluster_hist_ptr, C + 1)); else chk(up(p->d_cluster_hist_ptr, std::vector<int>(1, 0)));
+    {
+        std::vector<int> slot_hist((size_t)std::max(C, 0) * E + 1, 0);
+        for (int c = 0; c < C; ++c) for (int x = 0; x < E; ++x) slot_hist[(size_t)c * E + x] = d->cluster_hist_ptr[c];
+        chk(up(p->d_slot_hist_ptr, slot_hist));
+    }
     chk(up(p->d_sv_frag_ptr, sv_frag_ptr));
     chk(up(p->d_sv_frag, sv_frag));
     chk(up(p->d_sv_numchanged, sv_numchanged));
@@ -688,7 +693,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     dp.cluster_cc_off = p->d_cluster_cc_off.p; dp.sub_cc_scratch = p->d_sub_cc_scratch.p; dp.sub_cc_maxleaf = p->d_sub_cc_maxleaf.p;
     dp.cluster_leaf_ptr = p->d_cluster_leaf_ptr.p; dp.leaf_owner = p->d_leaf_owner.p; dp.aln_esp_leaf = p->d_aln_esp_leaf.p;
     dp.cluster_root_ptr = p->d_cluster_root_ptr.p; dp.root_leaf_ptr = p->d_root_leaf_ptr.p; dp.root_leaf = p->d_root_leaf.p;
-    dp.cluster_hist_ptr = p->d_cluster_hist_ptr.p; dp.sv_frag_ptr = p->d_sv_frag_ptr.p; dp.sv_frag = p->d_sv_frag.p;
+    dp.cluster_hist_ptr = p->d_cluster_hist_ptr.p; dp.slot_hist_ptr = p->d_slot_hist_ptr.p; dp.sv_frag_ptr = p->d_sv_frag_ptr.p; dp.sv_frag = p->d_sv_frag.p;
     dp.sv_mv = p->d_sv_mv.p; dp.sv_ent_ptr = p->d_sv_ent_ptr.p; dp.sv_ent = p->d_sv_ent.p; dp.aln_ent4 = nullptr;
     dp.sv_numchanged = p->d_sv_numchanged.p; dp.T = p->d_T.p; dp.logint = p->d_logint.p; dp.invint = p->d_invint.p; dp.exp_pseq = p->d_pseq.p;
     dp.exp_logp = p->d_logp.p; dp.exp_log1mp = p->d_log1mp.p;

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
                 if (slot < 0) continue;
                 const int n = MBSV_ST(F + slot);
                 if (d) {
-                    unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                    unsigned int* h = R.cluster_hist + P.slot_hist_ptr[c0 * E + slot];
                     if (n > 0) atomicAdd(&h[n], d);
                     if (n - 1 > 0) atomicAdd(&h[n - 1], 0u - d);
                 }
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
                 if (slot < 0) continue;
                 const int n = MBSV_ST(F + slot);
                 if (d) {
-                    unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                    unsigned int* h = R.cluster_hist + P.slot_hist_ptr[c0 * E + slot];
                     if (n > 0) atomicAdd(&h[n], d);
                     atomicAdd(&h[n + 1], 0u - d);
                 }

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
 #endif
     const int f0 = P.sub_frag_ptr[sub], F = alive ? P.sub_frag_ptr[sub + 1] - f0 : 0;
     const int c0 = P.sub_cluster_ptr[sub], C = alive ? P.sub_cluster_ptr[sub + 1] - c0 : 0;
-    const int E = P.n_exp;
+    const int E = MAXE <= 2 ? MAXE : P.n_exp;       // the buckets 1 and 2 are exact (kern_*.cu), so E is a constant there
     const int sv0 = P.sub_sv_ptr[sub], nsv = P.sub_sv_ptr[sub + 1] - sv0;
     const int Tstride = P.max_support + 1;
     const long long sc = (long long)sub * R.n_chains + chain;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
                 const int slot = P.aln_esp_slot[rec.z + j];
                 if (slot < 0) continue;
                 const int n = MBSV_ST(F + slot);
-                unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                unsigned int* h = R.cluster_hist + P.slot_hist_ptr[c0 * E + slot];
                 if (n - 1 > 0) atomicAdd(&h[n - 1], d);
                 if (n > 0) atomicAdd(&h[n], 0u - d);
                 MBSV_ST(F + slot) = n - 1;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
                 const int slot = P.aln_esp_slot[rec.z + j];
                 if (slot < 0) continue;
                 const int n = MBSV_ST(F + slot);
-                unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + slot / E];
+                unsigned int* h = R.cluster_hist + P.slot_hist_ptr[c0 * E + slot];
                 if (n + 1 > 0) atomicAdd(&h[n + 1], d);
                 if (n > 0) atomicAdd(&h[n], 0u - d);
                 MBSV_ST(F + slot) = n + 1;
@@ -549,116 +549,43 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
         unsigned touched = 0;
         bool written = false;
         double newlogprob, arg;
-        // ---- tentative application ----
-        for (int q = 0; q < nmoves; ++q) {
-            int ga0 = a0, from = prev, to = now;
-            if (!naive) {
-                const int g = P.sv_frag[q0 + q] - f0;
-                ga0 = P.frag_aln_ptr[f0 + g];
-                from = MBSV_ST(g);
-                to = (from == -1) ? 0 : -1;
-            }
-            move_counts(ga0, from, to, dcov, derr, touched);
-        }
-        if (has_cc) {
-            // conn-comps derive their selected ESPs from the assignments: write them tentatively, then
-            // recompute every touched component once (stamp = t + 1), saving the old multisets
-            written = true;
+        bool accept = false;
+        // Pass 0 applies the proposal's moves tentatively and decides; pass 1, for rejected proposals only, applies the same
+        // moves backwards (count changes commute, so the order within the list does not matter).  ONE copy of the move code
+        // serves both: the proposal loop is longer than the SM's 32 KB instruction cache can hold for 20 warps at different
+        // places in it (ncu: ~1.7 no-instruction stall cycles per issued instruction), every instruction less counts.
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
             for (int q = 0; q < nmoves; ++q) {
-                if (naive) MBSV_ST(f) = now;
-                else { const int g = P.sv_frag[q0 + q] - f0; const int pv = MBSV_ST(g); MBSV_ST(g) = (pv == -1) ? 0 : -1; }
-            }
-            auto touch = [&](int cl) {
-                const int o = cc_base + P.cluster_cc_off[c0 + cl];
-                if (MBSV_ST(o) == t + 1) return;
-                MBSV_ST(o) = t + 1;
-                const int sz = E * (1 + cc_nroots(cl));
-                const double before = cc_lpc(cl);
-                for (int i = 0; i < sz; ++i) MBSV_ST(o + 1 + sz + i) = MBSV_ST(o + 1 + i);
-                cc_recompute(cl);
-                dcov = dcov + (cc_lpc(cl) - before);
-            };
-            for (int q = 0; q < nmoves; ++q) {
-                int ga0 = a0, from = prev, to = now;
+                int g = f, ga0 = a0, from = prev, to = now;
                 if (!naive) {
-                    const int g = P.sv_frag[q0 + q] - f0;
+                    g = P.sv_frag[q0 + q] - f0;
                     ga0 = P.frag_aln_ptr[f0 + g];
-                    to = MBSV_ST(g);
-                    from = (to == -1) ? 0 : -1;
+                    const int cur = MBSV_ST(g);      // old value unless the CC path already wrote the new one
+                    from = (pass && written) ? ((cur == -1) ? 0 : -1) : cur;
+                    to = (from == -1) ? 0 : -1;
                 }
-                if (from != -1) cc_visit(ga0 + from, touch);
-                if (to != -1) cc_visit(ga0 + to, touch);
+                move_counts(ga0, pass ? to : from, pass ? from : to, dcov, derr, touched);
+                if (pass && written) MBSV_ST(g) = from;
             }
-            if (err) { done = true; live = false; continue; }   // set cover failed to cover: the reference throws Error
-        }
-        // ---- acceptance ratio (:1146) ----
-        if (use_full) {
-            // full re-sum in the reference's order; the assignment change only enters through nerr, counts, totals
-#pragma unroll
-            for (int x = 0; x < MAXE; ++x) newLB.set(x, LB.get(x));
-            newlogprob = full_logprob();
-            arg = (newlogprob + Alogq) - (logprob + Anewlogq);
-        } else {
-            double dlb = 0.0;
-#pragma unroll
-            for (int x = 0; x < MAXE; ++x) newLB.set(x, LB.get(x));
-            // Each lane walks ITS touched experiments in ascending order (same summation order as before), so lanes
-            // whose proposals touch different platforms evaluate logBinomial together instead of one platform at a time.
-            unsigned mask = touched & ((1u << E) - 1u);
-            while (mask) {
-                const int x = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const double nl = lb_of(x, Etot.get(x), Ltot.get(x));
-                newLB.set(x, nl);
-                dlb = dlb + (nl - LB.get(x));
-            }
-            const double delta = (dcov + derr) + dlb;
-            newlogprob = logprob + delta;
-            arg = (delta + Alogq) - Anewlogq;
-        }
-        const double e = INLINE_MATH ? jm_exp(arg) : exp_dev(arg);
-        const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);   // Math.min(1, e)
-        const double r_acc = rng.nextDouble();
-        const bool accept = ratio > r_acc;
-        if (accept) {
-            logprob = newlogprob;
-#pragma unroll
-            for (int x = 0; x < MAXE; ++x) LB.set(x, newLB.get(x));
-            cnt.add(naive ? C_NACC : C_SVACC, 1);
-            if (t > win_base) {
-                // support-histogram difference tallies: walk the move backwards, then re-apply it
-                for (int q = nmoves - 1; q >= 0; --q) {
-                    int ga0 = a0, from = prev, to = now;
-                    if (!naive) {
-                        const int g = P.sv_frag[q0 + q] - f0;
-                        ga0 = P.frag_aln_ptr[f0 + g];
-                        const int cur = MBSV_ST(g);     // old value unless the CC path already wrote the new one
-                        from = written ? ((cur == -1) ? 0 : -1) : cur;
-                        to = (from == -1) ? 0 : -1;
-                    }
-                    retally_fragment(ga0, from, to, t);
-                }
-                for (int q = 0; q < nmoves; ++q) {
-                    int g = f, ga0 = a0, from = prev, to = now;
-                    if (!naive) {
-                        g = P.sv_frag[q0 + q] - f0;
-                        ga0 = P.frag_aln_ptr[f0 + g];
-                        const int cur = MBSV_ST(g);
-                        from = written ? ((cur == -1) ? 0 : -1) : cur;
-                        to = (from == -1) ? 0 : -1;
-                    }
-                    reapply_fragment(ga0, from, to);
-                    tally_frag(g, ga0, from, to, t);
-                }
-            }
+            if (pass) break;
             if (has_cc) {
-                // conn-comp multisets that changed: old elements leave, new ones enter; clear the stamps
-                const unsigned d = t > win_base ? (unsigned)(t - win_base) : 0u;
-                auto settle = [&](int cl) {
+                // conn-comps derive their selected ESPs from the assignments: write them tentatively, then
+                // recompute every touched component once (stamp = t + 1), saving the old multisets
+                written = true;
+                for (int q = 0; q < nmoves; ++q) {
+                    if (naive) MBSV_ST(f) = now;
+                    else { const int g = P.sv_frag[q0 + q] - f0; const int pv = MBSV_ST(g); MBSV_ST(g) = (pv == -1) ? 0 : -1; }
+                }
+                auto touch = [&](int cl) {
                     const int o = cc_base + P.cluster_cc_off[c0 + cl];
-                    if (MBSV_ST(o) != t + 1) return;
-                    MBSV_ST(o) = 0;
-                    if (d) { cc_hist(cl, 1, d); cc_hist(cl, 0, 0u - d); }
+                    if (MBSV_ST(o) == t + 1) return;
+                    MBSV_ST(o) = t + 1;
+                    const int sz = E * (1 + cc_nroots(cl));
+                    const double before = cc_lpc(cl);
+                    for (int i = 0; i < sz; ++i) MBSV_ST(o + 1 + sz + i) = MBSV_ST(o + 1 + i);
+                    cc_recompute(cl);
+                    dcov = dcov + (cc_lpc(cl) - before);
                 };
                 for (int q = 0; q < nmoves; ++q) {
                     int ga0 = a0, from = prev, to = now;
@@ -668,24 +595,106 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
                         to = MBSV_ST(g);
                         from = (to == -1) ? 0 : -1;
                     }
-                    if (from != -1) cc_visit(ga0 + from, settle);
-                    if (to != -1) cc_visit(ga0 + to, settle);
+                    if (from != -1) cc_visit(ga0 + from, touch);
+                    if (to != -1) cc_visit(ga0 + to, touch);
                 }
+                if (err) { done = true; live = false; break; }   // set cover failed to cover: the reference throws Error
             }
-            if (!written) {
-                for (int q = 0; q < nmoves; ++q) {
-                    if (naive) MBSV_ST(f) = now;
-                    else {
-                        const int g = P.sv_frag[q0 + q] - f0;
-                        const int pv = MBSV_ST(g);
-                        MBSV_ST(g) = (pv == -1) ? 0 : -1;
+            // ---- acceptance ratio (:1146) ----
+            if (use_full) {
+                // full re-sum in the reference's order; the assignment change only enters through nerr, counts, totals
+#pragma unroll
+                for (int x = 0; x < MAXE; ++x) newLB.set(x, LB.get(x));
+                newlogprob = full_logprob();
+                arg = (newlogprob + Alogq) - (logprob + Anewlogq);
+            } else {
+                double dlb = 0.0;
+#pragma unroll
+                for (int x = 0; x < MAXE; ++x) newLB.set(x, LB.get(x));
+                // Each lane walks ITS touched experiments in ascending order (same summation order as before), so lanes
+                // whose proposals touch different platforms evaluate logBinomial together instead of one platform at a time.
+                unsigned mask = touched & ((1u << E) - 1u);
+                while (mask) {
+                    const int x = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const double nl = lb_of(x, Etot.get(x), Ltot.get(x));
+                    newLB.set(x, nl);
+                    dlb = dlb + (nl - LB.get(x));
+                }
+                const double delta = (dcov + derr) + dlb;
+                newlogprob = logprob + delta;
+                arg = (delta + Alogq) - Anewlogq;
+            }
+            const double e = INLINE_MATH ? jm_exp(arg) : exp_dev(arg);
+            const double ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);   // Math.min(1, e)
+            const double r_acc = rng.nextDouble();
+            accept = ratio > r_acc;
+            if (accept) {
+                logprob = newlogprob;
+#pragma unroll
+                for (int x = 0; x < MAXE; ++x) LB.set(x, newLB.get(x));
+                cnt.add(naive ? C_NACC : C_SVACC, 1);
+                if (t > win_base) {
+                    // support-histogram difference tallies: walk the move backwards, then re-apply it
+                    for (int q = nmoves - 1; q >= 0; --q) {
+                        int ga0 = a0, from = prev, to = now;
+                        if (!naive) {
+                            const int g = P.sv_frag[q0 + q] - f0;
+                            ga0 = P.frag_aln_ptr[f0 + g];
+                            const int cur = MBSV_ST(g);     // old value unless the CC path already wrote the new one
+                            from = written ? ((cur == -1) ? 0 : -1) : cur;
+                            to = (from == -1) ? 0 : -1;
+                        }
+                        retally_fragment(ga0, from, to, t);
+                    }
+                    for (int q = 0; q < nmoves; ++q) {
+                        int g = f, ga0 = a0, from = prev, to = now;
+                        if (!naive) {
+                            g = P.sv_frag[q0 + q] - f0;
+                            ga0 = P.frag_aln_ptr[f0 + g];
+                            const int cur = MBSV_ST(g);
+                            from = written ? ((cur == -1) ? 0 : -1) : cur;
+                            to = (from == -1) ? 0 : -1;
+                        }
+                        reapply_fragment(ga0, from, to);
+                        tally_frag(g, ga0, from, to, t);
                     }
                 }
+                if (has_cc) {
+                    // conn-comp multisets that changed: old elements leave, new ones enter; clear the stamps
+                    const unsigned d = t > win_base ? (unsigned)(t - win_base) : 0u;
+                    auto settle = [&](int cl) {
+                        const int o = cc_base + P.cluster_cc_off[c0 + cl];
+                        if (MBSV_ST(o) != t + 1) return;
+                        MBSV_ST(o) = 0;
+                        if (d) { cc_hist(cl, 1, d); cc_hist(cl, 0, 0u - d); }
+                    };
+                    for (int q = 0; q < nmoves; ++q) {
+                        int ga0 = a0, from = prev, to = now;
+                        if (!naive) {
+                            const int g = P.sv_frag[q0 + q] - f0;
+                            ga0 = P.frag_aln_ptr[f0 + g];
+                            to = MBSV_ST(g);
+                            from = (to == -1) ? 0 : -1;
+                        }
+                        if (from != -1) cc_visit(ga0 + from, settle);
+                        if (to != -1) cc_visit(ga0 + to, settle);
+                    }
+                }
+                if (!written) {
+                    for (int q = 0; q < nmoves; ++q) {
+                        if (naive) MBSV_ST(f) = now;
+                        else {
+                            const int g = P.sv_frag[q0 + q] - f0;
+                            const int pv = MBSV_ST(g);
+                            MBSV_ST(g) = (pv == -1) ? 0 : -1;
+                        }
+                    }
+                }
+                break;
             }
-        } else {
-            // revert the counts (and, on the CC path, the tentative assignments and the saved multisets)
-            double d1 = 0.0, d2 = 0.0;
-            unsigned tt = 0;
+            // rejected: restore the saved multisets of the touched connected components, then revert the counts (and, on the CC
+            // path, the tentative assignments) in pass 1
             if (has_cc) {
                 auto restore = [&](int cl) {
                     const int o = cc_base + P.cluster_cc_off[c0 + cl];
@@ -706,19 +715,8 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
                     if (to != -1) cc_visit(ga0 + to, restore);
                 }
             }
-            for (int q = nmoves - 1; q >= 0; --q) {
-                int g = f, ga0 = a0, from = prev, to = now;
-                if (!naive) {
-                    g = P.sv_frag[q0 + q] - f0;
-                    ga0 = P.frag_aln_ptr[f0 + g];
-                    const int cur = MBSV_ST(g);
-                    from = written ? ((cur == -1) ? 0 : -1) : cur;
-                    to = (from == -1) ? 0 : -1;
-                }
-                move_counts(ga0, to, from, d1, d2, tt);
-                if (written) MBSV_ST(g) = from;
-            }
         }
+        if (err) continue;
         if (TRACE) {
             R.trace_logprob[sc * N + t] = logprob;
             R.trace_move_frag[sc * N + t] = accept ? (naive ? f0 + f : -(2 + svk)) : -1;
@@ -757,7 +755,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
                     n[k] = ok ? MBSV_ST(F + sb + k) : 0;
                 }
 #pragma unroll
-                for (int k = 0; k < EB; ++k) hp[k] = n[k] > 0 ? P.cluster_hist_ptr[c0 + (sb + k) / E] : 0;
+                for (int k = 0; k < EB; ++k) hp[k] = n[k] > 0 ? P.slot_hist_ptr[c0 * E + sb + k] : 0;
 #pragma unroll
                 for (int k = 0; k < EB; ++k) if (n[k] > 0) atomicAdd(&R.cluster_hist[hp[k] + n[k]], d);
             }

@@ -27,6 +27,7 @@ struct DevProblem {
     const int* root_leaf_ptr;
     const int* root_leaf;
     const int* cluster_hist_ptr;
+    const int* slot_hist_ptr;        // per (cluster, experiment) count slot: cluster_hist_ptr of its cluster (saves slot / E)
     const int* sv_frag_ptr;
     const int* sv_frag;
     const int* sv_numchanged;
