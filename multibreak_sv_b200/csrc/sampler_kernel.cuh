@@ -504,14 +504,18 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
         if (__all_sync(0xffffffffu, done && !live)) break;
         // AlterSV proposals (one in ten where a subproblem has candidates) walk a list of fragments while the Naive lanes of
         // the warp wait, and with 32 chains nearly every round has one.  Chains are independent, so a lane that drew an
-        // AlterSV proposal HOLDS it until MBSV_SV_BATCH lanes of the warp hold one (or no other lane can advance); the list
+        // AlterSV proposal HOLDS it until enough lanes of the warp hold one (or no other lane can advance); the list
         // walk then runs once for all of them.  Only the interleaving of the chains changes, not any chain.
         bool hold = false;
         if (MBSV_SV_BATCH > 1) {
             const unsigned svm = __ballot_sync(0xffffffffu, live && !h_naive);
             if (svm) {
                 const unsigned prog = __ballot_sync(0xffffffffu, (live && h_naive) || (!live && !done));
-                if (__popc(svm) < MBSV_SV_BATCH && prog != 0) hold = live && !h_naive;
+                // a quarter of the chains the warp still runs, at most MBSV_SV_BATCH: narrow warps (small batches) and the
+                // tail of a run must not leave a chain waiting for company that is not there
+                const int unfinished = __popc(__ballot_sync(0xffffffffu, live || !done));
+                const int need = min(MBSV_SV_BATCH, max(1, unfinished >> 2));
+                if (__popc(svm) < need && prog != 0) hold = live && !h_naive;
             }
         }
         if (hold || !live) continue;

@@ -29,6 +29,20 @@ STALLS = ["wait", "no_instruction", "branch_resolving", "long_scoreboard", "shor
           "math_pipe_throttle", "dispatch_stall", "lg_throttle", "mio_throttle", "barrier", "selected"]
 
 
+def state_rows(name, shm):
+    """Rows of a chain's state tile from the launch's dynamic shared memory: 4 warps x rows x 128 bytes; the general kernel's
+    SMTOT instantiations (last template argument) keep 2560 + 4096 * MAXE bytes of counters and totals behind the tiles."""
+    if "giant" in name or not shm:
+        return 0
+    if "mbsv_chain_kernel<" in name:
+        args = [a.strip() for a in name.split("mbsv_chain_kernel<")[1].split(">")[0].split(",")]
+        if len(args) >= 8 and args[7] in ("1", "true"):
+            shm -= 2560 + 4096 * int(args[3])
+        if args[2] in ("0", "false"):
+            return 0
+    return int(shm // 512)
+
+
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -72,7 +86,7 @@ def main():
             issue, lanes = num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"), num(r, "smsp__thread_inst_executed_per_inst_executed.ratio")
             ks.append({"kernel": name.replace("void ", "").split("(")[0], "grid": int(num(r, "launch__grid_size")),
                        "block": int(num(r, "launch__block_size")), "smem_bytes": int(shm),
-                       "state_rows": int(shm // 512) if "giant" not in name and shm else 0,
+                       "state_rows": state_rows(name, shm),
                        "ms": num(r, "gpu__time_duration.sum") * du, "issue_active_pct": issue, "active_lanes": lanes,
                        "frac": issue * lanes / 3200.0 if issue is not None and lanes is not None else None, "warps_active_per_smsp": num(r, "smsp__warps_active.avg.per_cycle_active"),
                        "long_scoreboard_per_issue": num(r, "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),

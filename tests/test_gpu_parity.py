@@ -585,3 +585,66 @@ def test_rhat_across_chain_groups(mbsv):
     assert 0.99 < mh["max"] < 1.1
     short = diagnostics.rhat(dp, mbsv.MODE_GIBBS, 12, chains_per_group=2, groups=4, burnin=10, perr=0.05)
     assert short["max"] > 1.2
+
+
+def _many_slot_problem(mbsv, seed):
+    """Subproblems whose alignments carry 1..7 ESPs each (several of them in one cluster now and then): more counted slots
+    than the 16-byte slot record of an alignment holds (aln_ent4 marks those and the kernel walks aln_esp_slot), and the
+    same slot twice in one record.  Sizes chosen to land in the 48-row, the 96-row and the global-workspace class."""
+    from multibreak_sv_b200 import synth
+    rng = np.random.default_rng(seed)
+    base = synth.generate("cfg4", n_frag=50, seed=3)
+    E, pseq, lam = 2, np.array([0.01, 0.15]), np.array([10.0, 3.0])
+    sub_frag_ptr, sub_cluster_ptr, frag_aln_ptr, aln_esp_ptr = [0], [0], [0], [0]
+    numerr, alen, aexp, esp_cluster, esp_leaf, sup_order = [], [], [], [], [], []
+    leaves = []                                               # per cluster: owning fragment of every leaf
+    for F_s, C_s in ((14, 12), (30, 20), (60, 50)):
+        f0, c0 = sub_frag_ptr[-1], sub_cluster_ptr[-1]
+        leaves += [[] for _ in range(C_s)]
+        spread = list(rng.permutation(C_s))                   # every cluster gets at least one leaf
+        for f in range(F_s):
+            x = int(rng.integers(0, E))
+            for _ in range(int(rng.integers(2, 4))):
+                numerr.append(int(rng.integers(0, 9))); alen.append(int(rng.integers(200, 3000))); aexp.append(x)
+                for _ in range(int(rng.integers(1, 8))):
+                    c = c0 + (int(spread.pop()) if spread else int(rng.integers(0, C_s)))
+                    esp_cluster.append(c); esp_leaf.append(len(leaves[c])); leaves[c].append(f0 + f)
+                aln_esp_ptr.append(len(esp_cluster))
+            frag_aln_ptr.append(len(numerr))
+        sub_frag_ptr.append(f0 + F_s); sub_cluster_ptr.append(c0 + C_s)
+        sup_order += list(c0 + rng.permutation(C_s))
+    C, nl = len(leaves), np.array([len(l) for l in leaves])
+    assert nl.min() >= 1
+    max_support = int(nl.max())
+    cum = lambda v: np.concatenate([[0], np.cumsum(v)]).astype(np.int32)
+    a = dict(sub_frag_ptr=sub_frag_ptr, sub_cluster_ptr=sub_cluster_ptr, sub_sv_ptr=np.zeros(len(sub_frag_ptr)),
+             frag_aln_ptr=frag_aln_ptr, aln_numerrors=numerr, aln_len=alen, aln_exp=aexp, aln_esp_ptr=aln_esp_ptr,
+             aln_esp_cluster=esp_cluster, aln_esp_leaf=esp_leaf, cluster_kind=np.zeros(C), supports_order=sup_order,
+             cluster_hist_ptr=cum(nl + 1), cluster_leaf_ptr=cum(nl), leaf_owner=[f for l in leaves for f in l],
+             cluster_root_ptr=np.arange(C + 1), root_leaf_ptr=cum(nl), root_leaf=[i for l in leaves for i in range(len(l))],
+             sv_cluster=np.zeros(0), sv_frag_ptr=np.zeros(1), sv_frag=np.zeros(0), sv_numchanged=np.zeros(0),
+             exp_pseq=pseq, exp_lambda=lam,
+             logprobcov=np.concatenate([synth.logprobcov_table(float(l), max_support) for l in lam]))
+    a = {k: np.asarray(v, dtype=base.arrays[k].dtype) for k, v in a.items()}
+    sc = dict(base.scalars)
+    sc.update(n_sub=len(sub_frag_ptr) - 1, n_frag=sub_frag_ptr[-1], n_aln=len(numerr), n_aln_esp=len(esp_cluster), n_cluster=C,
+              n_exp=E, max_support=max_support, n_sv=0, n_sv_frag=0, n_leaf=int(nl.sum()), n_root=C, n_root_leaf=int(nl.sum()),
+              n_hist=int((nl + 1).sum()))
+    return sc, a
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_chains", [3, 64])
+def test_alignments_with_more_slots_than_the_slot_record(oracle, mbsv, n_chains):
+    sc, a = _many_slot_problem(mbsv, seed=11)
+    nesp = np.diff(a["aln_esp_ptr"])
+    assert nesp.max() >= 6 and (nesp <= 4).any()
+    p, op = mbsv.PackedProblem(sc, a), oracle.Problem(sc, a)
+    dp = mbsv.DeviceProblem(p)
+    o = oracle.run(op, "incremental", 3000, n_chains=n_chains, nthreads=8, java_int_wrap=False, memo_states=0)
+    g = dp.run(mbsv.MODE_FAST, 3000, n_chains=n_chains, memo_states=0)
+    assert_same(o, g)
+    assert {abs(li["rows"]) for li in dp.launch_info()} >= ({48, 96, 0} if n_chains == 64 else {0})
+    o = oracle.run(op, "faithful", 1500, n_chains=n_chains, nthreads=8, trace=True, memo_states=0)
+    g = dp.run(mbsv.MODE_REPLAY_EXACT, 1500, n_chains=n_chains, trace=True, memo_states=0)
+    assert_same(o, g, trace=True)
