@@ -648,3 +648,29 @@ def test_alignments_with_more_slots_than_the_slot_record(oracle, mbsv, n_chains)
     o = oracle.run(op, "faithful", 1500, n_chains=n_chains, nthreads=8, trace=True, memo_states=0)
     g = dp.run(mbsv.MODE_REPLAY_EXACT, 1500, n_chains=n_chains, trace=True, memo_states=0)
     assert_same(o, g, trace=True)
+
+
+@pytest.mark.gpu
+def test_device_memory_pool_across_problems(oracle, mbsv):
+    """Blocks of a destroyed problem serve the next one (mbsv_core.cu DevPool): results do not depend on whether a buffer is
+    fresh or reused (every run initialises what it reads), and mbsv_trim gives the kept blocks back."""
+    import torch
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg4", n_frag=60000, seed=21)          # large enough for blocks above the pool's 1 MB threshold
+    q = synth.generate("cfg4", n_frag=45000, seed=22)
+    def run(pp):
+        dp = mbsv.DeviceProblem(pp)
+        g = dp.run(mbsv.MODE_FAST, 600, n_chains=32)
+        dp.close()
+        return g
+    mbsv.trim()
+    first = run(p)
+    free_kept = torch.cuda.mem_get_info()[0]
+    other = run(q)                                            # a different problem in between dirties the kept blocks
+    again = run(p)
+    for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "counters", "rng_state", "final_logprob"):
+        assert np.array_equal(getattr(first, k), getattr(again, k)), k
+    mbsv.trim()
+    assert torch.cuda.mem_get_info()[0] > free_kept           # the blocks went back to the driver
+    o = oracle.run(oracle.Problem(q.scalars, q.arrays), "incremental", 600, n_chains=32, nthreads=8, java_int_wrap=False)
+    assert_same(o, other)
