@@ -13,6 +13,9 @@
 // the first lane whose cumulative weight passes u.  All lanes of a group carry the same RNG state and the same
 // per-experiment totals (uniform registers), so nothing needs broadcasting; the groups of a warp run independent chains
 // and only ever synchronise within their own lane mask.  Small subproblems (two or three candidates) use G = 4.
+// A subproblem whose state does not fit the shared-memory classes runs with GLOBAL = true: one chain per warp (G = 32), the
+// state a contiguous column of the global workspace (as kern_packed.cu does for the MH chain), only the option weights in
+// shared memory; same arithmetic, same draws, bit-identical results.
 // Connected-component clusters are not supported here (MBSV_ERR_UNSUPPORTED).
 #pragma once
 #include "sampler_common.cuh"
@@ -30,7 +33,7 @@ template <int G> __device__ __forceinline__ double group_sum(unsigned mask, doub
     return v;
 }
 
-template <int G>
+template <int G, bool GLOBAL = false>
 __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
     constexpr int GPW = 32 / G;                                    // groups (chains) per warp
@@ -43,11 +46,13 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
     if (item >= R.n_items) return;                                 // (the other groups never name these lanes in a mask)
     const int sub = R.sub_order[item / R.n_chains];
     const int chain = (int)(item % R.n_chains);
-    int* st = smem_tile + ((size_t)wic * GPW + grp) * R.rows_per_warp;   // [F] assignments, [C*E] counts, then the option weights
+    // [F] assignments, [C*E] counts, then the option weights; GLOBAL: the state in the workspace, the weights in shared memory
+    int* st = GLOBAL ? R.workspace + R.warp_row_off[warp - R.global_warp0] : smem_tile + ((size_t)wic * GPW + grp) * R.rows_per_warp;
     const int f0 = P.sub_frag_ptr[sub], F = P.sub_frag_ptr[sub + 1] - f0;
     const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
     const int E = P.n_exp, Tstride = P.max_support + 1;
-    double* wopt = reinterpret_cast<double*>(st + ((F + C * E + 1) & ~1));
+    double* wopt = GLOBAL ? reinterpret_cast<double*>(smem_tile + (size_t)wic * R.rows_per_warp)
+                          : reinterpret_cast<double*>(st + ((F + C * E + 1) & ~1));
     const long long sc = (long long)sub * R.n_chains + chain;
     const int N = R.num_iters, win_base = R.win_base;
     const double logperr = R.logperr;

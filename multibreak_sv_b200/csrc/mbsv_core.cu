@@ -997,7 +997,9 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
         const int extra = 2 * (p->dp.maxn + 2);
         static const int gcls[] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288};
         int lo = 0;
+        const bool all_global = std::getenv("MBSV_GIBBS_GLOBAL") != nullptr;       // (tests: every state in the workspace)
         for (int c : gcls) {
+            if (all_global) break;
             int a = lo, b = S;
             while (a < b) { const int m = a + (b - a) / 2; if (p->sub_W[p->sub_order[m]] + extra <= c) a = m + 1; else b = m; }
             int group = c <= 128 ? 4 : c <= 1024 ? 8 : 32;
@@ -1006,7 +1008,9 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             if (a > lo) launches.push_back({0, 0, c, true, false, (int64_t)lo * X, (int64_t)a * X, 32 / group});
             lo = a;
         }
-        if (lo < S) return fail(MBSV_ERR_UNSUPPORTED, "MBSV_MODE_GIBBS keeps a chain's state in shared memory: a subproblem is too large");
+        // larger states: one chain per warp, the state a contiguous column of the global workspace (rows = the ints of shared
+        // memory a warp keeps for its option weights)
+        if (lo < S) launches.push_back({0, 0, extra, false, false, (int64_t)lo * X, (int64_t)S * X, 1});
     } else {
         add_group(0, p->n_tab_subs, true);
         add_group(p->n_tab_subs, S, false);
@@ -1107,7 +1111,7 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     for (const Launch& l : launches) {
         mbsv::DevRun r = dr;
         r.warp_begin = l.wb; r.warp_end = l.we;
-        r.rows_per_warp = l.smem ? l.rows : 0;
+        r.rows_per_warp = (l.smem || gibbs) ? l.rows : 0;
         r.warp_row_off = l.smem ? nullptr : p->row_off_cache.p;
         r.workspace = l.smem ? nullptr : p->ws_cache.p;
         r.global_warp0 = l.wb;
@@ -1136,13 +1140,13 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             }
         }
         size_t extra_smem = 0;
-        KernelFn fn = gibbs ? mbsv::get_kernel_gibbs(32 / l.lanes)
+        KernelFn fn = gibbs ? mbsv::get_kernel_gibbs(32 / l.lanes, !l.smem)
                      : l.giant ? mbsv::get_kernel_giant(p->n_exp, giant_cs, &giant_threads, &giant_smem)
                      : l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : (!l.smem && l.lanes == 1 && !rp->trace) ? mbsv::get_kernel_packed(rp->mode, p->has_cc)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
                                  : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp, l.rows, &extra_smem);
-        const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * l.lanes * l.rows * sizeof(int) : l.giant ? giant_smem
+        const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * (l.smem ? l.lanes : 1) * l.rows * sizeof(int) : l.giant ? giant_smem
                            : (l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0) + extra_smem;
         if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         // MBSV_SERIAL_LAUNCHES=1 (tuning aid): run the size classes back to back on one stream

@@ -97,7 +97,7 @@ KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_E
 KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
 KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with connected-component clusters
 KernelFn get_kernel_packed(int mode, bool cc);                   // one chain per warp, contiguous state in the global workspace
-KernelFn get_kernel_gibbs(int group);                            // heat-bath sampler, `group` (4, 8, 32) lanes per chain (gibbs_kernel.cuh)
+KernelFn get_kernel_gibbs(int group, bool global_state);                            // heat-bath sampler, `group` (4, 8, 32) lanes per chain; global_state: a warp per chain, state in the workspace (gibbs_kernel.cuh)
 KernelFn get_kernel_memo(bool trace, bool mixed);               // memoised subproblems (memo_kernel.cuh)
 // speculative-window kernel, one CTA per (subproblem, chain) (giant_kernel.cuh): FAST, no trace, no connected components
 KernelFn get_kernel_giant(int n_exp, int cluster, int* threads, size_t* smem_bytes);   // cluster = CTAs per chain: 1, 2, 4, 8

@@ -561,6 +561,24 @@ def test_gibbs_mode_limits_and_determinism(mbsv, example_problem):
         for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "counters", "rng_state"):
             assert np.array_equal(getattr(a, k), getattr(c, k)), (group, k)
         assert np.allclose(a.final_logprob, c.final_logprob, rtol=1e-12, atol=1e-9)
+    # the state in the global workspace (the path of subproblems beyond the shared-memory classes) is the same chain again
+    os.environ["MBSV_GIBBS_GLOBAL"] = "1"
+    try:
+        c = dp.run(mbsv.MODE_GIBBS, 500, n_chains=8)
+        assert [li["rows"] for li in dp.launch_info()] == [0]
+    finally:
+        del os.environ["MBSV_GIBBS_GLOBAL"]
+    for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "counters", "rng_state"):
+        assert np.array_equal(getattr(a, k), getattr(c, k)), ("global", k)
+    assert np.allclose(a.final_logprob, c.final_logprob, rtol=1e-12, atol=1e-9)
+    # a component too large for shared memory (a giant-component shape: 6000 fragments, ~18 000 state rows) runs there by itself
+    big = mbsv.DeviceProblem(synth.generate("cfg5", n_frag=6000, seed=4))
+    gb = big.run(mbsv.MODE_GIBBS, 3000, n_chains=4)
+    assert [li["rows"] for li in big.launch_info()] == [0] and int(gb.totals[0]) == 3000 * 4
+    gb2 = big.run(mbsv.MODE_GIBBS, 3000, n_chains=4)
+    assert np.array_equal(gb.aln_count, gb2.aln_count) and np.array_equal(gb.final_assign, gb2.final_assign)
+    nwin = 3000 - (3000 - mbsv.reference_burnin(3000) + 1)
+    assert nwin > 0 and (gb.aln_count.sum() + gb.frag_err_count.sum()) == 4 * nwin * 6000     # every fragment is somewhere, every window iteration
     # the shipped example has a fragment with 32 alignments: 33 options, two lane chunks
     de = mbsv.DeviceProblem(to_packed(mbsv, example_problem))
     g = de.run(mbsv.MODE_GIBBS, 4000, n_chains=64)
