@@ -60,8 +60,8 @@ typedef enum mbsv_mode {
                                    Gibbs on the same posterior, 4 / 8 / 32 lanes per (subproblem, chain), the candidate alignments of
                                    the redrawn fragment across those lanes.  One iteration = one fragment redrawn from its exact
                                    conditional (counters: [0] = [4] = updates, [1] = updates that changed the state).  Same
-                                   outputs; no trace; no connected-component clusters; subproblem state must fit shared
-                                   memory (else MBSV_ERR_UNSUPPORTED) */
+                                   outputs; no trace.  Connected-component clusters and states beyond shared memory (a warp
+                                   per chain, state in the global workspace) are supported */
 } mbsv_mode;
 
 /*

@@ -16,7 +16,13 @@
 // A subproblem whose state does not fit the shared-memory classes runs with GLOBAL = true: one chain per warp (G = 32), the
 // state a contiguous column of the global workspace (as kern_packed.cu does for the MH chain), only the option weights in
 // shared memory; same arithmetic, same draws, bit-identical results.
-// Connected-component clusters are not supported here (MBSV_ERR_UNSUPPORTED).
+// Connected-component clusters (GASV localization -1): their support is the multiset of a greedy set cover over the assigned
+// leaves (MultiBreakSVAssignmentMatrix.java:337-409), a function of the assignments, not of counts.  Lane 0 of the group
+// evaluates it: for every option of the redrawn fragment, each component the option's alignment touches is recomputed with the
+// fragment unassigned and with the option, the difference of the two log terms joins the option's weight; after the draw the
+// touched components are recomputed for the new state and their multisets' difference tallies are emitted, as the MH kernel
+// does (sampler_kernel.cuh).  State layout of the components = the MH kernel's (stamp, current multisets, saved multisets,
+// set-cover scratch behind the counts).
 #pragma once
 #include "sampler_common.cuh"
 
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
     const int c0 = P.sub_cluster_ptr[sub], C = P.sub_cluster_ptr[sub + 1] - c0;
     const int E = P.n_exp, Tstride = P.max_support + 1;
     double* wopt = GLOBAL ? reinterpret_cast<double*>(smem_tile + (size_t)wic * R.rows_per_warp)
-                          : reinterpret_cast<double*>(st + ((F + C * E + 1) & ~1));
+                          : reinterpret_cast<double*>(st + ((R.sub_W[sub] + 1) & ~1));
     const long long sc = (long long)sub * R.n_chains + chain;
     const int N = R.num_iters, win_base = R.win_base;
     const double logperr = R.logperr;
@@ -100,6 +106,106 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
             st[F + slot] = n + sgn;
         }
     };
+    // ---- connected components (lane 0 only; see the header) ----
+    const bool has_cc = P.sub_cc_scratch != nullptr && P.sub_cc_scratch[sub] >= 0;
+    const int cc_base = F + C * E;
+    int err = 0;
+    auto cc_nroots = [&](int cl) -> int { return P.cluster_root_ptr[c0 + cl + 1] - P.cluster_root_ptr[c0 + cl]; };
+    auto cc_lpc = [&](int cl) -> double {
+        const int nr = cc_nroots(cl);
+        const int b0 = cc_base + P.cluster_cc_off[c0 + cl] + 1;
+        double lpc = 0.0;
+        for (int x = 0; x < E; ++x) {
+            const int b = b0 + x * (1 + nr);
+            const int len = st[b];
+            for (int i = 0; i < len; ++i) lpc = lpc + P.T[(size_t)x * Tstride + st[b + 1 + i]];
+        }
+        return lpc;
+    };
+    // setBreakpoints for one connected component from the current assignments (AM.java:264-414)
+    auto cc_recompute = [&](int cl) {
+        const int cg = c0 + cl;
+        const int l0 = P.cluster_leaf_ptr[cg], nl = P.cluster_leaf_ptr[cg + 1] - l0;
+        const int r0 = P.cluster_root_ptr[cg], nr = P.cluster_root_ptr[cg + 1] - r0;
+        const int b0 = cc_base + P.cluster_cc_off[cg] + 1;
+        const int sl = cc_base + P.sub_cc_scratch[sub];       // leaf flags: exp + 1 (0 = not selected), bit 8 = found
+        const int sr = sl + P.sub_cc_maxleaf[sub];            // root flags: 1 = already taken
+        int numselected = 0;
+        for (int l = 0; l < nl; ++l) {
+            int flag = 0;
+            const int fg = P.leaf_owner[l0 + l];
+            if (fg >= 0) {
+                const int a = st[fg - f0];
+                if (a != -1) {
+                    const int4 rec = P.aln_rec[P.frag_aln_ptr[fg] + a];
+                    const int ne = rec.w >> 8;
+                    for (int j = 0; j < ne; ++j)
+                        if (P.aln_esp_slot[rec.z + j] == -(2 + cl) && P.aln_esp_leaf[rec.z + j] == l) { flag = (rec.w & 0xff) + 1; ++numselected; }
+                }
+            }
+            st[sl + l] = flag;
+        }
+        for (int x = 0; x < E; ++x) st[b0 + x * (1 + nr)] = 0;
+        if (numselected == 0) return;
+        for (int x = 0; x < E; ++x) {
+            const int b = b0 + x * (1 + nr);
+            for (int l = 0; l < nl; ++l) st[sl + l] &= 0xff;
+            for (int r = 0; r < nr; ++r) st[sr + r] = 0;
+            int len = 0;
+            for (;;) {
+                int maxcount = 0, maxind = -1;
+                for (int r = 0; r < nr; ++r) {
+                    if (st[sr + r]) continue;
+                    int cur = 0;
+                    for (int j = P.root_leaf_ptr[r0 + r]; j < P.root_leaf_ptr[r0 + r + 1]; ++j)
+                        if (st[sl + P.root_leaf[j]] == x + 1) ++cur;
+                    if (cur > maxcount) { maxcount = cur; maxind = r; }
+                }
+                if (maxind == -1) {
+                    for (int l = 0; l < nl; ++l) if (st[sl + l] == x + 1) err = -5;   // Error at AM.java:375-376
+                    break;
+                }
+                for (int j = P.root_leaf_ptr[r0 + maxind]; j < P.root_leaf_ptr[r0 + maxind + 1]; ++j)
+                    if ((st[sl + P.root_leaf[j]] & 0xff) == x + 1) st[sl + P.root_leaf[j]] = (x + 1) | 0x100;
+                int pos = len;                                   // sorted insert (Collections.sort at AM.java:403)
+                while (pos > 0 && st[b + pos] > maxcount) { st[b + 1 + pos] = st[b + pos]; --pos; }
+                st[b + 1 + pos] = maxcount;
+                ++len;
+                st[sr + maxind] = 1;
+                bool all = true;
+                for (int l = 0; l < nl; ++l) if (st[sl + l] == x + 1) all = false;
+                if (all) break;
+            }
+            st[b] = len;
+        }
+    };
+    // visit the connected components touched by fragment-alignment `al` (entries coded -(2+cluster))
+    auto cc_visit = [&](int al, auto&& fn) {
+        const int4 rec = P.aln_rec[al];
+        const int ne = rec.w >> 8;
+        for (int j = 0; j < ne; ++j) {
+            const int code = P.aln_esp_slot[rec.z + j];
+            if (code < -1) fn(-code - 2);
+        }
+    };
+    auto cc_hist = [&](int cl, int which, unsigned d) {   // which: 0 current multisets, 1 saved multisets
+        const int nr = cc_nroots(cl);
+        const int b0 = cc_base + P.cluster_cc_off[c0 + cl] + 1 + which * E * (1 + nr);
+        unsigned int* h = R.cluster_hist + P.cluster_hist_ptr[c0 + cl];
+        for (int x = 0; x < E; ++x) {
+            const int b = b0 + x * (1 + nr);
+            const int len = st[b];
+            for (int i = 0; i < len; ++i) atomicAdd(&h[st[b + 1 + i]], d);
+        }
+    };
+    // the log terms of every connected component (lane 0's value is the group's: broadcast by the caller)
+    auto cc_total = [&]() -> double {
+        double lp = 0.0;
+        if (has_cc && lane == 0)
+            for (int cl = 0; cl < C; ++cl) if (P.cluster_cc_off[c0 + cl] >= 0) lp += cc_lpc(cl);
+        return __shfl_sync(gmask, lp, 0, G);
+    };
+
     auto full_logprob = [&]() {
         double lp = 0.0;
         for (int i = lane; i < C * E; i += G) {
@@ -107,13 +213,14 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
             if (n > 0) lp += P.T[(size_t)(i % E) * Tstride + n];
         }
         lp = group_sum<G>(gmask, lp);
+        if (has_cc) lp += cc_total();
         lp += (double)nerr * logperr;
         for (int x = 0; x < E; ++x) lp += get_LB(x);
         return lp;
     };
 
     // ---------------- initial state: the reference's draws (MultiBreakSV.java:999-1015) or the supplied one ----------------
-    for (int i = lane; i < F + C * E; i += G) st[i] = 0;
+    for (int i = lane; i < R.sub_W[sub]; i += G) st[i] = 0;
     __syncwarp(gmask);
     for (int f = 0; f < F; ++f) {
         const int a0 = P.frag_aln_ptr[f0 + f];
@@ -134,6 +241,10 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
         }
     }
     __syncwarp(gmask);
+    if (has_cc) {
+        if (lane == 0) for (int cl = 0; cl < C; ++cl) if (P.cluster_cc_off[c0 + cl] >= 0) { st[cc_base + P.cluster_cc_off[c0 + cl]] = 0; cc_recompute(cl); }
+        __syncwarp(gmask);
+    }
     for (int x = 0; x < E; ++x) set_LB(x, lb_of(x, get_E(x), get_L(x)));
     if (R.initial_logprob) { const double lp = full_logprob(); if (lane == 0) R.initial_logprob[sc] = lp; }
 
@@ -154,6 +265,44 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
         } else --nerr;
         __syncwarp(gmask);
         const double lb_cur_removed = xcur >= 0 ? lb_of(xcur, get_E(xcur), get_L(xcur)) : 0.0;
+        if (has_cc) {
+            // lane 0: wopt[o] = sum over the components option o touches of (log term with the option - log term with the
+            // fragment unassigned); the multisets as they were before this iteration are saved once per touched component
+            if (lane == 0) {
+                auto save = [&](int cl) {
+                    const int o = cc_base + P.cluster_cc_off[c0 + cl];
+                    if (st[o] == t + 1) return;
+                    st[o] = t + 1;
+                    const int sz = E * (1 + cc_nroots(cl));
+                    for (int i = 0; i < sz; ++i) st[o + 1 + sz + i] = st[o + 1 + i];
+                };
+                if (cur != -1) cc_visit(a0 + cur, save);
+                wopt[0] = 0.0;
+                for (int o = 1; o <= n; ++o) {
+                    double dcc = 0.0;
+                    const int4 rec = P.aln_rec[a0 + o - 1];
+                    const int ne = rec.w >> 8;
+                    for (int j = 0; j < ne; ++j) {
+                        const int code = P.aln_esp_slot[rec.z + j];
+                        if (code >= -1) continue;
+                        bool seen = false;                       // an alignment may hold several leaves of one component
+                        for (int i = 0; i < j; ++i) if (P.aln_esp_slot[rec.z + i] == code) seen = true;
+                        if (seen) continue;
+                        const int cl = -code - 2;
+                        save(cl);
+                        st[f] = -1;
+                        cc_recompute(cl);
+                        const double base = cc_lpc(cl);
+                        st[f] = o - 1;
+                        cc_recompute(cl);
+                        dcc += cc_lpc(cl) - base;
+                    }
+                    wopt[o] = dcc;
+                }
+                st[f] = cur;
+            }
+            __syncwarp(gmask);
+        }
         // log P(option | rest) up to a constant: option 0 = "unmapped", option k = alignment k-1
         const int nopt = n + 1;
         double m = -1.7976931348623157e308;
@@ -174,6 +323,7 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
                 const double base = x == xcur ? lb_cur_removed : get_LB(x);
                 dl = dcov + (lb_of(x, get_E(x) + rec.x, get_L(x) + rec.y) - base);
             }
+            if (has_cc) dl += wopt[o];
             wopt[o] = dl;
             m = dl > m ? dl : m;
         }
@@ -213,7 +363,19 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
                 }
                 st[f] = now;
             }
+            if (has_cc) {
+                // every component an alignment of this fragment touches: the multisets of the state after the draw, then
+                // (inside the window) old elements leave, new ones enter; the stamps are cleared
+                for (int o = 0; o < n; ++o) cc_visit(a0 + o, [&](int cl) {
+                    const int b = cc_base + P.cluster_cc_off[c0 + cl];
+                    if (st[b] != t + 1) return;
+                    st[b] = 0;
+                    cc_recompute(cl);
+                    if (d) { cc_hist(cl, 1, d); cc_hist(cl, 0, 0u - d); }
+                });
+            }
         }
+        if (has_cc && __any_sync(gmask, err != 0)) break;      // set cover failed to cover: the reference throws Error
         if (now != -1) {
             const int4 rec = P.aln_rec[a0 + now];
             const int x = rec.w & 0xff;
@@ -226,7 +388,8 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
 
     // ---------------- epilogue: the final state stays until the end of the window ----------------
     const long long nwin = (long long)N - win_base;
-    if (nwin > 0) {
+    const bool failed = has_cc && __any_sync(gmask, err != 0);
+    if (nwin > 0 && !failed) {
         const unsigned d = (unsigned)nwin;
         for (int f = lane; f < F; f += G) {
             const int a = st[f];
@@ -237,6 +400,7 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
             const int nn = st[F + i];
             if (nn > 0) atomicAdd(&(R.cluster_hist + P.slot_hist_ptr[c0 * E + i])[nn], d);
         }
+        if (has_cc && lane == 0) for (int cl = 0; cl < C; ++cl) if (P.cluster_cc_off[c0 + cl] >= 0) cc_hist(cl, 0, d);
     }
     if (R.final_assign) for (int f = lane; f < F; f += G) R.final_assign[(size_t)chain * P.n_frag + f0 + f] = st[f];
     const double lpf = full_logprob();
@@ -244,10 +408,11 @@ __global__ void __launch_bounds__(128) mbsv_gibbs_kernel(const __grid_constant__
         if (R.final_logprob) R.final_logprob[sc] = lpf;
         if (R.counters) { long long* k = R.counters + sc * 5; k[0] = N; k[1] = n_changed; k[2] = 0; k[3] = 0; k[4] = N; }
         if (R.rng_state) R.rng_state[sc] = rng.state();
-        if (R.error) R.error[sc] = 0;
+        if (R.error) R.error[sc] = err;
         if (R.totals) {
             atomicAdd(&R.totals[0], (unsigned long long)N); atomicAdd(&R.totals[1], (unsigned long long)n_changed);
             atomicAdd(&R.totals[4], (unsigned long long)N);
+            if (err) atomicCAS(&R.totals[5], 0ULL, (unsigned long long)(long long)err);
         }
     }
 }

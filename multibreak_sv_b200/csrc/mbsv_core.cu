@@ -854,7 +854,6 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     if (rp->mode != MBSV_MODE_REPLAY_EXACT && rp->mode != MBSV_MODE_FAST && rp->mode != MBSV_MODE_GIBBS) return fail(MBSV_ERR_ARG, "unknown mode");
     const bool gibbs = rp->mode == MBSV_MODE_GIBBS;
     if (gibbs && rp->trace) return fail(MBSV_ERR_ARG, "MBSV_MODE_GIBBS has no per-iteration trace");
-    if (gibbs && p->has_cc) return fail(MBSV_ERR_UNSUPPORTED, "MBSV_MODE_GIBBS does not support connected-component clusters");
     if (rp->n_chains < 1 || rp->num_iters < 0 || rp->burnin < 0) return fail(MBSV_ERR_ARG, "bad run parameters");
     if (!(rp->perr >= 0 && rp->perr <= 1)) return fail(MBSV_ERR_ARG, "--perr must be a value between 0 and 1.");
     if (rp->device != p->device) return fail(MBSV_ERR_ARG, "run device differs from the problem's device");

@@ -586,10 +586,50 @@ def test_gibbs_mode_limits_and_determinism(mbsv, example_problem):
     with pytest.raises(mbsv.MbsvError) as e:
         de.run(mbsv.MODE_GIBBS, 10, trace=True)
     assert e.value.status == -1
-    cc = mbsv.DeviceProblem(synth.generate("cfg4", n_frag=200, seed=3, conncomp_frac=0.5))
-    with pytest.raises(mbsv.MbsvError) as e:
-        cc.run(mbsv.MODE_GIBBS, 10)
-    assert e.value.status == -6
+    # connected components run (their set cover is evaluated per option); deterministic, every fragment tallied once per sample
+    pc = synth.generate("cfg4", n_frag=200, seed=3, conncomp_frac=0.5)
+    cc = mbsv.DeviceProblem(pc)
+    c1, c2 = cc.run(mbsv.MODE_GIBBS, 400, n_chains=8), cc.run(mbsv.MODE_GIBBS, 400, n_chains=8)
+    for k in ("aln_count", "frag_err_count", "cluster_hist", "final_assign", "rng_state"):
+        assert np.array_equal(getattr(c1, k), getattr(c2, k)), k
+    fp = pc.arrays["frag_aln_ptr"]
+    nwin = (400 - (400 - mbsv.reference_burnin(400) + 1)) * 8
+    assert all(int(c1.frag_err_count[f]) + int(c1.aln_count[fp[f]:fp[f + 1]].sum()) == nwin for f in range(200))
+
+
+@pytest.mark.gpu
+def test_gibbs_mode_with_connected_components(oracle, mbsv):
+    """Gibbs mode on a tiny subproblem with a GASV connected component: the fragment marginals agree with the enumerated
+    posterior, and the support histograms (set-cover multisets for the component) with the MH chain's, whose connected-
+    component path is compared bit for bit with the oracle elsewhere.  Fragments have <= 2 alignments (quirk Q1 cannot bite)."""
+    from multibreak_sv_b200 import synth
+    p = None
+    for seed in range(400):
+        q = synth.generate("cfg4", n_frag=6, seed=7000 + seed, conncomp_frac=0.7)
+        if q.scalars["n_sub"] == 1 and np.diff(q.arrays["frag_aln_ptr"]).max() == 2 and (q.arrays["cluster_kind"] != 0).any():
+            p = q
+            break
+    assert p is not None
+    frag, _ = _exact_posterior(oracle, p)
+    dp = mbsv.DeviceProblem(p)
+    B, X, N, win = 10, 256, 20000, 10000
+    fp, F = p.arrays["frag_aln_ptr"], p.scalars["n_frag"]
+    est = {mbsv.MODE_GIBBS: ([], []), mbsv.MODE_FAST: ([], [])}
+    for mode in est:
+        for b in range(B):
+            g = dp.run(mode, N, n_chains=X, perr=0.05, seed=555 * (b + 1), burnin=win, per_chain=False, want_state=False)
+            assert int(g.totals[5]) == 0
+            nwin = (N - max(N - win + 1, 0)) * X
+            est[mode][0].append(np.concatenate([np.concatenate([[g.frag_err_count[f]], g.aln_count[fp[f]:fp[f + 1]]]) for f in range(F)]) / nwin)
+            est[mode][1].append(g.cluster_hist / nwin)
+    gf, gh = (np.array(v) for v in est[mbsv.MODE_GIBBS])
+    mf, mh = (np.array(v) for v in est[mbsv.MODE_FAST])
+    z = np.abs(gf.mean(0) - np.concatenate(frag)) / np.maximum(gf.std(0, ddof=1) / np.sqrt(B), 1e-4)
+    assert z.max() < 4.5, ("fragment marginals", z.max())
+    se = np.sqrt(gh.var(0, ddof=1) / B + mh.var(0, ddof=1) / B)
+    z = np.abs(gh.mean(0) - mh.mean(0)) / np.maximum(se, 1e-4)
+    assert z.max() < 4.5, ("support histograms vs the MH chain", z.max())
+    assert gh.mean(0)[p.arrays["cluster_hist_ptr"][int(np.nonzero(p.arrays["cluster_kind"])[0][0])]:].sum() > 0
 
 
 def test_rhat_across_chain_groups(mbsv):
