@@ -165,6 +165,7 @@ struct mbsv_problem {
     std::vector<int> frag_nal;    // alignments per fragment (validation of a host-supplied initial state)
     std::vector<int> sub_maxent;  // most count entries / toggled fragments of one AlterSV proposal (giant_kernel.cuh)
     std::vector<int> sub_maxpos;  // most counted slots of one alignment
+    bool narrow_ok = false;       // every assignment (-1 .. alignments - 1) and every count (<= max_support) fits a signed char
     DevBuf<int4> d_aln_ent4, d_sv_mv;      // flattened views for the speculative-window kernel
     DevBuf<int> d_sv_ent_ptr;
     DevBuf<int2> d_sv_ent;
@@ -550,6 +551,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
             maxn = std::max(maxn, t_maxn[t]);
         }
     }
+    const int max_nal = maxn;            // most alignments of one fragment (maxn grows below for the log table)
     lap("pack");
     std::vector<int> sub_sv_ptr(S + 1, 0), sv_frag_ptr(1, 0), sv_frag, sv_numchanged, sv_ent_ptr(1, 0);
     std::vector<int4> sv_mv;
@@ -633,6 +635,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     p->frag_nal.resize(F);
     for (int f = 0; f < F; ++f) p->frag_nal[f] = d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f];
     p->sub_maxpos = sub_maxpos;
+    p->narrow_ok = max_nal <= 127 && d->max_support <= 127;
 
     auto up = [&](auto& buf, const auto& vec) -> cudaError_t { return buf.upload(vec); };
     cudaError_t e = cudaSuccess;
@@ -753,10 +756,11 @@ int mbsv_problem_stats(const mbsv_problem* p, int64_t* out, int32_t n) {
 namespace {
 
 using mbsv::KernelFn;
-KernelFn pick(int mode, bool trace, bool smem, int E, int rows, size_t* extra_smem) {
+KernelFn pick(int mode, bool trace, bool smem, int E, int rows, bool narrow_ok, size_t* extra_smem, int* state_bytes) {
     *extra_smem = 0;
+    *state_bytes = 4;
     if (trace) return mbsv::get_kernel_trace(mode, smem, E);
-    return mode == 0 ? mbsv::get_kernel_replay(smem, E) : mbsv::get_kernel_fast(smem, E, rows, extra_smem);
+    return mode == 0 ? mbsv::get_kernel_replay(smem, E) : mbsv::get_kernel_fast(smem, E, rows, narrow_ok, extra_smem, state_bytes);
 }
 
 // (Re)build the launch plan: which subproblems use the memoised arithmetic (memo_states), which of those run in the
@@ -952,6 +956,10 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
     CUDA_TRY(cudaMemsetAsync(p->d_launch_totals.p, 0, sizeof(unsigned long long) * 6 * NSTREAM, s0));
 
     // ---- plan: warps of 32 consecutive (sorted subproblem, chain) items; size classes by state rows ----
+    // 8-bit state words for some shared-memory classes of the MODE_FAST kernels (kern_fast.cu) when every value fits;
+    // MBSV_STATE_BITS=32 forces int (tests, A/B)
+    const char* bits_env = std::getenv("MBSV_STATE_BITS");
+    const bool narrow = p->narrow_ok && !(bits_env && std::atoi(bits_env) == 32);
     std::vector<int> cls = {16, 24, 32, 48, 64, 96, 128};
     if (const char* env = std::getenv("MBSV_SMEM_CLASSES")) {
         cls.clear();
@@ -1139,14 +1147,15 @@ int run_impl(mbsv_problem* p, const mbsv_run_params* rp, mbsv_results* res, bool
             }
         }
         size_t extra_smem = 0;
+        int sb = 4;                   // bytes of a state word of the kernel chosen (1: kern_fast8.cu)
         KernelFn fn = gibbs ? mbsv::get_kernel_gibbs(32 / l.lanes, !l.smem)
                      : l.giant ? mbsv::get_kernel_giant(p->n_exp, giant_cs, &giant_threads, &giant_smem)
                      : l.memo ? mbsv::get_kernel_memo(rp->trace != 0, mixed)
                      : (!l.smem && l.lanes == 1 && !rp->trace) ? mbsv::get_kernel_packed(rp->mode, p->has_cc)
                      : p->has_cc ? mbsv::get_kernel_cc(rp->mode, rp->trace != 0, l.smem)
-                                 : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp, l.rows, &extra_smem);
+                                 : pick(rp->mode, rp->trace != 0, l.smem, p->n_exp, l.rows, narrow, &extra_smem, &sb);
         const size_t shm = gibbs ? (size_t)WARPS_PER_CTA * (l.smem ? l.lanes : 1) * l.rows * sizeof(int) : l.giant ? giant_smem
-                           : (l.smem ? (size_t)WARPS_PER_CTA * l.rows * 128 : 0) + extra_smem;
+                           : (l.smem ? (size_t)WARPS_PER_CTA * l.rows * 32 * sb : 0) + extra_smem;
         if (shm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
         // MBSV_SERIAL_LAUNCHES=1 (tuning aid): run the size classes back to back on one stream
         static const bool serial = std::getenv("MBSV_SERIAL_LAUNCHES") != nullptr;

@@ -50,7 +50,8 @@ static __device__ MBSV_MATH_INLINE double exp_dev(double x) { return jm_exp(x); 
 // workspace packs the rows of narrow warps, st_stride = chains per warp).  The checked build (make check) traps on a row outside
 // the subproblem's rows instead of corrupting a neighbour's state; `st_rows` is defined next to `st` in each kernel.
 #ifdef MBSV_BOUNDS_CHECK
-static __device__ __noinline__ int& mbsv_st_checked(int* st, long long i, int rows, int line, int stride) {
+template <typename T>
+static __device__ __noinline__ T& mbsv_st_checked(T* st, long long i, int rows, int line, int stride) {
     if (i < 0 || i >= rows) {
         printf("MBSV_ST: row %lld outside [0,%d) at line %d (block %d thread %d)\n", i, rows, line, blockIdx.x, threadIdx.x);
         __trap();

@@ -82,7 +82,12 @@ template <typename T, int N> struct LaneArr<T, N, true> {
 // 64 rows 118 -> 102 ms at MINB 4; 48 rows and below are fastest at 5; 6 and 8 CTAs/SM are 1.6x and 2.1x slower).
 // SMTOT = the per-experiment totals and logBinomial terms of the chain live in shared memory (4 * MAXE * 8 bytes per thread
 // behind the counters) instead of registers.
-template <int MODE, bool TRACE, bool SMEM, int MAXE, bool CC = false, bool PACKED = false, int MINB = 0, bool SMTOT = false>
+// ST_T = type of a state word (assignment of a fragment: -1 .. alignments - 1; count of a slot: 0 .. maxSupport).  int everywhere
+// except the FAST kernels of kern_fast8.cu, which run with signed char when every fragment has at most 127 alignments and
+// maxSupport <= 127 (the host checks): a quarter of the shared memory per tile (more L1 for the CSR, larger subproblems in
+// shared memory) and a quarter of the global workspace (more of it stays in L2).
+template <int MODE, bool TRACE, bool SMEM, int MAXE, bool CC = false, bool PACKED = false, int MINB = 0, bool SMTOT = false,
+          typename ST_T = int>
 __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MBSV_MIN_BLOCKS_GLOBAL) mbsv_chain_kernel(const __grid_constant__ DevProblem P,
                                                          const __grid_constant__ DevRun R) {
     extern __shared__ int smem_tile[];
@@ -103,8 +108,9 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
     // workspace).  PACKED (one chain per warp, global workspace): the column is stored contiguously, so that the few
     // chains of a giant component take 4 bytes per row instead of a 128-byte row each and stay L2-resident.
     constexpr int st_stride = (!SMEM && PACKED) ? 1 : 32;
-    int* st = SMEM ? (smem_tile + (size_t)wic * R.rows_per_warp * 32 + lane)
-                   : (R.workspace + (size_t)R.warp_row_off[warp - R.global_warp0] * st_stride + (PACKED ? 0 : lane));
+    ST_T* st = SMEM ? (reinterpret_cast<ST_T*>(smem_tile) + (size_t)wic * R.rows_per_warp * 32 + lane)
+                    : (reinterpret_cast<ST_T*>(R.workspace) + (size_t)R.warp_row_off[warp - R.global_warp0] * st_stride + (PACKED ? 0 : lane));
+    const int tile_ints = SMEM ? R.rows_per_warp * 32 * (int)sizeof(ST_T) : 0;     // the four tiles of the CTA, in ints
 
 #ifdef MBSV_BOUNDS_CHECK
     const int st_rows = !alive ? 0 : SMEM ? min(R.sub_W[sub], R.rows_per_warp) : R.sub_W[sub];
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
     const int nst = (alive && R.sub_memo) ? R.sub_memo[sub] : 0;
     const bool use_full = (MODE == 0) || (nst > 0);
 
-    char* const tot_base = (char*)(smem_tile + (SMEM ? 4 * R.rows_per_warp * 32 : 0) + 5 * 128);
+    char* const tot_base = (char*)(smem_tile + tile_ints + 5 * 128);
     LaneArr<long long, MAXE, SMTOT> Etot(tot_base), Ltot(tot_base + MAXE * 1024);
     LaneArr<double, MAXE, SMTOT> LB(tot_base + 2 * MAXE * 1024), newLB(tot_base + 3 * MAXE * 1024);
 #pragma unroll
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
     // classes with large tiles have registers to spare and need their shared memory: more of it per CTA pushes the SM to the
     // next carve-out step and halves the L1 that serves the CSR reads (measured: 128-row class 68 -> 88 ms).
     int n_naive_prop = 0;                        // <= num_iters
-    LaneArr<int, 5, SMTOT> cnt(smem_tile + (SMEM ? 4 * R.rows_per_warp * 32 : 0));
+    LaneArr<int, 5, SMTOT> cnt(smem_tile + tile_ints);
     constexpr int C_NACC = 0, C_SVPROP = 1, C_SVACC = 2, C_RLO = 3, C_RHI = 4;   // Naive accepted, AlterSV proposed / accepted,
 #pragma unroll
     for (int i = 0; i < 5; ++i) cnt.set(i, 0);                                    // fragments toggled by AlterSV proposals (64 bit)
@@ -442,7 +448,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : SMEM ? MBSV_MIN_BLOCKS : MB
                 for (int j = 0; j < ne; ++j) {
                     const int slot = P.aln_esp_slot[rec[k].z + j];
                     if (slot < 0) continue;
-                    if (SMEM) MBSV_ST(F + slot) += 1; else atomicAdd(&MBSV_ST(F + slot), 1);
+                    if constexpr (SMEM || sizeof(ST_T) != 4) MBSV_ST(F + slot) += 1; else atomicAdd(&MBSV_ST(F + slot), 1);
                 }
                 Etot.add(x, rec[k].x); Ltot.add(x, rec[k].y);
             }

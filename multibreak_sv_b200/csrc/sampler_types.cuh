@@ -92,7 +92,7 @@ struct DevRun {
 
 using KernelFn = void (*)(const DevProblem, const DevRun);
 // kernel selectors, one per translation unit (kern_fast.cu / kern_replay.cu / kern_trace.cu)
-KernelFn get_kernel_fast(bool smem, int n_exp, int rows, size_t* extra_smem);   // MODE_FAST, no trace: the throughput path (rows = shared-memory class)
+KernelFn get_kernel_fast(bool smem, int n_exp, int rows, bool narrow_ok, size_t* extra_smem, int* state_bytes);   // MODE_FAST, no trace: the throughput path (rows = shared-memory class)
 KernelFn get_kernel_replay(bool smem, int n_exp);               // MODE_REPLAY_EXACT, no trace
 KernelFn get_kernel_trace(int mode, bool smem, int n_exp);      // either mode with the per-iteration trace
 KernelFn get_kernel_cc(int mode, bool trace, bool smem);        // batches with connected-component clusters

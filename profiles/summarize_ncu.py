@@ -30,7 +30,7 @@ STALLS = ["wait", "no_instruction", "branch_resolving", "long_scoreboard", "shor
 
 
 def state_rows(name, shm):
-    """Rows of a chain's state tile from the launch's dynamic shared memory: 4 warps x rows x 128 bytes; the general kernel's
+    """Rows of a chain's state tile from the launch's dynamic shared memory: 4 warps x rows x 32 state words of 4 bytes (1 byte in the kern_fast8.cu instantiations); the general kernel's
     SMTOT instantiations (last template argument) keep 2560 + 4096 * MAXE bytes of counters and totals behind the tiles."""
     if "giant" in name or not shm:
         return 0
@@ -40,6 +40,8 @@ def state_rows(name, shm):
             shm -= 2560 + 4096 * int(args[3])
         if args[2] in ("0", "false"):
             return 0
+        if len(args) >= 9 and "char" in args[8]:          # 8-bit state words (kern_fast8.cu)
+            return int(shm // 128)
     return int(shm // 512)
 
 
