@@ -42,6 +42,8 @@ public class MultiBreakSVGpu extends MultiBreakSV {
     static final MethodHandle CREATE = h("mbsv_problem_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
     static final MethodHandle RUN = h("mbsv_run", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle DESTROY = h("mbsv_problem_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    // the library keeps large device blocks of destroyed problems for the next one; TRIM gives them back (device < 0: all)
+    static final MethodHandle TRIM = h("mbsv_trim", FunctionDescriptor.of(JAVA_INT, JAVA_INT));
     static final MethodHandle LAST_ERROR = h("mbsv_last_error", FunctionDescriptor.of(ADDRESS));
     // giant component on every GPU of the box: chains split over the devices, tallies pooled with one ncclReduce
     // (include/mbsv_b200.h: mbsv_run_multi; problems = one handle per device, created from the same descriptor)
