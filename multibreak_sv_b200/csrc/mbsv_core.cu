@@ -123,6 +123,18 @@ struct DevPool {
 };
 DevPool g_pool;
 
+// fn(begin, end) over [0, n) on up to 16 host threads (the scans of mbsv_problem_create over millions of entries)
+template <typename Fn>
+void parallel_for(int64_t n, Fn fn) {
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), 16, n / 65536}));
+    if (nt <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    const int64_t chunk = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) th.emplace_back([&, t] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
+    fn((int64_t)0, std::min(n, chunk));
+    for (auto& x : th) x.join();
+}
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -313,7 +325,9 @@ static int validate(const mbsv_problem_desc* d) {
         return fail(MBSV_ERR_ARG, "descriptor has n_sv > 0 but NULL AlterSV arrays");
     auto mono = [&](const int32_t* p, int n, int last, const char* name) -> int {
         if (p[0] != 0 || p[n] != last) return fail(MBSV_ERR_ARG, std::string(name) + ": bad first/last offset");
-        for (int i = 0; i < n; ++i) if (p[i + 1] < p[i]) return fail(MBSV_ERR_ARG, std::string(name) + ": not monotone");
+        std::atomic<int> bad{0};
+        parallel_for(n, [&](int64_t b, int64_t e) { for (int64_t i = b; i < e; ++i) if (p[i + 1] < p[i]) { bad = 1; return; } });
+        if (bad) return fail(MBSV_ERR_ARG, std::string(name) + ": not monotone");
         return 0;
     };
     int rc;
@@ -330,8 +344,13 @@ static int validate(const mbsv_problem_desc* d) {
         if (d->sub_frag_ptr[s + 1] == d->sub_frag_ptr[s])
             return fail(MBSV_ERR_ARG, "a subproblem has no fragments (the reference would index an empty keySet, "
                                       "MultiBreakSV.java:1401)");
-    for (int f = 0; f < d->n_frag; ++f)
-        if (d->frag_aln_ptr[f + 1] == d->frag_aln_ptr[f]) return fail(MBSV_ERR_ARG, "a fragment has no alignment");
+    {
+        std::atomic<int> bad{0};
+        parallel_for(d->n_frag, [&](int64_t b, int64_t e) {
+            for (int64_t f = b; f < e; ++f) if (d->frag_aln_ptr[f + 1] == d->frag_aln_ptr[f]) { bad = 1; return; }
+        });
+        if (bad) return fail(MBSV_ERR_ARG, "a fragment has no alignment");
+    }
     bool any_cc = false;
     for (int c = 0; c < d->n_cluster; ++c) {
         if (d->cluster_kind[c] > 1) return fail(MBSV_ERR_ARG, "cluster_kind must be 0 (cluster) or 1 (connected component)");
@@ -360,9 +379,16 @@ static int validate(const mbsv_problem_desc* d) {
     for (int x = 0; x < d->n_exp; ++x)
         if (d->logprobcov[(size_t)x * (d->max_support + 1)] != 0.0)
             return fail(MBSV_ERR_ARG, "logprobcov[x][0] must be 0 (MultiBreakSV.java:612-614 fills k = 1..maxSupport)");
-    for (int a = 0; a < d->n_aln; ++a) {
-        if (d->aln_exp[a] < 0 || d->aln_exp[a] >= d->n_exp) return fail(MBSV_ERR_ARG, "aln_exp out of range");
-        if (d->aln_esp_ptr[a + 1] - d->aln_esp_ptr[a] >= (1 << 23)) return fail(MBSV_ERR_ARG, "alignment with too many ESPs");
+    {
+        std::atomic<int> bad{0};
+        parallel_for(d->n_aln, [&](int64_t b, int64_t e) {
+            for (int64_t a = b; a < e; ++a) {
+                if (d->aln_exp[a] < 0 || d->aln_exp[a] >= d->n_exp) { bad = 1; return; }
+                if (d->aln_esp_ptr[a + 1] - d->aln_esp_ptr[a] >= (1 << 23)) { bad = 2; return; }
+            }
+        });
+        if (bad == 1) return fail(MBSV_ERR_ARG, "aln_exp out of range");
+        if (bad == 2) return fail(MBSV_ERR_ARG, "alignment with too many ESPs");
     }
     return 0;
 }
@@ -384,6 +410,8 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     const int S = d->n_sub, F = d->n_frag, A = d->n_aln, K = d->n_aln_esp, C = d->n_cluster, E = d->n_exp;
     // Packing + per-subproblem checks, parallel over subproblems (they are independent and contiguous).
     // uninitialised buffers: the worker threads touch (and page in) their own parts
+    // (page-locked staging buffers were measured: the upload drops from ~75 to ~40 ms, but the worker threads then write into
+    // pages one thread touched, and packing rises from ~100 to ~170 ms: ordinary memory, first touched by its worker, stays)
     std::unique_ptr<int4[]> rec(new (std::nothrow) int4[(size_t)A]);
     std::unique_ptr<int[]> slot(new (std::nothrow) int[(size_t)K + 1]);
     std::unique_ptr<int[]> sup_local(new (std::nothrow) int[(size_t)C + 1]);
@@ -587,11 +615,13 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         if (pmin > 0) maxn = std::max(maxn, (int)std::min(65536.0, 5.0 / pmin + 2));
     }
     std::vector<double> logF(S), neglogNsv(S, 0.0), logint(maxn + 1, 0.0), logp(E), log1mp(E);
-    for (int s = 0; s < S; ++s) {
-        logF[s] = mbsv::jm_log((double)(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]));
-        const int nsv = sub_sv_ptr[s + 1] - sub_sv_ptr[s];
-        if (nsv > 0) neglogNsv[s] = -mbsv::jm_log((double)nsv);
-    }
+    parallel_for(S, [&](int64_t b, int64_t e) {
+        for (int64_t s = b; s < e; ++s) {
+            logF[s] = mbsv::jm_log((double)(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]));
+            const int nsv = sub_sv_ptr[s + 1] - sub_sv_ptr[s];
+            if (nsv > 0) neglogNsv[s] = -mbsv::jm_log((double)nsv);
+        }
+    });
     for (int n = 1; n <= maxn; ++n) logint[n] = mbsv::jm_log((double)n);
     std::vector<double> invint(maxn + 1);
     for (int n = 0; n <= maxn; ++n) invint[n] = (double)1 / n;
@@ -611,29 +641,35 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
     p->sub_W.resize(S);
     // chain state rows: assignments + counts (+ per conn-comp {stamp, current and saved multisets} + set-cover scratch)
     std::vector<int> cluster_cc_off(C, -1), sub_cc_scratch(S, -1), sub_cc_maxleaf(S, 0);
-    for (int s = 0; s < S; ++s) {
-        int W = (d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]) + (d->sub_cluster_ptr[s + 1] - d->sub_cluster_ptr[s]) * E;
-        int off = 0, maxleaf = 0, maxroot = 0;
-        for (int c = d->sub_cluster_ptr[s]; c < d->sub_cluster_ptr[s + 1]; ++c) {
-            if (d->cluster_kind[c] != 1) continue;
-            const int nr = d->cluster_root_ptr[c + 1] - d->cluster_root_ptr[c];
-            cluster_cc_off[c] = off;
-            off += 1 + 2 * E * (1 + nr);
-            maxleaf = std::max(maxleaf, d->cluster_leaf_ptr[c + 1] - d->cluster_leaf_ptr[c]);
-            maxroot = std::max(maxroot, nr);
+    p->sub_nstates.resize(S); p->sub_F.resize(S); p->sub_nsv.resize(S);
+    std::atomic<int> any_cc{0};
+    parallel_for(S, [&](int64_t sb, int64_t se) {
+        for (int64_t s = sb; s < se; ++s) {
+            int W = (d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]) + (d->sub_cluster_ptr[s + 1] - d->sub_cluster_ptr[s]) * E;
+            int off = 0, maxleaf = 0, maxroot = 0;
+            for (int c = d->sub_cluster_ptr[s]; c < d->sub_cluster_ptr[s + 1]; ++c) {
+                if (d->cluster_kind[c] != 1) continue;
+                const int nr = d->cluster_root_ptr[c + 1] - d->cluster_root_ptr[c];
+                cluster_cc_off[c] = off;
+                off += 1 + 2 * E * (1 + nr);
+                maxleaf = std::max(maxleaf, d->cluster_leaf_ptr[c + 1] - d->cluster_leaf_ptr[c]);
+                maxroot = std::max(maxroot, nr);
+            }
+            if (off > 0) { sub_cc_scratch[s] = off; sub_cc_maxleaf[s] = maxleaf; W += off + maxleaf + maxroot; any_cc = 1; }
+            p->sub_W[s] = W;
+            long long nst = off > 0 ? 0 : 1;
+            for (int f = d->sub_frag_ptr[s]; f < d->sub_frag_ptr[s + 1] && nst > 0 && nst < (1LL << 30); ++f)
+                nst *= (long long)(d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]) + 1;
+            p->sub_nstates[s] = (int)std::min<long long>(nst, 1LL << 30);
+            p->sub_F[s] = d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s];
+            p->sub_nsv[s] = sub_sv_ptr[s + 1] - sub_sv_ptr[s];
         }
-        if (off > 0) { sub_cc_scratch[s] = off; sub_cc_maxleaf[s] = maxleaf; W += off + maxleaf + maxroot; p->has_cc = true; }
-        p->sub_W[s] = W;
-        long long nst = off > 0 ? 0 : 1;
-        for (int f = d->sub_frag_ptr[s]; f < d->sub_frag_ptr[s + 1] && nst > 0 && nst < (1LL << 30); ++f)
-            nst *= (long long)(d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]) + 1;
-        p->sub_nstates.push_back((int)std::min<long long>(nst, 1LL << 30));
-        p->sub_F.push_back(d->sub_frag_ptr[s + 1] - d->sub_frag_ptr[s]);
-        p->sub_nsv.push_back(sub_sv_ptr[s + 1] - sub_sv_ptr[s]);
-    }
+    });
+    if (any_cc) p->has_cc = true;
     p->sub_maxent = sub_maxent;
     p->frag_nal.resize(F);
-    for (int f = 0; f < F; ++f) p->frag_nal[f] = d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f];
+    parallel_for(F, [&](int64_t b, int64_t e2) { for (int64_t f = b; f < e2; ++f) p->frag_nal[f] = d->frag_aln_ptr[f + 1] - d->frag_aln_ptr[f]; });
+    lap("rows");
     p->sub_maxpos = sub_maxpos;
     p->narrow_ok = max_nal <= 127 && d->max_support <= 127;
 
@@ -683,6 +719,7 @@ int mbsv_problem_create(const mbsv_problem_desc* d, int32_t device, mbsv_problem
         chk(up(p->d_root_leaf, std::vector<int>(d->root_leaf, d->root_leaf + d->n_root_leaf)));
     }
     chk(up(p->d_sub_W, p->sub_W));
+    lap("upload");
     if (e != cudaSuccess) {
         delete p;
         return fail(e == cudaErrorMemoryAllocation ? MBSV_ERR_OOM : MBSV_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e));
