@@ -804,7 +804,7 @@ KernelFn pick(int mode, bool trace, bool smem, int E, int rows, bool narrow_ok, 
 // memoised kernel (only when every warp holds chains of one subproblem, i.e. n_chains % 32 == 0, and the table fits
 // the largest shared-memory class), tile rows per warp, launch order.
 constexpr int MAX_SMEM_ROWS = 128;     // largest shared-memory size class (rows per chain)
-constexpr int SMEM_TABLE_ROWS = 48;   // tiles up to this many rows keep the table in shared memory
+constexpr int SMEM_TABLE_ROWS = mbsv::MEMO_SMEM_TABLE_ROWS;   // tiles up to this many rows keep the table in shared memory
 // tab_mode: 0 = no memoised kernel (memo-eligible subproblems re-sum the posterior per proposal in the general kernel),
 // 1 = warps of one subproblem (strides and, when small, the table in the warp's shared memory), 2 = mixed warps (every
 // lane its own subproblem: strides in the lane's column, every table in device memory).  The arithmetic is the same in
@@ -832,8 +832,12 @@ int ensure_plan(mbsv_problem* p, int memo_states, int tab_mode) {
             const int fr = (p->sub_F[s] + 1) & ~1;
             // one-fragment subproblems without AlterSV candidates also tabulate the acceptance ratios (nst^2)
             // (64-bit: nst may be 65536; a ratio table that cannot fit simply makes with_table exceed SMEM_TABLE_ROWS)
-            const long long ratio_words = (p->sub_F[s] == 1 && p->sub_nsv[s] == 0) ? 2LL * nst * nst : 0;
-            const long long with_table = rows + (fr + 2LL * nst + ratio_words + 31) / 32;
+            // so do small subproblems of several fragments without AlterSV candidates (memo_kernel.cuh `rt`); if their ratio
+            // table does not fit, the log-posterior table alone may
+            const bool multi_rt = p->sub_F[s] > 1 && p->sub_nsv[s] == 0 && nst <= mbsv::MEMO_RT_MAX_STATES;
+            long long ratio_words = ((p->sub_F[s] == 1 && p->sub_nsv[s] == 0) || multi_rt) ? 2LL * nst * nst : 0;
+            long long with_table = rows + (fr + 2LL * nst + ratio_words + 31) / 32;
+            if (multi_rt && with_table > SMEM_TABLE_ROWS) { ratio_words = 0; with_table = rows + (fr + 2LL * nst + 31) / 32; }
             int trows = 0;
             bool global_table = true;
             if (tab_mode == 1 && with_table <= SMEM_TABLE_ROWS) { trows = (int)with_table; global_table = false; }

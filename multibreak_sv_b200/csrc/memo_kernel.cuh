@@ -122,10 +122,14 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
     // One-fragment subproblems without AlterSV candidates (the bulk of a power-law batch): the whole acceptance
     // ratio min(1, exp(..)) of every (previous, proposed) pair is tabulated too, so a proposal needs no exp.
     const bool f1 = (F == 1) && (nsv == 0) && (tab_off < 0);
+    // Small subproblems of several fragments without AlterSV candidates tabulate the ratios of their single-fragment moves the
+    // same way (every proposal of theirs is one): rtab[state][state'] for the pairs that differ in exactly one fragment.
+    const bool rt = !f1 && !MIXED && tab_off < 0 && nsv == 0 && nst <= MEMO_RT_MAX_STATES &&
+                    W + (((F + 1) & ~1) + 2 * nst + 2 * nst * nst + 31) / 32 <= MEMO_SMEM_TABLE_ROWS;
     double* rtab = tab + nst;
 #ifdef MBSV_BOUNDS_CHECK
     {   // strides, table and ratio table must end inside this warp's rows of the tile
-        const int* end = mixed ? smem_tile : tab_off >= 0 ? strides + ((F + 1) & ~1) : reinterpret_cast<const int*>(rtab + (f1 ? nst * nst : 0));
+        const int* end = mixed ? smem_tile : tab_off >= 0 ? strides + ((F + 1) & ~1) : reinterpret_cast<const int*>(rtab + ((f1 || rt) ? nst * nst : 0));
         if ((mixed && tab_off < 0) || end > smem_tile + (size_t)(wic + 1) * R.rows_per_warp * 32) {
             printf("memo tables of subproblem %d overrun the %d-row tile\n", sub, R.rows_per_warp);
             __trap();
@@ -191,6 +195,25 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
                     double Alogq, Anewlogq;
                     naive_logq(n, pv, nw, neglogF, logperr, R.log1mperr, P.logint, Alogq, Anewlogq);
                     const double e = exp_dev((tab[nw + 1] + Alogq) - (tab[pv + 1] + Anewlogq));   // :1146
+                    ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);
+                }
+                rtab[idx] = ratio;
+            }
+        }
+        if (rt && alive) {
+            for (int idx = lane; idx < nst * nst; idx += nalive) {
+                const int s1 = idx / nst, s2 = idx % nst;
+                int nd = 0, n = 0, pv = 0, nw = 0;
+                for (int f = 0; f < F; ++f) {
+                    const int nf = P.frag_aln_ptr[f0 + f + 1] - P.frag_aln_ptr[f0 + f];
+                    const int d1 = (s1 / strides[f]) % (nf + 1), d2 = (s2 / strides[f]) % (nf + 1);
+                    if (d1 != d2) { ++nd; n = nf; pv = d1 - 1; nw = d2 - 1; }
+                }
+                double ratio = 0.0;
+                if (nd == 1) {
+                    double Alogq, Anewlogq;
+                    naive_logq(n, pv, nw, neglogF, logperr, R.log1mperr, P.logint, Alogq, Anewlogq);
+                    const double e = exp_dev((tab[s2] + Alogq) - (tab[s1] + Anewlogq));   // :1146
                     ratio = (e != e) ? e : (1.0 < e ? 1.0 : e);
                 }
                 rtab[idx] = ratio;
@@ -321,6 +344,19 @@ __global__ void __launch_bounds__(128, MBSV_MEMO_MIN_BLOCKS) mbsv_memo_kernel(co
             now = naive_draw(rng, nst - 1, prev, perr_thr, P.invint);
             if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
             newidx = now + 1;
+            newlogprob = tab[newidx];
+            ratio = rtab[sidx * nst + newidx];
+        } else if (rt) {
+            // no AlterSV candidate (the move-type coin cannot matter), several fragments; the ratio comes from the table
+            rng.skip<2>();
+            const double u = rng.nextDouble();
+            ++n_naive_prop;
+            f = (int)(u * (double)F);
+            a0 = P.frag_aln_ptr[f0 + f];
+            prev = MBSV_ST(f);
+            now = naive_draw(rng, P.frag_aln_ptr[f0 + f + 1] - a0, prev, perr_thr, P.invint);
+            if (now == prev) { err = -5; done = true; continue; }   // Error at :1122-1123
+            newidx += (now - prev) * strides[f * sstr];
             newlogprob = tab[newidx];
             ratio = rtab[sidx * nst + newidx];
         } else {

@@ -90,6 +90,15 @@ struct DevRun {
 
 // MultiBreakSV.java:1661-1695 (logBinomial, logbinomialcoefficient, logNormal)
 
+// Memoised kernel: tiles up to MEMO_SMEM_TABLE_ROWS rows keep the log-posterior table (and, for subproblems without AlterSV
+// candidates of at most MEMO_RT_MAX_STATES joint states, or with one fragment, the acceptance-ratio table) in shared memory.
+// Host planner (mbsv_core.cu ensure_plan) and kernel (memo_kernel.cuh) evaluate the same predicate.
+constexpr int MEMO_SMEM_TABLE_ROWS = 48;
+#ifndef MBSV_RT_MAX
+#define MBSV_RT_MAX 32
+#endif
+constexpr int MEMO_RT_MAX_STATES = MBSV_RT_MAX;
+
 using KernelFn = void (*)(const DevProblem, const DevRun);
 // kernel selectors, one per translation unit (kern_fast.cu / kern_replay.cu / kern_trace.cu)
 KernelFn get_kernel_fast(bool smem, int n_exp, int rows, bool narrow_ok, size_t* extra_smem, int* state_bytes);   // MODE_FAST, no trace: the throughput path (rows = shared-memory class)

@@ -732,3 +732,26 @@ def test_device_memory_pool_across_problems(oracle, mbsv):
     assert torch.cuda.mem_get_info()[0] > free_kept           # the blocks went back to the driver
     o = oracle.run(oracle.Problem(q.scalars, q.arrays), "incremental", 600, n_chains=32, nthreads=8, java_int_wrap=False)
     assert_same(o, other)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_chains", [32, 64])
+def test_ratio_tables_of_small_multi_fragment_subproblems(oracle, mbsv, n_chains):
+    """Full warps of one subproblem (chains a multiple of 32): subproblems of several fragments without AlterSV candidates
+    and at most 32 joint states take their acceptance ratios from a table built in shared memory (memo_kernel.cuh `rt`),
+    one-fragment ones likewise (`f1`); both against the oracle, in both modes."""
+    from multibreak_sv_b200 import synth
+    p = synth.generate("cfg4", n_frag=4000, seed=17, shuffle_orders=True)
+    a = p.arrays
+    F, nsv = np.diff(a["sub_frag_ptr"]), np.diff(a["sub_sv_ptr"])
+    nst = np.exp(np.add.reduceat(np.log(np.diff(a["frag_aln_ptr"]) + 1.0), a["sub_frag_ptr"][:-1]))
+    assert ((F >= 2) & (nsv == 0) & (nst <= 32.5)).sum() >= 20 and ((F == 1) & (nsv == 0)).sum() >= 100
+    op = oracle.Problem(p.scalars, p.arrays)
+    dp = mbsv.DeviceProblem(p)
+    o = oracle.run(op, "incremental", 2500, n_chains=n_chains, nthreads=8, java_int_wrap=False)
+    g = dp.run(mbsv.MODE_FAST, 2500, n_chains=n_chains)
+    assert_same(o, g)
+    assert any(li["rows"] < 0 for li in dp.launch_info())          # the memoised kernel ran
+    o = oracle.run(op, "faithful", 800, n_chains=n_chains, nthreads=8, trace=True)
+    g = dp.run(mbsv.MODE_REPLAY_EXACT, 800, n_chains=n_chains, trace=True)
+    assert_same(o, g, trace=True)
