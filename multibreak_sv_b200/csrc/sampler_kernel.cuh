@@ -21,32 +21,30 @@
 
 namespace mbsv {
 
+// ---- build parameters (tuning aids; the defaults are the measured optima, profiles/r02_general_kernel_ab.json) ----
+// CTAs per SM the registers are bounded for: shared-memory classes (see MINB below for the per-class exceptions) and the
+// global-workspace class.  6-8 CTAs/SM (80-64 registers) spill and are 1.6-2.1x slower.
 #ifndef MBSV_MIN_BLOCKS
 #define MBSV_MIN_BLOCKS 5
-#endif
-// Launch bounds of the global-workspace class (large subproblems).  Measured on B200: 8 blocks/SM (64 registers, spills)
-// is slower than 5 (96 registers) both alone (289 vs 267 ms) and next to the other classes.
-// Read-only evaluation of Naive proposals (no tentative write, no undo pass) was built and measured in round 2: slower in
-// every class (register lists -> ~1 KB of spills per thread; profiles/r02_readonly_eval_ab.json), so do/undo stays.
-//
-// Drawing the NEXT proposal's header right after the current proposal's acceptance coin (no draw lies between them), so that
-// its fragment -> alignment-range / assignment loads overlap the current evaluation, plus L1 prefetches of its alignment
-// records, was built and measured in round 2 as well: 15-40 % slower in every class (the carried header costs registers the
-// kernel does not have).  What stayed from that work: the counted slots of an alignment come from one 16-byte record
-// (aln_ent4) instead of a walk over aln_esp_slot.
-// AlterSV proposals are held until this many lanes of the warp have one pending (1 = run them as they come)
-#ifndef MBSV_INLINE_MATH_GLOBAL
-#define MBSV_INLINE_MATH_GLOBAL 1
-#endif
-#ifndef MBSV_SV_BATCH
-#define MBSV_SV_BATCH 8
 #endif
 #ifndef MBSV_MIN_BLOCKS_GLOBAL
 #define MBSV_MIN_BLOCKS_GLOBAL 5
 #endif
+// logBinomial / exp inlined into the proposal code of the global-workspace class (406 -> 364 ms; the shared-memory classes
+// lose 20 % with it: instruction cache)
+#ifndef MBSV_INLINE_MATH_GLOBAL
+#define MBSV_INLINE_MATH_GLOBAL 1
+#endif
+// AlterSV proposals are held until this many lanes of the warp have one pending (1 = run them as they come)
+#ifndef MBSV_SV_BATCH
+#define MBSV_SV_BATCH 8
+#endif
+// Built, measured and dropped in round 2 (every class slower): read-only evaluation of Naive proposals without tentative write
+// and undo pass (register lists -> ~1 KB of spills per thread; profiles/r02_readonly_eval_ab.json), and drawing the NEXT
+// proposal's header right after the current acceptance coin so that its fragment loads overlap the current evaluation, with L1
+// prefetches of its alignment records (15-40 % slower: the carried header costs registers the kernel does not have).  What
+// stayed from the latter: the counted slots of an alignment come from one 16-byte record (aln_ent4).
 
-// CC = the batch contains connected-component clusters (GASV localization -1): their support is the sorted
-// multiset of a greedy set cover (MultiBreakSVAssignmentMatrix.java:337-409) kept per chain next to the counts.
 // A per-thread array of N values indexed at run time: in registers (selected by compare chains) or, INSMEM, in the thread's
 // column of a [N][128] block of shared memory (plain address arithmetic, and no registers held across the proposal).
 template <typename T, int N, bool INSMEM> struct LaneArr;
@@ -76,6 +74,8 @@ template <typename T, int N> struct LaneArr<T, N, true> {
     __device__ __forceinline__ void add(int x, T d) { p[x * 128] += d; }
 };
 
+// CC = the batch contains connected-component clusters (GASV localization -1): their support is the sorted
+// multiset of a greedy set cover (MultiBreakSVAssignmentMatrix.java:337-409) kept per chain next to the counts.
 // MINB = CTAs per SM the register allocation is bounded for (0 = the build default).  The kernel wants ~190 registers; at 5
 // CTAs/SM it gets 96 and spills, and the spills cost more than the occupancy buys once the state tile limits a class to 3 or
 // 4 CTAs/SM anyway (measured per class on B200, 6000 iterations: 128 rows 87 -> 68 ms at MINB 3, 96 rows 129 -> 98 ms and
